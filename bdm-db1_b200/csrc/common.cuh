@@ -1,0 +1,37 @@
+// Host-side helpers shared by all translation units of libdb1_sm100.so.
+#pragma once
+#include <cuda.h>
+#include <cuda_fp16.h>
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <string.h>
+
+namespace db1 {
+
+// thread-local last-error string returned by db1_last_error()
+char* err_buf();
+int set_err(int code, const char* fmt, ...);
+
+#define DB1_CHECK_ARG(cond, ...)                    \
+  do {                                              \
+    if (!(cond)) return db1::set_err(-1, __VA_ARGS__); \
+  } while (0)
+
+#define DB1_CUDA(expr)                                                                  \
+  do {                                                                                  \
+    cudaError_t _e = (expr);                                                            \
+    if (_e != cudaSuccess)                                                              \
+      return db1::set_err((int)_e, "%s failed: %s (%s:%d)", #expr, cudaGetErrorString(_e), __FILE__, __LINE__); \
+  } while (0)
+
+// Encode a 2-D/3-D fp16 tensor map with 128-byte swizzle. dims/strides innermost first; strides in BYTES for
+// dims 1.. (dim 0 is contiguous). Returns 0 or a negative error after set_err().
+int make_tmap_f16(CUtensorMap* out, const void* base, int rank, const uint64_t* dims, const uint64_t* strides_bytes,
+                  const uint32_t* box);
+
+int sm_count();
+
+static inline int cdiv(int a, int b) { return (a + b - 1) / b; }
+
+}  // namespace db1
