@@ -1,3 +1,4 @@
+#include "../../include/db1_sm100.h"
 #include "common.cuh"
 
 #include <stdarg.h>
@@ -74,3 +75,4 @@ int sm_count() {
 }  // namespace db1
 
 extern "C" const char* db1_last_error() { return db1::err_buf(); }
+extern "C" int db1_abi_version() { return 1; }

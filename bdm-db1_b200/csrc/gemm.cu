@@ -1,9 +1,10 @@
 // Persistent warp-specialised tcgen05 GEMM for sm_100a.
 //
-//   C[M,N] = epilogue( A[M,K] * B[N,K]^T ),  fp16 operands, fp32 accumulation in TMEM.
+//   for every batch (z1, z2):  C[M,N] (+)= epilogue( alpha * A[M,K] * B[N,K]^T ),  fp16 operands, fp32 accumulation in TMEM.
 //
 // One CTA per SM walks output tiles (128 x BN) round-robin. Roles:
-//   warp 0     TMA producer : global -> smem ring (STAGES x [A 128x64 | B BNx64], 128B swizzle)
+//   warp 0     TMA producer : global -> smem ring (STAGES x [A 128x64 | B BNx64], 128B swizzle, 4-D tensor maps
+//                             (inner, rows, z1, z2) so batched / strided operands need no gather)
 //   warp 1     MMA issuer   : one elected thread issues tcgen05.mma (M=128, N=BN, K=16), accumulators in TMEM;
 //                             the accumulator is double-buffered (2 x BN columns) so tile i+1's main loop
 //                             overlaps tile i's epilogue
@@ -13,10 +14,10 @@
 // MN-contiguous ("MN-major": weights in dgrad, both operands in wgrad) - the UMMA descriptors transpose for free,
 // so dgrad/wgrad never materialise a transposed copy.
 //
-// Replaces the cuBLAS calls behind nn.Linear / F.linear in the reference
-// (src/model/transformer_xl.py:138-139, 228, 265-268, 595) and their autograd backward.
+// Replaces the cuBLAS calls behind nn.Linear / F.linear / einsum in the reference
+// (src/model/transformer_xl.py:138-139, 163-170, 220, 228, 265-268, 595) and their autograd backward.
+#include "../../include/db1_sm100.h"
 #include "common.cuh"
-#include "gemm.cuh"
 #include "ptx.cuh"
 
 namespace db1 {
@@ -26,12 +27,43 @@ constexpr int BK = 64;
 constexpr int GEMM_THREADS = 192;
 constexpr int A_STAGE_BYTES = BM * BK * 2;  // 16 KB
 
+struct GemmParams {
+  int M, N, K;
+  int a_mn, b_mn;
+  int Z1, Z2;
+  int a_z1on, a_z2on, b_z1on, b_z2on;
+  int reduce_z2;
+  int k_mode;
+  int skip_upper;
+  float alpha;
+  __half* C;
+  long long ldc, c_z1, c_z2;
+  const __half* bias;
+  const __half* resid;
+  long long ldr;
+  int accumulate;
+  uint32_t drop_thr16;
+  float drop_scale;
+  uint64_t seed;
+  const __half* u;
+  const __half* v;
+  int d_model;
+  __half* H;
+  long long ldh;
+  int F;
+  const __half* P;
+  __half* C2;
+  const float* Drow;
+  int window;
+};
+
 template <int BN>
 struct GemmCfg {
   static constexpr int STAGES = (BN == 256) ? 4 : 6;
   static constexpr int B_STAGE_BYTES = BN * BK * 2;
   static constexpr int STAGE_BYTES = A_STAGE_BYTES + B_STAGE_BYTES;
-  static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /*align*/ + 256 /*barriers*/;
+  static constexpr int STAGING_BYTES = 4 * 32 * 80;  // DS epilogue: per-warp 32 rows x (64 B + 16 B pad)
+  static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + STAGING_BYTES + 1024 /*align*/ + 256 /*barriers*/;
   static constexpr int TMEM_COLS = 2 * BN;  // 512 or 256
 };
 
@@ -60,6 +92,37 @@ DEVI Half8 float_to_half8(const float (&f)[8]) {
   return v;
 }
 
+struct TileCoord {
+  int mt, nt, z1, z2;
+  int kb0, kb1;  // k-block range
+  bool skip;
+};
+
+template <int BN, int EPI>
+DEVI TileCoord decode_tile(const GemmParams& p, int tile, int MT, int NT, int KB) {
+  TileCoord t;
+  t.mt = tile % MT;
+  int r = tile / MT;
+  t.nt = r % NT;
+  r /= NT;
+  t.z1 = r % p.Z1;
+  t.z2 = r / p.Z1;
+  t.kb0 = 0;
+  t.kb1 = KB;
+  if (p.k_mode == DB1_K_END_BY_ROW) {
+    int e = ((t.mt + 1) * BM + BK - 1) / BK;
+    t.kb1 = e < KB ? e : KB;
+  } else if (p.k_mode == DB1_K_BEGIN_BY_ROW) {
+    t.kb0 = (t.mt * BM) / BK;
+  } else if (p.k_mode == DB1_K_BEGIN_REV) {
+    int b = p.K - (t.mt + 1) * BM;
+    t.kb0 = b > 0 ? b / BK : 0;
+  }
+  t.skip = p.skip_upper && (t.nt * BN > t.mt * BM + BM - 1);
+  if (t.kb0 >= t.kb1) t.skip = true;
+  return t;
+}
+
 template <int BN, int EPI>
 __global__ void __launch_bounds__(GEMM_THREADS, 1)
 gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const GemmParams p) {
@@ -67,7 +130,8 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
   constexpr int STAGES = Cfg::STAGES;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
-  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + STAGES * Cfg::STAGE_BYTES);
+  uint8_t* staging = smem + STAGES * Cfg::STAGE_BYTES;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(staging + Cfg::STAGING_BYTES);
   uint64_t* full = bars;
   uint64_t* empty = bars + STAGES;
   uint64_t* tfull = bars + 2 * STAGES;
@@ -78,9 +142,11 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
   const int lane = threadIdx.x & 31;
 
   const int MT = (p.M + BM - 1) / BM;
-  const int NT = (EPI == EPI_GEGLU) ? (p.F / (BN / 2)) : (p.N + BN - 1) / BN;
-  const int num_tiles = MT * NT;
+  const int NT = (EPI == DB1_EPI_GEGLU) ? (p.F / (BN / 2)) : (p.N + BN - 1) / BN;
+  const int ZO = p.reduce_z2 ? 1 : p.Z2;
+  const int num_tiles = MT * NT * p.Z1 * ZO;
   const int KB = (p.K + BK - 1) / BK;
+  const int KZ = p.reduce_z2 ? p.Z2 : 1;  // extra contraction loop over z2
 
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&tmA);
@@ -112,35 +178,42 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
       int s = 0;
       uint32_t ph = 0;
       for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
-        const int mt = tile % MT, nt = tile / MT;
-        const int m0 = mt * BM;
-        for (int kb = 0; kb < KB; ++kb) {
-          mbar_wait(&empty[s], ph ^ 1);
-          uint8_t* sa = smem + s * Cfg::STAGE_BYTES;
-          uint8_t* sb = sa + A_STAGE_BYTES;
-          mbar_expect_tx(&full[s], Cfg::STAGE_BYTES);
-          const int k0 = kb * BK;
-          if (!p.a_mn) {
-            tma_load_2d(sa, &tmA, &full[s], k0, m0);
-          } else {
-            tma_load_2d(sa, &tmA, &full[s], m0, k0);
-            tma_load_2d(sa + 8192, &tmA, &full[s], m0 + 64, k0);
-          }
-          if (!p.b_mn) {
-#pragma unroll
-            for (int j = 0; j < BN / 128; ++j) {
-              int row0;
-              if (EPI == EPI_GEGLU) row0 = j * p.F + nt * (BN / 2);
-              else row0 = nt * BN + j * 128;
-              tma_load_2d(sb + j * 16384, &tmB, &full[s], k0, row0);
+        const TileCoord t = decode_tile<BN, EPI>(p, tile, MT, NT, KB);
+        if (t.skip) continue;
+        const int m0 = t.mt * BM;
+        for (int kz = 0; kz < KZ; ++kz) {
+          const int z2 = p.reduce_z2 ? kz : t.z2;
+          const int az1 = p.a_z1on ? t.z1 : 0, az2 = p.a_z2on ? z2 : 0;
+          const int bz1 = p.b_z1on ? t.z1 : 0, bz2 = p.b_z2on ? z2 : 0;
+          for (int kb = t.kb0; kb < t.kb1; ++kb) {
+            mbar_wait(&empty[s], ph ^ 1);
+            uint8_t* sa = smem + s * Cfg::STAGE_BYTES;
+            uint8_t* sb = sa + A_STAGE_BYTES;
+            mbar_expect_tx(&full[s], Cfg::STAGE_BYTES);
+            const int k0 = kb * BK;
+            if (!p.a_mn) {
+              tma_load_4d(sa, &tmA, &full[s], k0, m0, az1, az2);
+            } else {
+              tma_load_4d(sa, &tmA, &full[s], m0, k0, az1, az2);
+              tma_load_4d(sa + 8192, &tmA, &full[s], m0 + 64, k0, az1, az2);
             }
-          } else {
+            if (!p.b_mn) {
 #pragma unroll
-            for (int j = 0; j < BN / 64; ++j) tma_load_2d(sb + j * 8192, &tmB, &full[s], nt * BN + j * 64, k0);
-          }
-          if (++s == STAGES) {
-            s = 0;
-            ph ^= 1;
+              for (int j = 0; j < BN / 128; ++j) {
+                int row0;
+                if (EPI == DB1_EPI_GEGLU) row0 = j * p.F + t.nt * (BN / 2);
+                else row0 = t.nt * BN + j * 128;
+                tma_load_4d(sb + j * 16384, &tmB, &full[s], k0, row0, bz1, bz2);
+              }
+            } else {
+#pragma unroll
+              for (int j = 0; j < BN / 64; ++j)
+                tma_load_4d(sb + j * 8192, &tmB, &full[s], t.nt * BN + j * 64, k0, bz1, bz2);
+            }
+            if (++s == STAGES) {
+              s = 0;
+              ph ^= 1;
+            }
           }
         }
       }
@@ -155,25 +228,33 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
       int s = 0;
       uint32_t ph = 0;
       int it = 0;
-      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++it) {
+      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+        const TileCoord t = decode_tile<BN, EPI>(p, tile, MT, NT, KB);
+        if (t.skip) continue;
         const int as = it & 1;
         const uint32_t aph = (it >> 1) & 1;
+        ++it;
         mbar_wait(&tempty[as], aph ^ 1);
         tc_fence_after();
         const uint32_t tacc = tmem_base + as * BN;
-        for (int kb = 0; kb < KB; ++kb) {
-          mbar_wait(&full[s], ph);
-          tc_fence_after();
-          const uint32_t sa = smem_u32(smem + s * Cfg::STAGE_BYTES);
-          const uint64_t adesc = umma_smem_desc(sa, a_lbo, 1024);
-          const uint64_t bdesc = umma_smem_desc(sa + A_STAGE_BYTES, b_lbo, 1024);
+        uint32_t acc = 0;
+        for (int kz = 0; kz < KZ; ++kz) {
+          for (int kb = t.kb0; kb < t.kb1; ++kb) {
+            mbar_wait(&full[s], ph);
+            tc_fence_after();
+            const uint32_t sa = smem_u32(smem + s * Cfg::STAGE_BYTES);
+            const uint64_t adesc = umma_smem_desc(sa, a_lbo, 1024);
+            const uint64_t bdesc = umma_smem_desc(sa + A_STAGE_BYTES, b_lbo, 1024);
 #pragma unroll
-          for (int k = 0; k < BK / 16; ++k)
-            umma_ss(tacc, adesc + (uint64_t)(k * a_kadv), bdesc + (uint64_t)(k * b_kadv), idesc, (kb | k) ? 1u : 0u);
-          umma_commit(&empty[s]);
-          if (++s == STAGES) {
-            s = 0;
-            ph ^= 1;
+            for (int k = 0; k < BK / 16; ++k) {
+              umma_ss(tacc, adesc + (uint64_t)(k * a_kadv), bdesc + (uint64_t)(k * b_kadv), idesc, acc);
+              acc = 1;
+            }
+            umma_commit(&empty[s]);
+            if (++s == STAGES) {
+              s = 0;
+              ph ^= 1;
+            }
           }
         }
         umma_commit(&tfull[as]);
@@ -183,17 +264,21 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
     // ------------------------------------------------------------ epilogue warps (2..5)
     const int quad = warp & 3;  // TMEM lane quadrant this warp may access
     int it = 0;
-    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++it) {
-      const int mt = tile % MT, nt = tile / MT;
+    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+      const TileCoord t = decode_tile<BN, EPI>(p, tile, MT, NT, KB);
+      if (t.skip) continue;
+      const int mt = t.mt, nt = t.nt;
       const int as = it & 1;
       const uint32_t aph = (it >> 1) & 1;
+      ++it;
       const int row = mt * BM + quad * 32 + lane;
       const bool row_ok = row < p.M;
+      const long long zoff = (long long)t.z1 * p.c_z1 + (long long)t.z2 * p.c_z2;
       mbar_wait(&tfull[as], aph);
       tc_fence_after();
       const uint32_t tacc = tmem_base + as * BN + ((uint32_t)(quad * 32) << 16);
 
-      if (EPI == EPI_PLAIN || EPI == EPI_QKV) {
+      if (EPI == DB1_EPI_PLAIN || EPI == DB1_EPI_QKV) {
 #pragma unroll 1
         for (int c = 0; c < BN / 32; ++c) {
           uint32_t r[32];
@@ -208,7 +293,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
               float f[8];
 #pragma unroll
               for (int i = 0; i < 8; ++i) f[i] = __uint_as_float(r[g * 8 + i]) * p.alpha;
-              if (EPI == EPI_QKV) {
+              if (EPI == DB1_EPI_QKV) {
                 const size_t orow = (size_t)row * p.ldc;
                 if (col < p.d_model) {
                   float uu[8], vv[8], o[8];
@@ -245,27 +330,79 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
 #pragma unroll
                   for (int i = 0; i < 8; ++i) f[i] += b[i];
                 }
-                __half* dst = p.C + (size_t)row * p.ldc + col;
-                if (p.accumulate) {
-                  float b[8];
-                  half8_to_float(ld_half8(dst), b);
+                __half* dst = p.C + zoff + (size_t)row * p.ldc + col;
+                if (col + 8 <= p.N) {
+                  if (p.accumulate) {
+                    float b[8];
+                    half8_to_float(ld_half8(dst), b);
 #pragma unroll
-                  for (int i = 0; i < 8; ++i) f[i] += b[i];
+                    for (int i = 0; i < 8; ++i) f[i] += b[i];
+                  }
+                  st_half8(dst, float_to_half8(f));
+                } else {
+                  // ragged last group (N not a multiple of 8): scalar tail
+                  for (int i = 0; i < p.N - col; ++i) {
+                    float x = f[i];
+                    if (p.accumulate) x += __half2float(dst[i]);
+                    dst[i] = __float2half_rn(x);
+                  }
                 }
-                st_half8(dst, float_to_half8(f));
               }
             }
           }
+        }
+      } else if (EPI == DB1_EPI_DS) {
+        // dS = P * (dP - Drow) * alpha on the causal / windowed region, 0 elsewhere; second copy in
+        // relative-position order (the adjoint of _rel_shift, transformer_xl.py:98-110).
+        const long long zlin = (long long)t.z2 * p.Z1 + t.z1;
+        const float drow = row_ok ? p.Drow[zlin * p.M + row] : 0.f;
+        uint8_t* stg = staging + (warp - 2) * (32 * 80);
+        const int row_base = mt * BM + quad * 32;
+#pragma unroll 1
+        for (int c = 0; c < BN / 32; ++c) {
+          const int col0 = nt * BN + c * 32;
+          if (col0 > row_base + 31 || col0 >= p.N) break;  // warp-uniform: chunk entirely above the diagonal
+          uint32_t r[32];
+          tmem_ld32(tacc + c * 32, r);
+          tmem_ld_wait();
+#pragma unroll
+          for (int g = 0; g < 4; ++g) {
+            const int col = col0 + g * 8;
+            float pv[8], o[8];
+            const bool any = row_ok && col <= row && col < p.N;
+            if (any) half8_to_float(ld_half8(p.P + zoff + (size_t)row * p.ldc + col), pv);
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+              const int j = col + i;
+              const bool ok = any && j <= row && (row - j) < p.window;
+              o[i] = ok ? pv[i] * (__uint_as_float(r[g * 8 + i]) - drow) * p.alpha : 0.f;
+            }
+            const Half8 hv = float_to_half8(o);
+            if (row_ok && col < p.N) st_half8(p.C + zoff + (size_t)row * p.ldc + col, hv);
+            *reinterpret_cast<Half8*>(stg + lane * 80 + g * 16) = hv;
+          }
+          __syncwarp();
+          // coalesced un-shift: lane t writes element (rr, col0+t) of the staged 32x32 tile
+#pragma unroll 4
+          for (int rr = 0; rr < 32; ++rr) {
+            const int i = row_base + rr;
+            const int j = col0 + lane;
+            if (i < p.M && j <= i && j < p.N) {
+              const __half hvv = *reinterpret_cast<const __half*>(stg + rr * 80 + lane * 2);
+              p.C2[zoff + (size_t)i * p.ldc + (size_t)(j + p.N - 1 - i)] = hvv;
+            }
+          }
+          __syncwarp();
         }
       } else {
         // GeGLU forward / backward: accumulator columns [0,BN/2) pair with [BN/2,BN) (forward) or the tile's
         // BN output columns pair with saved a|g (backward).
         constexpr int HALF = BN / 2;
 #pragma unroll 1
-        for (int c = 0; c < (EPI == EPI_GEGLU ? HALF : BN) / 32; ++c) {
+        for (int c = 0; c < (EPI == DB1_EPI_GEGLU ? HALF : BN) / 32; ++c) {
           uint32_t ra[32];
           tmem_ld32(tacc + c * 32, ra);
-          if (EPI == EPI_GEGLU) {
+          if (EPI == DB1_EPI_GEGLU) {
             uint32_t rg[32];
             tmem_ld32(tacc + HALF + c * 32, rg);
             tmem_ld_wait();
@@ -288,10 +425,14 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
 #pragma unroll
                   for (int i = 0; i < 8; ++i) gg[i] += b[i];
                 }
+                // round the pre-activations to fp16 first so that forward and backward see the same values
+                const Half8 ha = float_to_half8(a), hg = float_to_half8(gg);
+                half8_to_float(ha, a);
+                half8_to_float(hg, gg);
 #pragma unroll
                 for (int i = 0; i < 8; ++i) y[i] = a[i] * gelu_erf(gg[i]);
-                st_half8(p.H + (size_t)row * p.ldh + n, float_to_half8(a));
-                st_half8(p.H + (size_t)row * p.ldh + p.F + n, float_to_half8(gg));
+                st_half8(p.H + (size_t)row * p.ldh + n, ha);
+                st_half8(p.H + (size_t)row * p.ldh + p.F + n, hg);
                 st_half8(p.C + (size_t)row * p.ldc + n, float_to_half8(y));
               }
             }
@@ -343,87 +484,117 @@ static int launch_gemm(const CUtensorMap& tmA, const CUtensorMap& tmB, const Gem
     DB1_CUDA(cudaFuncSetAttribute(gemm_kernel<BN, EPI>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES));
     configured = true;
   }
-  const int MT = cdiv(p.M, BM);
-  const int NT = (EPI == EPI_GEGLU) ? p.F / (BN / 2) : cdiv(p.N, BN);
-  int grid = MT * NT;
-  if (grid > sm_count()) grid = sm_count();
+  const long long MT = cdiv(p.M, BM);
+  const long long NT = (EPI == DB1_EPI_GEGLU) ? p.F / (BN / 2) : cdiv(p.N, BN);
+  long long tiles = MT * NT * p.Z1 * (p.reduce_z2 ? 1 : p.Z2);
+  int grid = tiles > sm_count() ? sm_count() : (int)tiles;
   gemm_kernel<BN, EPI><<<grid, GEMM_THREADS, Cfg::SMEM_BYTES, stream>>>(tmA, tmB, p);
   DB1_CUDA(cudaGetLastError());
   return 0;
+}
+
+// 4-D map (inner, rows, z1, z2). A broadcast batch dim (stride 0) is encoded as a dim of size 1.
+static int make_operand_map(CUtensorMap* tm, const void* base, int mn_major, long long mn, long long k, long long ld,
+                            int Z1, long long z1s, int Z2, long long z2s, int mn_box_rows) {
+  uint64_t dims[4], str[3];
+  uint32_t box[4];
+  if (!mn_major) {
+    dims[0] = (uint64_t)k; dims[1] = (uint64_t)mn; box[0] = 64; box[1] = (uint32_t)mn_box_rows;
+  } else {
+    dims[0] = (uint64_t)mn; dims[1] = (uint64_t)k; box[0] = 64; box[1] = 64;
+  }
+  dims[2] = z1s ? (uint64_t)Z1 : 1; dims[3] = z2s ? (uint64_t)Z2 : 1;
+  box[2] = 1; box[3] = 1;
+  str[0] = (uint64_t)ld * 2;
+  str[1] = z1s ? (uint64_t)z1s * 2 : str[0] * dims[1];
+  str[2] = z2s ? (uint64_t)z2s * 2 : (z1s ? str[1] * dims[2] : str[0] * dims[1]);
+  return make_tmap_f16(tm, base, 4, dims, str, box);
 }
 
 }  // namespace db1
 
 using namespace db1;
 
-// See include/db1_sm100.h for the contract.
-extern "C" int db1_gemm_f16(int epilogue, const void* A, int lda, int a_mn, const void* B, int ldb, int b_mn, void* C,
-                            int ldc, int M, int N, int K, float alpha, int accumulate, const void* bias,
-                            const void* resid, int ldr, float drop_p, uint64_t seed, const void* u, const void* v,
-                            int d_model, void* H, int ldh, int F, int bn_hint, void* stream_) {
+extern "C" int db1_gemm_f16(const db1_gemm_desc* d, void* stream_) {
   cudaStream_t stream = (cudaStream_t)stream_;
+  DB1_CHECK_ARG(d != nullptr, "gemm: null descriptor");
+  const int M = d->M, N = d->N, K = d->K, epilogue = d->epilogue;
   DB1_CHECK_ARG(M > 0 && N > 0 && K > 0, "gemm: bad shape M=%d N=%d K=%d", M, N, K);
-  DB1_CHECK_ARG(lda % 8 == 0 && ldb % 8 == 0 && ldc % 8 == 0, "gemm: leading dims must be multiples of 8 (%d %d %d)",
-                lda, ldb, ldc);
-  DB1_CHECK_ARG(epilogue >= 0 && epilogue <= 3, "gemm: unknown epilogue %d", epilogue);
-  DB1_CHECK_ARG(drop_p >= 0.f && drop_p < 1.f, "gemm: dropout p=%f out of range", drop_p);
+  DB1_CHECK_ARG(d->A && d->B && d->C, "gemm: null operand");
+  DB1_CHECK_ARG(d->lda % 8 == 0 && d->ldb % 8 == 0 && d->ldc % 8 == 0,
+                "gemm: leading dims must be multiples of 8 (%lld %lld %lld)", (long long)d->lda, (long long)d->ldb,
+                (long long)d->ldc);
+  DB1_CHECK_ARG(epilogue >= 0 && epilogue <= 4, "gemm: unknown epilogue %d", epilogue);
+  DB1_CHECK_ARG(d->drop_p >= 0.f && d->drop_p < 1.f, "gemm: dropout p=%f out of range", d->drop_p);
+  DB1_CHECK_ARG(d->k_mode >= 0 && d->k_mode <= 3, "gemm: unknown k_mode %d", d->k_mode);
+  const int Z1 = d->Z1 > 0 ? d->Z1 : 1, Z2 = d->Z2 > 0 ? d->Z2 : 1;
+  const bool batched = Z1 * Z2 > 1;
+  DB1_CHECK_ARG((d->a_z1 % 8 == 0) && (d->a_z2 % 8 == 0) && (d->b_z1 % 8 == 0) && (d->b_z2 % 8 == 0) &&
+                    (d->c_z1 % 8 == 0) && (d->c_z2 % 8 == 0),
+                "gemm: batch strides must be multiples of 8 elements");
   GemmParams p;
   memset(&p, 0, sizeof(p));
-  p.M = M; p.N = N; p.K = K; p.a_mn = a_mn ? 1 : 0; p.b_mn = b_mn ? 1 : 0;
-  p.alpha = alpha; p.C = (__half*)C; p.ldc = ldc; p.bias = (const __half*)bias;
-  p.resid = (const __half*)resid; p.ldr = ldr; p.accumulate = accumulate;
-  p.drop_thr16 = (uint32_t)(drop_p * 65536.0f + 0.5f);
+  p.M = M; p.N = N; p.K = K; p.a_mn = d->a_mn ? 1 : 0; p.b_mn = d->b_mn ? 1 : 0;
+  p.Z1 = Z1; p.Z2 = Z2;
+  p.a_z1on = d->a_z1 != 0; p.a_z2on = d->a_z2 != 0; p.b_z1on = d->b_z1 != 0; p.b_z2on = d->b_z2 != 0;
+  p.reduce_z2 = d->reduce_z2 ? 1 : 0; p.k_mode = d->k_mode; p.skip_upper = d->skip_upper ? 1 : 0;
+  p.alpha = d->alpha; p.C = (__half*)d->C; p.ldc = d->ldc; p.c_z1 = d->c_z1; p.c_z2 = d->c_z2;
+  p.bias = (const __half*)d->bias; p.resid = (const __half*)d->resid; p.ldr = d->ldr; p.accumulate = d->accumulate;
+  p.drop_thr16 = (uint32_t)(d->drop_p * 65536.0f + 0.5f);
   p.drop_scale = p.drop_thr16 ? 65536.0f / (65536.0f - (float)p.drop_thr16) : 1.0f;
-  p.seed = seed; p.u = (const __half*)u; p.v = (const __half*)v; p.d_model = d_model;
-  p.H = (__half*)H; p.ldh = ldh; p.F = F;
+  p.seed = d->seed; p.u = (const __half*)d->u; p.v = (const __half*)d->v; p.d_model = d->d_model;
+  p.H = (__half*)d->H; p.ldh = d->ldh; p.F = d->F;
+  p.P = (const __half*)d->P; p.C2 = (__half*)d->C2; p.Drow = d->Drow; p.window = d->window;
+  if (p.reduce_z2) DB1_CHECK_ARG(d->c_z2 == 0, "gemm: reduce_z2 needs c_z2 == 0");
 
   int BNsel = 256;
-  if (epilogue == EPI_PLAIN || epilogue == EPI_DGEGLU) {
-    if (bn_hint == 128 || (bn_hint == 0 && N <= 128)) BNsel = 128;
+  if (epilogue == DB1_EPI_PLAIN || epilogue == DB1_EPI_DGEGLU) {
+    if (d->bn_hint == 128 || (d->bn_hint == 0 && N <= 128)) BNsel = 128;
   }
-  if (epilogue == EPI_QKV) {
-    DB1_CHECK_ARG(u && v && d_model > 0 && N == 3 * d_model, "gemm(qkv): need u, v and N == 3*d_model");
-    DB1_CHECK_ARG(d_model % 128 == 0, "gemm(qkv): d_model %d must be a multiple of 128", d_model);
-    DB1_CHECK_ARG(!accumulate && !bias && !resid && drop_p == 0.f, "gemm(qkv): unsupported fused option");
-    BNsel = (d_model % 256 == 0 && bn_hint != 128) ? 256 : 128;
+  if (epilogue == DB1_EPI_QKV) {
+    DB1_CHECK_ARG(d->u && d->v && d->d_model > 0 && N == 3 * d->d_model, "gemm(qkv): need u, v and N == 3*d_model");
+    DB1_CHECK_ARG(d->d_model % 128 == 0, "gemm(qkv): d_model %d must be a multiple of 128", d->d_model);
+    DB1_CHECK_ARG(!d->accumulate && !d->bias && !d->resid && d->drop_p == 0.f && !batched,
+                  "gemm(qkv): unsupported fused option");
+    BNsel = (d->d_model % 256 == 0 && d->bn_hint != 128) ? 256 : 128;
   }
-  if (epilogue == EPI_GEGLU) {
-    DB1_CHECK_ARG(H && F > 0 && N == 2 * F && F % 128 == 0 && !b_mn, "gemm(geglu): need H, N == 2F, F %% 128 == 0");
+  if (epilogue == DB1_EPI_GEGLU) {
+    DB1_CHECK_ARG(d->H && d->F > 0 && N == 2 * d->F && d->F % 128 == 0 && !d->b_mn && !batched,
+                  "gemm(geglu): need H, N == 2F, F %% 128 == 0, K-major B, no batching");
   }
-  if (epilogue == EPI_DGEGLU) {
-    DB1_CHECK_ARG(H && F > 0 && N == F && F % 8 == 0, "gemm(dgeglu): need H and N == F");
+  if (epilogue == DB1_EPI_DGEGLU) {
+    DB1_CHECK_ARG(d->H && d->F > 0 && N == d->F && d->F % 8 == 0 && !batched, "gemm(dgeglu): need H and N == F");
   }
-  if (epilogue == EPI_PLAIN && (bias || resid || accumulate || p.drop_thr16))
-    DB1_CHECK_ARG(N % 8 == 0, "gemm: fused bias/residual/dropout/accumulate need N %% 8 == 0 (N=%d)", N);
-  if (p.drop_thr16) DB1_CHECK_ARG(N % 4 == 0, "gemm: dropout needs N %% 4 == 0");
+  if (epilogue == DB1_EPI_DS) {
+    DB1_CHECK_ARG(d->P && d->C2 && d->Drow && M == N && N % 8 == 0 && d->window > 0,
+                  "gemm(ds): need P, C2, Drow, square M == N (multiple of 8) and window > 0");
+    BNsel = 128;
+  }
+  if (epilogue == DB1_EPI_PLAIN && (d->bias || d->resid || p.drop_thr16))
+    DB1_CHECK_ARG(N % 8 == 0, "gemm: fused bias/residual/dropout need N %% 8 == 0 (N=%d)", N);
+  if (d->resid) DB1_CHECK_ARG(!batched, "gemm: residual only for un-batched calls");
 
   CUtensorMap tmA, tmB;
-  {
-    uint64_t dims[2], str[1];
-    uint32_t box[2];
-    if (!p.a_mn) { dims[0] = (uint64_t)K; dims[1] = (uint64_t)M; box[0] = 64; box[1] = 128; }
-    else         { dims[0] = (uint64_t)M; dims[1] = (uint64_t)K; box[0] = 64; box[1] = 64; }
-    str[0] = (uint64_t)lda * 2;
-    int e = make_tmap_f16(&tmA, A, 2, dims, str, box);
-    if (e) return e;
-    if (!p.b_mn) { dims[0] = (uint64_t)K; dims[1] = (uint64_t)N; box[0] = 64; box[1] = 128; }
-    else         { dims[0] = (uint64_t)N; dims[1] = (uint64_t)K; box[0] = 64; box[1] = 64; }
-    str[0] = (uint64_t)ldb * 2;
-    e = make_tmap_f16(&tmB, B, 2, dims, str, box);
-    if (e) return e;
-  }
+  int e = make_operand_map(&tmA, d->A, p.a_mn, M, K, d->lda, Z1, d->a_z1, Z2, d->a_z2, 128);
+  if (e) return e;
+  // EPI_GEGLU addresses rows up to 2F; the tensor's row count is N in every case
+  e = make_operand_map(&tmB, d->B, p.b_mn, N, K, d->ldb, Z1, d->b_z1, Z2, d->b_z2, 128);
+  if (e) return e;
+
   switch (epilogue) {
-    case EPI_PLAIN:
-      return BNsel == 256 ? launch_gemm<256, EPI_PLAIN>(tmA, tmB, p, stream)
-                          : launch_gemm<128, EPI_PLAIN>(tmA, tmB, p, stream);
-    case EPI_QKV:
-      return BNsel == 256 ? launch_gemm<256, EPI_QKV>(tmA, tmB, p, stream)
-                          : launch_gemm<128, EPI_QKV>(tmA, tmB, p, stream);
-    case EPI_GEGLU:
-      return launch_gemm<256, EPI_GEGLU>(tmA, tmB, p, stream);
-    case EPI_DGEGLU:
-      return BNsel == 256 ? launch_gemm<256, EPI_DGEGLU>(tmA, tmB, p, stream)
-                          : launch_gemm<128, EPI_DGEGLU>(tmA, tmB, p, stream);
+    case DB1_EPI_PLAIN:
+      return BNsel == 256 ? launch_gemm<256, DB1_EPI_PLAIN>(tmA, tmB, p, stream)
+                          : launch_gemm<128, DB1_EPI_PLAIN>(tmA, tmB, p, stream);
+    case DB1_EPI_QKV:
+      return BNsel == 256 ? launch_gemm<256, DB1_EPI_QKV>(tmA, tmB, p, stream)
+                          : launch_gemm<128, DB1_EPI_QKV>(tmA, tmB, p, stream);
+    case DB1_EPI_GEGLU:
+      return launch_gemm<256, DB1_EPI_GEGLU>(tmA, tmB, p, stream);
+    case DB1_EPI_DGEGLU:
+      return BNsel == 256 ? launch_gemm<256, DB1_EPI_DGEGLU>(tmA, tmB, p, stream)
+                          : launch_gemm<128, DB1_EPI_DGEGLU>(tmA, tmB, p, stream);
+    case DB1_EPI_DS:
+      return launch_gemm<128, DB1_EPI_DS>(tmA, tmB, p, stream);
   }
   return set_err(-1, "gemm: unreachable");
 }

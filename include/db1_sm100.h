@@ -1,0 +1,95 @@
+/*
+ * db1_sm100.h — C ABI of libdb1_sm100.so: the B200 (sm_100a) kernels behind DB1's Transformer-XL forward/backward.
+ *
+ * The reference (Shanghai-Digital-Brain-Laboratory/BDM-DB1) has no FFI of its own for this path: every numeric op is
+ * a PyTorch library call made from src/model/transformer_xl.py and src/tokenizer/vision_embedding.py. Each entry
+ * point below names the reference call site(s) it replaces. The Python side (bdm-db1_b200/db1_sm100/_lib.py) binds
+ * these with ctypes; INTEGRATION.md shows the stub a reference maintainer would add.
+ *
+ * Conventions
+ *   - every pointer is a raw DEVICE pointer unless the name says host; no torch types cross this boundary
+ *   - all 16-bit tensors are IEEE fp16 ("half"); reductions / statistics are fp32
+ *   - `stream` is a cudaStream_t passed as void*; nothing here synchronises, allocates or frees device memory
+ *   - return value: 0 = ok, < 0 = argument / environment error, > 0 = cudaError_t; db1_last_error() (thread-local)
+ *     describes the last non-zero return
+ */
+#ifndef DB1_SM100_H_
+#define DB1_SM100_H_
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+const char* db1_last_error(void);
+/* ABI version of this header; bumped whenever a struct layout changes. */
+int db1_abi_version(void);
+
+/* ------------------------------------------------------------------------------------------------------------------
+ * Tensor-core GEMM (tcgen05.mma, TMEM accumulators, TMA-fed smem ring; persistent, one CTA per SM).
+ *
+ *   for every batch index (z1, z2):   C[M,N] (+)= epilogue( alpha * A[M,K] . B[N,K]^T )
+ *
+ * Replaces: nn.Linear / F.linear / torch.einsum and their autograd backward at
+ *   transformer_xl.py:138 (qkv_net), :139 (r_net), :228 (o_net), :265-268 (CoreNet), :595 (tied head),
+ *   vision_embedding.py:53-55 (16x16/stride-16 projection conv == GEMM),
+ *   and, in the attention backward, the einsum adjoints of :163-170 and :220.
+ * ------------------------------------------------------------------------------------------------------------------ */
+enum {
+  DB1_EPI_PLAIN = 0,  /* C = [resid +] dropout(alpha*acc [+ bias]) [+ C]                                              */
+  DB1_EPI_QKV = 1,    /* N = 3*d_model: columns < d_model are written twice (+u, +v): C row = [q+u | q+v | k | v]       */
+  DB1_EPI_GEGLU = 2,  /* N = 2F, tile pairs column n with n+F: H = [a|g] + bias (pre-activation), C = a * gelu_erf(g)   */
+  DB1_EPI_DGEGLU = 3, /* N = F, acc = dY: reads H = [a|g]; C = [dY*gelu(g) | dY*a*gelu'(g)] (width 2F)                 */
+  DB1_EPI_DS = 4      /* attention backward: acc = dP; dS = P*(dP - Drow)*alpha on j<=i (and i-j<window), else 0;
+                         writes C = dS[i][j] and C2 = dS "un-shifted" to relative-position order: C2[i][j + N-1-i]      */
+};
+enum {
+  DB1_K_FULL = 0,        /* k in [0, K)                                                                                */
+  DB1_K_END_BY_ROW = 1,  /* k in [0, min(K, (mt+1)*128))          (causal: contraction over keys j <= i)               */
+  DB1_K_BEGIN_BY_ROW = 2,/* k in [mt*128, K)                      (causal: contraction over queries i >= j)            */
+  DB1_K_BEGIN_REV = 3    /* k in [max(0, K - (mt+1)*128), K)      (relative-position order: c >= K-1-i)                */
+};
+
+typedef struct db1_gemm_desc {
+  int32_t epilogue; /* DB1_EPI_* */
+  int32_t M, N, K;
+  int32_t a_mn;     /* 0: A stored [M][K] (K contiguous); 1: stored [K][M] (M contiguous) — no transposed copy needed */
+  int32_t b_mn;     /* 0: B stored [N][K];                1: stored [K][N]                                              */
+  const void* A;
+  const void* B;
+  void* C;
+  int64_t lda, ldb, ldc; /* row strides of the STORED 2-D matrices, in elements (multiples of 8) */
+  /* batching: z1 (inner, e.g. head) and z2 (outer, e.g. sequence in the batch); strides in elements, 0 = broadcast */
+  int32_t Z1, Z2;
+  int64_t a_z1, a_z2, b_z1, b_z2, c_z1, c_z2;
+  int32_t reduce_z2; /* 1: the contraction also runs over z2 (C has no z2 dimension) */
+  int32_t k_mode;    /* DB1_K_* */
+  int32_t skip_upper;/* 1: output tiles entirely above the diagonal (first col > last row) are skipped */
+  float alpha;
+  int32_t accumulate; /* C += */
+  const void* bias;   /* [N] fp16 or NULL */
+  const void* resid;  /* [M, ldr] fp16 or NULL (un-batched calls only) */
+  int64_t ldr;
+  float drop_p;       /* dropout on (alpha*acc + bias) before the residual add; mask = f(seed, row*N + col) */
+  uint64_t seed;
+  const void* u;      /* QKV: r_w_bias flattened [d_model] */
+  const void* v;      /* QKV: r_r_bias flattened [d_model] */
+  int32_t d_model;
+  void* H;            /* GEGLU: out [M, ldh]; DGEGLU: in */
+  int64_t ldh;
+  int32_t F;
+  /* DS epilogue */
+  const void* P;      /* fp16, same layout/strides as C */
+  void* C2;           /* fp16, same layout/strides as C */
+  const float* Drow;  /* fp32 [Z2][Z1][M] contiguous */
+  int32_t window;     /* attend iff 0 <= i-j < window */
+  int32_t bn_hint;    /* 0 = auto, 128 or 256 */
+} db1_gemm_desc;
+
+int db1_gemm_f16(const db1_gemm_desc* d, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* DB1_SM100_H_ */

@@ -1,0 +1,185 @@
+"""GPU parity of the tcgen05 GEMM (db1_gemm_f16) against torch fp32 matmuls on the same fp16 inputs."""
+import math
+
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+
+def _rel(a, b):
+    return (a.float() - b.float()).abs().max().item() / (b.float().abs().max().item() + 1e-12)
+
+
+def _mk(shape, dev, scale=1.0, seed=0):
+    g = torch.Generator(device="cpu").manual_seed(seed)
+    return (torch.randn(*shape, generator=g) * scale).half().to(dev)
+
+
+@pytest.mark.parametrize("M,N,K", [(128, 256, 64), (300, 520, 200), (4096, 2048, 2048), (1024, 6144, 2048)])
+@pytest.mark.parametrize("a_mn,b_mn", [(0, 0), (0, 1), (1, 0), (1, 1)])
+def test_gemm_layouts(cuda, M, N, K, a_mn, b_mn):
+    from db1_sm100 import ops
+    if (a_mn or b_mn) and (M % 8 or N % 8):
+        pytest.skip("MN-major operands need 16-byte aligned rows")
+    A = _mk((M, K), cuda, 1.0, 1)
+    B = _mk((N, K), cuda, 1.0, 2)
+    As = A.t().contiguous() if a_mn else A
+    Bs = B.t().contiguous() if b_mn else B
+    Cc = torch.empty(M, N, dtype=torch.half, device=cuda)
+    ops.gemm(As, Bs, Cc, M, N, K, lda=As.stride(0), ldb=Bs.stride(0), ldc=N, a_mn=a_mn, b_mn=b_mn)
+    ref = A.float() @ B.float().t()
+    assert _rel(Cc, ref) < 2e-3
+
+
+def test_gemm_bn128_and_ragged_n(cuda):
+    from db1_sm100 import ops
+    M, N, K = 500, 1001, 136
+    A = _mk((M, K), cuda, 1.0, 3)
+    B = _mk((N, K), cuda, 1.0, 4)
+    ldc = 1008
+    Cc = torch.zeros(M, ldc, dtype=torch.half, device=cuda)
+    ops.gemm(A, B, Cc, M, N, K, lda=K, ldb=K, ldc=ldc)
+    ref = A.float() @ B.float().t()
+    assert _rel(Cc[:, :N], ref) < 2e-3
+    assert Cc[:, N:].abs().max().item() == 0
+    C2 = torch.zeros(M, ldc, dtype=torch.half, device=cuda)
+    ops.gemm(A, B, C2, M, N, K, lda=K, ldb=K, ldc=ldc, bn_hint=128)
+    assert _rel(C2[:, :N], ref) < 2e-3
+
+
+def test_gemm_bias_resid_accumulate(cuda):
+    from db1_sm100 import ops
+    M, N, K = 384, 512, 320
+    A = _mk((M, K), cuda, 1.0, 5)
+    B = _mk((N, K), cuda, 0.1, 6)
+    bias = _mk((N,), cuda, 1.0, 7)
+    resid = _mk((M, N), cuda, 1.0, 8)
+    C0 = _mk((M, N), cuda, 1.0, 9)
+    Cc = C0.clone()
+    ops.gemm(A, B, Cc, M, N, K, lda=K, ldb=K, ldc=N, alpha=0.5, bias=bias, resid=resid, ldr=N, accumulate=True)
+    ref = 0.5 * (A.float() @ B.float().t()) + bias.float() + resid.float() + C0.float()
+    assert _rel(Cc, ref) < 2e-3
+
+
+def test_gemm_dropout_mask_is_reproducible(cuda):
+    from db1_sm100 import ops
+    M, N, K = 256, 512, 128
+    A = _mk((M, K), cuda, 1.0, 10)
+    B = _mk((N, K), cuda, 1.0, 11)
+    C1 = torch.empty(M, N, dtype=torch.half, device=cuda)
+    C2 = torch.empty_like(C1)
+    C3 = torch.empty_like(C1)
+    ops.gemm(A, B, C1, M, N, K, lda=K, ldb=K, ldc=N, drop_p=0.25, seed=1234)
+    ops.gemm(A, B, C2, M, N, K, lda=K, ldb=K, ldc=N, drop_p=0.25, seed=1234)
+    ops.gemm(A, B, C3, M, N, K, lda=K, ldb=K, ldc=N)
+    assert torch.equal(C1, C2)
+    keep = (C1 != 0)
+    frac = keep.float().mean().item()
+    assert abs(frac - 0.75) < 0.01
+    assert _rel(C1[keep], (C3.float() / 0.75)[keep]) < 2e-3
+
+
+def test_gemm_qkv_epilogue(cuda):
+    from db1_sm100 import ops
+    M, d, K = 512, 256, 256
+    A = _mk((M, K), cuda, 1.0, 12)
+    W = _mk((3 * d, K), cuda, 0.1, 13)
+    u = _mk((d,), cuda, 1.0, 14)
+    v = _mk((d,), cuda, 1.0, 15)
+    Cc = torch.empty(M, 4 * d, dtype=torch.half, device=cuda)
+    ops.gemm(A, W, Cc, M, 3 * d, K, lda=K, ldb=K, ldc=4 * d, epilogue=ops.EPI_QKV, u=u, v=v, d_model=d)
+    ref = A.float() @ W.float().t()
+    q, k, vv = ref[:, :d], ref[:, d:2 * d], ref[:, 2 * d:]
+    refc = torch.cat([q + u.float(), q + v.float(), k, vv], 1)
+    assert _rel(Cc, refc) < 2e-3
+
+
+def test_gemm_geglu_fwd_bwd(cuda):
+    from db1_sm100 import ops
+    M, F, K = 384, 256, 192
+    A = _mk((M, K), cuda, 1.0, 16)
+    W1 = _mk((2 * F, K), cuda, 0.1, 17)
+    b1 = _mk((2 * F,), cuda, 0.5, 18)
+    H = torch.empty(M, 2 * F, dtype=torch.half, device=cuda)
+    Y = torch.empty(M, F, dtype=torch.half, device=cuda)
+    ops.gemm(A, W1, Y, M, 2 * F, K, lda=K, ldb=K, ldc=F, epilogue=ops.EPI_GEGLU, bias=b1, H=H, ldh=2 * F, F=F)
+    h = A.float() @ W1.float().t() + b1.float()
+    a, g = h[:, :F], h[:, F:]
+    y = a * torch.nn.functional.gelu(g)
+    assert _rel(H, h) < 2e-3
+    assert _rel(Y, y) < 3e-3
+    # backward epilogue: dH = [dY*gelu(g) | dY*a*gelu'(g)] with dY = G @ W2 (W2 stored [N2, F] -> MN-major B)
+    N2 = 320
+    G = _mk((M, N2), cuda, 1.0, 19)
+    W2 = _mk((N2, F), cuda, 0.1, 20)
+    dH = torch.empty(M, 2 * F, dtype=torch.half, device=cuda)
+    ops.gemm(G, W2, dH, M, F, N2, lda=N2, ldb=F, ldc=2 * F, b_mn=True, epilogue=ops.EPI_DGEGLU, H=H, ldh=2 * F, F=F)
+    dY = G.float() @ W2.float()
+    hh = H.float().requires_grad_(True)
+    yy = hh[:, :F] * torch.nn.functional.gelu(hh[:, F:])
+    yy.backward(dY)
+    assert _rel(dH, hh.grad) < 3e-3
+
+
+def _attn_ref(L, dh, B, Hh, dev, window):
+    torch.manual_seed(0)
+    dO = _mk((B, L, Hh, dh), dev, 1.0, 21)
+    V = _mk((B, L, Hh, dh), dev, 1.0, 22)
+    P = torch.softmax(torch.randn(B, Hh, L, L, device=dev) + torch.triu(torch.full((L, L), -1e30, device=dev), 1), -1)
+    P = P.half()
+    D = torch.randn(B, Hh, L, device=dev) * 0.1
+    return dO, V, P, D
+
+
+@pytest.mark.parametrize("L,dh,window", [(256, 128, 1 << 30), (384, 64, 100), (200, 32, 1 << 30)])
+def test_gemm_ds_epilogue_and_causal_kmodes(cuda, L, dh, window):
+    """The attention-backward GEMM chain on materialised P: dS/dS_rel (DS epilogue), then the causal contractions."""
+    from db1_sm100 import ops
+    B, Hh = 2, 3
+    d = Hh * dh
+    dO, V, P, D = _attn_ref(L, dh, B, Hh, cuda, window)
+    scale = 1.0 / math.sqrt(dh)
+    dS = torch.zeros(B, Hh, L, L, dtype=torch.half, device=cuda)
+    dSr = torch.zeros(B, Hh, L, L, dtype=torch.half, device=cuda)
+    ops.gemm(dO, V, dS, L, L, dh, lda=d, ldb=d, ldc=L, epilogue=ops.EPI_DS, alpha=scale, Z1=Hh, Z2=B,
+             a_z=(dh, L * d), b_z=(dh, L * d), c_z=(L * L, Hh * L * L), skip_upper=True, P=P, C2=dSr, Drow=D,
+             window=window)
+    i = torch.arange(L, device=cuda)[:, None]
+    j = torch.arange(L, device=cuda)[None, :]
+    ok = (j <= i) & ((i - j) < window)
+    dP = torch.einsum("bihd,bjhd->bhij", dO.float(), V.float())
+    ref = torch.where(ok, P.float() * (dP - D[..., None]) * scale, torch.zeros((), device=cuda))
+    assert _rel(dS, ref) < 3e-3
+    # relative-position order: dSr[i, j + L-1-i] = dS[i, j]
+    ref_r = torch.zeros_like(ref)
+    ii, jj = torch.nonzero(j <= i, as_tuple=True)
+    ref_r[:, :, ii, jj + L - 1 - ii] = ref[:, :, ii, jj]
+    assert _rel(dSr, ref_r) < 3e-3
+
+    # dV[j] = sum_{i>=j} P[i,j] dO[i]   (A = P^T MN-major, B = dO MN-major, k begins at the row tile)
+    dV = torch.empty(B, L, Hh, dh, dtype=torch.half, device=cuda)
+    ops.gemm(P, dO, dV, L, dh, L, lda=L, ldb=d, ldc=d, a_mn=True, b_mn=True, Z1=Hh, Z2=B,
+             a_z=(L * L, Hh * L * L), b_z=(dh, L * d), c_z=(dh, L * d), k_mode=ops.K_BEGIN_BY_ROW)
+    refV = torch.einsum("bhij,bihd->bjhd", P.float(), dO.float())
+    assert _rel(dV, refV) < 3e-3
+    # dQ[i] = sum_{j<=i} dS[i,j] K[j]   (A = dS K-major, B = K MN-major, k ends at the row tile)
+    Kt = V
+    dQ = torch.empty(B, L, Hh, dh, dtype=torch.half, device=cuda)
+    ops.gemm(dS, Kt, dQ, L, dh, L, lda=L, ldb=d, ldc=d, b_mn=True, Z1=Hh, Z2=B,
+             a_z=(L * L, Hh * L * L), b_z=(dh, L * d), c_z=(dh, L * d), k_mode=ops.K_END_BY_ROW)
+    refQ = torch.einsum("bhij,bjhd->bihd", dS.float(), Kt.float())
+    assert _rel(dQ, refQ) < 3e-3
+    # dQv[i] = sum_c dSr[i,c] R[c]   (R shared over the batch: broadcast z2; k begins at K-(mt+1)*128)
+    R = _mk((L, Hh, dh), cuda, 1.0, 23)
+    dQv = torch.empty(B, L, Hh, dh, dtype=torch.half, device=cuda)
+    ops.gemm(dSr, R, dQv, L, dh, L, lda=L, ldb=d, ldc=d, b_mn=True, Z1=Hh, Z2=B,
+             a_z=(L * L, Hh * L * L), b_z=(dh, 0), c_z=(dh, L * d), k_mode=ops.K_BEGIN_REV)
+    refQv = torch.einsum("bhic,chd->bihd", dSr.float(), R.float())
+    assert _rel(dQv, refQv) < 3e-3
+    # dR[c] = sum_b sum_i dSr[b,i,c] Qv[b,i]   (contraction over z2 as well)
+    dR = torch.empty(L, Hh, dh, dtype=torch.half, device=cuda)
+    ops.gemm(dSr, dO, dR, L, dh, L, lda=L, ldb=d, ldc=d, a_mn=True, b_mn=True, Z1=Hh, Z2=B,
+             a_z=(L * L, Hh * L * L), b_z=(dh, L * d), c_z=(dh, 0), reduce_z2=True, k_mode=ops.K_BEGIN_REV)
+    refR = torch.einsum("bhic,bihd->chd", dSr.float(), dO.float())
+    assert _rel(dR, refR) < 3e-3
