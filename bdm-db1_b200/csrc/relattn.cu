@@ -1,0 +1,391 @@
+// Fused relative-position ("Transformer-XL") causal attention forward for sm_100a.
+//
+//   S[i,j] = scale * ( (q_i+u).k_j + (q_i+v).r[j + L-1-i] )      (transformer_xl.py:161-174; the index on r IS
+//   P      = softmax_j(S) on  0 <= i-j < window                    _rel_shift, :98-110, for qlen == klen == L)
+//   O[i]   = sum_j P[i,j] v_j                                      (:209-225)
+//
+// One CTA per (128-query tile, head, sequence). Key tiles are walked from the diagonal outwards; per step three
+// tcgen05 MMAs run on TMEM accumulators:
+//     S   = Qu . K_j^T                     (128x128, fp32)
+//     BDc = Qv . Rchunk^T                  (128x128: the 128 new relative positions this step needs; the other
+//                                           128 are the previous step's chunk, kept in a 2-slot TMEM ring)
+//     O  += P . V_j                        (128xD)
+// The per-row shift of the position term cannot be expressed by tcgen05.ld (lanes share the column address), so each
+// softmax warp pulls the 64-column window its 32 rows need, stages it in shared memory and reads it back at a
+// lane-dependent offset. Softmax is online (fp32, exp2 with folded scale, lazy rescale of O), no mask tensor exists:
+// the causal / sliding-window predicate is computed from indices.
+//
+// Roles: warp 0 = TMA producer, warp 1 = MMA issuer (one elected thread), warps 2..5 = softmax (one query row per thread).
+//
+// mode 0: writes O [B*L, ldo] fp16 and LSE2 [B,H,L] fp32 (log2 domain).
+// mode 1: reads LSE2 and writes the normalised probabilities P [B,H,L,L] fp16 (recompute for the backward pass).
+#include "../../include/db1_sm100.h"
+#include "common.cuh"
+#include "ptx.cuh"
+
+namespace db1 {
+
+constexpr int AT_THREADS = 192;
+constexpr float NEG_BIG = -1e30f;
+constexpr int STG_PITCH = 68;  // floats per staged row (64 + 4): 16-byte stores and odd-stride reads are conflict-free
+
+struct AttnParams {
+  int L, H, B, dh;
+  int window;
+  float scale_log2;
+  __half* O;
+  long long ldo;
+  float* lse2;
+  __half* P;
+  int mode;
+};
+
+template <int D>
+struct AttnSmem {
+  static constexpr int TILE = 128 * D * 2;  // bytes of one [128][D] fp16 tile
+  static constexpr int QU = 0;
+  static constexpr int QV = QU + TILE;
+  static constexpr int KT = QV + TILE;
+  static constexpr int VT = KT + TILE;
+  static constexpr int RT = VT + TILE;
+  static constexpr int PT = RT + TILE;            // [128][128] fp16 = 32 KB
+  static constexpr int STG = PT + 128 * 128 * 2;  // 4 warps x 32 rows x 68 floats
+  static constexpr int BARS = STG + 4 * 32 * STG_PITCH * 4;
+  static constexpr int TOTAL = BARS + 128;
+};
+
+template <int D>
+__global__ void __launch_bounds__(AT_THREADS, 1)
+relattn_fwd_kernel(const __grid_constant__ CUtensorMap tmQu, const __grid_constant__ CUtensorMap tmQv,
+                   const __grid_constant__ CUtensorMap tmK, const __grid_constant__ CUtensorMap tmV,
+                   const __grid_constant__ CUtensorMap tmR, const AttnParams p) {
+  using SM = AttnSmem<D>;
+  extern __shared__ __align__(1024) uint8_t smem[];
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + SM::BARS);
+  uint64_t* bar_q = bars + 0;
+  uint64_t* bar_k = bars + 1;
+  uint64_t* bar_v = bars + 2;
+  uint64_t* bar_kfree = bars + 3;
+  uint64_t* bar_s = bars + 4;
+  uint64_t* bar_p = bars + 5;
+  uint64_t* bar_o = bars + 6;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 8);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const int nq = (p.L + 127) / 128;
+  const int I = nq - 1 - blockIdx.x;  // heaviest tiles first
+  const int h = blockIdx.y, b = blockIdx.z;
+  const int I0 = I * 128;
+  // oldest key any row of this tile may attend: j >= I0 - window + 1
+  int jlo = I0 - p.window + 1;
+  if (jlo < 0) jlo = 0;
+  const int Jmin = jlo / 128;
+  const int nsteps = I - Jmin + 1;
+
+  if ((smem_u32(smem) & 1023u) != 0) __trap();
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&tmQu);
+    tma_prefetch_desc(&tmQv);
+    tma_prefetch_desc(&tmK);
+    tma_prefetch_desc(&tmV);
+    tma_prefetch_desc(&tmR);
+  }
+  if (warp == 1) {
+    if (lane == 0) {
+      mbar_init(bar_q, 1);
+      mbar_init(bar_k, 1);
+      mbar_init(bar_v, 1);
+      mbar_init(bar_kfree, 1);
+      mbar_init(bar_s, 1);
+      mbar_init(bar_p, 4);
+      mbar_init(bar_o, 1);
+      mbar_fence_init();
+    }
+    __syncwarp();
+    tmem_alloc<512>(tmem_slot);
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+  const uint32_t T_S = tmem_base;          // 128 columns
+  const uint32_t T_BD = tmem_base + 128;   // 2 x 128 columns
+  const uint32_t T_O = tmem_base + 384;    // D columns
+
+  constexpr int NSLAB = D / 64;
+
+  if (warp == 0) {
+    // ------------------------------------------------------------------ TMA producer
+    if (lane == 0) {
+      mbar_expect_tx(bar_q, 2 * SM::TILE);
+#pragma unroll
+      for (int s = 0; s < NSLAB; ++s) {
+        tma_load_4d(smem + SM::QU + s * 16384, &tmQu, bar_q, s * 64, I0, h, b);
+        tma_load_4d(smem + SM::QV + s * 16384, &tmQv, bar_q, s * 64, I0, h, b);
+      }
+      for (int st = 0; st < nsteps; ++st) {
+        const int J0 = (I - st) * 128;
+        const int cb = p.L - 128 - I0 + J0;  // first row of the new chunk of r
+        if (st > 0) mbar_wait(bar_kfree, (st - 1) & 1);
+        mbar_expect_tx(bar_k, 2 * SM::TILE);
+#pragma unroll
+        for (int s = 0; s < NSLAB; ++s) {
+          tma_load_4d(smem + SM::KT + s * 16384, &tmK, bar_k, s * 64, J0, h, b);
+          tma_load_4d(smem + SM::RT + s * 16384, &tmR, bar_k, s * 64, cb, h, 0);
+        }
+        if (p.mode == 0) {
+          if (st > 0) mbar_wait(bar_o, (st - 1) & 1);
+          mbar_expect_tx(bar_v, SM::TILE);
+#pragma unroll
+          for (int s = 0; s < NSLAB; ++s) tma_load_4d(smem + SM::VT + s * 16384, &tmV, bar_v, s * 64, J0, h, b);
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ------------------------------------------------------------------ MMA issuer
+    if (lane == 0) {
+      const uint32_t idesc_s = umma_idesc(128, 128, 0, 0, 0);
+      const uint32_t idesc_o = umma_idesc(128, D, 0, 1, 0);
+      const uint32_t qu = smem_u32(smem + SM::QU), qv = smem_u32(smem + SM::QV), kt = smem_u32(smem + SM::KT),
+                     vt = smem_u32(smem + SM::VT), rt = smem_u32(smem + SM::RT), pt = smem_u32(smem + SM::PT);
+      auto issue_scores = [&](int st) {
+        mbar_wait(bar_k, st & 1);
+        tc_fence_after();
+        const uint32_t tbd = T_BD + (st & 1) * 128;
+#pragma unroll
+        for (int k = 0; k < D / 16; ++k) {
+          const uint32_t off = (k >> 2) * 16384 + (k & 3) * 32;
+          umma_ss(T_S, umma_smem_desc(qu + off, 16, 1024), umma_smem_desc(kt + off, 16, 1024), idesc_s, k ? 1u : 0u);
+        }
+#pragma unroll
+        for (int k = 0; k < D / 16; ++k) {
+          const uint32_t off = (k >> 2) * 16384 + (k & 3) * 32;
+          umma_ss(tbd, umma_smem_desc(qv + off, 16, 1024), umma_smem_desc(rt + off, 16, 1024), idesc_s, k ? 1u : 0u);
+        }
+        umma_commit(bar_kfree);
+        umma_commit(bar_s);
+      };
+      mbar_wait(bar_q, 0);
+      tc_fence_after();
+      issue_scores(0);
+      for (int st = 0; st < nsteps; ++st) {
+        mbar_wait(bar_p, st & 1);
+        tc_fence_after();
+        if (st + 1 < nsteps) issue_scores(st + 1);
+        if (p.mode == 0) {
+          mbar_wait(bar_v, st & 1);
+          tc_fence_after();
+#pragma unroll
+          for (int k = 0; k < 8; ++k) {  // 128 keys / 16
+            const uint64_t adesc = umma_smem_desc(pt + (k >> 2) * 16384 + (k & 3) * 32, 16, 1024);
+            const uint64_t bdesc = umma_smem_desc(vt + k * 2048, 16384, 1024);
+            umma_ss(T_O, adesc, bdesc, idesc_o, (st | k) ? 1u : 0u);
+          }
+        }
+        umma_commit(bar_o);
+      }
+    }
+  } else {
+    // ------------------------------------------------------------------ softmax warps: one query row per thread
+    const int q = warp & 3;
+    const int r = q * 32 + lane;
+    const int i = I0 + r;
+    const uint32_t lane_off = (uint32_t)(q * 32) << 16;
+    float* stg = reinterpret_cast<float*>(smem + SM::STG) + (warp - 2) * 32 * STG_PITCH + lane * STG_PITCH;
+    uint8_t* prow = smem + SM::PT + r * 128;
+    float m_run = NEG_BIG, l_run = 0.f;
+    float lse_row = 0.f;
+    if (p.mode == 1) lse_row = (i < p.L) ? p.lse2[((long long)b * p.H + h) * p.L + i] : 0.f;
+
+    for (int st = 0; st < nsteps; ++st) {
+      const int J0 = (I - st) * 128;
+      const uint32_t tnew = T_BD + (st & 1) * 128, tprev = T_BD + ((st + 1) & 1) * 128;
+      mbar_wait(bar_s, st & 1);
+      tc_fence_after();
+      // ---- pass 1: combine content + shifted position scores, mask, row max; write the result back over S
+      float mx = NEG_BIG;
+#pragma unroll 1
+      for (int cc = 0; cc < 4; ++cc) {
+        uint32_t s[32], w0[32], w1[32];
+        const int blk = cc - q + 3;  // 32-column block of the 256-wide [new | prev] window
+        tmem_ld32(T_S + lane_off + cc * 32, s);
+        tmem_ld32(((blk < 4) ? tnew + blk * 32 : tprev + (blk - 4) * 32) + lane_off, w0);
+        tmem_ld32(((blk + 1 < 4) ? tnew + (blk + 1) * 32 : tprev + (blk - 3) * 32) + lane_off, w1);
+        tmem_ld_wait();
+#pragma unroll
+        for (int k = 0; k < 8; ++k) {
+          reinterpret_cast<uint4*>(stg)[k] = make_uint4(w0[4 * k], w0[4 * k + 1], w0[4 * k + 2], w0[4 * k + 3]);
+          reinterpret_cast<uint4*>(stg)[8 + k] = make_uint4(w1[4 * k], w1[4 * k + 1], w1[4 * k + 2], w1[4 * k + 3]);
+        }
+        __syncwarp();
+        const float* rd = stg + (31 - lane);
+#pragma unroll
+        for (int t = 0; t < 32; ++t) {
+          const int j = J0 + cc * 32 + t;
+          const bool ok = (j <= i) && (i - j < p.window) && (j < p.L);
+          const float sc = ok ? (__uint_as_float(s[t]) + rd[t]) * p.scale_log2 : NEG_BIG;
+          mx = fmaxf(mx, sc);
+          s[t] = __float_as_uint(sc);
+        }
+        __syncwarp();
+        tmem_st32(T_S + lane_off + cc * 32, s);
+      }
+      tmem_st_wait();
+
+      if (p.mode == 0) {
+        // ---- online softmax bookkeeping with lazy rescale (rescale only when the max grew by more than 2^8)
+        if (st > 0) {
+          mbar_wait(bar_o, (st - 1) & 1);  // O accumulated, P smem free
+          tc_fence_after();
+        }
+        const bool grow = (st == 0) || (mx > m_run + 8.0f);
+        if (__any_sync(0xffffffffu, grow)) {
+          const float m_new = grow ? mx : m_run;
+          const float f = (st == 0) ? 0.f : exp2f(m_run - m_new);
+          l_run *= f;
+          m_run = m_new;
+          if (st > 0) {
+#pragma unroll 1
+            for (int c = 0; c < D / 32; ++c) {
+              uint32_t o[32];
+              tmem_ld32(T_O + lane_off + c * 32, o);
+              tmem_ld_wait();
+#pragma unroll
+              for (int t = 0; t < 32; ++t) o[t] = __float_as_uint(__uint_as_float(o[t]) * f);
+              tmem_st32(T_O + lane_off + c * 32, o);
+            }
+            tmem_st_wait();
+          }
+        }
+      }
+      const float m_use = (p.mode == 0) ? m_run : lse_row;
+      // ---- pass 2: probabilities
+      float sum = 0.f;
+#pragma unroll 1
+      for (int cc = 0; cc < 4; ++cc) {
+        uint32_t s[32];
+        tmem_ld32(T_S + lane_off + cc * 32, s);
+        tmem_ld_wait();
+        uint32_t pk[16];
+#pragma unroll
+        for (int t = 0; t < 16; ++t) {
+          const float p0 = exp2f(__uint_as_float(s[2 * t]) - m_use);
+          const float p1 = exp2f(__uint_as_float(s[2 * t + 1]) - m_use);
+          sum += p0 + p1;
+          pk[t] = pack_half2(p0, p1);
+        }
+        if (p.mode == 0) {
+          // K-major SW128 tile: slab = cc/2 (64 keys each), 16-byte chunk index within the row = (cc&1)*4 + g
+          uint8_t* dst = prow + (cc >> 1) * 16384;
+#pragma unroll
+          for (int g = 0; g < 4; ++g) {
+            const int chunk = ((cc & 1) * 4 + g) ^ (r & 7);
+            *reinterpret_cast<uint4*>(dst + chunk * 16) = make_uint4(pk[4 * g], pk[4 * g + 1], pk[4 * g + 2], pk[4 * g + 3]);
+          }
+        } else if (i < p.L) {
+          __half* dst = p.P + (((long long)b * p.H + h) * p.L + i) * p.L + J0 + cc * 32;
+#pragma unroll
+          for (int g = 0; g < 4; ++g)
+            if (J0 + cc * 32 + g * 8 < p.L)
+              *reinterpret_cast<uint4*>(dst + g * 8) = make_uint4(pk[4 * g], pk[4 * g + 1], pk[4 * g + 2], pk[4 * g + 3]);
+        }
+      }
+      l_run += sum;
+      // publish: P is in smem (generic proxy -> async proxy), S / BD TMEM reads are complete
+      fence_proxy_async_smem();
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(bar_p);
+    }
+
+    if (p.mode == 0) {
+      mbar_wait(bar_o, (nsteps - 1) & 1);
+      tc_fence_after();
+      const float inv = 1.0f / l_run;
+      if (i < p.L) p.lse2[((long long)b * p.H + h) * p.L + i] = m_run + log2f(l_run);
+      __half* orow = p.O + ((long long)b * p.L + i) * p.ldo + (long long)h * p.dh;
+#pragma unroll 1
+      for (int c = 0; c < D / 32; ++c) {
+        uint32_t o[32];
+        tmem_ld32(T_O + lane_off + c * 32, o);
+        tmem_ld_wait();
+        if (i < p.L) {
+#pragma unroll
+          for (int g = 0; g < 4; ++g) {
+            const int col = c * 32 + g * 8;
+            if (col < p.dh) {
+              uint4 vv;
+              vv.x = pack_half2(__uint_as_float(o[g * 8 + 0]) * inv, __uint_as_float(o[g * 8 + 1]) * inv);
+              vv.y = pack_half2(__uint_as_float(o[g * 8 + 2]) * inv, __uint_as_float(o[g * 8 + 3]) * inv);
+              vv.z = pack_half2(__uint_as_float(o[g * 8 + 4]) * inv, __uint_as_float(o[g * 8 + 5]) * inv);
+              vv.w = pack_half2(__uint_as_float(o[g * 8 + 6]) * inv, __uint_as_float(o[g * 8 + 7]) * inv);
+              *reinterpret_cast<uint4*>(orow + col) = vv;
+            }
+          }
+        }
+      }
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc<512>(tmem_base);
+  }
+}
+
+// 4-D map over a [B, L, H, dh] view of a row-major buffer: dims (dh, L, H, B).
+static int make_head_map(CUtensorMap* tm, const void* base, int dh, int L, int H, int B, long long ld) {
+  uint64_t dims[4] = {(uint64_t)dh, (uint64_t)L, (uint64_t)H, (uint64_t)(B > 0 ? B : 1)};
+  uint64_t str[3] = {(uint64_t)ld * 2, (uint64_t)dh * 2, (uint64_t)L * (uint64_t)ld * 2};
+  uint32_t box[4] = {64, 128, 1, 1};
+  return make_tmap_f16(tm, base, 4, dims, str, box);
+}
+
+template <int D>
+static int launch_attn(const CUtensorMap* tm, const AttnParams& p, cudaStream_t stream) {
+  using SM = AttnSmem<D>;
+  static bool configured = false;
+  if (!configured) {
+    DB1_CUDA(cudaFuncSetAttribute(relattn_fwd_kernel<D>, cudaFuncAttributeMaxDynamicSharedMemorySize, SM::TOTAL));
+    configured = true;
+  }
+  dim3 grid((p.L + 127) / 128, p.H, p.B);
+  relattn_fwd_kernel<D><<<grid, AT_THREADS, SM::TOTAL, stream>>>(tm[0], tm[1], tm[2], tm[3], tm[4], p);
+  DB1_CUDA(cudaGetLastError());
+  return 0;
+}
+
+}  // namespace db1
+
+using namespace db1;
+
+extern "C" int db1_relattn_fwd(const void* qu, const void* qv, const void* k, const void* v, long long ld_qkv,
+                               const void* r, long long ld_r, void* out, long long ld_out, float* lse2, void* probs,
+                               int B, int L, int H, int dh, int window, float scale, int mode, void* stream_) {
+  cudaStream_t stream = (cudaStream_t)stream_;
+  DB1_CHECK_ARG(qu && qv && k && r && lse2, "relattn: null pointer");
+  DB1_CHECK_ARG(mode == 0 || mode == 1, "relattn: mode must be 0 (O, LSE) or 1 (P)");
+  DB1_CHECK_ARG((mode == 0 && v && out) || (mode == 1 && probs), "relattn: missing output for mode %d", mode);
+  DB1_CHECK_ARG(B > 0 && L > 0 && H > 0, "relattn: bad shape B=%d L=%d H=%d", B, L, H);
+  DB1_CHECK_ARG(dh % 8 == 0 && dh >= 8 && dh <= 128, "relattn: head dim %d unsupported (multiple of 8, <= 128)", dh);
+  DB1_CHECK_ARG(L % 8 == 0, "relattn: sequence length %d must be a multiple of 8", L);
+  DB1_CHECK_ARG(ld_qkv % 8 == 0 && ld_r % 8 == 0 && ld_out % 8 == 0, "relattn: row strides must be multiples of 8");
+  DB1_CHECK_ARG(window > 0, "relattn: window (mem_len) must be > 0; mem_len == 0 masks every key");
+  AttnParams p;
+  p.L = L; p.H = H; p.B = B; p.dh = dh; p.window = window;
+  p.scale_log2 = scale * 1.4426950408889634f;
+  p.O = (__half*)out; p.ldo = ld_out; p.lse2 = lse2; p.P = (__half*)probs; p.mode = mode;
+  CUtensorMap tm[5];
+  int e;
+  if ((e = make_head_map(&tm[0], qu, dh, L, H, B, ld_qkv))) return e;
+  if ((e = make_head_map(&tm[1], qv, dh, L, H, B, ld_qkv))) return e;
+  if ((e = make_head_map(&tm[2], k, dh, L, H, B, ld_qkv))) return e;
+  if ((e = make_head_map(&tm[3], mode == 0 ? v : k, dh, L, H, B, ld_qkv))) return e;
+  if ((e = make_head_map(&tm[4], r, dh, L, H, 1, ld_r))) return e;
+  if (dh <= 64) return launch_attn<64>(tm, p, stream);
+  return launch_attn<128>(tm, p, stream);
+}

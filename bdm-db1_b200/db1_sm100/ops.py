@@ -59,3 +59,18 @@ def gemm(A, B, C_out, M, N, K, *, lda, ldb, ldc, a_mn=False, b_mn=False, epilogu
     d.bn_hint = bn_hint
     check(_lib.lib().db1_gemm_f16(C.byref(d), cur_stream()), "db1_gemm_f16")
     return C_out
+
+
+def relattn_fwd(qkv4, r, out, lse2, B, L, H, dh, window, scale, probs=None):
+    """qkv4: [B*L, 4*H*dh] = [q+u | q+v | k | v]; r: [L, H*dh]. mode 0 (probs is None): out, lse2 written;
+    mode 1: probs [B,H,L,L] written from lse2. include/db1_sm100.h:db1_relattn_fwd."""
+    _need_cuda_half(qkv4, r, out, probs)
+    d = H * dh
+    es = qkv4.element_size()
+    base = qkv4.data_ptr()
+    ld = qkv4.stride(0)
+    mode = 0 if probs is None else 1
+    check(_lib.lib().db1_relattn_fwd(
+        C.c_void_p(base), C.c_void_p(base + d * es), C.c_void_p(base + 2 * d * es), C.c_void_p(base + 3 * d * es),
+        C.c_longlong(ld), ptr(r), C.c_longlong(r.stride(0)), ptr(out), C.c_longlong(out.stride(0) if out is not None else 0),
+        ptr(lse2), ptr(probs), B, L, H, dh, int(window), C.c_float(scale), mode, cur_stream()), "db1_relattn_fwd")

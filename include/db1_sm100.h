@@ -89,6 +89,22 @@ typedef struct db1_gemm_desc {
 
 int db1_gemm_f16(const db1_gemm_desc* d, void* stream);
 
+/* ------------------------------------------------------------------------------------------------------------------
+ * Fused relative-position causal attention, forward (tcgen05 QK^T / QR^T / PV on TMEM, online softmax, in-kernel
+ * _rel_shift, causal + sliding-window predicate from indices).
+ * Replaces transformer_xl.py:161-225 (AC/BD einsums, _rel_shift :98-110, scale, mask :177-204, softmax :209, PV :220)
+ * for qlen == klen == L (training; mems == None).
+ *   qu, qv, k, v : fp16 views [B, L, H, dh] with row stride ld_qkv (columns of the fused QKV buffer); qu = q + r_w_bias,
+ *                  qv = q + r_r_bias (written by db1_gemm_f16's QKV epilogue)
+ *   r            : fp16 [L, H*dh] = r_net(pos_emb) in the reference's row order (row c <-> distance L-1-c)
+ *   mode 0       : out [B*L, ld_out] fp16 (head h at column h*dh), lse2 [B,H,L] fp32 (log2-domain log-sum-exp) written
+ *   mode 1       : lse2 read; probs [B,H,L,L] fp16 written on the visited (causal) tiles — backward recompute
+ *   window       : attend iff 0 <= i-j < window   (same_length/mem_len semantics, transformer_xl.py:551-562)
+ * ------------------------------------------------------------------------------------------------------------------ */
+int db1_relattn_fwd(const void* qu, const void* qv, const void* k, const void* v, long long ld_qkv, const void* r,
+                    long long ld_r, void* out, long long ld_out, float* lse2, void* probs, int B, int L, int H, int dh,
+                    int window, float scale, int mode, void* stream);
+
 #ifdef __cplusplus
 }
 #endif
