@@ -1,0 +1,633 @@
+// HBM-bound kernels of the DB1 path: LayerNorm (+ dropout-mask replay, bias/affine grads), masked cross-entropy,
+// embedding assembly, small reductions. All are single-pass over their big operand, 16-byte vectorised, fp32 math.
+//
+// Reference call sites: nn.LayerNorm at transformer_xl.py:238, :290; embedding assembly :621-703; dropout :545, :575;
+// loss :602-613; PositionalEmbedding :34-50, :569-575.
+#include "../../include/db1_sm100.h"
+#include "common.cuh"
+#include "ptx.cuh"
+
+namespace db1 {
+
+struct alignas(16) H8 {
+  __half2 h[4];
+};
+DEVI void h8_to_f(const H8& v, float (&f)[8]) {
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    float2 t = __half22float2(v.h[i]);
+    f[2 * i] = t.x;
+    f[2 * i + 1] = t.y;
+  }
+}
+DEVI H8 f_to_h8(const float (&f)[8]) {
+  H8 v;
+#pragma unroll
+  for (int i = 0; i < 4; ++i) v.h[i] = __floats2half2_rn(f[2 * i], f[2 * i + 1]);
+  return v;
+}
+
+DEVI float warp_sum(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+DEVI float warp_max(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, o));
+  return v;
+}
+// block-wide sum of two values (blockDim.x multiple of 32, <= 1024); result broadcast to all threads
+DEVI float2 block_sum2(float a, float b, float2* scratch) {
+  a = warp_sum(a);
+  b = warp_sum(b);
+  const int w = threadIdx.x >> 5, l = threadIdx.x & 31, nw = blockDim.x >> 5;
+  __syncthreads();
+  if (l == 0) scratch[w] = make_float2(a, b);
+  __syncthreads();
+  float2 t = (l < nw) ? scratch[l] : make_float2(0.f, 0.f);
+  t.x = warp_sum(t.x);
+  t.y = warp_sum(t.y);
+  return t;
+}
+DEVI float block_max(float a, float* scratch) {
+  a = warp_max(a);
+  const int w = threadIdx.x >> 5, l = threadIdx.x & 31, nw = blockDim.x >> 5;
+  __syncthreads();
+  if (l == 0) scratch[w] = a;
+  __syncthreads();
+  float t = (l < nw) ? scratch[l] : -INFINITY;
+  return warp_max(t);
+}
+
+// ------------------------------------------------------------------------------------------------ LayerNorm forward
+// one CTA (256 threads) per row; d % 8 == 0; the row is kept in registers (up to LN_MAXC 16-byte chunks per thread)
+constexpr int LN_THREADS = 256;
+constexpr int LN_MAXC = 4;  // d <= 256 * 8 * 4 = 8192
+
+__global__ void __launch_bounds__(LN_THREADS)
+ln_fwd_kernel(const __half* __restrict__ y, const __half* __restrict__ gamma, const __half* __restrict__ beta,
+              __half* __restrict__ out, float* __restrict__ stats, int rows, int d, float eps) {
+  __shared__ float2 scratch[32];
+  const int nch = d / 8;
+  for (int row = blockIdx.x; row < rows; row += gridDim.x) {
+    const __half* yr = y + (size_t)row * d;
+    float x[LN_MAXC][8];
+    float s = 0.f;
+#pragma unroll
+    for (int c = 0; c < LN_MAXC; ++c) {
+      const int ch = threadIdx.x + c * LN_THREADS;
+      if (ch < nch) {
+        h8_to_f(*reinterpret_cast<const H8*>(yr + ch * 8), x[c]);
+#pragma unroll
+        for (int i = 0; i < 8; ++i) s += x[c][i];
+      }
+    }
+    const float mean = block_sum2(s, 0.f, scratch).x / (float)d;
+    float v = 0.f;
+#pragma unroll
+    for (int c = 0; c < LN_MAXC; ++c) {
+      const int ch = threadIdx.x + c * LN_THREADS;
+      if (ch < nch) {
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          const float t = x[c][i] - mean;
+          v += t * t;
+        }
+      }
+    }
+    const float var = block_sum2(v, 0.f, scratch).x / (float)d;
+    const float rstd = rsqrtf(var + eps);
+    if (threadIdx.x == 0) {
+      stats[2 * row] = mean;
+      stats[2 * row + 1] = rstd;
+    }
+#pragma unroll
+    for (int c = 0; c < LN_MAXC; ++c) {
+      const int ch = threadIdx.x + c * LN_THREADS;
+      if (ch < nch) {
+        float g[8], b[8], o[8];
+        h8_to_f(*reinterpret_cast<const H8*>(gamma + ch * 8), g);
+        h8_to_f(*reinterpret_cast<const H8*>(beta + ch * 8), b);
+#pragma unroll
+        for (int i = 0; i < 8; ++i) o[i] = (x[c][i] - mean) * rstd * g[i] + b[i];
+        *reinterpret_cast<H8*>(out + (size_t)row * d + ch * 8) = f_to_h8(o);
+      }
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------------ LayerNorm backward
+// dy = rstd * (dxhat - mean(dxhat) - xhat * mean(dxhat * xhat)),  dxhat = dout * gamma
+// dz = dy * dropout_mask * scale  (mask replayed from (seed, row*d + col), same stream as the GEMM epilogue)
+// column reductions (fp32 atomics, one per column per CTA): dgamma += dout*xhat, dbeta += dout, dbias += dz
+__global__ void __launch_bounds__(LN_THREADS)
+ln_bwd_kernel(const __half* __restrict__ dout, const __half* __restrict__ y, const __half* __restrict__ gamma,
+              const float* __restrict__ stats, __half* __restrict__ dy, __half* __restrict__ dz,
+              float* __restrict__ dgamma, float* __restrict__ dbeta, float* __restrict__ dbias, int rows, int d,
+              uint32_t drop_thr16, float drop_scale, uint64_t seed) {
+  __shared__ float2 scratch[32];
+  const int nch = d / 8;
+  float ag[LN_MAXC][8], ab[LN_MAXC][8], az[LN_MAXC][8];
+#pragma unroll
+  for (int c = 0; c < LN_MAXC; ++c)
+#pragma unroll
+    for (int i = 0; i < 8; ++i) ag[c][i] = ab[c][i] = az[c][i] = 0.f;
+
+  for (int row = blockIdx.x; row < rows; row += gridDim.x) {
+    const float mean = stats[2 * row], rstd = stats[2 * row + 1];
+    float xh[LN_MAXC][8], dx[LN_MAXC][8];
+    float s1 = 0.f, s2 = 0.f;
+#pragma unroll
+    for (int c = 0; c < LN_MAXC; ++c) {
+      const int ch = threadIdx.x + c * LN_THREADS;
+      if (ch < nch) {
+        float g[8], go[8], yv[8];
+        h8_to_f(*reinterpret_cast<const H8*>(gamma + ch * 8), g);
+        h8_to_f(*reinterpret_cast<const H8*>(dout + (size_t)row * d + ch * 8), go);
+        h8_to_f(*reinterpret_cast<const H8*>(y + (size_t)row * d + ch * 8), yv);
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          xh[c][i] = (yv[i] - mean) * rstd;
+          dx[c][i] = go[i] * g[i];
+          s1 += dx[c][i];
+          s2 += dx[c][i] * xh[c][i];
+          ag[c][i] += go[i] * xh[c][i];
+          ab[c][i] += go[i];
+        }
+      }
+    }
+    const float2 t = block_sum2(s1, s2, scratch);
+    const float m1 = t.x / (float)d, m2 = t.y / (float)d;
+#pragma unroll
+    for (int c = 0; c < LN_MAXC; ++c) {
+      const int ch = threadIdx.x + c * LN_THREADS;
+      if (ch < nch) {
+        float o[8];
+#pragma unroll
+        for (int i = 0; i < 8; ++i) o[i] = rstd * (dx[c][i] - m1 - xh[c][i] * m2);
+        const H8 hv = f_to_h8(o);
+        *reinterpret_cast<H8*>(dy + (size_t)row * d + ch * 8) = hv;
+        if (dz != nullptr || dbias != nullptr) {
+          float z[8];
+          h8_to_f(hv, z);  // the GEMM branch sees the fp16-rounded dy
+          if (drop_thr16 && dz != nullptr) {
+            const uint64_t e = (uint64_t)row * (uint64_t)d + (uint64_t)ch * 8;
+            const uint64_t b0 = rng64(seed, e >> 2), b1 = rng64(seed, (e >> 2) + 1);
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+              z[i] = dropout_keep(b0, i, drop_thr16) ? z[i] * drop_scale : 0.f;
+              z[4 + i] = dropout_keep(b1, i, drop_thr16) ? z[4 + i] * drop_scale : 0.f;
+            }
+            *reinterpret_cast<H8*>(dz + (size_t)row * d + ch * 8) = f_to_h8(z);
+          }
+          if (dbias != nullptr) {
+#pragma unroll
+            for (int i = 0; i < 8; ++i) az[c][i] += z[i];
+          }
+        }
+      }
+    }
+  }
+#pragma unroll
+  for (int c = 0; c < LN_MAXC; ++c) {
+    const int ch = threadIdx.x + c * LN_THREADS;
+    if (ch < nch) {
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        atomicAdd(dgamma + ch * 8 + i, ag[c][i]);
+        atomicAdd(dbeta + ch * 8 + i, ab[c][i]);
+        if (dbias != nullptr) atomicAdd(dbias + ch * 8 + i, az[c][i]);
+      }
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------------ masked CE
+// one CTA per row: online (max, sum-exp) over V fp16 logits, fp32 math. loss_row = (lse - z[label]) * mask.
+constexpr int CE_THREADS = 256;
+
+__global__ void __launch_bounds__(CE_THREADS)
+ce_fwd_kernel(const __half* __restrict__ logits, long long ld, const long long* __restrict__ labels,
+              const float* __restrict__ mask, float* __restrict__ row_loss, float* __restrict__ row_lse, int rows,
+              int V) {
+  __shared__ float2 scratch[32];
+  __shared__ float fscr[32];
+  const int row = blockIdx.x;
+  const __half* z = logits + (size_t)row * ld;
+  const int nch = (V + 7) / 8;
+  float mx = -INFINITY, sm = 0.f;
+  for (int ch = threadIdx.x; ch < nch; ch += CE_THREADS) {
+    float f[8];
+    h8_to_f(*reinterpret_cast<const H8*>(z + ch * 8), f);
+    float cm = -INFINITY;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      if (ch * 8 + i >= V) f[i] = -INFINITY;
+      cm = fmaxf(cm, f[i]);
+    }
+    if (cm > mx) {
+      sm *= __expf(mx - cm);
+      mx = cm;
+    }
+#pragma unroll
+    for (int i = 0; i < 8; ++i) sm += __expf(f[i] - mx);
+  }
+  const float bm = block_max(mx, fscr);
+  sm = (mx == -INFINITY) ? 0.f : sm * __expf(mx - bm);
+  const float tot = block_sum2(sm, 0.f, scratch).x;
+  if (threadIdx.x == 0) {
+    const float lse = bm + logf(tot);
+    const long long lab = labels[row];
+    const float zl = __half2float(z[lab]);
+    row_lse[row] = lse;
+    row_loss[row] = (lse - zl) * mask[row];
+  }
+}
+
+// loss = sum(row_loss) / sum(mask); also keeps sum(mask) for the backward. Single CTA (rows is a few thousand).
+__global__ void ce_finalize_kernel(const float* __restrict__ row_loss, const float* __restrict__ mask, int rows,
+                                   float* __restrict__ out2) {
+  __shared__ float2 scratch[32];
+  float a = 0.f, b = 0.f;
+  for (int i = threadIdx.x; i < rows; i += blockDim.x) {
+    a += row_loss[i];
+    b += mask[i];
+  }
+  const float2 t = block_sum2(a, b, scratch);
+  if (threadIdx.x == 0) {
+    out2[0] = t.x / t.y;
+    out2[1] = t.y;
+  }
+}
+
+// dlogits[row, c] = (softmax - onehot) * mask[row] / sum(mask) * gscale   (gscale = upstream dLoss, a device scalar)
+__global__ void __launch_bounds__(CE_THREADS)
+ce_bwd_kernel(const __half* __restrict__ logits, long long ld, const long long* __restrict__ labels,
+              const float* __restrict__ mask, const float* __restrict__ row_lse, const float* __restrict__ loss2,
+              const float* __restrict__ gscale, __half* __restrict__ dlogits, long long ldd, int rows, int V) {
+  const int row = blockIdx.x;
+  const __half* z = logits + (size_t)row * ld;
+  __half* dzp = dlogits + (size_t)row * ldd;
+  const float w = mask[row] / loss2[1] * gscale[0];
+  const float lse = row_lse[row];
+  const int lab = (int)labels[row];
+  const int nch = (V + 7) / 8;
+  for (int ch = threadIdx.x; ch < nch; ch += CE_THREADS) {
+    float f[8], o[8];
+    h8_to_f(*reinterpret_cast<const H8*>(z + ch * 8), f);
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      const int c = ch * 8 + i;
+      float pr = (w == 0.f) ? 0.f : __expf(f[i] - lse);
+      if (c == lab) pr -= 1.f;
+      o[i] = (c < V) ? pr * w : 0.f;
+    }
+    *reinterpret_cast<H8*>(dzp + ch * 8) = f_to_h8(o);
+  }
+}
+
+// ------------------------------------------------------------------------------------------------ embedding assembly
+// slot[b,l] = number of image-patch slots (token == -1) strictly before l in row b  (transformer_xl.py:639-642)
+__global__ void embed_slots_kernel(const long long* __restrict__ tok, int* __restrict__ slot, int B, int L) {
+  const int b = blockIdx.x;
+  const int lane = threadIdx.x;  // 32 threads
+  int base = 0;
+  for (int l0 = 0; l0 < L; l0 += 32) {
+    const int l = l0 + lane;
+    const bool is = (l < L) && (tok[(size_t)b * L + l] == -1);
+    const unsigned m = __ballot_sync(0xffffffffu, is);
+    if (l < L) slot[(size_t)b * L + l] = base + __popc(m & ((1u << lane) - 1u));
+    base += __popc(m);
+  }
+}
+
+// out[b, l, :] = dropout( (tok >= 0 ? W[tok] : vis[b, slot]) + (pos ? T[pos] : 0) )
+// one warp per token; out row = out + b*out_bs + l*d
+__global__ void __launch_bounds__(256)
+embed_fwd_kernel(const long long* __restrict__ tok, const long long* __restrict__ pos, const int* __restrict__ slot,
+                 const __half* __restrict__ W, const __half* __restrict__ T, const __half* __restrict__ vis,
+                 long long vis_bs, int nvis, __half* __restrict__ out, long long out_bs, int B, int L, int d, int V,
+                 uint32_t drop_thr16, float drop_scale, uint64_t seed, long long seed_row0) {
+  const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int lane = threadIdx.x & 31;
+  if (warp >= B * L) return;
+  const int b = warp / L, l = warp % L;
+  const long long t = tok[warp];
+  const __half* src = nullptr;
+  if (t >= 0 && t < V) src = W + (size_t)t * d;
+  else if (t == -1 && vis != nullptr) {
+    const int s = slot[warp];
+    if (s < nvis) src = vis + (size_t)b * vis_bs + (size_t)s * d;
+  }
+  const __half* tp = nullptr;
+  if (pos != nullptr) tp = T + (size_t)pos[warp] * d;
+  __half* dst = out + (size_t)b * out_bs + (size_t)l * d;
+  for (int ch = lane; ch < d / 8; ch += 32) {
+    float f[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) f[i] = 0.f;
+    if (src) h8_to_f(*reinterpret_cast<const H8*>(src + ch * 8), f);
+    if (tp) {
+      float g[8];
+      h8_to_f(*reinterpret_cast<const H8*>(tp + ch * 8), g);
+      // the reference adds two fp16 tensors: round the sum once
+#pragma unroll
+      for (int i = 0; i < 8; ++i) f[i] += g[i];
+    }
+    if (drop_thr16) {
+      const uint64_t e = (uint64_t)(seed_row0 + warp) * (uint64_t)d + (uint64_t)ch * 8;
+      const uint64_t b0 = rng64(seed, e >> 2), b1 = rng64(seed, (e >> 2) + 1);
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        f[i] = dropout_keep(b0, i, drop_thr16) ? f[i] * drop_scale : 0.f;
+        f[4 + i] = dropout_keep(b1, i, drop_thr16) ? f[4 + i] * drop_scale : 0.f;
+      }
+    }
+    *reinterpret_cast<H8*>(dst + ch * 8) = f_to_h8(f);
+  }
+}
+
+// scatter-add of the embedding gradient: dW[tok] += g, dT[pos] += g, dvis[b, slot] = g   (g = dout * dropout mask)
+__global__ void __launch_bounds__(256)
+embed_bwd_kernel(const long long* __restrict__ tok, const long long* __restrict__ pos, const int* __restrict__ slot,
+                 const __half* __restrict__ dout, long long dout_bs, __half* __restrict__ dW, __half* __restrict__ dT,
+                 __half* __restrict__ dvis, long long vis_bs, int nvis, int B, int L, int d, int V,
+                 uint32_t drop_thr16, float drop_scale, uint64_t seed, long long seed_row0) {
+  const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int lane = threadIdx.x & 31;
+  if (warp >= B * L) return;
+  const int b = warp / L, l = warp % L;
+  const long long t = tok[warp];
+  const __half* src = dout + (size_t)b * dout_bs + (size_t)l * d;
+  __half* wdst = (t >= 0 && t < V && dW != nullptr) ? dW + (size_t)t * d : nullptr;
+  __half* tdst = (pos != nullptr && dT != nullptr) ? dT + (size_t)pos[warp] * d : nullptr;
+  __half* vdst = nullptr;
+  if (t == -1 && dvis != nullptr) {
+    const int s = slot[warp];
+    if (s < nvis) vdst = dvis + (size_t)b * vis_bs + (size_t)s * d;
+  }
+  for (int ch = lane; ch < d / 8; ch += 32) {
+    H8 hv = *reinterpret_cast<const H8*>(src + ch * 8);
+    if (drop_thr16) {
+      float f[8];
+      h8_to_f(hv, f);
+      const uint64_t e = (uint64_t)(seed_row0 + warp) * (uint64_t)d + (uint64_t)ch * 8;
+      const uint64_t b0 = rng64(seed, e >> 2), b1 = rng64(seed, (e >> 2) + 1);
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        f[i] = dropout_keep(b0, i, drop_thr16) ? f[i] * drop_scale : 0.f;
+        f[4 + i] = dropout_keep(b1, i, drop_thr16) ? f[4 + i] * drop_scale : 0.f;
+      }
+      hv = f_to_h8(f);
+    }
+    if (wdst) {
+#pragma unroll
+      for (int i = 0; i < 4; ++i) atomicAdd(reinterpret_cast<__half2*>(wdst + ch * 8) + i, hv.h[i]);
+    }
+    if (tdst) {
+#pragma unroll
+      for (int i = 0; i < 4; ++i) atomicAdd(reinterpret_cast<__half2*>(tdst + ch * 8) + i, hv.h[i]);
+    }
+    if (vdst) *reinterpret_cast<H8*>(vdst + ch * 8) = hv;
+  }
+}
+
+// ------------------------------------------------------------------------------------------------ small reductions
+// out[c] += sum_r in[r, c]   (fp16 in, fp32 accumulate via one atomic per column per CTA)
+__global__ void __launch_bounds__(256)
+colsum_kernel(const __half* __restrict__ in, long long ld, float* __restrict__ out, int rows, int n) {
+  const int ch = blockIdx.x * blockDim.x + threadIdx.x;  // 8-column chunk
+  if (ch * 8 >= n) return;
+  float acc[8];
+#pragma unroll
+  for (int i = 0; i < 8; ++i) acc[i] = 0.f;
+  for (int r = blockIdx.y; r < rows; r += gridDim.y) {
+    float f[8];
+    h8_to_f(*reinterpret_cast<const H8*>(in + (size_t)r * ld + ch * 8), f);
+#pragma unroll
+    for (int i = 0; i < 8; ++i) acc[i] += f[i];
+  }
+#pragma unroll
+  for (int i = 0; i < 8; ++i) atomicAdd(out + ch * 8 + i, acc[i]);
+}
+
+// dq = dqu + dqv (fp16 out, written into the fused dQKV buffer) and du += colsum(dqu), dv += colsum(dqv)
+__global__ void __launch_bounds__(256)
+dq_finalize_kernel(const __half* __restrict__ dqu, const __half* __restrict__ dqv, long long ld_in,
+                   __half* __restrict__ dq, long long ld_out, float* __restrict__ du, float* __restrict__ dv, int rows,
+                   int n) {
+  const int ch = blockIdx.x * blockDim.x + threadIdx.x;
+  if (ch * 8 >= n) return;
+  float au[8], av[8];
+#pragma unroll
+  for (int i = 0; i < 8; ++i) au[i] = av[i] = 0.f;
+  for (int r = blockIdx.y; r < rows; r += gridDim.y) {
+    float a[8], b[8], o[8];
+    h8_to_f(*reinterpret_cast<const H8*>(dqu + (size_t)r * ld_in + ch * 8), a);
+    h8_to_f(*reinterpret_cast<const H8*>(dqv + (size_t)r * ld_in + ch * 8), b);
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      o[i] = a[i] + b[i];
+      au[i] += a[i];
+      av[i] += b[i];
+    }
+    *reinterpret_cast<H8*>(dq + (size_t)r * ld_out + ch * 8) = f_to_h8(o);
+  }
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    atomicAdd(du + ch * 8 + i, au[i]);
+    atomicAdd(dv + ch * 8 + i, av[i]);
+  }
+}
+
+// D[b,h,i] = sum_d dO[b,i,h,d] * O[b,i,h,d]   (one warp per (b,i,h))
+__global__ void __launch_bounds__(256)
+rowdot_kernel(const __half* __restrict__ a, const __half* __restrict__ b, long long ld, float* __restrict__ out, int B,
+              int L, int H, int dh) {
+  const int w = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int lane = threadIdx.x & 31;
+  if (w >= B * L * H) return;
+  const int h = w % H;
+  const int bi = w / H;  // b*L + i
+  const __half* pa = a + (size_t)bi * ld + h * dh;
+  const __half* pb = b + (size_t)bi * ld + h * dh;
+  float s = 0.f;
+  for (int ch = lane; ch < dh / 8; ch += 32) {
+    float x[8], y[8];
+    h8_to_f(*reinterpret_cast<const H8*>(pa + ch * 8), x);
+    h8_to_f(*reinterpret_cast<const H8*>(pb + ch * 8), y);
+#pragma unroll
+    for (int i = 0; i < 8; ++i) s += x[i] * y[i];
+  }
+  s = warp_sum(s);
+  if (lane == 0) {
+    const int bb = bi / L, i = bi % L;
+    out[((size_t)bb * H + h) * L + i] = s;
+  }
+}
+
+// sinusoid rows in the reference order: row c <-> distance min(klen-1-c, clamp); [sin | cos]; fp32 math -> fp16, dropout
+__global__ void posemb_kernel(__half* __restrict__ out, const float* __restrict__ inv_freq, int klen, int d,
+                              int clamp_len, uint32_t drop_thr16, float drop_scale, uint64_t seed) {
+  const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+  const int half_d = d / 2;
+  if (idx >= klen * half_d) return;
+  const int c = idx / half_d, k = idx % half_d;
+  float pos = (float)(klen - 1 - c);
+  if (clamp_len > 0 && pos > (float)clamp_len) pos = (float)clamp_len;
+  // inv_freq is the module's registered buffer (transformer_xl.py:40-41), so both sides use identical frequencies
+  const float ang = pos * inv_freq[k];
+  float sv = sinf(ang), cv = cosf(ang);
+  if (drop_thr16) {
+    const uint64_t e1 = (uint64_t)c * d + k, e2 = (uint64_t)c * d + half_d + k;
+    const uint64_t b1 = rng64(seed, e1 >> 2), b2 = rng64(seed, e2 >> 2);
+    sv = dropout_keep(b1, (int)(e1 & 3), drop_thr16) ? sv * drop_scale : 0.f;
+    cv = dropout_keep(b2, (int)(e2 & 3), drop_thr16) ? cv * drop_scale : 0.f;
+  }
+  out[(size_t)c * d + k] = __float2half_rn(sv);
+  out[(size_t)c * d + half_d + k] = __float2half_rn(cv);
+}
+
+// dst(fp16) = src(fp32)   and   dst(fp16) += src(fp32)
+__global__ void f32_to_f16_kernel(const float* __restrict__ src, __half* __restrict__ dst, long long n, int accumulate) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  float v = src[i];
+  if (accumulate) v += __half2float(dst[i]);
+  dst[i] = __float2half_rn(v);
+}
+
+static inline uint32_t thr16(float p) { return (uint32_t)(p * 65536.0f + 0.5f); }
+static inline float dscale(uint32_t t) { return t ? 65536.0f / (65536.0f - (float)t) : 1.0f; }
+
+}  // namespace db1
+
+using namespace db1;
+
+extern "C" int db1_layernorm_fwd(const void* y, const void* gamma, const void* beta, void* out, float* stats, int rows,
+                                 int d, float eps, void* stream) {
+  DB1_CHECK_ARG(y && gamma && beta && out && stats, "layernorm_fwd: null pointer");
+  DB1_CHECK_ARG(rows > 0 && d > 0 && d % 8 == 0 && d <= LN_THREADS * 8 * LN_MAXC, "layernorm_fwd: bad shape %d x %d", rows, d);
+  const int grid = rows < 148 * 8 ? rows : 148 * 8;
+  ln_fwd_kernel<<<grid, LN_THREADS, 0, (cudaStream_t)stream>>>((const __half*)y, (const __half*)gamma,
+                                                             (const __half*)beta, (__half*)out, stats, rows, d, eps);
+  DB1_CUDA(cudaGetLastError());
+  return 0;
+}
+
+extern "C" int db1_layernorm_bwd(const void* dout, const void* y, const void* gamma, const float* stats, void* dy,
+                                 void* dz, float* dgamma, float* dbeta, float* dbias, int rows, int d, float drop_p,
+                                 uint64_t seed, void* stream) {
+  DB1_CHECK_ARG(dout && y && gamma && stats && dy && dgamma && dbeta, "layernorm_bwd: null pointer");
+  DB1_CHECK_ARG(rows > 0 && d > 0 && d % 8 == 0 && d <= LN_THREADS * 8 * LN_MAXC, "layernorm_bwd: bad shape %d x %d", rows, d);
+  DB1_CHECK_ARG(drop_p >= 0.f && drop_p < 1.f, "layernorm_bwd: bad dropout p");
+  DB1_CHECK_ARG(drop_p == 0.f || dz != nullptr, "layernorm_bwd: dropout needs a dz buffer");
+  const uint32_t t = thr16(drop_p);
+  const int grid = rows < 148 * 2 ? rows : 148 * 2;
+  ln_bwd_kernel<<<grid, LN_THREADS, 0, (cudaStream_t)stream>>>((const __half*)dout, (const __half*)y,
+                                                             (const __half*)gamma, stats, (__half*)dy, (__half*)dz,
+                                                             dgamma, dbeta, dbias, rows, d, t, dscale(t), seed);
+  DB1_CUDA(cudaGetLastError());
+  return 0;
+}
+
+extern "C" int db1_ce_fwd(const void* logits, long long ld, const long long* labels, const float* mask, float* row_loss,
+                          float* row_lse, float* loss2, int rows, int V, void* stream) {
+  DB1_CHECK_ARG(logits && labels && mask && row_loss && row_lse && loss2, "ce_fwd: null pointer");
+  DB1_CHECK_ARG(rows > 0 && V > 0 && ld % 8 == 0 && ld >= V, "ce_fwd: bad shape rows=%d V=%d ld=%lld", rows, V, ld);
+  ce_fwd_kernel<<<rows, CE_THREADS, 0, (cudaStream_t)stream>>>((const __half*)logits, ld, labels, mask, row_loss,
+                                                             row_lse, rows, V);
+  ce_finalize_kernel<<<1, 1024, 0, (cudaStream_t)stream>>>(row_loss, mask, rows, loss2);
+  DB1_CUDA(cudaGetLastError());
+  return 0;
+}
+
+extern "C" int db1_ce_bwd(const void* logits, long long ld, const long long* labels, const float* mask,
+                          const float* row_lse, const float* loss2, const float* gscale, void* dlogits, long long ldd,
+                          int rows, int V, void* stream) {
+  DB1_CHECK_ARG(logits && labels && mask && row_lse && loss2 && gscale && dlogits, "ce_bwd: null pointer");
+  DB1_CHECK_ARG(rows > 0 && V > 0 && ld % 8 == 0 && ldd % 8 == 0 && ld >= V && ldd >= ((V + 7) / 8) * 8,
+                "ce_bwd: bad shape rows=%d V=%d", rows, V);
+  ce_bwd_kernel<<<rows, CE_THREADS, 0, (cudaStream_t)stream>>>((const __half*)logits, ld, labels, mask, row_lse, loss2,
+                                                             gscale, (__half*)dlogits, ldd, rows, V);
+  DB1_CUDA(cudaGetLastError());
+  return 0;
+}
+
+extern "C" int db1_embed_fwd(const long long* tok, const long long* pos, int* slot, const void* W, const void* T,
+                             const void* vis, long long vis_bs, int nvis, void* out, long long out_bs, int B, int L,
+                             int d, int V, float drop_p, uint64_t seed, long long seed_row0, void* stream) {
+  DB1_CHECK_ARG(tok && W && out && slot, "embed_fwd: null pointer");
+  DB1_CHECK_ARG(B > 0 && L > 0 && d % 8 == 0, "embed_fwd: bad shape");
+  DB1_CHECK_ARG(pos == nullptr || T != nullptr, "embed_fwd: position ids need the timestep table");
+  embed_slots_kernel<<<B, 32, 0, (cudaStream_t)stream>>>(tok, slot, B, L);
+  const uint32_t t = thr16(drop_p);
+  const long long nthreads = (long long)B * L * 32;
+  embed_fwd_kernel<<<(unsigned)((nthreads + 255) / 256), 256, 0, (cudaStream_t)stream>>>(
+      tok, pos, slot, (const __half*)W, (const __half*)T, (const __half*)vis, vis_bs, nvis, (__half*)out, out_bs, B, L,
+      d, V, t, dscale(t), seed, seed_row0);
+  DB1_CUDA(cudaGetLastError());
+  return 0;
+}
+
+extern "C" int db1_embed_bwd(const long long* tok, const long long* pos, const int* slot, const void* dout,
+                             long long dout_bs, void* dW, void* dT, void* dvis, long long vis_bs, int nvis, int B, int L,
+                             int d, int V, float drop_p, uint64_t seed, long long seed_row0, void* stream) {
+  DB1_CHECK_ARG(tok && dout && slot, "embed_bwd: null pointer");
+  DB1_CHECK_ARG(B > 0 && L > 0 && d % 8 == 0, "embed_bwd: bad shape");
+  const uint32_t t = thr16(drop_p);
+  const long long nthreads = (long long)B * L * 32;
+  embed_bwd_kernel<<<(unsigned)((nthreads + 255) / 256), 256, 0, (cudaStream_t)stream>>>(
+      tok, pos, slot, (const __half*)dout, dout_bs, (__half*)dW, (__half*)dT, (__half*)dvis, vis_bs, nvis, B, L, d, V, t,
+      dscale(t), seed, seed_row0);
+  DB1_CUDA(cudaGetLastError());
+  return 0;
+}
+
+extern "C" int db1_colsum(const void* in, long long ld, float* out, int rows, int n, void* stream) {
+  DB1_CHECK_ARG(in && out && rows > 0 && n > 0 && n % 8 == 0 && ld % 8 == 0, "colsum: bad arguments");
+  dim3 grid((n / 8 + 255) / 256, rows < 296 ? rows : 296);
+  colsum_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>((const __half*)in, ld, out, rows, n);
+  DB1_CUDA(cudaGetLastError());
+  return 0;
+}
+
+extern "C" int db1_dq_finalize(const void* dqu, const void* dqv, long long ld_in, void* dq, long long ld_out, float* du,
+                               float* dv, int rows, int n, void* stream) {
+  DB1_CHECK_ARG(dqu && dqv && dq && du && dv && rows > 0 && n % 8 == 0 && ld_in % 8 == 0 && ld_out % 8 == 0,
+                "dq_finalize: bad arguments");
+  dim3 grid((n / 8 + 255) / 256, rows < 296 ? rows : 296);
+  dq_finalize_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>((const __half*)dqu, (const __half*)dqv, ld_in, (__half*)dq,
+                                                           ld_out, du, dv, rows, n);
+  DB1_CUDA(cudaGetLastError());
+  return 0;
+}
+
+extern "C" int db1_rowdot(const void* a, const void* b, long long ld, float* out, int B, int L, int H, int dh,
+                          void* stream) {
+  DB1_CHECK_ARG(a && b && out && B > 0 && L > 0 && H > 0 && dh % 8 == 0 && ld % 8 == 0, "rowdot: bad arguments");
+  const long long nthreads = (long long)B * L * H * 32;
+  rowdot_kernel<<<(unsigned)((nthreads + 255) / 256), 256, 0, (cudaStream_t)stream>>>((const __half*)a, (const __half*)b,
+                                                                                     ld, out, B, L, H, dh);
+  DB1_CUDA(cudaGetLastError());
+  return 0;
+}
+
+extern "C" int db1_posemb(void* out, const float* inv_freq, int klen, int d, int clamp_len, float drop_p, uint64_t seed,
+                          void* stream) {
+  DB1_CHECK_ARG(out && inv_freq && klen > 0 && d > 0 && d % 2 == 0, "posemb: bad arguments");
+  const uint32_t t = thr16(drop_p);
+  const int n = klen * (d / 2);
+  posemb_kernel<<<(n + 255) / 256, 256, 0, (cudaStream_t)stream>>>((__half*)out, inv_freq, klen, d, clamp_len, t, dscale(t),
+                                                                 seed);
+  DB1_CUDA(cudaGetLastError());
+  return 0;
+}
+
+extern "C" int db1_f32_to_f16(const float* src, void* dst, long long n, int accumulate, void* stream) {
+  DB1_CHECK_ARG(src && dst && n > 0, "f32_to_f16: bad arguments");
+  f32_to_f16_kernel<<<(unsigned)((n + 255) / 256), 256, 0, (cudaStream_t)stream>>>(src, (__half*)dst, n, accumulate);
+  DB1_CUDA(cudaGetLastError());
+  return 0;
+}

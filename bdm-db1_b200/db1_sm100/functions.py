@@ -1,0 +1,325 @@
+"""autograd.Function wrappers: each forward/backward is a fixed sequence of C-ABI kernel launches (db1_sm100.ops).
+
+Nothing here computes with torch ops on the data path; torch supplies device buffers, the current stream and the
+autograd graph. Shapes: activations are [rows = B*L, d] fp16 row-major.
+"""
+import math
+import threading
+
+import torch
+
+from . import ops
+
+_ws_lock = threading.Lock()
+_ws = {}
+
+
+def _workspace(key, shape, dtype, device, zero=True):
+    """Process-wide cached scratch (attention-backward score buffers, dlogits). Zero-filled once at creation: the kernels
+    rely on never-written regions (above-diagonal tiles) staying zero, and the write pattern depends only on the shape."""
+    k = (key, tuple(shape), dtype, device.index)
+    with _ws_lock:
+        t = _ws.get(k)
+        if t is None:
+            t = torch.zeros(shape, dtype=dtype, device=device) if zero else torch.empty(shape, dtype=dtype, device=device)
+            _ws[k] = t
+    return t
+
+
+def clear_workspaces():
+    with _ws_lock:
+        _ws.clear()
+
+
+class _Seeds:
+    """Counter-based dropout seeds: (torch.initial_seed(), call counter) -> 64-bit seed, one per dropout site per call."""
+
+    def __init__(self):
+        self.counter = 0
+
+    def next(self):
+        self.counter += 1
+        s = (torch.initial_seed() * 0x9E3779B97F4A7C15 + self.counter * 0xD1B54A32D192ED03) & 0xFFFFFFFFFFFFFFFF
+        return s
+
+
+seeds = _Seeds()
+
+
+def _f32zeros(n, dev):
+    return torch.zeros(n, dtype=torch.float32, device=dev)
+
+
+def _to_half(x32, shape):
+    out = torch.empty(shape, dtype=torch.float16, device=x32.device)
+    ops.f32_to_f16(x32, out)
+    return out
+
+
+class AttnBlockFn(torch.autograd.Function):
+    """RelPartialLearnableMultiHeadAttn.forward, post-LN branch (transformer_xl.py:112-243):
+    out = LayerNorm(w + dropout(o_net(rel_attention(qkv_net(w), r_net(r)))))."""
+
+    @staticmethod
+    def forward(ctx, w, r, Wqkv, Wr, Wo, u, v, gamma, beta, H, eps, drop_p, window):
+        B, L, d = w.shape
+        dh = d // H
+        rows = B * L
+        dev = w.device
+        x2 = w.reshape(rows, d)
+        if not x2.is_contiguous():
+            x2 = x2.contiguous()
+        uf = u.reshape(d)
+        vf = v.reshape(d)
+        qkv4 = torch.empty(rows, 4 * d, dtype=torch.float16, device=dev)
+        ops.gemm(x2, Wqkv, qkv4, rows, 3 * d, d, lda=d, ldb=d, ldc=4 * d, epilogue=ops.EPI_QKV, u=uf, v=vf, d_model=d)
+        rk = torch.empty(L, d, dtype=torch.float16, device=dev)
+        ops.gemm(r, Wr, rk, L, d, d, lda=d, ldb=d, ldc=d)
+        o = torch.empty(rows, d, dtype=torch.float16, device=dev)
+        lse2 = torch.empty(B, H, L, dtype=torch.float32, device=dev)
+        scale = 1.0 / math.sqrt(dh)
+        ops.relattn_fwd(qkv4, rk, o, lse2, B, L, H, dh, window, scale)
+        seed = seeds.next() if drop_p > 0 else 0
+        y = torch.empty(rows, d, dtype=torch.float16, device=dev)
+        ops.gemm(o, Wo, y, rows, d, d, lda=d, ldb=d, ldc=d, resid=x2, ldr=d, drop_p=drop_p, seed=seed)
+        out = torch.empty(rows, d, dtype=torch.float16, device=dev)
+        stats = torch.empty(rows, 2, dtype=torch.float32, device=dev)
+        ops.layernorm_fwd(y, gamma, beta, out, stats, eps)
+        ctx.save_for_backward(x2, r, Wqkv, Wr, Wo, gamma, qkv4, rk, o, lse2, y, stats)
+        ctx.cfg = (B, L, d, H, dh, drop_p, seed, window, scale)
+        return out.view(B, L, d)
+
+    @staticmethod
+    def backward(ctx, dout):
+        x2, r, Wqkv, Wr, Wo, gamma, qkv4, rk, o, lse2, y, stats = ctx.saved_tensors
+        B, L, d, H, dh, drop_p, seed, window, scale = ctx.cfg
+        rows = B * L
+        dev = x2.device
+        f16 = torch.float16
+        dout2 = dout.reshape(rows, d)
+        if not dout2.is_contiguous():
+            dout2 = dout2.contiguous()
+        dgamma = _f32zeros(d, dev)
+        dbeta = _f32zeros(d, dev)
+        dy = torch.empty(rows, d, dtype=f16, device=dev)
+        dz = torch.empty(rows, d, dtype=f16, device=dev) if drop_p > 0 else None
+        ops.layernorm_bwd(dout2, y, gamma, stats, dy, dz, dgamma, dbeta, None, drop_p, seed)
+        dzz = dz if dz is not None else dy
+        # o_net
+        dWo = torch.empty(d, d, dtype=f16, device=dev)
+        ops.gemm(dzz, o, dWo, d, d, rows, lda=d, ldb=d, ldc=d, a_mn=True, b_mn=True)
+        do = torch.empty(rows, d, dtype=f16, device=dev)
+        ops.gemm(dzz, Wo, do, rows, d, d, lda=d, ldb=d, ldc=d, b_mn=True)
+        # attention core: recompute P, then the causal contractions on tensor cores
+        Drow = torch.empty(B, H, L, dtype=torch.float32, device=dev)
+        ops.rowdot(do, o, Drow, B, L, H, dh)
+        P = _workspace("P", (B, H, L, L), f16, dev)
+        dS = _workspace("dS", (B, H, L, L), f16, dev)
+        dSr = _workspace("dSr", (B, H, L, L), f16, dev)
+        ops.relattn_fwd(qkv4, rk, None, lse2, B, L, H, dh, window, scale, probs=P)
+        qu = qkv4[:, 0:d]
+        qv = qkv4[:, d:2 * d]
+        kk = qkv4[:, 2 * d:3 * d]
+        vv = qkv4[:, 3 * d:4 * d]
+        LL = L * L
+        sz = (LL, H * LL)
+        ops.gemm(do, vv, dS, L, L, dh, lda=d, ldb=4 * d, ldc=L, epilogue=ops.EPI_DS, alpha=scale, Z1=H, Z2=B,
+                 a_z=(dh, L * d), b_z=(dh, L * 4 * d), c_z=sz, skip_upper=True, P=P, C2=dSr, Drow=Drow,
+                 window=window)
+        dqkv = torch.empty(rows, 3 * d, dtype=f16, device=dev)
+        ops.gemm(P, do, dqkv[:, 2 * d:], L, dh, L, lda=L, ldb=d, ldc=3 * d, a_mn=True, b_mn=True, Z1=H, Z2=B,
+                 a_z=sz, b_z=(dh, L * d), c_z=(dh, L * 3 * d), k_mode=ops.K_BEGIN_BY_ROW)
+        ops.gemm(dS, qu, dqkv[:, d:2 * d], L, dh, L, lda=L, ldb=4 * d, ldc=3 * d, a_mn=True, b_mn=True, Z1=H, Z2=B,
+                 a_z=sz, b_z=(dh, L * 4 * d), c_z=(dh, L * 3 * d), k_mode=ops.K_BEGIN_BY_ROW)
+        dqu = torch.empty(rows, d, dtype=f16, device=dev)
+        dqv = torch.empty(rows, d, dtype=f16, device=dev)
+        ops.gemm(dS, kk, dqu, L, dh, L, lda=L, ldb=4 * d, ldc=d, b_mn=True, Z1=H, Z2=B,
+                 a_z=sz, b_z=(dh, L * 4 * d), c_z=(dh, L * d), k_mode=ops.K_END_BY_ROW)
+        ops.gemm(dSr, rk, dqv, L, dh, L, lda=L, ldb=d, ldc=d, b_mn=True, Z1=H, Z2=B,
+                 a_z=sz, b_z=(dh, 0), c_z=(dh, L * d), k_mode=ops.K_BEGIN_REV)
+        drk = torch.empty(L, d, dtype=f16, device=dev)
+        ops.gemm(dSr, qv, drk, L, dh, L, lda=L, ldb=4 * d, ldc=d, a_mn=True, b_mn=True, Z1=H, Z2=B,
+                 a_z=sz, b_z=(dh, L * 4 * d), c_z=(dh, 0), reduce_z2=True, k_mode=ops.K_BEGIN_REV)
+        du = _f32zeros(d, dev)
+        dv = _f32zeros(d, dev)
+        ops.dq_finalize(dqu, dqv, dqkv[:, 0:d], du, dv, rows, d)
+        # r_net / qkv_net
+        dWr = torch.empty(d, d, dtype=f16, device=dev)
+        ops.gemm(drk, r, dWr, d, d, L, lda=d, ldb=d, ldc=d, a_mn=True, b_mn=True)
+        dWqkv = torch.empty(3 * d, d, dtype=f16, device=dev)
+        ops.gemm(dqkv, x2, dWqkv, 3 * d, d, rows, lda=3 * d, ldb=d, ldc=d, a_mn=True, b_mn=True)
+        dx = torch.empty(rows, d, dtype=f16, device=dev)
+        ops.gemm(dqkv, Wqkv, dx, rows, d, 3 * d, lda=3 * d, ldb=d, ldc=d, b_mn=True, resid=dy, ldr=d)
+        return (dx.view(B, L, d), None, dWqkv, dWr, dWo, _to_half(du, (H, dh)), _to_half(dv, (H, dh)),
+                _to_half(dgamma, (d,)), _to_half(dbeta, (d,)), None, None, None, None)
+
+
+class FFBlockFn(torch.autograd.Function):
+    """PositionwiseFF.forward, post-LN branch with GeGLU (transformer_xl.py:276-292, activations.py:19-32):
+    out = LayerNorm(x + dropout(W2 (a * gelu(g)) + b2)), [a|g] = W1 x + b1."""
+
+    @staticmethod
+    def forward(ctx, x, W1, b1, W2, b2, gamma, beta, eps, drop_p):
+        B, L, d = x.shape
+        rows = B * L
+        dev = x.device
+        F2 = W1.shape[0]
+        F = F2 // 2
+        x2 = x.reshape(rows, d)
+        if not x2.is_contiguous():
+            x2 = x2.contiguous()
+        Hb = torch.empty(rows, F2, dtype=torch.float16, device=dev)
+        g = torch.empty(rows, F, dtype=torch.float16, device=dev)
+        ops.gemm(x2, W1, g, rows, F2, d, lda=d, ldb=d, ldc=F, epilogue=ops.EPI_GEGLU, bias=b1, H=Hb, ldh=F2, F=F)
+        seed = seeds.next() if drop_p > 0 else 0
+        y = torch.empty(rows, d, dtype=torch.float16, device=dev)
+        ops.gemm(g, W2, y, rows, d, F, lda=F, ldb=F, ldc=d, bias=b2, resid=x2, ldr=d, drop_p=drop_p, seed=seed)
+        out = torch.empty(rows, d, dtype=torch.float16, device=dev)
+        stats = torch.empty(rows, 2, dtype=torch.float32, device=dev)
+        ops.layernorm_fwd(y, gamma, beta, out, stats, eps)
+        ctx.save_for_backward(x2, W1, W2, gamma, Hb, g, y, stats)
+        ctx.cfg = (B, L, d, F, drop_p, seed)
+        return out.view(B, L, d)
+
+    @staticmethod
+    def backward(ctx, dout):
+        x2, W1, W2, gamma, Hb, g, y, stats = ctx.saved_tensors
+        B, L, d, F, drop_p, seed = ctx.cfg
+        rows = B * L
+        dev = x2.device
+        f16 = torch.float16
+        dout2 = dout.reshape(rows, d)
+        if not dout2.is_contiguous():
+            dout2 = dout2.contiguous()
+        dgamma = _f32zeros(d, dev)
+        dbeta = _f32zeros(d, dev)
+        db2 = _f32zeros(d, dev)
+        dy = torch.empty(rows, d, dtype=f16, device=dev)
+        dz = torch.empty(rows, d, dtype=f16, device=dev) if drop_p > 0 else None
+        ops.layernorm_bwd(dout2, y, gamma, stats, dy, dz, dgamma, dbeta, db2, drop_p, seed)
+        dzz = dz if dz is not None else dy
+        dW2 = torch.empty(d, F, dtype=f16, device=dev)
+        ops.gemm(dzz, g, dW2, d, F, rows, lda=d, ldb=F, ldc=F, a_mn=True, b_mn=True)
+        dH = torch.empty(rows, 2 * F, dtype=f16, device=dev)
+        ops.gemm(dzz, W2, dH, rows, F, d, lda=d, ldb=F, ldc=2 * F, b_mn=True, epilogue=ops.EPI_DGEGLU, H=Hb,
+                 ldh=2 * F, F=F)
+        db1 = _f32zeros(2 * F, dev)
+        ops.colsum(dH, db1, rows, 2 * F)
+        dW1 = torch.empty(2 * F, d, dtype=f16, device=dev)
+        ops.gemm(dH, x2, dW1, 2 * F, d, rows, lda=2 * F, ldb=d, ldc=d, a_mn=True, b_mn=True)
+        dx = torch.empty(rows, d, dtype=f16, device=dev)
+        ops.gemm(dH, W1, dx, rows, d, 2 * F, lda=2 * F, ldb=d, ldc=d, b_mn=True, resid=dy, ldr=d)
+        return (dx.view(B, L, d), dW1, _to_half(db1, (2 * F,)), dW2, _to_half(db2, (d,)), _to_half(dgamma, (d,)),
+                _to_half(dbeta, (d,)), None, None)
+
+
+def _pad8(n):
+    return (n + 7) // 8 * 8
+
+
+class HeadLossFn(torch.autograd.Function):
+    """Tied LM head + masked-mean cross-entropy (transformer_xl.py:593-613). Returns (logits view [B,L,V], loss)."""
+
+    @staticmethod
+    def forward(ctx, hidden, W, labels, mask):
+        B, L, d = hidden.shape
+        rows = B * L
+        V = W.shape[0]
+        Vp = (V + 127) // 128 * 128
+        dev = hidden.device
+        h2 = hidden.reshape(rows, d)
+        if not h2.is_contiguous():
+            h2 = h2.contiguous()
+        buf = torch.empty(rows, Vp, dtype=torch.float16, device=dev)
+        ops.gemm(h2, W, buf, rows, V, d, lda=d, ldb=d, ldc=Vp)
+        lab = labels.reshape(rows).contiguous()
+        msk = mask.reshape(rows).to(torch.float32).contiguous()
+        row_loss = torch.empty(rows, dtype=torch.float32, device=dev)
+        row_lse = torch.empty(rows, dtype=torch.float32, device=dev)
+        loss2 = torch.empty(2, dtype=torch.float32, device=dev)
+        ops.ce_fwd(buf, lab, msk, row_loss, row_lse, loss2, V)
+        logits = buf.view(B, L, Vp)[:, :, :V]
+        ctx.save_for_backward(h2, W, buf, lab, msk, row_lse, loss2)
+        ctx.cfg = (B, L, d, V, Vp)
+        ctx.mark_non_differentiable(logits)
+        return logits, loss2[0]
+
+    @staticmethod
+    def backward(ctx, _dlogits, dloss):
+        h2, W, buf, lab, msk, row_lse, loss2 = ctx.saved_tensors
+        B, L, d, V, Vp = ctx.cfg
+        rows = B * L
+        dev = h2.device
+        gs = dloss.reshape(1).to(torch.float32)
+        dl = _workspace("dlogits", (rows, Vp), torch.float16, dev)
+        ops.ce_bwd(buf, lab, msk, row_lse, loss2, gs, dl, V)
+        dW = torch.empty(V, d, dtype=torch.float16, device=dev)
+        ops.gemm(dl, h2, dW, V, d, rows, lda=Vp, ldb=d, ldc=d, a_mn=True, b_mn=True)
+        dh = torch.empty(rows, d, dtype=torch.float16, device=dev)
+        ops.gemm(dl, W, dh, rows, d, V, lda=Vp, ldb=d, ldc=d, b_mn=True)
+        return dh.view(B, L, d), dW, None, None
+
+
+def head_logits(hidden, W):
+    """Inference-only tied head (no autograd)."""
+    B, L, d = hidden.shape
+    rows = B * L
+    V = W.shape[0]
+    Vp = (V + 127) // 128 * 128
+    h2 = hidden.reshape(rows, d).contiguous()
+    buf = torch.empty(rows, Vp, dtype=torch.float16, device=hidden.device)
+    ops.gemm(h2, W, buf, rows, V, d, lda=d, ldb=d, ldc=Vp)
+    return buf.view(B, L, Vp)[:, :, :V]
+
+
+class EmbedFn(torch.autograd.Function):
+    """Embedding assembly for one task segment (transformer_xl.py:627-649 / :665): word lookup, image-patch slots,
+    RL local-timestep embedding, embedding dropout (:545)."""
+
+    @staticmethod
+    def forward(ctx, tok, pos, W, T, vis, drop_p):
+        B, L = tok.shape
+        V, d = W.shape
+        dev = W.device
+        tok = tok.contiguous()
+        pos = pos.contiguous() if pos is not None else None
+        if vis is not None and not vis.is_contiguous():
+            vis = vis.contiguous()
+        out = torch.empty(B, L, d, dtype=torch.float16, device=dev)
+        slot = torch.empty(B, L, dtype=torch.int32, device=dev)
+        seed = seeds.next() if drop_p > 0 else 0
+        ops.embed_fwd(tok, pos, slot, W, T if pos is not None else None, vis, out, L * d, B, L, d, V, drop_p, seed, 0)
+        ctx.save_for_backward(tok, pos, slot)
+        ctx.cfg = (B, L, d, V, drop_p, seed, T.shape[0] if T is not None else 0,
+                   tuple(vis.shape) if vis is not None else None)
+        return out
+
+    @staticmethod
+    def backward(ctx, dout):
+        tok, pos, slot = ctx.saved_tensors
+        B, L, d, V, drop_p, seed, nT, vshape = ctx.cfg
+        dev = dout.device
+        dout = dout.contiguous()
+        dW = torch.zeros(V, d, dtype=torch.float16, device=dev)
+        dT = torch.zeros(nT, d, dtype=torch.float16, device=dev) if pos is not None else None
+        dvis = torch.zeros(vshape, dtype=torch.float16, device=dev) if vshape is not None else None
+        ops.embed_bwd(tok, pos, slot, dout, L * d, dW, dT, dvis, B, L, d, V, drop_p, seed, 0)
+        return None, None, dW, dT, dvis, None
+
+
+def positional_rows(inv_freq, klen, d, clamp_len, drop_p):
+    """PositionalEmbedding + its dropout (transformer_xl.py:569-575) -> [klen, d] fp16, reference row order."""
+    out = torch.empty(klen, d, dtype=torch.float16, device=inv_freq.device)
+    seed = seeds.next() if drop_p > 0 else 0
+    ops.posemb(out, inv_freq, klen, d, clamp_len, drop_p, seed)
+    return out
+
+
+def patch_embed(module, pixel_values, pos_sum):
+    """PatchEmbeddings.forward (vision_embedding.py:65-86) on the sm_100a kernels."""
+    from . import vision
+    return vision.patch_embed(module, pixel_values, pos_sum)
+
+
+def dropout_rows(x, p):
+    raise NotImplementedError("embedding dropout on image-caption patch embeddings is not built yet")

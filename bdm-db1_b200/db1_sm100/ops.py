@@ -74,3 +74,93 @@ def relattn_fwd(qkv4, r, out, lse2, B, L, H, dh, window, scale, probs=None):
         C.c_void_p(base), C.c_void_p(base + d * es), C.c_void_p(base + 2 * d * es), C.c_void_p(base + 3 * d * es),
         C.c_longlong(ld), ptr(r), C.c_longlong(r.stride(0)), ptr(out), C.c_longlong(out.stride(0) if out is not None else 0),
         ptr(lse2), ptr(probs), B, L, H, dh, int(window), C.c_float(scale), mode, cur_stream()), "db1_relattn_fwd")
+
+
+def _f32(t):
+    if t is not None and (not t.is_cuda or t.dtype != torch.float32):
+        raise _lib.Db1Error("expected a CUDA fp32 tensor, got %s on %s" % (t.dtype, t.device))
+    return ptr(t)
+
+
+def _i64(t):
+    if t is not None and (not t.is_cuda or t.dtype != torch.int64 or not t.is_contiguous()):
+        raise _lib.Db1Error("expected a contiguous CUDA int64 tensor")
+    return ptr(t)
+
+
+def layernorm_fwd(y, gamma, beta, out, stats, eps):
+    _need_cuda_half(y, gamma, beta, out)
+    rows, d = y.shape
+    check(_lib.lib().db1_layernorm_fwd(ptr(y), ptr(gamma), ptr(beta), ptr(out), _f32(stats), rows, d, C.c_float(eps),
+                                       cur_stream()), "db1_layernorm_fwd")
+
+
+def layernorm_bwd(dout, y, gamma, stats, dy, dz, dgamma, dbeta, dbias, drop_p=0.0, seed=0):
+    _need_cuda_half(dout, y, gamma, dy, dz)
+    rows, d = y.shape
+    check(_lib.lib().db1_layernorm_bwd(ptr(dout), ptr(y), ptr(gamma), _f32(stats), ptr(dy), ptr(dz), _f32(dgamma),
+                                       _f32(dbeta), _f32(dbias), rows, d, C.c_float(drop_p), C.c_uint64(seed),
+                                       cur_stream()), "db1_layernorm_bwd")
+
+
+def ce_fwd(logits, labels, mask, row_loss, row_lse, loss2, V):
+    _need_cuda_half(logits)
+    rows = logits.shape[0]
+    check(_lib.lib().db1_ce_fwd(ptr(logits), C.c_longlong(logits.stride(0)), _i64(labels), _f32(mask), _f32(row_loss),
+                                _f32(row_lse), _f32(loss2), rows, V, cur_stream()), "db1_ce_fwd")
+
+
+def ce_bwd(logits, labels, mask, row_lse, loss2, gscale, dlogits, V):
+    _need_cuda_half(logits, dlogits)
+    rows = logits.shape[0]
+    check(_lib.lib().db1_ce_bwd(ptr(logits), C.c_longlong(logits.stride(0)), _i64(labels), _f32(mask), _f32(row_lse),
+                                _f32(loss2), _f32(gscale), ptr(dlogits), C.c_longlong(dlogits.stride(0)), rows, V,
+                                cur_stream()), "db1_ce_bwd")
+
+
+def embed_fwd(tok, pos, slot, W, T, vis, out, out_bs, B, L, d, V, drop_p=0.0, seed=0, seed_row0=0):
+    """out is addressed as out.data_ptr() + b*out_bs + l*d (elements); vis [B, nvis, d] contiguous or None."""
+    _need_cuda_half(W, T, vis, out)
+    nvis = vis.shape[1] if vis is not None else 0
+    vis_bs = vis.stride(0) if vis is not None else 0
+    check(_lib.lib().db1_embed_fwd(_i64(tok), _i64(pos), ptr(slot), ptr(W), ptr(T), ptr(vis), C.c_longlong(vis_bs), nvis,
+                                   ptr(out), C.c_longlong(out_bs), B, L, d, V, C.c_float(drop_p), C.c_uint64(seed),
+                                   C.c_longlong(seed_row0), cur_stream()), "db1_embed_fwd")
+
+
+def embed_bwd(tok, pos, slot, dout, dout_bs, dW, dT, dvis, B, L, d, V, drop_p=0.0, seed=0, seed_row0=0):
+    _need_cuda_half(dout, dW, dT, dvis)
+    nvis = dvis.shape[1] if dvis is not None else 0
+    vis_bs = dvis.stride(0) if dvis is not None else 0
+    check(_lib.lib().db1_embed_bwd(_i64(tok), _i64(pos), ptr(slot), ptr(dout), C.c_longlong(dout_bs), ptr(dW), ptr(dT),
+                                   ptr(dvis), C.c_longlong(vis_bs), nvis, B, L, d, V, C.c_float(drop_p),
+                                   C.c_uint64(seed), C.c_longlong(seed_row0), cur_stream()), "db1_embed_bwd")
+
+
+def colsum(x, out, rows, n):
+    _need_cuda_half(x)
+    check(_lib.lib().db1_colsum(ptr(x), C.c_longlong(x.stride(0)), _f32(out), rows, n, cur_stream()), "db1_colsum")
+
+
+def dq_finalize(dqu, dqv, dq, du, dv, rows, n):
+    _need_cuda_half(dqu, dqv, dq)
+    check(_lib.lib().db1_dq_finalize(ptr(dqu), ptr(dqv), C.c_longlong(dqu.stride(0)), ptr(dq), C.c_longlong(dq.stride(0)),
+                                     _f32(du), _f32(dv), rows, n, cur_stream()), "db1_dq_finalize")
+
+
+def rowdot(a, b, out, B, L, H, dh):
+    _need_cuda_half(a, b)
+    check(_lib.lib().db1_rowdot(ptr(a), ptr(b), C.c_longlong(a.stride(0)), _f32(out), B, L, H, dh, cur_stream()),
+          "db1_rowdot")
+
+
+def posemb(out, inv_freq, klen, d, clamp_len, drop_p=0.0, seed=0):
+    _need_cuda_half(out)
+    check(_lib.lib().db1_posemb(ptr(out), _f32(inv_freq), klen, d, clamp_len, C.c_float(drop_p), C.c_uint64(seed),
+                                cur_stream()), "db1_posemb")
+
+
+def f32_to_f16(src, dst, accumulate=False):
+    _need_cuda_half(dst)
+    check(_lib.lib().db1_f32_to_f16(_f32(src), ptr(dst), C.c_longlong(src.numel()), int(accumulate), cur_stream()),
+          "db1_f32_to_f16")

@@ -105,6 +105,51 @@ int db1_relattn_fwd(const void* qu, const void* qv, const void* k, const void* v
                     long long ld_r, void* out, long long ld_out, float* lse2, void* probs, int B, int L, int H, int dh,
                     int window, float scale, int mode, void* stream);
 
+/* ------------------------------------------------------------------------------------------------------------------
+ * HBM-bound kernels (single pass over the large operand, 16-byte vector accesses, fp32 math).
+ * ------------------------------------------------------------------------------------------------------------------ */
+
+/* out = LayerNorm(y) * gamma + beta; stats[row] = (mean, rstd) fp32 kept for the backward.
+ * Replaces nn.LayerNorm at transformer_xl.py:238 and :290 (the residual sum y is produced by the GEMM epilogue). */
+int db1_layernorm_fwd(const void* y, const void* gamma, const void* beta, void* out, float* stats, int rows, int d,
+                      float eps, void* stream);
+/* dy = dLN(dout); dz = dy * dropout_mask(seed)/(1-p) (written only when drop_p > 0; the mask is the one the producing
+ * GEMM epilogue applied); fp32 accumulators: dgamma += dout*xhat, dbeta += dout, dbias += dz (dbias may be NULL). */
+int db1_layernorm_bwd(const void* dout, const void* y, const void* gamma, const float* stats, void* dy, void* dz,
+                      float* dgamma, float* dbeta, float* dbias, int rows, int d, float drop_p, uint64_t seed,
+                      void* stream);
+
+/* Masked cross-entropy (transformer_xl.py:602-609): row_loss = (lse - z[label]) * mask, loss2 = {sum(row_loss)/sum(mask),
+ * sum(mask)} (device scalars; no host sync). logits fp16 [rows, ld], V valid columns. */
+int db1_ce_fwd(const void* logits, long long ld, const long long* labels, const float* mask, float* row_loss,
+               float* row_lse, float* loss2, int rows, int V, void* stream);
+/* dlogits = (softmax - onehot) * mask / sum(mask) * gscale[0]  (gscale: device fp32 scalar, the upstream gradient) */
+int db1_ce_bwd(const void* logits, long long ld, const long long* labels, const float* mask, const float* row_lse,
+               const float* loss2, const float* gscale, void* dlogits, long long ldd, int rows, int V, void* stream);
+
+/* Embedding assembly (transformer_xl.py:627-649, :665, :677-695): out[b,l,:] = dropout((tok>=0 ? W[tok] : vis[b,slot])
+ * + (pos ? T[pos] : 0)); slot[b,l] = number of -1 tokens before l (written here, reused by the backward).
+ * out/vis are addressed as base + b*batch_stride + index*d so segments of a longer sequence can be written in place. */
+int db1_embed_fwd(const long long* tok, const long long* pos, int* slot, const void* W, const void* T, const void* vis,
+                  long long vis_bs, int nvis, void* out, long long out_bs, int B, int L, int d, int V, float drop_p,
+                  uint64_t seed, long long seed_row0, void* stream);
+/* Adjoint: dW[tok] += g, dT[pos] += g (fp16 atomics), dvis[b,slot] = g with g = dout * dropout mask. */
+int db1_embed_bwd(const long long* tok, const long long* pos, const int* slot, const void* dout, long long dout_bs,
+                  void* dW, void* dT, void* dvis, long long vis_bs, int nvis, int B, int L, int d, int V, float drop_p,
+                  uint64_t seed, long long seed_row0, void* stream);
+
+/* out[c] += sum_r in[r,c] (fp16 -> fp32): bias gradients. */
+int db1_colsum(const void* in, long long ld, float* out, int rows, int n, void* stream);
+/* dq = dqu + dqv; du += colsum(dqu); dv += colsum(dqv): gradients of q, r_w_bias, r_r_bias (transformer_xl.py:161,167) */
+int db1_dq_finalize(const void* dqu, const void* dqv, long long ld_in, void* dq, long long ld_out, float* du, float* dv,
+                    int rows, int n, void* stream);
+/* out[b,h,i] = sum_d a[b,i,h,d] * b[b,i,h,d]  (softmax-backward row term) */
+int db1_rowdot(const void* a, const void* b, long long ld, float* out, int B, int L, int H, int dh, void* stream);
+/* Sinusoid rows of PositionalEmbedding (transformer_xl.py:43-50, 569-575): row c = [sin|cos](min(klen-1-c, clamp)*inv_freq) */
+int db1_posemb(void* out, const float* inv_freq, int klen, int d, int clamp_len, float drop_p, uint64_t seed,
+               void* stream);
+int db1_f32_to_f16(const float* src, void* dst, long long n, int accumulate, void* stream);
+
 #ifdef __cplusplus
 }
 #endif
