@@ -1,0 +1,249 @@
+"""Data-parallel training engine with the protocol DB1's loops expect from DeepSpeed
+(src/train_utils/train.py:210-243, src/checkpointing.py:17-22, src/evaluation/evaluate_rl.py:508-512):
+
+    engine(inputs) -> (logits, loss);  engine.backward(loss);  engine.step();
+    engine.gradient_accumulation_steps();  engine.train()/eval();  engine.device;
+    engine.save_checkpoint(dir, client_state=..., tag=...);  engine.load_checkpoint(dir, tag) -> (path, client_state)
+
+What DeepSpeed 0.6.7 does after backward, serially (one fp16 gradient all-reduce over the data-parallel group at every
+accumulation boundary), is done here overlapped with backward:
+  * every parameter's .grad is a view into a flat per-bucket fp16 buffer (one bucket per decoder layer + one for the
+    embeddings / vision encoder / shared biases), so autograd accumulates straight into communication buffers;
+  * when the last gradient of a bucket has been accumulated (post-accumulate-grad hooks), an event is recorded on the
+    compute stream and the bucket's NCCL all-reduce (average) is enqueued on a dedicated high-priority stream — layer
+    l's reduction runs under layer l-1's backward kernels;
+  * parameters that received no gradient this step (e.g. the vision encoder on a text-only rank) keep their zero-filled
+    views, so every rank issues the same collectives in the same order;
+  * only the boundary micro-step of an accumulation window communicates.
+The same code runs over gloo on CPU tensors (tests) — the overlap machinery is skipped there.
+"""
+import os
+from collections import OrderedDict
+
+import torch
+import torch.distributed as dist
+
+
+def _default_bucket_of(name):
+    """Bucket key for a parameter name: decoder layer index, or 'rest' (embeddings, vision, shared u/v, head)."""
+    parts = name.split(".")
+    if len(parts) > 2 and parts[0] == "h" and parts[1].isdigit():
+        return "h.%s" % parts[1]
+    return "rest"
+
+
+class _Bucket:
+    def __init__(self, key, params, names):
+        self.key = key
+        self.params = params
+        self.names = names
+        self.flat = None
+        self.pending = 0
+        self.work = None
+        self.event = None
+
+
+class DB1Engine:
+    def __init__(self, model, optimizer=None, lr_scheduler=None, mpu=None, gradient_accumulation_steps=1,
+                 loss_scale=4096.0, clip_grad=0.0, bucket_of=_default_bucket_of, overlap_comm=True):
+        self.module = model
+        self.optimizer = optimizer
+        self.lr_scheduler = lr_scheduler
+        self.mpu = mpu
+        self._ga = int(gradient_accumulation_steps)
+        self.loss_scale = float(loss_scale)
+        self.clip_grad = float(clip_grad)
+        self.micro_steps = 0
+        self.global_steps = 0
+        self.enable_backward_allreduce = True
+        self._group = None
+        self._world = 1
+        if dist.is_available() and dist.is_initialized():
+            if mpu is not None and not mpu.is_unitialized():
+                self._group = mpu.get_data_parallel_group()
+                self._world = mpu.get_data_parallel_world_size()
+            else:
+                self._group = dist.group.WORLD
+                self._world = dist.get_world_size()
+        p0 = next(model.parameters())
+        self.device = p0.device
+        self._cuda = p0.is_cuda
+        self._overlap = bool(overlap_comm) and self._cuda and self._world > 1
+        self._comm_stream = torch.cuda.Stream(device=self.device, priority=-1) if self._overlap else None
+        self._build_buckets(bucket_of)
+        self._hooks = []
+        if self._world > 1:
+            self._install_hooks()
+
+    # ------------------------------------------------------------------------------------------ buckets
+    def _build_buckets(self, bucket_of):
+        groups = OrderedDict()
+        seen = set()
+        for name, p in self.module.named_parameters():  # shared parameters appear once
+            if not p.requires_grad or id(p) in seen:
+                continue
+            seen.add(id(p))
+            groups.setdefault(bucket_of(name), ([], []))
+            groups[bucket_of(name)][0].append(p)
+            groups[bucket_of(name)][1].append(name)
+        self.buckets = []
+        self._bucket_of_param = {}
+        for key, (params, names) in groups.items():
+            b = _Bucket(key, params, names)
+            n = sum((p.numel() + 7) // 8 * 8 for p in params)  # keep every view 16-byte aligned
+            b.flat = torch.zeros(n, dtype=params[0].dtype, device=params[0].device)
+            off = 0
+            for p in params:
+                p.grad = b.flat[off:off + p.numel()].view_as(p)
+                off += (p.numel() + 7) // 8 * 8
+                self._bucket_of_param[id(p)] = b
+            self.buckets.append(b)
+
+    def _install_hooks(self):
+        for b in self.buckets:
+            for p in b.params:
+                self._hooks.append(p.register_post_accumulate_grad_hook(self._make_hook(b)))
+
+    def _make_hook(self, bucket):
+        def hook(_param):
+            if not self._is_boundary() or not self.enable_backward_allreduce:
+                return
+            bucket.pending -= 1
+            if bucket.pending == 0:
+                self._launch_allreduce(bucket)
+        return hook
+
+    def _launch_allreduce(self, bucket):
+        if bucket.work is not None or self._world == 1:
+            return
+        if self._overlap:
+            ev = torch.cuda.Event()
+            ev.record(torch.cuda.current_stream(self.device))
+            with torch.cuda.stream(self._comm_stream):
+                self._comm_stream.wait_event(ev)
+                bucket.work = dist.all_reduce(bucket.flat, op=dist.ReduceOp.AVG, group=self._group, async_op=True)
+        else:
+            if dist.get_backend(self._group) == "gloo":
+                bucket.work = dist.all_reduce(bucket.flat, op=dist.ReduceOp.SUM, group=self._group, async_op=True)
+                bucket.post_scale = 1.0 / self._world
+            else:
+                bucket.work = dist.all_reduce(bucket.flat, op=dist.ReduceOp.AVG, group=self._group, async_op=True)
+
+    # ------------------------------------------------------------------------------------------ protocol
+    def __call__(self, *args, **kwargs):
+        return self.module(*args, **kwargs)
+
+    def train(self, mode=True):
+        self.module.train(mode)
+        return self
+
+    def eval(self):
+        self.module.eval()
+        return self
+
+    def gradient_accumulation_steps(self):
+        return self._ga
+
+    def _is_boundary(self):
+        return (self.micro_steps + 1) % self._ga == 0
+
+    def is_gradient_accumulation_boundary(self):
+        return self._is_boundary()
+
+    def zero_grad(self):
+        for b in self.buckets:
+            b.flat.zero_()
+
+    def backward(self, loss):
+        """Scale, back-propagate; on the boundary micro-step the bucket all-reduces start as their gradients complete."""
+        if self.micro_steps % self._ga == 0:
+            self.zero_grad()
+        for b in self.buckets:
+            b.pending = len(b.params)
+            b.work = None
+            b.post_scale = None
+        scaled = loss * (self.loss_scale / self._ga)
+        scaled.backward()
+        if self._world > 1 and self._is_boundary() and self.enable_backward_allreduce:
+            # buckets whose parameters got no gradient at all this step still take part (zero contribution)
+            for b in self.buckets:
+                if b.work is None:
+                    self._launch_allreduce(b)
+            self._finish_allreduce()
+        self.micro_steps += 1
+        return loss
+
+    def _finish_allreduce(self):
+        for b in self.buckets:
+            if b.work is not None:
+                b.work.wait()  # NCCL: makes the current stream wait for the collective; gloo: blocks the host
+                if getattr(b, "post_scale", None):
+                    b.flat.mul_(b.post_scale)
+        if self._overlap:
+            torch.cuda.current_stream(self.device).wait_stream(self._comm_stream)
+
+    def step(self):
+        """Optimizer step on accumulation boundaries: unscale, optional global-norm clip, skip on overflow."""
+        if self.micro_steps % self._ga != 0:
+            return
+        self.global_steps += 1
+        if self.optimizer is None:
+            return
+        inv = 1.0 / self.loss_scale
+        flats = [b.flat for b in self.buckets]
+        total = torch.zeros((), dtype=torch.float32, device=self.device)
+        for f in flats:
+            total += f.float().pow(2).sum()
+        norm = total.sqrt() * inv
+        if not torch.isfinite(norm):
+            self.loss_scale = max(self.loss_scale / 2, 1.0)
+            return
+        coef = inv
+        if self.clip_grad > 0:
+            coef = inv * min(1.0, self.clip_grad / (norm.item() + 1e-6))
+        for f in flats:
+            f.mul_(coef)
+        self.optimizer.step()
+        if self.lr_scheduler is not None:
+            self.lr_scheduler.step()
+
+    # ------------------------------------------------------------------------------------------ checkpoints
+    def save_checkpoint(self, save_dir, tag=None, client_state=None):
+        tag = tag if tag is not None else "global_step%d" % self.global_steps
+        path = os.path.join(save_dir, str(tag))
+        rank = dist.get_rank() if dist.is_available() and dist.is_initialized() else 0
+        if rank == 0:
+            os.makedirs(path, exist_ok=True)
+            state = {"module": self.module.state_dict(), "global_steps": self.global_steps,
+                     "micro_steps": self.micro_steps, "loss_scale": self.loss_scale}
+            if self.optimizer is not None:
+                state["optimizer"] = self.optimizer.state_dict()
+            state.update(client_state or {})
+            torch.save(state, os.path.join(path, "mp_rank_00_model_states.pt"))
+            with open(os.path.join(save_dir, "latest"), "w") as f:
+                f.write(str(tag))
+        if dist.is_available() and dist.is_initialized():
+            dist.barrier(group=self._group)
+        return True
+
+    def load_checkpoint(self, load_dir, tag=None, load_optimizer_states=True):
+        if tag is None:
+            with open(os.path.join(load_dir, "latest")) as f:
+                tag = f.read().strip()
+        path = os.path.join(load_dir, str(tag), "mp_rank_00_model_states.pt")
+        state = torch.load(path, map_location="cpu", weights_only=False)
+        self.module.load_state_dict(state["module"], strict=True)
+        self.global_steps = state.get("global_steps", 0)
+        self.micro_steps = state.get("micro_steps", 0)
+        self.loss_scale = state.get("loss_scale", self.loss_scale)
+        if load_optimizer_states and self.optimizer is not None and "optimizer" in state:
+            self.optimizer.load_state_dict(state["optimizer"])
+        known = {"module", "global_steps", "micro_steps", "loss_scale", "optimizer"}
+        return path, {k: v for k, v in state.items() if k not in known}
+
+
+def initialize(args=None, model=None, optimizer=None, lr_scheduler=None, mpu=None, **kw):
+    """deepspeed.initialize-shaped constructor: returns (engine, optimizer, None, lr_scheduler)."""
+    ga = kw.pop("gradient_accumulation_steps", getattr(args, "gradient_accumulation_steps", 1) if args else 1)
+    eng = DB1Engine(model, optimizer=optimizer, lr_scheduler=lr_scheduler, mpu=mpu, gradient_accumulation_steps=ga, **kw)
+    return eng, optimizer, None, lr_scheduler

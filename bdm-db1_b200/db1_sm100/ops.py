@@ -12,6 +12,63 @@ from ._lib import (EPI_DGEGLU, EPI_DS, EPI_GEGLU, EPI_PLAIN, EPI_QKV, K_BEGIN_BY
                    K_FULL, GemmDesc, check, cur_stream, ptr)
 
 
+class Profile:
+    """Launch accounting and optional per-launch CUDA-event timing (events are recorded on the launching stream)."""
+
+    def __init__(self, timing=False):
+        self.timing = timing
+        self.launches = 0
+        self.records = []  # (name, algorithmic flops, algorithmic bytes, start event, end event)
+
+    def summary(self):
+        """{name: dict(n, ms, flops, bytes)} — call after torch.cuda.synchronize()."""
+        out = {}
+        for name, fl, by, e0, e1 in self.records:
+            d = out.setdefault(name, dict(n=0, ms=0.0, flops=0.0, bytes=0.0))
+            d["n"] += 1
+            d["ms"] += e0.elapsed_time(e1)
+            d["flops"] += fl
+            d["bytes"] += by
+        return out
+
+
+_active = None
+
+
+def set_profile(prof):
+    global _active
+    _active = prof
+    return prof
+
+
+class _Launch:
+    """with _Launch(name, nkernels, flops, bytes): <C call>"""
+    __slots__ = ("name", "n", "flops", "bytes", "e0")
+
+    def __init__(self, name, n=1, flops=0.0, nbytes=0.0):
+        self.name, self.n, self.flops, self.bytes = name, n, flops, nbytes
+
+    def __enter__(self):
+        pr = _active
+        if pr is not None:
+            pr.launches += self.n
+            if pr.timing:
+                self.e0 = torch.cuda.Event(enable_timing=True)
+                self.e0.record()
+        return self
+
+    def __exit__(self, *exc):
+        pr = _active
+        if pr is not None and pr.timing and exc[0] is None:
+            e1 = torch.cuda.Event(enable_timing=True)
+            e1.record()
+            pr.records.append((self.name, self.flops, self.bytes, self.e0, e1))
+        return False
+
+
+_EPI_NAMES = {0: "plain", 1: "qkv", 2: "geglu", 3: "dgeglu", 4: "ds"}
+
+
 def _need_cuda_half(*ts):
     for t in ts:
         if t is None:
@@ -57,7 +114,11 @@ def gemm(A, B, C_out, M, N, K, *, lda, ldb, ldc, a_mn=False, b_mn=False, epilogu
     d.Drow = Drow.data_ptr() if Drow is not None else None
     d.window = window
     d.bn_hint = bn_hint
-    check(_lib.lib().db1_gemm_f16(C.byref(d), cur_stream()), "db1_gemm_f16")
+    flops = 2.0 * M * N * K * Z1 * Z2
+    if k_mode != K_FULL or skip_upper:
+        flops *= (M + 1) / (2.0 * M)  # causal: only unmasked (i, j) pairs are algorithmic work
+    with _Launch("gemm_" + _EPI_NAMES[epilogue] + ("_batched" if Z1 * Z2 > 1 else ""), 1, flops):
+        check(_lib.lib().db1_gemm_f16(C.byref(d), cur_stream()), "db1_gemm_f16")
     return C_out
 
 
@@ -70,7 +131,11 @@ def relattn_fwd(qkv4, r, out, lse2, B, L, H, dh, window, scale, probs=None):
     base = qkv4.data_ptr()
     ld = qkv4.stride(0)
     mode = 0 if probs is None else 1
-    check(_lib.lib().db1_relattn_fwd(
+    pairs = L * (L + 1) / 2.0 if window >= L else (window * (window + 1) / 2.0 + (L - window) * window)
+    flops = B * H * pairs * dh * (6.0 if mode == 0 else 4.0)
+    nbytes = B * H * (4.0 * L * dh * 2 + 4 * L) + H * L * dh * 2.0
+    with _Launch("relattn_fwd" if mode == 0 else "relattn_probs", 1, flops, nbytes):
+      check(_lib.lib().db1_relattn_fwd(
         C.c_void_p(base), C.c_void_p(base + d * es), C.c_void_p(base + 2 * d * es), C.c_void_p(base + 3 * d * es),
         C.c_longlong(ld), ptr(r), C.c_longlong(r.stride(0)), ptr(out), C.c_longlong(out.stride(0) if out is not None else 0),
         ptr(lse2), ptr(probs), B, L, H, dh, int(window), C.c_float(scale), mode, cur_stream()), "db1_relattn_fwd")
@@ -91,14 +156,16 @@ def _i64(t):
 def layernorm_fwd(y, gamma, beta, out, stats, eps):
     _need_cuda_half(y, gamma, beta, out)
     rows, d = y.shape
-    check(_lib.lib().db1_layernorm_fwd(ptr(y), ptr(gamma), ptr(beta), ptr(out), _f32(stats), rows, d, C.c_float(eps),
+    with _Launch("layernorm_fwd", 1):
+      check(_lib.lib().db1_layernorm_fwd(ptr(y), ptr(gamma), ptr(beta), ptr(out), _f32(stats), rows, d, C.c_float(eps),
                                        cur_stream()), "db1_layernorm_fwd")
 
 
 def layernorm_bwd(dout, y, gamma, stats, dy, dz, dgamma, dbeta, dbias, drop_p=0.0, seed=0):
     _need_cuda_half(dout, y, gamma, dy, dz)
     rows, d = y.shape
-    check(_lib.lib().db1_layernorm_bwd(ptr(dout), ptr(y), ptr(gamma), _f32(stats), ptr(dy), ptr(dz), _f32(dgamma),
+    with _Launch("layernorm_bwd", 1):
+      check(_lib.lib().db1_layernorm_bwd(ptr(dout), ptr(y), ptr(gamma), _f32(stats), ptr(dy), ptr(dz), _f32(dgamma),
                                        _f32(dbeta), _f32(dbias), rows, d, C.c_float(drop_p), C.c_uint64(seed),
                                        cur_stream()), "db1_layernorm_bwd")
 
@@ -106,14 +173,16 @@ def layernorm_bwd(dout, y, gamma, stats, dy, dz, dgamma, dbeta, dbias, drop_p=0.
 def ce_fwd(logits, labels, mask, row_loss, row_lse, loss2, V):
     _need_cuda_half(logits)
     rows = logits.shape[0]
-    check(_lib.lib().db1_ce_fwd(ptr(logits), C.c_longlong(logits.stride(0)), _i64(labels), _f32(mask), _f32(row_loss),
+    with _Launch("ce_fwd", 2):
+      check(_lib.lib().db1_ce_fwd(ptr(logits), C.c_longlong(logits.stride(0)), _i64(labels), _f32(mask), _f32(row_loss),
                                 _f32(row_lse), _f32(loss2), rows, V, cur_stream()), "db1_ce_fwd")
 
 
 def ce_bwd(logits, labels, mask, row_lse, loss2, gscale, dlogits, V):
     _need_cuda_half(logits, dlogits)
     rows = logits.shape[0]
-    check(_lib.lib().db1_ce_bwd(ptr(logits), C.c_longlong(logits.stride(0)), _i64(labels), _f32(mask), _f32(row_lse),
+    with _Launch("ce_bwd", 1):
+      check(_lib.lib().db1_ce_bwd(ptr(logits), C.c_longlong(logits.stride(0)), _i64(labels), _f32(mask), _f32(row_lse),
                                 _f32(loss2), _f32(gscale), ptr(dlogits), C.c_longlong(dlogits.stride(0)), rows, V,
                                 cur_stream()), "db1_ce_bwd")
 
@@ -123,7 +192,8 @@ def embed_fwd(tok, pos, slot, W, T, vis, out, out_bs, B, L, d, V, drop_p=0.0, se
     _need_cuda_half(W, T, vis, out)
     nvis = vis.shape[1] if vis is not None else 0
     vis_bs = vis.stride(0) if vis is not None else 0
-    check(_lib.lib().db1_embed_fwd(_i64(tok), _i64(pos), ptr(slot), ptr(W), ptr(T), ptr(vis), C.c_longlong(vis_bs), nvis,
+    with _Launch("embed_fwd", 2):
+      check(_lib.lib().db1_embed_fwd(_i64(tok), _i64(pos), ptr(slot), ptr(W), ptr(T), ptr(vis), C.c_longlong(vis_bs), nvis,
                                    ptr(out), C.c_longlong(out_bs), B, L, d, V, C.c_float(drop_p), C.c_uint64(seed),
                                    C.c_longlong(seed_row0), cur_stream()), "db1_embed_fwd")
 
@@ -132,35 +202,41 @@ def embed_bwd(tok, pos, slot, dout, dout_bs, dW, dT, dvis, B, L, d, V, drop_p=0.
     _need_cuda_half(dout, dW, dT, dvis)
     nvis = dvis.shape[1] if dvis is not None else 0
     vis_bs = dvis.stride(0) if dvis is not None else 0
-    check(_lib.lib().db1_embed_bwd(_i64(tok), _i64(pos), ptr(slot), ptr(dout), C.c_longlong(dout_bs), ptr(dW), ptr(dT),
+    with _Launch("embed_bwd", 1):
+      check(_lib.lib().db1_embed_bwd(_i64(tok), _i64(pos), ptr(slot), ptr(dout), C.c_longlong(dout_bs), ptr(dW), ptr(dT),
                                    ptr(dvis), C.c_longlong(vis_bs), nvis, B, L, d, V, C.c_float(drop_p),
                                    C.c_uint64(seed), C.c_longlong(seed_row0), cur_stream()), "db1_embed_bwd")
 
 
 def colsum(x, out, rows, n):
     _need_cuda_half(x)
-    check(_lib.lib().db1_colsum(ptr(x), C.c_longlong(x.stride(0)), _f32(out), rows, n, cur_stream()), "db1_colsum")
+    with _Launch("colsum", 1):
+      check(_lib.lib().db1_colsum(ptr(x), C.c_longlong(x.stride(0)), _f32(out), rows, n, cur_stream()), "db1_colsum")
 
 
 def dq_finalize(dqu, dqv, dq, du, dv, rows, n):
     _need_cuda_half(dqu, dqv, dq)
-    check(_lib.lib().db1_dq_finalize(ptr(dqu), ptr(dqv), C.c_longlong(dqu.stride(0)), ptr(dq), C.c_longlong(dq.stride(0)),
+    with _Launch("dq_finalize", 1):
+      check(_lib.lib().db1_dq_finalize(ptr(dqu), ptr(dqv), C.c_longlong(dqu.stride(0)), ptr(dq), C.c_longlong(dq.stride(0)),
                                      _f32(du), _f32(dv), rows, n, cur_stream()), "db1_dq_finalize")
 
 
 def rowdot(a, b, out, B, L, H, dh):
     _need_cuda_half(a, b)
-    check(_lib.lib().db1_rowdot(ptr(a), ptr(b), C.c_longlong(a.stride(0)), _f32(out), B, L, H, dh, cur_stream()),
+    with _Launch("rowdot", 1):
+      check(_lib.lib().db1_rowdot(ptr(a), ptr(b), C.c_longlong(a.stride(0)), _f32(out), B, L, H, dh, cur_stream()),
           "db1_rowdot")
 
 
 def posemb(out, inv_freq, klen, d, clamp_len, drop_p=0.0, seed=0):
     _need_cuda_half(out)
-    check(_lib.lib().db1_posemb(ptr(out), _f32(inv_freq), klen, d, clamp_len, C.c_float(drop_p), C.c_uint64(seed),
+    with _Launch("posemb", 1):
+      check(_lib.lib().db1_posemb(ptr(out), _f32(inv_freq), klen, d, clamp_len, C.c_float(drop_p), C.c_uint64(seed),
                                 cur_stream()), "db1_posemb")
 
 
 def f32_to_f16(src, dst, accumulate=False):
     _need_cuda_half(dst)
-    check(_lib.lib().db1_f32_to_f16(_f32(src), ptr(dst), C.c_longlong(src.numel()), int(accumulate), cur_stream()),
+    with _Launch("f32_to_f16", 1):
+      check(_lib.lib().db1_f32_to_f16(_f32(src), ptr(dst), C.c_longlong(src.numel()), int(accumulate), cur_stream()),
           "db1_f32_to_f16")

@@ -67,8 +67,8 @@ class RelPartialLearnableMultiHeadAttn(nn.Module):
         self.o_net = nn.Linear(n_head * d_head, d_model, bias=False)
         self.scale = 1 / (d_head ** 0.5)
         if r_r_bias is None or r_w_bias is None:
-            self.r_r_bias = nn.Parameter(torch.FloatTensor(n_head, d_head))
-            self.r_w_bias = nn.Parameter(torch.FloatTensor(n_head, d_head))
+            self.r_r_bias = nn.Parameter(torch.empty(n_head, d_head))
+            self.r_w_bias = nn.Parameter(torch.empty(n_head, d_head))
         else:
             self.r_r_bias = r_r_bias
             self.r_w_bias = r_w_bias
@@ -178,8 +178,8 @@ class TransformerXL(nn.Module):
         self.word_embedding = nn.Embedding(self.total_vocab_size, self.n_embed)
         self.pos_emb = PositionalEmbedding(self.n_embed)
         if not self.untie_r:
-            self.r_w_bias = nn.Parameter(torch.FloatTensor(self.n_head, self.d_head))
-            self.r_r_bias = nn.Parameter(torch.FloatTensor(self.n_head, self.d_head))
+            self.r_w_bias = nn.Parameter(torch.empty(self.n_head, self.d_head))
+            self.r_r_bias = nn.Parameter(torch.empty(self.n_head, self.d_head))
         self.vision_encoder = VisionEmbedding(config)
         self.ic_encoder = self.vision_encoder
         self.rl_local_timestep_embedding = nn.Embedding(512 + 1, self.n_embed)

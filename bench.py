@@ -1,0 +1,305 @@
+#!/usr/bin/env python
+"""bench.py — tokens/s of DB1-1.3B forward+backward at seq_len 1024 on N B200s (BASELINE.json metric).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node N ... bench.py --gpus N --steps K --warmup W
+
+A step = one forward+backward of the full 24-layer model over one synthetic micro-batch (config C2 of SURVEY.md 8d:
+RLTaskInput, B=4, L=1024, continuous-control layout obs 17 / act 6, tokens produced by the product's own mu-law
+discretiser and RL token layout), dropout on (the reference's training defaults), fp16 storage / fp32 accumulate,
+loss scale 4096; for N > 1 each rank runs its own micro-batch and the step includes the bucketed gradient all-reduce
+overlapped with backward (weak scaling). Prints ONE JSON line (rank 0).
+
+`--impl reference` times the reference's algorithm on the host CPU cores (the oracle port — the Python reference cannot
+travel to the GPU box) on the same metric; bounded sample, rank 0 only.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, os.path.join(ROOT, "bdm-db1_b200"))
+sys.path.insert(0, ROOT)
+
+METRIC = "tokens/sec DB1-1.3B seq1024 fwd+bwd"
+B_MICRO, SEQ = 4, 1024
+
+
+def algorithmic_flops(B, L, n_layer=24, d=2048, V=33025, window=None):
+    """forward = B*[n_layer*(83 886 080*L + 6*d*P) + 2*d*V*L] + n_layer*2*d*d*L; fwd+bwd = 3x forward."""
+    W = L if window is None or window >= L else window
+    P = W * (W + 1) // 2 + (L - W) * W
+    per_tok_layer = 2 * d * (3 * d + d + 4 * d + 2 * d)
+    fwd = B * (n_layer * (per_tok_layer * L + 6 * d * P) + 2 * d * V * L) + n_layer * 2 * d * d * L
+    return 3 * fwd
+
+
+def peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        with open(p) as f:
+            j = json.load(f)
+        return dict(tflops=j.get("bf16_tflops_sustained", j.get("bf16_tflops")), hbm=j.get("hbm_gbs"), src="measured")
+    return dict(tflops=1400.0, hbm=6650.0, src="fallback")
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled every 200 ms while the timed region runs."""
+    Q = "index,clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown," \
+        "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
+
+    def __init__(self, gpu_index):
+        self.idx = str(gpu_index)
+        self.rows = []
+        self.proc = None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "--query-gpu=" + self.Q, "--format=csv,noheader,nounits",
+                                          "-lms", "200"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            threading.Thread(target=self._read, daemon=True).start()
+        except OSError:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            parts = [x.strip() for x in line.split(",")]
+            if len(parts) >= 7 and parts[0] == self.idx:
+                self.rows.append(parts)
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        sm = sorted(int(r[1]) for r in self.rows if r[1].isdigit())
+        mx = [int(r[2]) for r in self.rows if r[2].isdigit()]
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        reasons = [n for i, n in enumerate(names) if any(r[3 + i].lower().startswith("active") for r in self.rows)]
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": max(mx) if mx else None, "reasons": reasons,
+                "samples": len(self.rows)}
+
+
+def make_config(fp16=True, **kw):
+    from types import SimpleNamespace
+    c = dict(n_embed=2048, n_position=1024, n_layer=24, n_head=16, n_inner=8192, pre_lnorm=False, mem_len=1024,
+             same_length=True, untie_r=False, text_vocab_size=32000, num_discrete_values=1024, num_continuous_bin=1024,
+             overlap_with_text=True, embd_pdrop=0.1, drop=0.1, dropattn=0.0, activation_fn="geglu",
+             layer_norm_epsilon=1e-5, share_input_output_embedding=True, use_deepnorm=False, fp16=fp16,
+             vision_patch_size=16, vision_num_input_channels=3, vision_position_vocab_size=128,
+             vision_hidden_dropout_prob=0.1)
+    c.update(kw)
+    return SimpleNamespace(**c)
+
+
+# ------------------------------------------------------------------------------------------------------------------
+def cpu_port_tokens_per_s(budget_s=25.0, max_iters=1, layers=24):
+    """Reference algorithm on the host cores: oracle port, fp32, B=1, L=1024, full model fwd+bwd."""
+    import torch
+    from oracle import db1_oracle as orc
+    from db1_sm100 import synth
+    torch.set_num_threads(os.cpu_count() or 1)
+    cfg = orc.default_config(n_layer=layers)
+    sd = orc.synth_state_dict(cfg, seed=0)
+    for k, v in sd.items():
+        if v.is_floating_point() and k != "pos_emb.inv_freq":
+            v.requires_grad_(True)
+    t = synth.rl_continuous_batch(cfg, 1, SEQ, seed=1234)
+    task = dict(type="rl", tensor_seq=t.tensor_seq.numpy(), label=t.label.numpy(), loss_mask=t.loss_mask.numpy(),
+                position_id=t.position_id.numpy(), vision_seq=None)
+    times = []
+    t_all = time.perf_counter()
+    while len(times) < max_iters and (not times or time.perf_counter() - t_all < budget_s):
+        t0 = time.perf_counter()
+        _logits, loss = orc.forward([task], sd, cfg)
+        loss.backward()
+        times.append(time.perf_counter() - t0)
+        for v in sd.values():
+            v.grad = None
+    dt = sum(times) / len(times)
+    return SEQ / dt, dt, len(times), torch.get_num_threads()
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    # bounded sample: 1 sequence x 1024 tokens through the full model per step; steps are capped by a time budget
+    tps, dt, n, threads = cpu_port_tokens_per_s(budget_s=150.0, max_iters=max(1, min(args.steps, 6)))
+    line = {"impl": "reference", "metric": METRIC, "value": tps, "unit": "tokens/s", "n_gpus": args.gpus,
+            "steps": n, "warmup": 0, "ms_per_step": dt * 1e3, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": "DB1-1.3B fwd+bwd, RL continuous-control batch (obs17/act6), seq_len 1024",
+                       "micro_batch": 1, "seq_len": SEQ},
+            "cpu_baseline": {"value": tps, "unit": "tokens/s", "cores": threads, "kind": "port",
+                             "sample": "oracle port (fp32 torch CPU restatement of the reference), B=1 x L=1024, "
+                                       "full 24-layer model fwd+bwd, %d timed iteration(s), no warm-up" % n},
+            "e2e": {"value": tps, "unit": "tokens/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    print(json.dumps(line), flush=True)
+
+
+# ------------------------------------------------------------------------------------------------------------------
+def run_ours(args):
+    import torch
+    import torch.distributed as dist
+    from db1_sm100 import engine as eng_mod, ops, synth
+    from src.model import TransformerXL
+    import src.mpu as mpu
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device: the DB1 sm_100a path has no CPU fallback")
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+        mpu.initialize_model_parallel()
+    torch.manual_seed(0)
+    cfg = make_config()
+    with torch.device(dev):
+        model = TransformerXL(cfg)
+    model = model.half().to(dev).train()
+    engine = eng_mod.DB1Engine(model, mpu=mpu if world > 1 else None, gradient_accumulation_steps=1, loss_scale=4096.0)
+
+    host = [synth.rl_continuous_batch(cfg, B_MICRO, SEQ, seed=1234 + rank, pin=True)]
+    resident = [synth.to_device(t, dev) for t in host]
+    tokens_per_step = B_MICRO * SEQ * world
+
+    def step(inputs):
+        _logits, loss = engine(inputs)
+        engine.backward(loss)
+        return loss
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    n_warm = args.warmup if args.profile_only else max(args.warmup, 3)
+    for _ in range(n_warm):
+        step(resident)
+    barrier()
+    if args.profile_only:  # used under ncu: warm-up + `steps` plain steps, nothing else
+        for _ in range(args.steps):
+            step(resident)
+        barrier()
+        return
+
+    # ---- timed region 1: inputs resident in HBM; per-launch CUDA events on the launching stream
+    sampler = ClockSampler(torch.cuda.current_device() if "CUDA_VISIBLE_DEVICES" not in os.environ else local)
+    count = ops.set_profile(ops.Profile(timing=False))  # launch counter only: no events inside the headline region
+    sampler.start()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    e0.record()
+    for _ in range(args.steps):
+        step(resident)
+    e1.record()
+    barrier()
+    clocks = sampler.stop()
+    ops.set_profile(None)
+    # same steps again with one CUDA-event pair per launch (on the launching stream) for the per-kernel roofline
+    prof = ops.set_profile(ops.Profile(timing=True))
+    n_prof = min(args.steps, 3)
+    for _ in range(n_prof):
+        step(resident)
+    barrier()
+    ops.set_profile(None)
+    ms = torch.tensor([e0.elapsed_time(e1)], device=dev)
+    if world > 1:
+        dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+    ms_total = ms.item()
+    value = tokens_per_step * args.steps / (ms_total / 1e3)
+
+    # ---- timed region 2 (e2e): host buffers -> device every step, loss read back every step
+    h2d = synth.input_bytes(host)
+    e2, e3 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    e2.record()
+    last = 0.0
+    for _ in range(args.steps):
+        inputs = [synth.to_device(t, dev, non_blocking=True) for t in host]
+        last = step(inputs).item()  # 4-byte device->host read of the step's loss
+    e3.record()
+    barrier()
+    ms2 = torch.tensor([e2.elapsed_time(e3)], device=dev)
+    if world > 1:
+        dist.all_reduce(ms2, op=dist.ReduceOp.MAX)
+    e2e_value = tokens_per_step * args.steps / (ms2.item() / 1e3)
+
+    if rank == 0:
+        pk = peaks()
+        summ = prof.summary()
+        gemm = [v for k, v in summ.items() if k.startswith("gemm_")]
+        g_flops = sum(v["flops"] for v in gemm)
+        g_ms = sum(v["ms"] for v in gemm)
+        achieved = g_flops / (g_ms / 1e3) / 1e12 if g_ms > 0 else 0.0
+        traffic = None
+        tpath = os.path.join(ROOT, "profiles", "traffic.json")
+        if os.path.exists(tpath):
+            with open(tpath) as f:
+                traffic = json.load(f).get("gemm_dram_bytes_per_launch")
+        step_flops = algorithmic_flops(B_MICRO, SEQ)
+        line = {
+            "metric": METRIC, "value": value, "unit": "tokens/s", "n_gpus": world, "steps": args.steps,
+            "warmup": max(args.warmup, 3), "ms_per_step": ms_total / args.steps, "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "f16", "data": "synthetic",
+            "config": {"workload": "DB1-1.3B (24 layers, d 2048, 16 heads, GeGLU 8192, vocab 33025) fwd+bwd, "
+                                   "RLTaskInput continuous-control batch obs17/act6, dropout 0.1, loss scale 4096",
+                       "micro_batch_per_gpu": B_MICRO, "seq_len": SEQ, "global_batch": B_MICRO * world,
+                       "parallelism": "dp%d" % world,
+                       "cache": "no L2 flush needed: 2.4 GB of weights + 6 GB of saved activations stream per step (>> 126 MB L2)"},
+            "e2e": {"value": e2e_value, "unit": "tokens/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 4},
+            "gpu_launches": count.launches,
+            "clocks": clocks,
+            "roofline": {"bound": "tensor", "achieved": achieved, "peak": pk["tflops"], "unit": "TFLOP/s",
+                         "frac": achieved / pk["tflops"] if pk["tflops"] else None, "traffic": traffic,
+                         "kernel": "gemm_kernel<BN,EPI> (all tcgen05 GEMM launches of the step)",
+                         "peak_source": pk["src"] + " sustained bf16",
+                         "launches_per_step": sum(v["n"] for v in gemm) / n_prof,
+                         "timing": "CUDA events around every launch, %d extra steps right after the timed region" % n_prof,
+                         "step_model_tflops": step_flops * world / (ms_total / args.steps / 1e3) / 1e12},
+            "loss": last,
+        }
+        breakdown = {k: {"n_per_step": v["n"] / n_prof, "ms_per_step": v["ms"] / n_prof,
+                         "tflops": (v["flops"] / (v["ms"] / 1e3) / 1e12) if v["ms"] > 0 and v["flops"] else None,
+                         "gbs": (v["bytes"] / (v["ms"] / 1e3) / 1e9) if v["ms"] > 0 and v["bytes"] else None}
+                     for k, v in sorted(summ.items(), key=lambda kv: -kv[1]["ms"])}
+        out_dir = os.path.join(ROOT, "gpurun_out")
+        if os.path.isdir(out_dir):
+            with open(os.path.join(out_dir, "bench_breakdown_n%d.json" % world), "w") as f:
+                json.dump(breakdown, f, indent=1)
+        sys.stderr.write("per-kernel breakdown (ms/step): " + json.dumps(breakdown) + "\n")
+        if world == 1 and not args.no_cpu_baseline:
+            tps, dt, n, threads = cpu_port_tokens_per_s(budget_s=25.0, max_iters=1)
+            line["cpu_baseline"] = {"value": tps, "unit": "tokens/s", "cores": threads, "kind": "port",
+                                    "sample": "oracle port (fp32 torch CPU), B=1 x L=1024, full 24-layer model "
+                                              "fwd+bwd, 1 iteration (%.1f s), no warm-up" % dt}
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--profile-only", action="store_true", help="warm-up + steps only (for runs under ncu)")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_ours(args)
+
+
+if __name__ == "__main__":
+    main()
