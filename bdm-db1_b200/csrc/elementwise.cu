@@ -203,6 +203,162 @@ ln_bwd_kernel(const __half* __restrict__ dout, const __half* __restrict__ y, con
   }
 }
 
+
+// ---- warp-per-row variants (d == 256 * CH, CH <= 8): no block barriers, 8 rows per CTA in flight
+template <int CH>
+__global__ void __launch_bounds__(256)
+ln_fwd_warp_kernel(const __half* __restrict__ y, const __half* __restrict__ gamma, const __half* __restrict__ beta,
+                   __half* __restrict__ out, float* __restrict__ stats, int rows, float eps) {
+  constexpr int d = 256 * CH;
+  const int lane = threadIdx.x & 31;
+  const int row = blockIdx.x * 8 + (threadIdx.x >> 5);
+  if (row >= rows) return;
+  const __half* yr = y + (size_t)row * d;
+  float x[CH][8];
+  float s = 0.f;
+#pragma unroll
+  for (int c = 0; c < CH; ++c) {
+    h8_to_f(*reinterpret_cast<const H8*>(yr + (c * 32 + lane) * 8), x[c]);
+#pragma unroll
+    for (int i = 0; i < 8; ++i) s += x[c][i];
+  }
+  const float mean = warp_sum(s) / (float)d;
+  float v = 0.f;
+#pragma unroll
+  for (int c = 0; c < CH; ++c)
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      const float t = x[c][i] - mean;
+      v += t * t;
+    }
+  const float rstd = rsqrtf(warp_sum(v) / (float)d + eps);
+  if (lane == 0) {
+    stats[2 * row] = mean;
+    stats[2 * row + 1] = rstd;
+  }
+#pragma unroll
+  for (int c = 0; c < CH; ++c) {
+    float g[8], b[8], o[8];
+    h8_to_f(*reinterpret_cast<const H8*>(gamma + (c * 32 + lane) * 8), g);
+    h8_to_f(*reinterpret_cast<const H8*>(beta + (c * 32 + lane) * 8), b);
+#pragma unroll
+    for (int i = 0; i < 8; ++i) o[i] = (x[c][i] - mean) * rstd * g[i] + b[i];
+    *reinterpret_cast<H8*>(out + (size_t)row * d + (c * 32 + lane) * 8) = f_to_h8(o);
+  }
+}
+
+// row part of the backward: dy (and dz = dy * dropout mask) — no column accumulators here
+template <int CH>
+__global__ void __launch_bounds__(256)
+ln_bwd_rows_kernel(const __half* __restrict__ dout, const __half* __restrict__ y, const __half* __restrict__ gamma,
+                   const float* __restrict__ stats, __half* __restrict__ dy, __half* __restrict__ dz, int rows,
+                   uint32_t drop_thr16, float drop_scale, uint64_t seed) {
+  constexpr int d = 256 * CH;
+  const int lane = threadIdx.x & 31;
+  const int row = blockIdx.x * 8 + (threadIdx.x >> 5);
+  if (row >= rows) return;
+  const float mean = stats[2 * row], rstd = stats[2 * row + 1];
+  float xh[CH][8], dx[CH][8];
+  float s1 = 0.f, s2 = 0.f;
+#pragma unroll
+  for (int c = 0; c < CH; ++c) {
+    const int off = (c * 32 + lane) * 8;
+    float g[8], go[8], yv[8];
+    h8_to_f(*reinterpret_cast<const H8*>(gamma + off), g);
+    h8_to_f(*reinterpret_cast<const H8*>(dout + (size_t)row * d + off), go);
+    h8_to_f(*reinterpret_cast<const H8*>(y + (size_t)row * d + off), yv);
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      xh[c][i] = (yv[i] - mean) * rstd;
+      dx[c][i] = go[i] * g[i];
+      s1 += dx[c][i];
+      s2 += dx[c][i] * xh[c][i];
+    }
+  }
+  const float m1 = warp_sum(s1) / (float)d, m2 = warp_sum(s2) / (float)d;
+#pragma unroll
+  for (int c = 0; c < CH; ++c) {
+    const int off = (c * 32 + lane) * 8;
+    float o[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) o[i] = rstd * (dx[c][i] - m1 - xh[c][i] * m2);
+    const H8 hv = f_to_h8(o);
+    *reinterpret_cast<H8*>(dy + (size_t)row * d + off) = hv;
+    if (drop_thr16 && dz != nullptr) {
+      float z[8];
+      h8_to_f(hv, z);
+      const uint64_t e = (uint64_t)row * (uint64_t)d + (uint64_t)off;
+      const uint64_t b0 = rng64(seed, e >> 2), b1 = rng64(seed, (e >> 2) + 1);
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        z[i] = dropout_keep(b0, i, drop_thr16) ? z[i] * drop_scale : 0.f;
+        z[4 + i] = dropout_keep(b1, i, drop_thr16) ? z[4 + i] * drop_scale : 0.f;
+      }
+      *reinterpret_cast<H8*>(dz + (size_t)row * d + off) = f_to_h8(z);
+    }
+  }
+}
+
+// column part: dgamma += sum_r dout*xhat, dbeta += sum_r dout, dbias += sum_r dz  (dzsrc = dz if dropout else dy)
+__global__ void __launch_bounds__(256)
+ln_bwd_cols_kernel(const __half* __restrict__ dout, const __half* __restrict__ y, const float* __restrict__ stats,
+                   const __half* __restrict__ dzsrc, float* __restrict__ dgamma, float* __restrict__ dbeta,
+                   float* __restrict__ dbias, int rows, int d) {
+  const int ch = blockIdx.x * blockDim.x + threadIdx.x;
+  if (ch * 8 >= d) return;
+  float ag[8], ab[8], az[8];
+#pragma unroll
+  for (int i = 0; i < 8; ++i) ag[i] = ab[i] = az[i] = 0.f;
+#pragma unroll 4
+  for (int r = blockIdx.y; r < rows; r += gridDim.y) {
+    float go[8], yv[8];
+    h8_to_f(*reinterpret_cast<const H8*>(dout + (size_t)r * d + ch * 8), go);
+    h8_to_f(*reinterpret_cast<const H8*>(y + (size_t)r * d + ch * 8), yv);
+    const float mean = stats[2 * r], rstd = stats[2 * r + 1];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      ag[i] += go[i] * (yv[i] - mean) * rstd;
+      ab[i] += go[i];
+    }
+    if (dbias != nullptr) {
+      float z[8];
+      h8_to_f(*reinterpret_cast<const H8*>(dzsrc + (size_t)r * d + ch * 8), z);
+#pragma unroll
+      for (int i = 0; i < 8; ++i) az[i] += z[i];
+    }
+  }
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    atomicAdd(dgamma + ch * 8 + i, ag[i]);
+    atomicAdd(dbeta + ch * 8 + i, ab[i]);
+    if (dbias != nullptr) atomicAdd(dbias + ch * 8 + i, az[i]);
+  }
+}
+
+// dSr[z][i][c] = dS[z][i][c - (L-1-i)] for c >= L-1-i, 0 below: the adjoint of _rel_shift (transformer_xl.py:98-110)
+// as a pure re-layout. One CTA per row; the row is staged in shared memory so that both the read of dS and the write
+// of dSr are 16-byte aligned and fully coalesced.
+__global__ void __launch_bounds__(128)
+rel_unshift_kernel(const __half* __restrict__ ds, __half* __restrict__ dsr, int L) {
+  extern __shared__ __half rowbuf[];
+  const int i = blockIdx.x;
+  const size_t zrow = ((size_t)blockIdx.y * L + i) * (size_t)L;
+  const int n8 = (i + 8) / 8 * 8;  // elements 0..i, rounded up to a multiple of 8 (the tail is zero in dS)
+  for (int j = threadIdx.x * 8; j < n8; j += 128 * 8)
+    *reinterpret_cast<H8*>(rowbuf + j) = *reinterpret_cast<const H8*>(ds + zrow + j);
+  __syncthreads();
+  const int c_lo = L - 1 - i;
+  for (int c8 = (c_lo / 8) * 8 + threadIdx.x * 8; c8 < L; c8 += 128 * 8) {
+    __half v[8];
+#pragma unroll
+    for (int t = 0; t < 8; ++t) {
+      const int j = c8 + t - c_lo;
+      v[t] = (j >= 0 && j <= i) ? rowbuf[j] : __float2half_rn(0.f);
+    }
+    *reinterpret_cast<H8*>(dsr + zrow + c8) = *reinterpret_cast<const H8*>(v);
+  }
+}
+
 // ------------------------------------------------------------------------------------------------ masked CE
 // one CTA per row: online (max, sum-exp) over V fp16 logits, fp32 math. loss_row = (lse - z[label]) * mask.
 constexpr int CE_THREADS = 256;
@@ -509,9 +665,17 @@ extern "C" int db1_layernorm_fwd(const void* y, const void* gamma, const void* b
                                  int d, float eps, void* stream) {
   DB1_CHECK_ARG(y && gamma && beta && out && stats, "layernorm_fwd: null pointer");
   DB1_CHECK_ARG(rows > 0 && d > 0 && d % 8 == 0 && d <= LN_THREADS * 8 * LN_MAXC, "layernorm_fwd: bad shape %d x %d", rows, d);
-  const int grid = rows < 148 * 8 ? rows : 148 * 8;
-  ln_fwd_kernel<<<grid, LN_THREADS, 0, (cudaStream_t)stream>>>((const __half*)y, (const __half*)gamma,
-                                                             (const __half*)beta, (__half*)out, stats, rows, d, eps);
+  cudaStream_t st = (cudaStream_t)stream;
+  const __half *yy = (const __half*)y, *gg = (const __half*)gamma, *bb = (const __half*)beta;
+  const int g8 = (rows + 7) / 8;
+  if (d == 2048) ln_fwd_warp_kernel<8><<<g8, 256, 0, st>>>(yy, gg, bb, (__half*)out, stats, rows, eps);
+  else if (d == 1024) ln_fwd_warp_kernel<4><<<g8, 256, 0, st>>>(yy, gg, bb, (__half*)out, stats, rows, eps);
+  else if (d == 512) ln_fwd_warp_kernel<2><<<g8, 256, 0, st>>>(yy, gg, bb, (__half*)out, stats, rows, eps);
+  else if (d == 256) ln_fwd_warp_kernel<1><<<g8, 256, 0, st>>>(yy, gg, bb, (__half*)out, stats, rows, eps);
+  else {
+    const int grid = rows < 148 * 8 ? rows : 148 * 8;
+    ln_fwd_kernel<<<grid, LN_THREADS, 0, st>>>(yy, gg, bb, (__half*)out, stats, rows, d, eps);
+  }
   DB1_CUDA(cudaGetLastError());
   return 0;
 }
@@ -524,10 +688,23 @@ extern "C" int db1_layernorm_bwd(const void* dout, const void* y, const void* ga
   DB1_CHECK_ARG(drop_p >= 0.f && drop_p < 1.f, "layernorm_bwd: bad dropout p");
   DB1_CHECK_ARG(drop_p == 0.f || dz != nullptr, "layernorm_bwd: dropout needs a dz buffer");
   const uint32_t t = thr16(drop_p);
-  const int grid = rows < 148 * 2 ? rows : 148 * 2;
-  ln_bwd_kernel<<<grid, LN_THREADS, 0, (cudaStream_t)stream>>>((const __half*)dout, (const __half*)y,
-                                                             (const __half*)gamma, stats, (__half*)dy, (__half*)dz,
-                                                             dgamma, dbeta, dbias, rows, d, t, dscale(t), seed);
+  cudaStream_t st = (cudaStream_t)stream;
+  const __half *go = (const __half*)dout, *yy = (const __half*)y, *gg = (const __half*)gamma;
+  if (d == 2048 || d == 1024 || d == 512 || d == 256) {
+    const int g8 = (rows + 7) / 8;
+    __half *o1 = (__half*)dy, *o2 = (__half*)dz;
+    if (d == 2048) ln_bwd_rows_kernel<8><<<g8, 256, 0, st>>>(go, yy, gg, stats, o1, o2, rows, t, dscale(t), seed);
+    else if (d == 1024) ln_bwd_rows_kernel<4><<<g8, 256, 0, st>>>(go, yy, gg, stats, o1, o2, rows, t, dscale(t), seed);
+    else if (d == 512) ln_bwd_rows_kernel<2><<<g8, 256, 0, st>>>(go, yy, gg, stats, o1, o2, rows, t, dscale(t), seed);
+    else ln_bwd_rows_kernel<1><<<g8, 256, 0, st>>>(go, yy, gg, stats, o1, o2, rows, t, dscale(t), seed);
+    dim3 grid((d / 8 + 255) / 256, rows < 592 ? rows : 592);
+    ln_bwd_cols_kernel<<<grid, 256, 0, st>>>(go, yy, stats, (t && dz) ? (const __half*)dz : (const __half*)dy, dgamma,
+                                             dbeta, dbias, rows, d);
+  } else {
+    const int grid = rows < 148 * 2 ? rows : 148 * 2;
+    ln_bwd_kernel<<<grid, LN_THREADS, 0, st>>>(go, yy, gg, stats, (__half*)dy, (__half*)dz, dgamma, dbeta, dbias, rows,
+                                               d, t, dscale(t), seed);
+  }
   DB1_CUDA(cudaGetLastError());
   return 0;
 }
@@ -621,6 +798,14 @@ extern "C" int db1_posemb(void* out, const float* inv_freq, int klen, int d, int
   const int n = klen * (d / 2);
   posemb_kernel<<<(n + 255) / 256, 256, 0, (cudaStream_t)stream>>>((__half*)out, inv_freq, klen, d, clamp_len, t, dscale(t),
                                                                  seed);
+  DB1_CUDA(cudaGetLastError());
+  return 0;
+}
+
+extern "C" int db1_rel_unshift(const void* ds, void* dsr, int Z, int L, void* stream) {
+  DB1_CHECK_ARG(ds && dsr && Z > 0 && L > 0 && L % 8 == 0 && L <= 16384, "rel_unshift: bad arguments");
+  dim3 grid(L, Z);
+  rel_unshift_kernel<<<grid, 128, (size_t)L * 2 + 16, (cudaStream_t)stream>>>((const __half*)ds, (__half*)dsr, L);
   DB1_CUDA(cudaGetLastError());
   return 0;
 }

@@ -8,7 +8,8 @@
 //   warp 1     MMA issuer   : one elected thread issues tcgen05.mma (M=128, N=BN, K=16), accumulators in TMEM;
 //                             the accumulator is double-buffered (2 x BN columns) so tile i+1's main loop
 //                             overlaps tile i's epilogue
-//   warps 2..5 epilogue     : tcgen05.ld -> registers -> fused epilogue -> 16-byte global stores
+//   warps 2..9 epilogue     : tcgen05.ld -> registers -> fused epilogue -> 16-byte global stores (two warps per
+//                             TMEM lane quadrant, next chunk's global operands prefetched)
 //
 // Either operand may be K-contiguous ("K-major", e.g. activations x weights^T in the forward pass) or
 // MN-contiguous ("MN-major": weights in dgrad, both operands in wgrad) - the UMMA descriptors transpose for free,
@@ -20,12 +21,18 @@
 #include "common.cuh"
 #include "ptx.cuh"
 
+#include <stdlib.h>
+
 namespace db1 {
 
 constexpr int BM = 128;
 constexpr int BK = 64;
-constexpr int GEMM_THREADS = 192;
+constexpr int GEMM_THREADS = 320;  // TMA warp + MMA warp + 8 epilogue warps
 constexpr int A_STAGE_BYTES = BM * BK * 2;  // 16 KB
+#ifndef DB1_PF_DIST
+#define DB1_PF_DIST 0
+#endif
+constexpr int PF_DIST = DB1_PF_DIST;  // L2 prefetch distance of the TMA producer, in k-blocks
 
 struct GemmParams {
   int M, N, K;
@@ -55,6 +62,7 @@ struct GemmParams {
   __half* C2;
   const float* Drow;
   int window;
+  int dbg;  // development switches (DB1_GEMM_DBG): 1 = epilogue skips global stores, 2 = epilogue skips TMEM loads too
 };
 
 template <int BN>
@@ -62,7 +70,7 @@ struct GemmCfg {
   static constexpr int STAGES = (BN == 256) ? 4 : 6;
   static constexpr int B_STAGE_BYTES = BN * BK * 2;
   static constexpr int STAGE_BYTES = A_STAGE_BYTES + B_STAGE_BYTES;
-  static constexpr int STAGING_BYTES = 4 * 32 * 80;  // DS epilogue: per-warp 32 rows x (64 B + 16 B pad)
+  static constexpr int STAGING_BYTES = 8 * 32 * 80;  // DS epilogue: per-warp 32 rows x (64 B + 16 B pad)
   static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + STAGING_BYTES + 1024 /*align*/ + 256 /*barriers*/;
   static constexpr int TMEM_COLS = 2 * BN;  // 512 or 256
 };
@@ -92,17 +100,63 @@ DEVI Half8 float_to_half8(const float (&f)[8]) {
   return v;
 }
 
+// Store a warp's 32 x 32 fp16 tile (thread = row, hv = its 32 columns) with full-sector writes: the tile is transposed
+// through a per-warp staging buffer so that every store instruction covers 8 rows x 64 contiguous bytes. (16-byte
+// row-strided stores straight from the accumulator layout write half sectors, which the L2 turns into
+// read-modify-write fills: measured 2.5x slower end to end on the K = 2048 GEMMs.)
+DEVI void warp_store_tile(uint8_t* stg, int lane, const Half8 (&hv)[4], __half* base, long long ld, int rows_valid,
+                          int cols_valid, bool accumulate) {
+#pragma unroll
+  for (int g = 0; g < 4; ++g) *reinterpret_cast<Half8*>(stg + lane * 80 + g * 16) = hv[g];
+  __syncwarp();
+  const int piece = lane & 3;
+  const int col = piece * 8;
+#pragma unroll
+  for (int k = 0; k < 4; ++k) {
+    const int rr = k * 8 + (lane >> 2);
+    if (rr < rows_valid && col < cols_valid) {
+      Half8 v = *reinterpret_cast<const Half8*>(stg + rr * 80 + piece * 16);
+      __half* dst = base + (long long)rr * ld + col;
+      if (col + 8 <= cols_valid) {
+        if (accumulate) {
+          float a[8], b[8];
+          half8_to_float(v, a);
+          half8_to_float(ld_half8(dst), b);
+#pragma unroll
+          for (int i = 0; i < 8; ++i) a[i] += b[i];
+          v = float_to_half8(a);
+        }
+        st_half8(dst, v);
+      } else {
+        // ragged last group (N not a multiple of 8): scalar tail
+        const __half* hs = reinterpret_cast<const __half*>(&v);
+        for (int i = 0; i < cols_valid - col; ++i)
+          dst[i] = accumulate ? __float2half_rn(__half2float(hs[i]) + __half2float(dst[i])) : hs[i];
+      }
+    }
+  }
+  __syncwarp();
+}
+
 struct TileCoord {
   int mt, nt, z1, z2;
   int kb0, kb1;  // k-block range
   bool skip;
 };
 
-template <int BN, int EPI>
-DEVI TileCoord decode_tile(const GemmParams& p, int tile, int MT, int NT, int KB) {
+template <int BN, int EPI, int CL>
+DEVI TileCoord decode_tile(const GemmParams& p, int tile, int MT, int NT, int KB, int crank) {
   TileCoord t;
-  t.mt = tile % MT;
-  int r = tile / MT;
+  int r;
+  if (CL == 2) {
+    // `tile` indexes pairs of vertically adjacent tiles; the two CTAs of a cluster share the B tile
+    const int MT2 = (MT + 1) / 2;
+    t.mt = 2 * (tile % MT2) + crank;
+    r = tile / MT2;
+  } else {
+    t.mt = tile % MT;
+    r = tile / MT;
+  }
   t.nt = r % NT;
   r /= NT;
   t.z1 = r % p.Z1;
@@ -123,7 +177,7 @@ DEVI TileCoord decode_tile(const GemmParams& p, int tile, int MT, int NT, int KB
   return t;
 }
 
-template <int BN, int EPI>
+template <int BN, int EPI, int CL>
 __global__ void __launch_bounds__(GEMM_THREADS, 1)
 gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const GemmParams p) {
   using Cfg = GemmCfg<BN>;
@@ -144,8 +198,11 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
   const int MT = (p.M + BM - 1) / BM;
   const int NT = (EPI == DB1_EPI_GEGLU) ? (p.F / (BN / 2)) : (p.N + BN - 1) / BN;
   const int ZO = p.reduce_z2 ? 1 : p.Z2;
-  const int num_tiles = MT * NT * p.Z1 * ZO;
+  const int num_tiles = (CL == 2 ? (MT + 1) / 2 : MT) * NT * p.Z1 * ZO;  // tile pairs when clustered
   const int KB = (p.K + BK - 1) / BK;
+  const int crank = (CL == 2) ? (int)cluster_ctarank() : 0;
+  const int tile0 = (CL == 2) ? (int)(blockIdx.x >> 1) : (int)blockIdx.x;
+  const int tstep = (CL == 2) ? (int)(gridDim.x >> 1) : (int)gridDim.x;
   const int KZ = p.reduce_z2 ? p.Z2 : 1;  // extra contraction loop over z2
 
   if (warp == 0 && lane == 0) {
@@ -156,11 +213,11 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
     if (lane == 0) {
       for (int i = 0; i < STAGES; ++i) {
         mbar_init(&full[i], 1);
-        mbar_init(&empty[i], 1);
+        mbar_init(&empty[i], CL);  // with a cluster, the peer's multicast also writes this stage
       }
       for (int i = 0; i < 2; ++i) {
         mbar_init(&tfull[i], 1);
-        mbar_init(&tempty[i], 4);
+        mbar_init(&tempty[i], 8);
       }
       mbar_fence_init();
     }
@@ -169,6 +226,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
   }
   tc_fence_before();
   __syncthreads();
+  if (CL == 2) cluster_sync_all();  // barriers of both CTAs are initialised before any remote arrive / multicast
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
 
@@ -177,8 +235,8 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
     if (lane == 0) {
       int s = 0;
       uint32_t ph = 0;
-      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
-        const TileCoord t = decode_tile<BN, EPI>(p, tile, MT, NT, KB);
+      for (int tile = tile0; tile < num_tiles; tile += tstep) {
+        const TileCoord t = decode_tile<BN, EPI, CL>(p, tile, MT, NT, KB, crank);
         if (t.skip) continue;
         const int m0 = t.mt * BM;
         for (int kz = 0; kz < KZ; ++kz) {
@@ -186,6 +244,32 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
           const int az1 = p.a_z1on ? t.z1 : 0, az2 = p.a_z2on ? z2 : 0;
           const int bz1 = p.b_z1on ? t.z1 : 0, bz2 = p.b_z2on ? z2 : 0;
           for (int kb = t.kb0; kb < t.kb1; ++kb) {
+            if (PF_DIST > 0 && kb + PF_DIST < t.kb1) {
+              // pull the operands of a k-block PF_DIST ahead into L2 (DRAM latency >> the smem ring's look-ahead)
+              const int kp = (kb + PF_DIST) * BK;
+              if (!p.a_mn) tma_prefetch_4d(&tmA, kp, m0, az1, az2);
+              else {
+                tma_prefetch_4d(&tmA, m0, kp, az1, az2);
+                tma_prefetch_4d(&tmA, m0 + 64, kp, az1, az2);
+              }
+              if (CL == 2 && BN == 256) {
+                if (!p.b_mn) {
+                  const int row0 = (EPI == DB1_EPI_GEGLU) ? crank * p.F + t.nt * (BN / 2) : t.nt * BN + crank * 128;
+                  tma_prefetch_4d(&tmB, kp, row0, bz1, bz2);
+                } else {
+                  tma_prefetch_4d(&tmB, t.nt * BN + 2 * crank * 64, kp, bz1, bz2);
+                  tma_prefetch_4d(&tmB, t.nt * BN + (2 * crank + 1) * 64, kp, bz1, bz2);
+                }
+              } else if (!p.b_mn) {
+#pragma unroll
+                for (int j = 0; j < BN / 128; ++j)
+                  tma_prefetch_4d(&tmB, kp, (EPI == DB1_EPI_GEGLU) ? j * p.F + t.nt * (BN / 2) : t.nt * BN + j * 128, bz1,
+                                  bz2);
+              } else {
+#pragma unroll
+                for (int j = 0; j < BN / 64; ++j) tma_prefetch_4d(&tmB, t.nt * BN + j * 64, kp, bz1, bz2);
+              }
+            }
             mbar_wait(&empty[s], ph ^ 1);
             uint8_t* sa = smem + s * Cfg::STAGE_BYTES;
             uint8_t* sb = sa + A_STAGE_BYTES;
@@ -197,7 +281,20 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
               tma_load_4d(sa, &tmA, &full[s], m0, k0, az1, az2);
               tma_load_4d(sa + 8192, &tmA, &full[s], m0 + 64, k0, az1, az2);
             }
-            if (!p.b_mn) {
+            if (CL == 2 && BN == 256) {
+              // each CTA fetches half of the shared B tile and multicasts it to both
+              if (!p.b_mn) {
+                int row0;
+                if (EPI == DB1_EPI_GEGLU) row0 = crank * p.F + t.nt * (BN / 2);
+                else row0 = t.nt * BN + crank * 128;
+                tma_load_4d_mc(sb + crank * 16384, &tmB, &full[s], k0, row0, bz1, bz2, (uint16_t)3);
+              } else {
+#pragma unroll
+                for (int j = 0; j < 2; ++j)
+                  tma_load_4d_mc(sb + (2 * crank + j) * 8192, &tmB, &full[s], t.nt * BN + (2 * crank + j) * 64, k0, bz1,
+                                 bz2, (uint16_t)3);
+              }
+            } else if (!p.b_mn) {
 #pragma unroll
               for (int j = 0; j < BN / 128; ++j) {
                 int row0;
@@ -228,8 +325,8 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
       int s = 0;
       uint32_t ph = 0;
       int it = 0;
-      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
-        const TileCoord t = decode_tile<BN, EPI>(p, tile, MT, NT, KB);
+      for (int tile = tile0; tile < num_tiles; tile += tstep) {
+        const TileCoord t = decode_tile<BN, EPI, CL>(p, tile, MT, NT, KB, crank);
         if (t.skip) continue;
         const int as = it & 1;
         const uint32_t aph = (it >> 1) & 1;
@@ -250,7 +347,8 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
               umma_ss(tacc, adesc + (uint64_t)(k * a_kadv), bdesc + (uint64_t)(k * b_kadv), idesc, acc);
               acc = 1;
             }
-            umma_commit(&empty[s]);
+            if (CL == 2) umma_commit_mc(&empty[s], (uint16_t)3);
+            else umma_commit(&empty[s]);
             if (++s == STAGES) {
               s = 0;
               ph ^= 1;
@@ -261,11 +359,16 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
       }
     }
   } else {
-    // ------------------------------------------------------------ epilogue warps (2..5)
-    const int quad = warp & 3;  // TMEM lane quadrant this warp may access
+    // ------------------------------------------------------------ epilogue warps (2..9)
+    // Two warps per TMEM lane quadrant (a warp may only touch lanes 32*(warp%4)..+31); each takes half of the
+    // tile's 32-column chunks. Global operands of the next chunk (residual / saved activations / P) are fetched
+    // before waiting on the current chunk's TMEM load so their latency overlaps.
+    const int ew = warp - 2;
+    const int quad = warp & 3;
+    const int half = ew >> 2;
     int it = 0;
-    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
-      const TileCoord t = decode_tile<BN, EPI>(p, tile, MT, NT, KB);
+    for (int tile = tile0; tile < num_tiles; tile += tstep) {
+      const TileCoord t = decode_tile<BN, EPI, CL>(p, tile, MT, NT, KB, crank);
       if (t.skip) continue;
       const int mt = t.mt, nt = t.nt;
       const int as = it & 1;
@@ -274,41 +377,60 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
       const int row = mt * BM + quad * 32 + lane;
       const bool row_ok = row < p.M;
       const long long zoff = (long long)t.z1 * p.c_z1 + (long long)t.z2 * p.c_z2;
-      mbar_wait(&tfull[as], aph);
-      tc_fence_after();
       const uint32_t tacc = tmem_base + as * BN + ((uint32_t)(quad * 32) << 16);
+      uint8_t* stg = staging + ew * (32 * 80);
+      const int row_base = mt * BM + quad * 32;
 
       if (EPI == DB1_EPI_PLAIN || EPI == DB1_EPI_QKV) {
-#pragma unroll 1
-        for (int c = 0; c < BN / 32; ++c) {
+        constexpr int CPW = BN / 64;  // chunks per warp
+        const int c_first = half * CPW;
+        Half8 rs[CPW][4];
+        auto load_resid = [&](int c, Half8 (&dst)[4]) {
+          if (EPI == DB1_EPI_PLAIN && p.resid != nullptr && row_ok) {
+#pragma unroll
+            for (int g = 0; g < 4; ++g) {
+              const int col = nt * BN + c * 32 + g * 8;
+              if (col < p.N) dst[g] = ld_half8(p.resid + (size_t)row * p.ldr + col);
+            }
+          }
+        };
+#pragma unroll
+        for (int ci = 0; ci < CPW; ++ci) load_resid(c_first + ci, rs[ci]);  // independent of the accumulator
+        mbar_wait(&tfull[as], aph);
+        tc_fence_after();
+#pragma unroll
+        for (int ci = 0; ci < CPW; ++ci) {
+          const int c = c_first + ci;
           uint32_t r[32];
+          if (p.dbg & 2) continue;
           tmem_ld32(tacc + c * 32, r);
           tmem_ld_wait();
           const int col0 = nt * BN + c * 32;
-          if (row_ok) {
+          if (col0 >= p.N) break;  // warp-uniform
+          const int rows_valid = p.M - row_base;
+          Half8 h0[4], h1[4];
 #pragma unroll
-            for (int g = 0; g < 4; ++g) {
-              const int col = col0 + g * 8;
-              if (col >= p.N) break;
-              float f[8];
+          for (int g = 0; g < 4; ++g) {
+            const int col = col0 + g * 8;
+            float f[8];
 #pragma unroll
-              for (int i = 0; i < 8; ++i) f[i] = __uint_as_float(r[g * 8 + i]) * p.alpha;
-              if (EPI == DB1_EPI_QKV) {
-                const size_t orow = (size_t)row * p.ldc;
-                if (col < p.d_model) {
-                  float uu[8], vv[8], o[8];
-                  half8_to_float(ld_half8(p.u + col), uu);
-                  half8_to_float(ld_half8(p.v + col), vv);
+            for (int i = 0; i < 8; ++i) f[i] = __uint_as_float(r[g * 8 + i]) * p.alpha;
+            if (EPI == DB1_EPI_QKV) {
+              if (col < p.d_model) {
+                float uu[8], vv[8], o[8];
+                half8_to_float(ld_half8(p.u + col), uu);
+                half8_to_float(ld_half8(p.v + col), vv);
 #pragma unroll
-                  for (int i = 0; i < 8; ++i) o[i] = f[i] + uu[i];
-                  st_half8(p.C + orow + col, float_to_half8(o));
+                for (int i = 0; i < 8; ++i) o[i] = f[i] + uu[i];
+                h0[g] = float_to_half8(o);
 #pragma unroll
-                  for (int i = 0; i < 8; ++i) o[i] = f[i] + vv[i];
-                  st_half8(p.C + orow + p.d_model + col, float_to_half8(o));
-                } else {
-                  st_half8(p.C + orow + p.d_model + col, float_to_half8(f));
-                }
+                for (int i = 0; i < 8; ++i) o[i] = f[i] + vv[i];
+                h1[g] = float_to_half8(o);
               } else {
+                h1[g] = float_to_half8(f);
+              }
+            } else {
+              if (col < p.N) {
                 if (p.bias) {
                   float b[8];
                   half8_to_float(ld_half8(p.bias + col), b);
@@ -324,140 +446,160 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
                     f[4 + i] = dropout_keep(b1, i, p.drop_thr16) ? f[4 + i] * p.drop_scale : 0.f;
                   }
                 }
-                if (p.resid) {
+                if (p.resid && row_ok) {
                   float b[8];
-                  half8_to_float(ld_half8(p.resid + (size_t)row * p.ldr + col), b);
+                  half8_to_float(rs[ci][g], b);
 #pragma unroll
                   for (int i = 0; i < 8; ++i) f[i] += b[i];
                 }
-                __half* dst = p.C + zoff + (size_t)row * p.ldc + col;
-                if (col + 8 <= p.N) {
-                  if (p.accumulate) {
-                    float b[8];
-                    half8_to_float(ld_half8(dst), b);
-#pragma unroll
-                    for (int i = 0; i < 8; ++i) f[i] += b[i];
-                  }
-                  st_half8(dst, float_to_half8(f));
-                } else {
-                  // ragged last group (N not a multiple of 8): scalar tail
-                  for (int i = 0; i < p.N - col; ++i) {
-                    float x = f[i];
-                    if (p.accumulate) x += __half2float(dst[i]);
-                    dst[i] = __float2half_rn(x);
-                  }
-                }
               }
+              h0[g] = float_to_half8(f);
             }
+          }
+          if (p.dbg & 1) continue;
+          if (EPI == DB1_EPI_QKV) {
+            // columns < d_model are written twice (q+u at col, q+v at d_model+col); k, v shift right by d_model
+            __half* crow = p.C + (size_t)row_base * p.ldc;
+            if (col0 < p.d_model) warp_store_tile(stg, lane, h0, crow + col0, p.ldc, rows_valid, 32, false);
+            warp_store_tile(stg, lane, h1, crow + p.d_model + col0, p.ldc, rows_valid, 32, false);
+          } else {
+            warp_store_tile(stg, lane, h0, p.C + zoff + (size_t)row_base * p.ldc + col0, p.ldc, rows_valid, p.N - col0,
+                            p.accumulate != 0);
           }
         }
       } else if (EPI == DB1_EPI_DS) {
         // dS = P * (dP - Drow) * alpha on the causal / windowed region, 0 elsewhere; second copy in
         // relative-position order (the adjoint of _rel_shift, transformer_xl.py:98-110).
+        constexpr int CPW = BN / 64;
+        const int c_first = half * CPW;
         const long long zlin = (long long)t.z2 * p.Z1 + t.z1;
         const float drow = row_ok ? p.Drow[zlin * p.M + row] : 0.f;
-        uint8_t* stg = staging + (warp - 2) * (32 * 80);
-        const int row_base = mt * BM + quad * 32;
-#pragma unroll 1
-        for (int c = 0; c < BN / 32; ++c) {
+        Half8 pp[2][4];
+        auto load_p = [&](int c, Half8 (&dst)[4]) {
+#pragma unroll
+          for (int g = 0; g < 4; ++g) {
+            const int col = nt * BN + c * 32 + g * 8;
+            if (row_ok && col <= row && col < p.N) dst[g] = ld_half8(p.P + zoff + (size_t)row * p.ldc + col);
+          }
+        };
+        load_p(c_first, pp[0]);
+        mbar_wait(&tfull[as], aph);
+        tc_fence_after();
+#pragma unroll
+        for (int ci = 0; ci < CPW; ++ci) {
+          const int c = c_first + ci;
           const int col0 = nt * BN + c * 32;
           if (col0 > row_base + 31 || col0 >= p.N) break;  // warp-uniform: chunk entirely above the diagonal
           uint32_t r[32];
           tmem_ld32(tacc + c * 32, r);
+          if (ci + 1 < CPW) load_p(c + 1, pp[(ci + 1) & 1]);
           tmem_ld_wait();
+          Half8 hv[4];
 #pragma unroll
           for (int g = 0; g < 4; ++g) {
             const int col = col0 + g * 8;
             float pv[8], o[8];
             const bool any = row_ok && col <= row && col < p.N;
-            if (any) half8_to_float(ld_half8(p.P + zoff + (size_t)row * p.ldc + col), pv);
+            half8_to_float(pp[ci & 1][g], pv);
 #pragma unroll
             for (int i = 0; i < 8; ++i) {
               const int j = col + i;
               const bool ok = any && j <= row && (row - j) < p.window;
               o[i] = ok ? pv[i] * (__uint_as_float(r[g * 8 + i]) - drow) * p.alpha : 0.f;
             }
-            const Half8 hv = float_to_half8(o);
-            if (row_ok && col < p.N) st_half8(p.C + zoff + (size_t)row * p.ldc + col, hv);
-            *reinterpret_cast<Half8*>(stg + lane * 80 + g * 16) = hv;
+            hv[g] = float_to_half8(o);
           }
-          __syncwarp();
-          // coalesced un-shift: lane t writes element (rr, col0+t) of the staged 32x32 tile
-#pragma unroll 4
-          for (int rr = 0; rr < 32; ++rr) {
-            const int i = row_base + rr;
-            const int j = col0 + lane;
-            if (i < p.M && j <= i && j < p.N) {
-              const __half hvv = *reinterpret_cast<const __half*>(stg + rr * 80 + lane * 2);
-              p.C2[zoff + (size_t)i * p.ldc + (size_t)(j + p.N - 1 - i)] = hvv;
-            }
-          }
-          __syncwarp();
+          warp_store_tile(stg, lane, hv, p.C + zoff + (size_t)row_base * p.ldc + col0, p.ldc, p.M - row_base,
+                          p.N - col0, false);
         }
       } else {
         // GeGLU forward / backward: accumulator columns [0,BN/2) pair with [BN/2,BN) (forward) or the tile's
         // BN output columns pair with saved a|g (backward).
         constexpr int HALF = BN / 2;
-#pragma unroll 1
-        for (int c = 0; c < (EPI == DB1_EPI_GEGLU ? HALF : BN) / 32; ++c) {
+        constexpr int NCH = (EPI == DB1_EPI_GEGLU ? HALF : BN) / 32;
+        constexpr int CPW = NCH / 2;
+        const int c_first = half * CPW;
+        Half8 ha[2][4], hg[2][4];
+        auto load_h = [&](int c, Half8 (&da)[4], Half8 (&dg)[4]) {
+          if (EPI == DB1_EPI_DGEGLU && row_ok) {
+#pragma unroll
+            for (int g = 0; g < 4; ++g) {
+              const int n = nt * BN + c * 32 + g * 8;
+              if (n < p.N) {
+                da[g] = ld_half8(p.H + (size_t)row * p.ldh + n);
+                dg[g] = ld_half8(p.H + (size_t)row * p.ldh + p.F + n);
+              }
+            }
+          }
+        };
+        load_h(c_first, ha[0], hg[0]);
+        mbar_wait(&tfull[as], aph);
+        tc_fence_after();
+#pragma unroll
+        for (int ci = 0; ci < CPW; ++ci) {
+          const int c = c_first + ci;
           uint32_t ra[32];
           tmem_ld32(tacc + c * 32, ra);
           if (EPI == DB1_EPI_GEGLU) {
             uint32_t rg[32];
             tmem_ld32(tacc + HALF + c * 32, rg);
             tmem_ld_wait();
-            if (row_ok) {
-              const int n0 = nt * HALF + c * 32;  // column within [0,F)
+            const int n0 = nt * HALF + c * 32;  // column within [0,F)
+            Half8 xa[4], xg[4], xy[4];
 #pragma unroll
-              for (int g = 0; g < 4; ++g) {
-                const int n = n0 + g * 8;
-                float a[8], gg[8], y[8], b[8];
+            for (int g = 0; g < 4; ++g) {
+              const int n = n0 + g * 8;
+              float a[8], gg[8], y[8], b[8];
 #pragma unroll
-                for (int i = 0; i < 8; ++i) {
-                  a[i] = __uint_as_float(ra[g * 8 + i]);
-                  gg[i] = __uint_as_float(rg[g * 8 + i]);
-                }
-                if (p.bias) {
-                  half8_to_float(ld_half8(p.bias + n), b);
-#pragma unroll
-                  for (int i = 0; i < 8; ++i) a[i] += b[i];
-                  half8_to_float(ld_half8(p.bias + p.F + n), b);
-#pragma unroll
-                  for (int i = 0; i < 8; ++i) gg[i] += b[i];
-                }
-                // round the pre-activations to fp16 first so that forward and backward see the same values
-                const Half8 ha = float_to_half8(a), hg = float_to_half8(gg);
-                half8_to_float(ha, a);
-                half8_to_float(hg, gg);
-#pragma unroll
-                for (int i = 0; i < 8; ++i) y[i] = a[i] * gelu_erf(gg[i]);
-                st_half8(p.H + (size_t)row * p.ldh + n, ha);
-                st_half8(p.H + (size_t)row * p.ldh + p.F + n, hg);
-                st_half8(p.C + (size_t)row * p.ldc + n, float_to_half8(y));
+              for (int i = 0; i < 8; ++i) {
+                a[i] = __uint_as_float(ra[g * 8 + i]);
+                gg[i] = __uint_as_float(rg[g * 8 + i]);
               }
+              if (p.bias) {
+                half8_to_float(ld_half8(p.bias + n), b);
+#pragma unroll
+                for (int i = 0; i < 8; ++i) a[i] += b[i];
+                half8_to_float(ld_half8(p.bias + p.F + n), b);
+#pragma unroll
+                for (int i = 0; i < 8; ++i) gg[i] += b[i];
+              }
+              // round the pre-activations to fp16 first so that forward and backward see the same values
+              xa[g] = float_to_half8(a);
+              xg[g] = float_to_half8(gg);
+              half8_to_float(xa[g], a);
+              half8_to_float(xg[g], gg);
+#pragma unroll
+              for (int i = 0; i < 8; ++i) y[i] = a[i] * gelu_erf(gg[i]);
+              xy[g] = float_to_half8(y);
             }
+            const int rows_valid = p.M - row_base;
+            warp_store_tile(stg, lane, xa, p.H + (size_t)row_base * p.ldh + n0, p.ldh, rows_valid, 32, false);
+            warp_store_tile(stg, lane, xg, p.H + (size_t)row_base * p.ldh + p.F + n0, p.ldh, rows_valid, 32, false);
+            warp_store_tile(stg, lane, xy, p.C + (size_t)row_base * p.ldc + n0, p.ldc, rows_valid, 32, false);
           } else {
+            if (ci + 1 < CPW) load_h(c + 1, ha[(ci + 1) & 1], hg[(ci + 1) & 1]);
             tmem_ld_wait();
-            if (row_ok) {
-              const int n0 = nt * BN + c * 32;
+            const int n0 = nt * BN + c * 32;
+            if (n0 >= p.N) break;  // warp-uniform
+            Half8 xda[4], xdg[4];
 #pragma unroll
-              for (int g = 0; g < 4; ++g) {
-                const int n = n0 + g * 8;
-                if (n >= p.N) break;
-                float dy[8], a[8], gg[8], da[8], dg[8];
+            for (int g = 0; g < 4; ++g) {
+              float dy[8], a[8], gg[8], da[8], dg[8];
 #pragma unroll
-                for (int i = 0; i < 8; ++i) dy[i] = __uint_as_float(ra[g * 8 + i]) * p.alpha;
-                half8_to_float(ld_half8(p.H + (size_t)row * p.ldh + n), a);
-                half8_to_float(ld_half8(p.H + (size_t)row * p.ldh + p.F + n), gg);
+              for (int i = 0; i < 8; ++i) dy[i] = __uint_as_float(ra[g * 8 + i]) * p.alpha;
+              half8_to_float(ha[ci & 1][g], a);
+              half8_to_float(hg[ci & 1][g], gg);
 #pragma unroll
-                for (int i = 0; i < 8; ++i) {
-                  da[i] = dy[i] * gelu_erf(gg[i]);
-                  dg[i] = dy[i] * a[i] * gelu_erf_grad(gg[i]);
-                }
-                st_half8(p.C + (size_t)row * p.ldc + n, float_to_half8(da));
-                st_half8(p.C + (size_t)row * p.ldc + p.F + n, float_to_half8(dg));
+              for (int i = 0; i < 8; ++i) {
+                da[i] = dy[i] * gelu_erf(gg[i]);
+                dg[i] = dy[i] * a[i] * gelu_erf_grad(gg[i]);
               }
+              xda[g] = float_to_half8(da);
+              xdg[g] = float_to_half8(dg);
             }
+            const int rows_valid = p.M - row_base;
+            warp_store_tile(stg, lane, xda, p.C + (size_t)row_base * p.ldc + n0, p.ldc, rows_valid, p.N - n0, false);
+            warp_store_tile(stg, lane, xdg, p.C + (size_t)row_base * p.ldc + p.F + n0, p.ldc, rows_valid, p.N - n0, false);
           }
         }
       }
@@ -470,27 +612,53 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
 
   tc_fence_before();
   __syncthreads();
+  if (CL == 2) cluster_sync_all();  // the peer may still multicast into / arrive on this CTA's shared memory
   if (warp == 1) {
     tc_fence_after();
     tmem_dealloc<Cfg::TMEM_COLS>(tmem_base);
   }
 }
 
-template <int BN, int EPI>
-static int launch_gemm(const CUtensorMap& tmA, const CUtensorMap& tmB, const GemmParams& p, cudaStream_t stream) {
+template <int BN, int EPI, int CL>
+static int launch_gemm_cl(const CUtensorMap& tmA, const CUtensorMap& tmB, const GemmParams& p, cudaStream_t stream) {
   using Cfg = GemmCfg<BN>;
   static bool configured = false;
   if (!configured) {
-    DB1_CUDA(cudaFuncSetAttribute(gemm_kernel<BN, EPI>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES));
+    DB1_CUDA(cudaFuncSetAttribute(gemm_kernel<BN, EPI, CL>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                  Cfg::SMEM_BYTES));
     configured = true;
   }
   const long long MT = cdiv(p.M, BM);
   const long long NT = (EPI == DB1_EPI_GEGLU) ? p.F / (BN / 2) : cdiv(p.N, BN);
-  long long tiles = MT * NT * p.Z1 * (p.reduce_z2 ? 1 : p.Z2);
-  int grid = tiles > sm_count() ? sm_count() : (int)tiles;
-  gemm_kernel<BN, EPI><<<grid, GEMM_THREADS, Cfg::SMEM_BYTES, stream>>>(tmA, tmB, p);
-  DB1_CUDA(cudaGetLastError());
+  long long tiles = (CL == 2 ? (MT + 1) / 2 : MT) * NT * p.Z1 * (p.reduce_z2 ? 1 : p.Z2);
+  const int slots = sm_count() / CL;
+  int grid = (int)(tiles > slots ? slots : tiles) * CL;
+  cudaLaunchConfig_t cfg;
+  memset(&cfg, 0, sizeof(cfg));
+  cfg.gridDim = dim3(grid);
+  cfg.blockDim = dim3(GEMM_THREADS);
+  cfg.dynamicSmemBytes = Cfg::SMEM_BYTES;
+  cfg.stream = stream;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = CL;
+  attr[0].val.clusterDim.y = 1;
+  attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  DB1_CUDA(cudaLaunchKernelEx(&cfg, gemm_kernel<BN, EPI, CL>, tmA, tmB, p));
   return 0;
+}
+
+// Clusters of two CTAs (vertically adjacent tiles sharing the B tile through TMA multicast) cut the L2 -> SM operand
+// traffic per tile from 48 KB to 32 KB per k-block; used whenever both CTAs see the same k-range.
+template <int BN, int EPI>
+static int launch_gemm(const CUtensorMap& tmA, const CUtensorMap& tmB, const GemmParams& p, cudaStream_t stream) {
+  const bool batched = p.Z1 * p.Z2 > 1;
+  if (BN == 256 && EPI != DB1_EPI_DS && !batched && p.k_mode == DB1_K_FULL && !p.skip_upper && p.M > BM &&
+      !getenv("DB1_GEMM_NO_CLUSTER"))
+    return launch_gemm_cl<BN, EPI, (BN == 256 && EPI != DB1_EPI_DS) ? 2 : 1>(tmA, tmB, p, stream);
+  return launch_gemm_cl<BN, EPI, 1>(tmA, tmB, p, stream);
 }
 
 // 4-D map (inner, rows, z1, z2). A broadcast batch dim (stride 0) is encoded as a dim of size 1.
@@ -545,6 +713,7 @@ extern "C" int db1_gemm_f16(const db1_gemm_desc* d, void* stream_) {
   p.seed = d->seed; p.u = (const __half*)d->u; p.v = (const __half*)d->v; p.d_model = d->d_model;
   p.H = (__half*)d->H; p.ldh = d->ldh; p.F = d->F;
   p.P = (const __half*)d->P; p.C2 = (__half*)d->C2; p.Drow = d->Drow; p.window = d->window;
+  { const char* e = getenv("DB1_GEMM_DBG"); p.dbg = e ? atoi(e) : 0; }
   if (p.reduce_z2) DB1_CHECK_ARG(d->c_z2 == 0, "gemm: reduce_z2 needs c_z2 == 0");
 
   int BNsel = 256;
@@ -566,8 +735,8 @@ extern "C" int db1_gemm_f16(const db1_gemm_desc* d, void* stream_) {
     DB1_CHECK_ARG(d->H && d->F > 0 && N == d->F && d->F % 8 == 0 && !batched, "gemm(dgeglu): need H and N == F");
   }
   if (epilogue == DB1_EPI_DS) {
-    DB1_CHECK_ARG(d->P && d->C2 && d->Drow && M == N && N % 8 == 0 && d->window > 0,
-                  "gemm(ds): need P, C2, Drow, square M == N (multiple of 8) and window > 0");
+    DB1_CHECK_ARG(d->P && d->Drow && M == N && N % 8 == 0 && d->window > 0,
+                  "gemm(ds): need P, Drow, square M == N (multiple of 8) and window > 0");
     BNsel = 128;
   }
   if (epilogue == DB1_EPI_PLAIN && (d->bias || d->resid || p.drop_thr16))

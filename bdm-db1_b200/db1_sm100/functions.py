@@ -99,8 +99,8 @@ class AttnBlockFn(torch.autograd.Function):
         dout2 = dout.reshape(rows, d)
         if not dout2.is_contiguous():
             dout2 = dout2.contiguous()
-        dgamma = _f32zeros(d, dev)
-        dbeta = _f32zeros(d, dev)
+        small = _f32zeros(4 * d, dev)  # [du | dv | dgamma | dbeta], converted to fp16 by one launch at the end
+        du, dv, dgamma, dbeta = small[0:d], small[d:2 * d], small[2 * d:3 * d], small[3 * d:4 * d]
         dy = torch.empty(rows, d, dtype=f16, device=dev)
         dz = torch.empty(rows, d, dtype=f16, device=dev) if drop_p > 0 else None
         ops.layernorm_bwd(dout2, y, gamma, stats, dy, dz, dgamma, dbeta, None, drop_p, seed)
@@ -124,8 +124,9 @@ class AttnBlockFn(torch.autograd.Function):
         LL = L * L
         sz = (LL, H * LL)
         ops.gemm(do, vv, dS, L, L, dh, lda=d, ldb=4 * d, ldc=L, epilogue=ops.EPI_DS, alpha=scale, Z1=H, Z2=B,
-                 a_z=(dh, L * d), b_z=(dh, L * 4 * d), c_z=sz, skip_upper=True, P=P, C2=dSr, Drow=Drow,
+                 a_z=(dh, L * d), b_z=(dh, L * 4 * d), c_z=sz, skip_upper=True, P=P, Drow=Drow,
                  window=window)
+        ops.rel_unshift(dS, dSr, B * H, L)
         dqkv = torch.empty(rows, 3 * d, dtype=f16, device=dev)
         ops.gemm(P, do, dqkv[:, 2 * d:], L, dh, L, lda=L, ldb=d, ldc=3 * d, a_mn=True, b_mn=True, Z1=H, Z2=B,
                  a_z=sz, b_z=(dh, L * d), c_z=(dh, L * 3 * d), k_mode=ops.K_BEGIN_BY_ROW)
@@ -140,8 +141,6 @@ class AttnBlockFn(torch.autograd.Function):
         drk = torch.empty(L, d, dtype=f16, device=dev)
         ops.gemm(dSr, qv, drk, L, dh, L, lda=L, ldb=4 * d, ldc=d, a_mn=True, b_mn=True, Z1=H, Z2=B,
                  a_z=sz, b_z=(dh, L * 4 * d), c_z=(dh, 0), reduce_z2=True, k_mode=ops.K_BEGIN_REV)
-        du = _f32zeros(d, dev)
-        dv = _f32zeros(d, dev)
         ops.dq_finalize(dqu, dqv, dqkv[:, 0:d], du, dv, rows, d)
         # r_net / qkv_net
         dWr = torch.empty(d, d, dtype=f16, device=dev)
@@ -150,8 +149,9 @@ class AttnBlockFn(torch.autograd.Function):
         ops.gemm(dqkv, x2, dWqkv, 3 * d, d, rows, lda=3 * d, ldb=d, ldc=d, a_mn=True, b_mn=True)
         dx = torch.empty(rows, d, dtype=f16, device=dev)
         ops.gemm(dqkv, Wqkv, dx, rows, d, 3 * d, lda=3 * d, ldb=d, ldc=d, b_mn=True, resid=dy, ldr=d)
-        return (dx.view(B, L, d), None, dWqkv, dWr, dWo, _to_half(du, (H, dh)), _to_half(dv, (H, dh)),
-                _to_half(dgamma, (d,)), _to_half(dbeta, (d,)), None, None, None, None)
+        sh = _to_half(small, (4 * d,))
+        return (dx.view(B, L, d), None, dWqkv, dWr, dWo, sh[0:d].view(H, dh), sh[d:2 * d].view(H, dh),
+                sh[2 * d:3 * d], sh[3 * d:4 * d], None, None, None, None)
 
 
 class FFBlockFn(torch.autograd.Function):
@@ -191,9 +191,8 @@ class FFBlockFn(torch.autograd.Function):
         dout2 = dout.reshape(rows, d)
         if not dout2.is_contiguous():
             dout2 = dout2.contiguous()
-        dgamma = _f32zeros(d, dev)
-        dbeta = _f32zeros(d, dev)
-        db2 = _f32zeros(d, dev)
+        small = _f32zeros(3 * d + 2 * F, dev)  # [dgamma | dbeta | db2 | db1]
+        dgamma, dbeta, db2, db1 = small[0:d], small[d:2 * d], small[2 * d:3 * d], small[3 * d:]
         dy = torch.empty(rows, d, dtype=f16, device=dev)
         dz = torch.empty(rows, d, dtype=f16, device=dev) if drop_p > 0 else None
         ops.layernorm_bwd(dout2, y, gamma, stats, dy, dz, dgamma, dbeta, db2, drop_p, seed)
@@ -203,14 +202,13 @@ class FFBlockFn(torch.autograd.Function):
         dH = torch.empty(rows, 2 * F, dtype=f16, device=dev)
         ops.gemm(dzz, W2, dH, rows, F, d, lda=d, ldb=F, ldc=2 * F, b_mn=True, epilogue=ops.EPI_DGEGLU, H=Hb,
                  ldh=2 * F, F=F)
-        db1 = _f32zeros(2 * F, dev)
         ops.colsum(dH, db1, rows, 2 * F)
         dW1 = torch.empty(2 * F, d, dtype=f16, device=dev)
         ops.gemm(dH, x2, dW1, 2 * F, d, rows, lda=2 * F, ldb=d, ldc=d, a_mn=True, b_mn=True)
         dx = torch.empty(rows, d, dtype=f16, device=dev)
         ops.gemm(dH, W1, dx, rows, d, 2 * F, lda=2 * F, ldb=d, ldc=d, b_mn=True, resid=dy, ldr=d)
-        return (dx.view(B, L, d), dW1, _to_half(db1, (2 * F,)), dW2, _to_half(db2, (d,)), _to_half(dgamma, (d,)),
-                _to_half(dbeta, (d,)), None, None)
+        sh = _to_half(small, (3 * d + 2 * F,))
+        return (dx.view(B, L, d), dW1, sh[3 * d:], dW2, sh[2 * d:3 * d], sh[0:d], sh[d:2 * d], None, None)
 
 
 def _pad8(n):

@@ -240,3 +240,10 @@ def f32_to_f16(src, dst, accumulate=False):
     with _Launch("f32_to_f16", 1):
       check(_lib.lib().db1_f32_to_f16(_f32(src), ptr(dst), C.c_longlong(src.numel()), int(accumulate), cur_stream()),
           "db1_f32_to_f16")
+
+
+def rel_unshift(ds, dsr, Z, L):
+    """dsr[z,i,c] = ds[z,i,c-(L-1-i)] (0 where c < L-1-i): relative-position re-layout of dS."""
+    _need_cuda_half(ds, dsr)
+    with _Launch("rel_unshift", 1, 0.0, 2.0 * Z * L * (L + 1)):
+      check(_lib.lib().db1_rel_unshift(ptr(ds), ptr(dsr), Z, L, cur_stream()), "db1_rel_unshift")

@@ -41,8 +41,7 @@ enum {
   DB1_EPI_QKV = 1,    /* N = 3*d_model: columns < d_model are written twice (+u, +v): C row = [q+u | q+v | k | v]       */
   DB1_EPI_GEGLU = 2,  /* N = 2F, tile pairs column n with n+F: H = [a|g] + bias (pre-activation), C = a * gelu_erf(g)   */
   DB1_EPI_DGEGLU = 3, /* N = F, acc = dY: reads H = [a|g]; C = [dY*gelu(g) | dY*a*gelu'(g)] (width 2F)                 */
-  DB1_EPI_DS = 4      /* attention backward: acc = dP; dS = P*(dP - Drow)*alpha on j<=i (and i-j<window), else 0;
-                         writes C = dS[i][j] and C2 = dS "un-shifted" to relative-position order: C2[i][j + N-1-i]      */
+  DB1_EPI_DS = 4      /* attention backward: acc = dP; C = dS = P*(dP - Drow)*alpha on j<=i (and i-j<window), else 0    */
 };
 enum {
   DB1_K_FULL = 0,        /* k in [0, K)                                                                                */
@@ -81,7 +80,7 @@ typedef struct db1_gemm_desc {
   int32_t F;
   /* DS epilogue */
   const void* P;      /* fp16, same layout/strides as C */
-  void* C2;           /* fp16, same layout/strides as C */
+  void* C2;           /* reserved (unused) */
   const float* Drow;  /* fp32 [Z2][Z1][M] contiguous */
   int32_t window;     /* attend iff 0 <= i-j < window */
   int32_t bn_hint;    /* 0 = auto, 128 or 256 */
@@ -148,6 +147,8 @@ int db1_rowdot(const void* a, const void* b, long long ld, float* out, int B, in
 /* Sinusoid rows of PositionalEmbedding (transformer_xl.py:43-50, 569-575): row c = [sin|cos](min(klen-1-c, clamp)*inv_freq) */
 int db1_posemb(void* out, const float* inv_freq, int klen, int d, int clamp_len, float drop_p, uint64_t seed,
                void* stream);
+/* dsr[z][i][c] = ds[z][i][c-(L-1-i)] for c >= L-1-i, else 0: adjoint of _rel_shift (transformer_xl.py:98-110) */
+int db1_rel_unshift(const void* ds, void* dsr, int Z, int L, void* stream);
 int db1_f32_to_f16(const float* src, void* dst, long long n, int accumulate, void* stream);
 
 #ifdef __cplusplus

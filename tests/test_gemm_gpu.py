@@ -143,8 +143,9 @@ def test_gemm_ds_epilogue_and_causal_kmodes(cuda, L, dh, window):
     dS = torch.zeros(B, Hh, L, L, dtype=torch.half, device=cuda)
     dSr = torch.zeros(B, Hh, L, L, dtype=torch.half, device=cuda)
     ops.gemm(dO, V, dS, L, L, dh, lda=d, ldb=d, ldc=L, epilogue=ops.EPI_DS, alpha=scale, Z1=Hh, Z2=B,
-             a_z=(dh, L * d), b_z=(dh, L * d), c_z=(L * L, Hh * L * L), skip_upper=True, P=P, C2=dSr, Drow=D,
+             a_z=(dh, L * d), b_z=(dh, L * d), c_z=(L * L, Hh * L * L), skip_upper=True, P=P, Drow=D,
              window=window)
+    ops.rel_unshift(dS, dSr, B * Hh, L)
     i = torch.arange(L, device=cuda)[:, None]
     j = torch.arange(L, device=cuda)[None, :]
     ok = (j <= i) & ((i - j) < window)
