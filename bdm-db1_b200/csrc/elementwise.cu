@@ -247,91 +247,124 @@ ln_fwd_warp_kernel(const __half* __restrict__ y, const __half* __restrict__ gamm
   }
 }
 
-// row part of the backward: dy (and dz = dy * dropout mask) — no column accumulators here
-template <int CH>
-__global__ void __launch_bounds__(256)
-ln_bwd_rows_kernel(const __half* __restrict__ dout, const __half* __restrict__ y, const __half* __restrict__ gamma,
-                   const float* __restrict__ stats, __half* __restrict__ dy, __half* __restrict__ dz, int rows,
-                   uint32_t drop_thr16, float drop_scale, uint64_t seed) {
-  constexpr int d = 256 * CH;
-  const int lane = threadIdx.x & 31;
-  const int row = blockIdx.x * 8 + (threadIdx.x >> 5);
-  if (row >= rows) return;
-  const float mean = stats[2 * row], rstd = stats[2 * row + 1];
-  float xh[CH][8], dx[CH][8];
-  float s1 = 0.f, s2 = 0.f;
-#pragma unroll
-  for (int c = 0; c < CH; ++c) {
-    const int off = (c * 32 + lane) * 8;
-    float g[8], go[8], yv[8];
-    h8_to_f(*reinterpret_cast<const H8*>(gamma + off), g);
-    h8_to_f(*reinterpret_cast<const H8*>(dout + (size_t)row * d + off), go);
-    h8_to_f(*reinterpret_cast<const H8*>(y + (size_t)row * d + off), yv);
-#pragma unroll
-    for (int i = 0; i < 8; ++i) {
-      xh[c][i] = (yv[i] - mean) * rstd;
-      dx[c][i] = go[i] * g[i];
-      s1 += dx[c][i];
-      s2 += dx[c][i] * xh[c][i];
-    }
-  }
-  const float m1 = warp_sum(s1) / (float)d, m2 = warp_sum(s2) / (float)d;
-#pragma unroll
-  for (int c = 0; c < CH; ++c) {
-    const int off = (c * 32 + lane) * 8;
-    float o[8];
-#pragma unroll
-    for (int i = 0; i < 8; ++i) o[i] = rstd * (dx[c][i] - m1 - xh[c][i] * m2);
-    const H8 hv = f_to_h8(o);
-    *reinterpret_cast<H8*>(dy + (size_t)row * d + off) = hv;
-    if (drop_thr16 && dz != nullptr) {
-      float z[8];
-      h8_to_f(hv, z);
-      const uint64_t e = (uint64_t)row * (uint64_t)d + (uint64_t)off;
-      const uint64_t b0 = rng64(seed, e >> 2), b1 = rng64(seed, (e >> 2) + 1);
-#pragma unroll
-      for (int i = 0; i < 4; ++i) {
-        z[i] = dropout_keep(b0, i, drop_thr16) ? z[i] * drop_scale : 0.f;
-        z[4 + i] = dropout_keep(b1, i, drop_thr16) ? z[4 + i] * drop_scale : 0.f;
-      }
-      *reinterpret_cast<H8*>(dz + (size_t)row * d + off) = f_to_h8(z);
-    }
-  }
+// Fused backward for d == THREADS * 8: every thread owns one 16-byte column chunk, a CTA walks groups of LNB_ROWS rows.
+// Per group: one pass over dout / y (kept in registers), ONE block reduction for the 2 * LNB_ROWS row sums, dy (and
+// dz = dy * dropout mask) written, and the column sums dgamma / dbeta / dbias accumulated in registers across all the
+// CTA's rows; one vector reduction per column chunk per CTA at the end. Single pass: dout, y read once; dy, dz written once.
+constexpr int LNB_ROWS = 4;
+
+DEVI void red_add_f32x4(float* addr, float a, float b, float c, float d) {
+  asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(addr), "f"(a), "f"(b), "f"(c), "f"(d) : "memory");
 }
 
-// column part: dgamma += sum_r dout*xhat, dbeta += sum_r dout, dbias += sum_r dz  (dzsrc = dz if dropout else dy)
-__global__ void __launch_bounds__(256)
-ln_bwd_cols_kernel(const __half* __restrict__ dout, const __half* __restrict__ y, const float* __restrict__ stats,
-                   const __half* __restrict__ dzsrc, float* __restrict__ dgamma, float* __restrict__ dbeta,
-                   float* __restrict__ dbias, int rows, int d) {
-  const int ch = blockIdx.x * blockDim.x + threadIdx.x;
-  if (ch * 8 >= d) return;
+template <int THREADS>
+__global__ void __launch_bounds__(THREADS, (THREADS <= 256) ? 2 : 1)
+ln_bwd_fused_kernel(const __half* __restrict__ dout, const __half* __restrict__ y, const __half* __restrict__ gamma,
+                    const float* __restrict__ stats, __half* __restrict__ dy, __half* __restrict__ dz,
+                    float* __restrict__ dgamma, float* __restrict__ dbeta, float* __restrict__ dbias, int rows,
+                    uint32_t drop_thr16, float drop_scale, uint64_t seed) {
+  constexpr int d = THREADS * 8;
+  constexpr int NW = THREADS / 32;
+  __shared__ float red[NW][2 * LNB_ROWS];
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int off = tid * 8;
+  float g[8];
+  h8_to_f(*reinterpret_cast<const H8*>(gamma + off), g);
   float ag[8], ab[8], az[8];
 #pragma unroll
   for (int i = 0; i < 8; ++i) ag[i] = ab[i] = az[i] = 0.f;
-#pragma unroll 4
-  for (int r = blockIdx.y; r < rows; r += gridDim.y) {
-    float go[8], yv[8];
-    h8_to_f(*reinterpret_cast<const H8*>(dout + (size_t)r * d + ch * 8), go);
-    h8_to_f(*reinterpret_cast<const H8*>(y + (size_t)r * d + ch * 8), yv);
-    const float mean = stats[2 * r], rstd = stats[2 * r + 1];
+  const int ngroups = (rows + LNB_ROWS - 1) / LNB_ROWS;
+  for (int grp = blockIdx.x; grp < ngroups; grp += gridDim.x) {
+    const int r0 = grp * LNB_ROWS;
+    H8 hgo[LNB_ROWS], hy[LNB_ROWS];
 #pragma unroll
-    for (int i = 0; i < 8; ++i) {
-      ag[i] += go[i] * (yv[i] - mean) * rstd;
-      ab[i] += go[i];
+    for (int r = 0; r < LNB_ROWS; ++r) {
+      if (r0 + r < rows) {
+        hgo[r] = *reinterpret_cast<const H8*>(dout + (size_t)(r0 + r) * d + off);
+        hy[r] = *reinterpret_cast<const H8*>(y + (size_t)(r0 + r) * d + off);
+      } else {
+#pragma unroll
+        for (int i = 0; i < 4; ++i) hgo[r].h[i] = hy[r].h[i] = __floats2half2_rn(0.f, 0.f);
+      }
     }
-    if (dbias != nullptr) {
-      float z[8];
-      h8_to_f(*reinterpret_cast<const H8*>(dzsrc + (size_t)r * d + ch * 8), z);
+    // the packed fp16 inputs stay in registers (4 regs per row each); xhat / dxhat are recomputed in the second phase
+    float mean[LNB_ROWS], rstd[LNB_ROWS], part[2 * LNB_ROWS];
 #pragma unroll
-      for (int i = 0; i < 8; ++i) az[i] += z[i];
+    for (int r = 0; r < LNB_ROWS; ++r) {
+      const int rr = (r0 + r < rows) ? r0 + r : rows - 1;
+      mean[r] = stats[2 * rr];
+      rstd[r] = stats[2 * rr + 1];
+      float go[8], yv[8];
+      h8_to_f(hgo[r], go);
+      h8_to_f(hy[r], yv);
+      float s1 = 0.f, s2 = 0.f;
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        const float xh = (yv[i] - mean[r]) * rstd[r];
+        const float dx = go[i] * g[i];
+        s1 += dx;
+        s2 += dx * xh;
+        ag[i] += go[i] * xh;  // out-of-range rows contribute go == 0
+        ab[i] += go[i];
+      }
+      part[2 * r] = s1;
+      part[2 * r + 1] = s2;
+    }
+#pragma unroll
+    for (int k = 0; k < 2 * LNB_ROWS; ++k) part[k] = warp_sum(part[k]);
+    __syncthreads();  // previous group's readers are done with `red`
+    if (lane == 0) {
+#pragma unroll
+      for (int k = 0; k < 2 * LNB_ROWS; ++k) red[warp][k] = part[k];
+    }
+    __syncthreads();
+#pragma unroll
+    for (int k = 0; k < 2 * LNB_ROWS; ++k) {
+      float t = 0.f;
+#pragma unroll
+      for (int w = 0; w < NW; ++w) t += red[w][k];
+      part[k] = t * (1.0f / (float)d);
+    }
+#pragma unroll
+    for (int r = 0; r < LNB_ROWS; ++r) {
+      if (r0 + r >= rows) break;
+      float o[8], go[8], yv[8];
+      h8_to_f(hgo[r], go);
+      h8_to_f(hy[r], yv);
+#pragma unroll
+      for (int i = 0; i < 8; ++i)
+        o[i] = rstd[r] * (go[i] * g[i] - part[2 * r] - (yv[i] - mean[r]) * rstd[r] * part[2 * r + 1]);
+      const H8 hv = f_to_h8(o);
+      *reinterpret_cast<H8*>(dy + (size_t)(r0 + r) * d + off) = hv;
+      if (dz != nullptr || dbias != nullptr) {
+        float z[8];
+        h8_to_f(hv, z);  // the GEMM branch sees the fp16-rounded dy
+        if (drop_thr16 && dz != nullptr) {
+          const uint64_t e = (uint64_t)(r0 + r) * (uint64_t)d + (uint64_t)off;
+          const uint64_t b0 = rng64(seed, e >> 2), b1 = rng64(seed, (e >> 2) + 1);
+#pragma unroll
+          for (int i = 0; i < 4; ++i) {
+            z[i] = dropout_keep(b0, i, drop_thr16) ? z[i] * drop_scale : 0.f;
+            z[4 + i] = dropout_keep(b1, i, drop_thr16) ? z[4 + i] * drop_scale : 0.f;
+          }
+          const H8 hz = f_to_h8(z);
+          *reinterpret_cast<H8*>(dz + (size_t)(r0 + r) * d + off) = hz;
+          h8_to_f(hz, z);
+        }
+        if (dbias != nullptr) {
+#pragma unroll
+          for (int i = 0; i < 8; ++i) az[i] += z[i];
+        }
+      }
     }
   }
-#pragma unroll
-  for (int i = 0; i < 8; ++i) {
-    atomicAdd(dgamma + ch * 8 + i, ag[i]);
-    atomicAdd(dbeta + ch * 8 + i, ab[i]);
-    if (dbias != nullptr) atomicAdd(dbias + ch * 8 + i, az[i]);
+  red_add_f32x4(dgamma + off, ag[0], ag[1], ag[2], ag[3]);
+  red_add_f32x4(dgamma + off + 4, ag[4], ag[5], ag[6], ag[7]);
+  red_add_f32x4(dbeta + off, ab[0], ab[1], ab[2], ab[3]);
+  red_add_f32x4(dbeta + off + 4, ab[4], ab[5], ab[6], ab[7]);
+  if (dbias != nullptr) {
+    red_add_f32x4(dbias + off, az[0], az[1], az[2], az[3]);
+    red_add_f32x4(dbias + off + 4, az[4], az[5], az[6], az[7]);
   }
 }
 
@@ -550,22 +583,52 @@ embed_bwd_kernel(const long long* __restrict__ tok, const long long* __restrict_
 }
 
 // ------------------------------------------------------------------------------------------------ small reductions
-// out[c] += sum_r in[r, c]   (fp16 in, fp32 accumulate via one atomic per column per CTA)
+// out[c] += sum_r in[r, c]   (fp16 in, fp32 accumulate). A CTA owns a 64-column strip and a block of rows: thread
+// (cx = tid % 8, ry = tid / 8) streams rows ry, ry + 32, ... of its 16-byte column chunk (a warp reads 4 rows x 128
+// contiguous bytes per step, 8 loads in flight per thread), the 32 row-lanes are folded through shared memory and
+// each column issues ONE atomic per CTA.
+constexpr int CS_ROWS_PER_CTA = 512;
 __global__ void __launch_bounds__(256)
 colsum_kernel(const __half* __restrict__ in, long long ld, float* __restrict__ out, int rows, int n) {
-  const int ch = blockIdx.x * blockDim.x + threadIdx.x;  // 8-column chunk
-  if (ch * 8 >= n) return;
+  __shared__ float red[32][65];
+  const int cx = threadIdx.x & 7, ry = threadIdx.x >> 3;
+  const int col = blockIdx.x * 64 + cx * 8;
+  const int r_begin = blockIdx.y * CS_ROWS_PER_CTA;
+  const int r_end = min(rows, r_begin + CS_ROWS_PER_CTA);
   float acc[8];
 #pragma unroll
   for (int i = 0; i < 8; ++i) acc[i] = 0.f;
-  for (int r = blockIdx.y; r < rows; r += gridDim.y) {
-    float f[8];
-    h8_to_f(*reinterpret_cast<const H8*>(in + (size_t)r * ld + ch * 8), f);
+  if (col < n) {
+    int r = r_begin + ry;
+    for (; r + 7 * 32 < r_end; r += 8 * 32) {
+      H8 v[8];
 #pragma unroll
-    for (int i = 0; i < 8; ++i) acc[i] += f[i];
+      for (int u = 0; u < 8; ++u) v[u] = *reinterpret_cast<const H8*>(in + (size_t)(r + u * 32) * ld + col);
+#pragma unroll
+      for (int u = 0; u < 8; ++u) {
+        float f[8];
+        h8_to_f(v[u], f);
+#pragma unroll
+        for (int i = 0; i < 8; ++i) acc[i] += f[i];
+      }
+    }
+    for (; r < r_end; r += 32) {
+      float f[8];
+      h8_to_f(*reinterpret_cast<const H8*>(in + (size_t)r * ld + col), f);
+#pragma unroll
+      for (int i = 0; i < 8; ++i) acc[i] += f[i];
+    }
   }
 #pragma unroll
-  for (int i = 0; i < 8; ++i) atomicAdd(out + ch * 8 + i, acc[i]);
+  for (int i = 0; i < 8; ++i) red[ry][cx * 8 + i] = acc[i];
+  __syncthreads();
+  if (threadIdx.x < 64) {
+    const int c = blockIdx.x * 64 + threadIdx.x;
+    float t = 0.f;
+#pragma unroll
+    for (int k = 0; k < 32; ++k) t += red[k][threadIdx.x];
+    if (c < n) atomicAdd(out + c, t);
+  }
 }
 
 // dq = dqu + dqv (fp16 out, written into the fused dQKV buffer) and du += colsum(dqu), dv += colsum(dqv)
@@ -690,16 +753,22 @@ extern "C" int db1_layernorm_bwd(const void* dout, const void* y, const void* ga
   const uint32_t t = thr16(drop_p);
   cudaStream_t st = (cudaStream_t)stream;
   const __half *go = (const __half*)dout, *yy = (const __half*)y, *gg = (const __half*)gamma;
-  if (d == 2048 || d == 1024 || d == 512 || d == 256) {
-    const int g8 = (rows + 7) / 8;
+  if (d == 4096 || d == 2048 || d == 1024 || d == 512 || d == 256) {
+    DB1_CHECK_ARG(((uintptr_t)dgamma & 15) == 0 && ((uintptr_t)dbeta & 15) == 0 && ((uintptr_t)dbias & 15) == 0,
+                  "layernorm_bwd: dgamma / dbeta / dbias must be 16-byte aligned");
     __half *o1 = (__half*)dy, *o2 = (__half*)dz;
-    if (d == 2048) ln_bwd_rows_kernel<8><<<g8, 256, 0, st>>>(go, yy, gg, stats, o1, o2, rows, t, dscale(t), seed);
-    else if (d == 1024) ln_bwd_rows_kernel<4><<<g8, 256, 0, st>>>(go, yy, gg, stats, o1, o2, rows, t, dscale(t), seed);
-    else if (d == 512) ln_bwd_rows_kernel<2><<<g8, 256, 0, st>>>(go, yy, gg, stats, o1, o2, rows, t, dscale(t), seed);
-    else ln_bwd_rows_kernel<1><<<g8, 256, 0, st>>>(go, yy, gg, stats, o1, o2, rows, t, dscale(t), seed);
-    dim3 grid((d / 8 + 255) / 256, rows < 592 ? rows : 592);
-    ln_bwd_cols_kernel<<<grid, 256, 0, st>>>(go, yy, stats, (t && dz) ? (const __half*)dz : (const __half*)dy, dgamma,
-                                             dbeta, dbias, rows, d);
+    const int ngroups = (rows + LNB_ROWS - 1) / LNB_ROWS;
+    const int slots = sm_count() * 2;
+    // whole waves of equally loaded CTAs: ceil(ngroups / k) CTAs with k groups each
+    const int k = (ngroups + slots - 1) / slots;
+    const int grid = (ngroups + k - 1) / k;
+#define DB1_LNB(T) ln_bwd_fused_kernel<T><<<grid, T, 0, st>>>(go, yy, gg, stats, o1, o2, dgamma, dbeta, dbias, rows, t, dscale(t), seed)
+    if (d == 4096) DB1_LNB(512);
+    else if (d == 2048) DB1_LNB(256);
+    else if (d == 1024) DB1_LNB(128);
+    else if (d == 512) DB1_LNB(64);
+    else DB1_LNB(32);
+#undef DB1_LNB
   } else {
     const int grid = rows < 148 * 2 ? rows : 148 * 2;
     ln_bwd_kernel<<<grid, LN_THREADS, 0, st>>>(go, yy, gg, stats, (__half*)dy, (__half*)dz, dgamma, dbeta, dbias, rows,
@@ -764,7 +833,7 @@ extern "C" int db1_embed_bwd(const long long* tok, const long long* pos, const i
 
 extern "C" int db1_colsum(const void* in, long long ld, float* out, int rows, int n, void* stream) {
   DB1_CHECK_ARG(in && out && rows > 0 && n > 0 && n % 8 == 0 && ld % 8 == 0, "colsum: bad arguments");
-  dim3 grid((n / 8 + 255) / 256, rows < 296 ? rows : 296);
+  dim3 grid((n + 63) / 64, (rows + CS_ROWS_PER_CTA - 1) / CS_ROWS_PER_CTA);
   colsum_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>((const __half*)in, ld, out, rows, n);
   DB1_CUDA(cudaGetLastError());
   return 0;

@@ -75,9 +75,28 @@ struct GemmCfg {
   static constexpr int TMEM_COLS = 2 * BN;  // 512 or 256
 };
 
-DEVI float gelu_erf(float x) { return 0.5f * x * (1.0f + erff(x * 0.70710678118654752f)); }
-DEVI float gelu_erf_grad(float x) {
-  return 0.5f * (1.0f + erff(x * 0.70710678118654752f)) + x * 0.3989422804014327f * __expf(-0.5f * x * x);
+// Exact-erf GELU (F.gelu default, activations.py:29) and its derivative from ONE exp and ONE reciprocal:
+// erf(t) = 1 - (a1 s + ... + a5 s^5) exp(-t^2), s = 1 / (1 + p t), t >= 0   (Abramowitz & Stegun 7.1.26, |err| <= 1.5e-7,
+// far below the fp16 resolution of the stored activations); exp(-t^2) with t = |x| / sqrt(2) is also the Gaussian
+// factor of gelu'(x) = Phi(x) + x * phi(x). erff() + expf() cost ~4x more issue slots and made the GeGLU-backward
+// epilogue, not the MMA, the pacing stage.
+DEVI void gelu_erf_both(float x, float& gl, float& dgl) {
+  const float t = fabsf(x) * 0.70710678118654752f;
+  const float e = __expf(-t * t);
+  const float s = __fdividef(1.0f, fmaf(0.3275911f, t, 1.0f));
+  float poly = fmaf(s, 1.061405429f, -1.453152027f);
+  poly = fmaf(poly, s, 1.421413741f);
+  poly = fmaf(poly, s, -0.284496736f);
+  poly = fmaf(poly, s, 0.254829592f);
+  const float erf_abs = fmaf(-poly * s, e, 1.0f);
+  const float cdf = 0.5f + 0.5f * copysignf(erf_abs, x);
+  gl = x * cdf;
+  dgl = fmaf(x * 0.3989422804014327f, e, cdf);
+}
+DEVI float gelu_erf(float x) {
+  float a, b;
+  gelu_erf_both(x, a, b);
+  return a;
 }
 
 struct alignas(16) Half8 {
@@ -591,8 +610,10 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
               half8_to_float(hg[ci & 1][g], gg);
 #pragma unroll
               for (int i = 0; i < 8; ++i) {
-                da[i] = dy[i] * gelu_erf(gg[i]);
-                dg[i] = dy[i] * a[i] * gelu_erf_grad(gg[i]);
+                float gl, dgl;
+                gelu_erf_both(gg[i], gl, dgl);
+                da[i] = dy[i] * gl;
+                dg[i] = dy[i] * a[i] * dgl;
               }
               xda[g] = float_to_half8(da);
               xdg[g] = float_to_half8(dg);
