@@ -9,23 +9,9 @@
 
 namespace db1 {
 
-struct alignas(16) H8 {
-  __half2 h[4];
-};
-DEVI void h8_to_f(const H8& v, float (&f)[8]) {
-#pragma unroll
-  for (int i = 0; i < 4; ++i) {
-    float2 t = __half22float2(v.h[i]);
-    f[2 * i] = t.x;
-    f[2 * i + 1] = t.y;
-  }
-}
-DEVI H8 f_to_h8(const float (&f)[8]) {
-  H8 v;
-#pragma unroll
-  for (int i = 0; i < 4; ++i) v.h[i] = __floats2half2_rn(f[2 * i], f[2 * i + 1]);
-  return v;
-}
+typedef Half8 H8;  // 8 x fp16 carried in a uint4 (ptx.cuh): one 128-bit access
+DEVI void h8_to_f(const H8& v, float (&f)[8]) { half8_to_float(v, f); }
+DEVI H8 f_to_h8(const float (&f)[8]) { return float_to_half8(f); }
 
 DEVI float warp_sum(float v) {
 #pragma unroll
@@ -283,8 +269,7 @@ ln_bwd_fused_kernel(const __half* __restrict__ dout, const __half* __restrict__ 
         hgo[r] = *reinterpret_cast<const H8*>(dout + (size_t)(r0 + r) * d + off);
         hy[r] = *reinterpret_cast<const H8*>(y + (size_t)(r0 + r) * d + off);
       } else {
-#pragma unroll
-        for (int i = 0; i < 4; ++i) hgo[r].h[i] = hy[r].h[i] = __floats2half2_rn(0.f, 0.f);
+        hgo[r] = hy[r] = half8_zero();
       }
     }
     // the packed fp16 inputs stay in registers (4 regs per row each); xhat / dxhat are recomputed in the second phase
@@ -572,11 +557,13 @@ embed_bwd_kernel(const long long* __restrict__ tok, const long long* __restrict_
     }
     if (wdst) {
 #pragma unroll
-      for (int i = 0; i < 4; ++i) atomicAdd(reinterpret_cast<__half2*>(wdst + ch * 8) + i, hv.h[i]);
+      for (int i = 0; i < 4; ++i)
+        atomicAdd(reinterpret_cast<__half2*>(wdst + ch * 8) + i, reinterpret_cast<const __half2*>(&hv.u)[i]);
     }
     if (tdst) {
 #pragma unroll
-      for (int i = 0; i < 4; ++i) atomicAdd(reinterpret_cast<__half2*>(tdst + ch * 8) + i, hv.h[i]);
+      for (int i = 0; i < 4; ++i)
+        atomicAdd(reinterpret_cast<__half2*>(tdst + ch * 8) + i, reinterpret_cast<const __half2*>(&hv.u)[i]);
     }
     if (vdst) *reinterpret_cast<H8*>(vdst + ch * 8) = hv;
   }

@@ -29,10 +29,6 @@ constexpr int BM = 128;
 constexpr int BK = 64;
 constexpr int GEMM_THREADS = 320;  // TMA warp + MMA warp + 8 epilogue warps
 constexpr int A_STAGE_BYTES = BM * BK * 2;  // 16 KB
-#ifndef DB1_PF_DIST
-#define DB1_PF_DIST 0
-#endif
-constexpr int PF_DIST = DB1_PF_DIST;  // L2 prefetch distance of the TMA producer, in k-blocks
 
 struct GemmParams {
   int M, N, K;
@@ -65,10 +61,12 @@ struct GemmParams {
   int dbg;  // development switches (DB1_GEMM_DBG): 1 = epilogue skips global stores, 2 = epilogue skips TMEM loads too
 };
 
-template <int BN>
+// CL == 2: the CTA pair of a cluster runs cta_group::2 MMAs (M = 256 across the pair); each CTA stages its own 128
+// rows of A and HALF of the B tile, so a stage is 32 KB instead of 48 KB and the ring gets deeper.
+template <int BN, int CL = 1>
 struct GemmCfg {
-  static constexpr int STAGES = (BN == 256) ? 4 : 6;
-  static constexpr int B_STAGE_BYTES = BN * BK * 2;
+  static constexpr int STAGES = (BN == 256) ? (CL == 2 ? 6 : 4) : 6;
+  static constexpr int B_STAGE_BYTES = BN / CL * BK * 2;
   static constexpr int STAGE_BYTES = A_STAGE_BYTES + B_STAGE_BYTES;
   static constexpr int STAGING_BYTES = 8 * 32 * 80;  // DS epilogue: per-warp 32 rows x (64 B + 16 B pad)
   static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + STAGING_BYTES + 1024 /*align*/ + 256 /*barriers*/;
@@ -99,34 +97,15 @@ DEVI float gelu_erf(float x) {
   return a;
 }
 
-struct alignas(16) Half8 {
-  __half2 h[4];
-};
-DEVI Half8 ld_half8(const __half* p) { return *reinterpret_cast<const Half8*>(p); }
-DEVI void st_half8(__half* p, const Half8& v) { *reinterpret_cast<Half8*>(p) = v; }
-DEVI void half8_to_float(const Half8& v, float (&f)[8]) {
-#pragma unroll
-  for (int i = 0; i < 4; ++i) {
-    float2 t = __half22float2(v.h[i]);
-    f[2 * i] = t.x;
-    f[2 * i + 1] = t.y;
-  }
-}
-DEVI Half8 float_to_half8(const float (&f)[8]) {
-  Half8 v;
-#pragma unroll
-  for (int i = 0; i < 4; ++i) v.h[i] = __floats2half2_rn(f[2 * i], f[2 * i + 1]);
-  return v;
-}
-
 // Store a warp's 32 x 32 fp16 tile (thread = row, hv = its 32 columns) with full-sector writes: the tile is transposed
 // through a per-warp staging buffer so that every store instruction covers 8 rows x 64 contiguous bytes. (16-byte
 // row-strided stores straight from the accumulator layout write half sectors, which the L2 turns into
 // read-modify-write fills: measured 2.5x slower end to end on the K = 2048 GEMMs.)
 DEVI void warp_store_tile(uint8_t* stg, int lane, const Half8 (&hv)[4], __half* base, long long ld, int rows_valid,
                           int cols_valid, bool accumulate) {
+  const uint32_t sbase = smem_u32(stg);
 #pragma unroll
-  for (int g = 0; g < 4; ++g) *reinterpret_cast<Half8*>(stg + lane * 80 + g * 16) = hv[g];
+  for (int g = 0; g < 4; ++g) sts_half8(sbase + lane * 80 + g * 16, hv[g]);
   __syncwarp();
   const int piece = lane & 3;
   const int col = piece * 8;
@@ -134,7 +113,7 @@ DEVI void warp_store_tile(uint8_t* stg, int lane, const Half8 (&hv)[4], __half* 
   for (int k = 0; k < 4; ++k) {
     const int rr = k * 8 + (lane >> 2);
     if (rr < rows_valid && col < cols_valid) {
-      Half8 v = *reinterpret_cast<const Half8*>(stg + rr * 80 + piece * 16);
+      Half8 v = lds_half8(sbase + rr * 80 + piece * 16);
       __half* dst = base + (long long)rr * ld + col;
       if (col + 8 <= cols_valid) {
         if (accumulate) {
@@ -157,6 +136,27 @@ DEVI void warp_store_tile(uint8_t* stg, int lane, const Half8 (&hv)[4], __half* 
   __syncwarp();
 }
 
+// Coalesced load of a warp's 32 x 32 fp16 tile (the mirror image of warp_store_tile): every load instruction covers
+// 8 rows x 64 contiguous bytes; the tile is handed to the row-owning threads through the staging buffer.
+// (Row-strided loads straight into the accumulator layout touch 32 different 128-byte lines per instruction.)
+DEVI void warp_load_tile(uint8_t* stg, int lane, Half8 (&hv)[4], const __half* base, long long ld, int rows_valid,
+                         int cols_valid) {
+  const uint32_t sbase = smem_u32(stg);
+  const int piece = lane & 3;
+  const int col = piece * 8;
+#pragma unroll
+  for (int k = 0; k < 4; ++k) {
+    const int rr = k * 8 + (lane >> 2);
+    Half8 v = half8_zero();
+    if (rr < rows_valid && col < cols_valid) v = ld_half8(base + (long long)rr * ld + col);
+    sts_half8(sbase + rr * 80 + piece * 16, v);
+  }
+  __syncwarp();
+#pragma unroll
+  for (int g = 0; g < 4; ++g) hv[g] = lds_half8(sbase + lane * 80 + g * 16);
+  __syncwarp();
+}
+
 struct TileCoord {
   int mt, nt, z1, z2;
   int kb0, kb1;  // k-block range
@@ -168,7 +168,7 @@ DEVI TileCoord decode_tile(const GemmParams& p, int tile, int MT, int NT, int KB
   TileCoord t;
   int r;
   if (CL == 2) {
-    // `tile` indexes pairs of vertically adjacent tiles; the two CTAs of a cluster share the B tile
+    // `tile` indexes pairs of vertically adjacent tiles: one cta_group::2 MMA tile of 256 rows
     const int MT2 = (MT + 1) / 2;
     t.mt = 2 * (tile % MT2) + crank;
     r = tile / MT2;
@@ -199,7 +199,7 @@ DEVI TileCoord decode_tile(const GemmParams& p, int tile, int MT, int NT, int KB
 template <int BN, int EPI, int CL>
 __global__ void __launch_bounds__(GEMM_THREADS, 1)
 gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const GemmParams p) {
-  using Cfg = GemmCfg<BN>;
+  using Cfg = GemmCfg<BN, CL>;
   constexpr int STAGES = Cfg::STAGES;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
@@ -231,17 +231,18 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
   if (warp == 1) {
     if (lane == 0) {
       for (int i = 0; i < STAGES; ++i) {
-        mbar_init(&full[i], 1);
-        mbar_init(&empty[i], CL);  // with a cluster, the peer's multicast also writes this stage
+        mbar_init(&full[i], 1);   // CL == 2: only the leader's is used; it counts the bytes of both CTAs' loads
+        mbar_init(&empty[i], 1);  // CL == 2: released in both CTAs by the leader's multicast commit
       }
       for (int i = 0; i < 2; ++i) {
         mbar_init(&tfull[i], 1);
-        mbar_init(&tempty[i], 8);
+        mbar_init(&tempty[i], 8 * CL);  // CL == 2: the epilogue warps of BOTH CTAs arrive on the leader's barrier
       }
       mbar_fence_init();
     }
     __syncwarp();
-    tmem_alloc<Cfg::TMEM_COLS>(tmem_slot);
+    if (CL == 2) tmem_alloc2<Cfg::TMEM_COLS>(tmem_slot);
+    else tmem_alloc<Cfg::TMEM_COLS>(tmem_slot);
   }
   tc_fence_before();
   __syncthreads();
@@ -263,68 +264,54 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
           const int az1 = p.a_z1on ? t.z1 : 0, az2 = p.a_z2on ? z2 : 0;
           const int bz1 = p.b_z1on ? t.z1 : 0, bz2 = p.b_z2on ? z2 : 0;
           for (int kb = t.kb0; kb < t.kb1; ++kb) {
-            if (PF_DIST > 0 && kb + PF_DIST < t.kb1) {
-              // pull the operands of a k-block PF_DIST ahead into L2 (DRAM latency >> the smem ring's look-ahead)
-              const int kp = (kb + PF_DIST) * BK;
-              if (!p.a_mn) tma_prefetch_4d(&tmA, kp, m0, az1, az2);
-              else {
-                tma_prefetch_4d(&tmA, m0, kp, az1, az2);
-                tma_prefetch_4d(&tmA, m0 + 64, kp, az1, az2);
-              }
-              if (CL == 2 && BN == 256) {
-                if (!p.b_mn) {
-                  const int row0 = (EPI == DB1_EPI_GEGLU) ? crank * p.F + t.nt * (BN / 2) : t.nt * BN + crank * 128;
-                  tma_prefetch_4d(&tmB, kp, row0, bz1, bz2);
-                } else {
-                  tma_prefetch_4d(&tmB, t.nt * BN + 2 * crank * 64, kp, bz1, bz2);
-                  tma_prefetch_4d(&tmB, t.nt * BN + (2 * crank + 1) * 64, kp, bz1, bz2);
-                }
-              } else if (!p.b_mn) {
-#pragma unroll
-                for (int j = 0; j < BN / 128; ++j)
-                  tma_prefetch_4d(&tmB, kp, (EPI == DB1_EPI_GEGLU) ? j * p.F + t.nt * (BN / 2) : t.nt * BN + j * 128, bz1,
-                                  bz2);
-              } else {
-#pragma unroll
-                for (int j = 0; j < BN / 64; ++j) tma_prefetch_4d(&tmB, t.nt * BN + j * 64, kp, bz1, bz2);
-              }
-            }
             mbar_wait(&empty[s], ph ^ 1);
             uint8_t* sa = smem + s * Cfg::STAGE_BYTES;
             uint8_t* sb = sa + A_STAGE_BYTES;
-            mbar_expect_tx(&full[s], Cfg::STAGE_BYTES);
             const int k0 = kb * BK;
-            if (!p.a_mn) {
-              tma_load_4d(sa, &tmA, &full[s], k0, m0, az1, az2);
-            } else {
-              tma_load_4d(sa, &tmA, &full[s], m0, k0, az1, az2);
-              tma_load_4d(sa + 8192, &tmA, &full[s], m0 + 64, k0, az1, az2);
-            }
-            if (CL == 2 && BN == 256) {
-              // each CTA fetches half of the shared B tile and multicasts it to both
+            if (CL == 2) {
+              // both CTAs' boxes are counted on the leader's barrier (the MMA issuer lives there)
+              if (crank == 0) mbar_expect_tx(&full[s], 2 * Cfg::STAGE_BYTES);
+              if (!p.a_mn) {
+                tma_load_4d_2sm(sa, &tmA, &full[s], k0, m0, az1, az2);
+              } else {
+                tma_load_4d_2sm(sa, &tmA, &full[s], m0, k0, az1, az2);
+                tma_load_4d_2sm(sa + 8192, &tmA, &full[s], m0 + 64, k0, az1, az2);
+              }
+              // this CTA's half of the B tile: rows (K-major) / columns (MN-major) [crank * BN/2, +BN/2)
               if (!p.b_mn) {
-                int row0;
-                if (EPI == DB1_EPI_GEGLU) row0 = crank * p.F + t.nt * (BN / 2);
-                else row0 = t.nt * BN + crank * 128;
-                tma_load_4d_mc(sb + crank * 16384, &tmB, &full[s], k0, row0, bz1, bz2, (uint16_t)3);
+#pragma unroll
+                for (int j = 0; j < BN / 256; ++j) {
+                  int row0;
+                  if (EPI == DB1_EPI_GEGLU) row0 = crank * p.F + t.nt * (BN / 2);
+                  else row0 = t.nt * BN + crank * (BN / 2);
+                  tma_load_4d_2sm(sb + j * 16384, &tmB, &full[s], k0, row0 + j * 128, bz1, bz2);
+                }
               } else {
 #pragma unroll
-                for (int j = 0; j < 2; ++j)
-                  tma_load_4d_mc(sb + (2 * crank + j) * 8192, &tmB, &full[s], t.nt * BN + (2 * crank + j) * 64, k0, bz1,
-                                 bz2, (uint16_t)3);
-              }
-            } else if (!p.b_mn) {
-#pragma unroll
-              for (int j = 0; j < BN / 128; ++j) {
-                int row0;
-                if (EPI == DB1_EPI_GEGLU) row0 = j * p.F + t.nt * (BN / 2);
-                else row0 = t.nt * BN + j * 128;
-                tma_load_4d(sb + j * 16384, &tmB, &full[s], k0, row0, bz1, bz2);
+                for (int j = 0; j < BN / 128; ++j)
+                  tma_load_4d_2sm(sb + j * 8192, &tmB, &full[s], t.nt * BN + crank * (BN / 2) + j * 64, k0, bz1, bz2);
               }
             } else {
+              mbar_expect_tx(&full[s], Cfg::STAGE_BYTES);
+              if (!p.a_mn) {
+                tma_load_4d(sa, &tmA, &full[s], k0, m0, az1, az2);
+              } else {
+                tma_load_4d(sa, &tmA, &full[s], m0, k0, az1, az2);
+                tma_load_4d(sa + 8192, &tmA, &full[s], m0 + 64, k0, az1, az2);
+              }
+              if (!p.b_mn) {
 #pragma unroll
-              for (int j = 0; j < BN / 64; ++j)
-                tma_load_4d(sb + j * 8192, &tmB, &full[s], t.nt * BN + j * 64, k0, bz1, bz2);
+                for (int j = 0; j < BN / 128; ++j) {
+                  int row0;
+                  if (EPI == DB1_EPI_GEGLU) row0 = j * p.F + t.nt * (BN / 2);
+                  else row0 = t.nt * BN + j * 128;
+                  tma_load_4d(sb + j * 16384, &tmB, &full[s], k0, row0, bz1, bz2);
+                }
+              } else {
+#pragma unroll
+                for (int j = 0; j < BN / 64; ++j)
+                  tma_load_4d(sb + j * 8192, &tmB, &full[s], t.nt * BN + j * 64, k0, bz1, bz2);
+              }
             }
             if (++s == STAGES) {
               s = 0;
@@ -336,8 +323,8 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
     }
   } else if (warp == 1) {
     // ------------------------------------------------------------ MMA issuer
-    if (lane == 0) {
-      const uint32_t idesc = umma_idesc(BM, BN, p.a_mn, p.b_mn, 0);
+    if (lane == 0 && crank == 0) {  // CL == 2: the leader issues for the pair
+      const uint32_t idesc = umma_idesc(BM * CL, BN, p.a_mn, p.b_mn, 0);
       const uint32_t a_lbo = p.a_mn ? 8192u : 16u, b_lbo = p.b_mn ? 8192u : 16u;
       const uint32_t a_kadv = p.a_mn ? (2048u >> 4) : (32u >> 4);  // descriptor start-address units of 16 B
       const uint32_t b_kadv = p.b_mn ? (2048u >> 4) : (32u >> 4);
@@ -363,10 +350,11 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
             const uint64_t bdesc = umma_smem_desc(sa + A_STAGE_BYTES, b_lbo, 1024);
 #pragma unroll
             for (int k = 0; k < BK / 16; ++k) {
-              umma_ss(tacc, adesc + (uint64_t)(k * a_kadv), bdesc + (uint64_t)(k * b_kadv), idesc, acc);
+              if (CL == 2) umma_ss2(tacc, adesc + (uint64_t)(k * a_kadv), bdesc + (uint64_t)(k * b_kadv), idesc, acc);
+              else umma_ss(tacc, adesc + (uint64_t)(k * a_kadv), bdesc + (uint64_t)(k * b_kadv), idesc, acc);
               acc = 1;
             }
-            if (CL == 2) umma_commit_mc(&empty[s], (uint16_t)3);
+            if (CL == 2) umma_commit2_mc(&empty[s], (uint16_t)3);
             else umma_commit(&empty[s]);
             if (++s == STAGES) {
               s = 0;
@@ -374,7 +362,8 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
             }
           }
         }
-        umma_commit(&tfull[as]);
+        if (CL == 2) umma_commit2_mc(&tfull[as], (uint16_t)3);
+        else umma_commit(&tfull[as]);
       }
     }
   } else {
@@ -404,17 +393,15 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
         constexpr int CPW = BN / 64;  // chunks per warp
         const int c_first = half * CPW;
         Half8 rs[CPW][4];
-        auto load_resid = [&](int c, Half8 (&dst)[4]) {
-          if (EPI == DB1_EPI_PLAIN && p.resid != nullptr && row_ok) {
+        if (EPI == DB1_EPI_PLAIN && p.resid != nullptr) {  // independent of the accumulator: fetched before the wait
 #pragma unroll
-            for (int g = 0; g < 4; ++g) {
-              const int col = nt * BN + c * 32 + g * 8;
-              if (col < p.N) dst[g] = ld_half8(p.resid + (size_t)row * p.ldr + col);
-            }
+          for (int ci = 0; ci < CPW; ++ci) {
+            const int col0 = nt * BN + (c_first + ci) * 32;
+            if (col0 < p.N)
+              warp_load_tile(stg, lane, rs[ci], p.resid + (size_t)row_base * p.ldr + col0, p.ldr, p.M - row_base,
+                             p.N - col0);
           }
-        };
-#pragma unroll
-        for (int ci = 0; ci < CPW; ++ci) load_resid(c_first + ci, rs[ci]);  // independent of the accumulator
+        }
         mbar_wait(&tfull[as], aph);
         tc_fence_after();
 #pragma unroll
@@ -540,14 +527,12 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
         const int c_first = half * CPW;
         Half8 ha[2][4], hg[2][4];
         auto load_h = [&](int c, Half8 (&da)[4], Half8 (&dg)[4]) {
-          if (EPI == DB1_EPI_DGEGLU && row_ok) {
-#pragma unroll
-            for (int g = 0; g < 4; ++g) {
-              const int n = nt * BN + c * 32 + g * 8;
-              if (n < p.N) {
-                da[g] = ld_half8(p.H + (size_t)row * p.ldh + n);
-                dg[g] = ld_half8(p.H + (size_t)row * p.ldh + p.F + n);
-              }
+          if (EPI == DB1_EPI_DGEGLU) {
+            const int n0 = nt * BN + c * 32;
+            if (n0 < p.N) {
+              const __half* hrow = p.H + (size_t)row_base * p.ldh + n0;
+              warp_load_tile(stg, lane, da, hrow, p.ldh, p.M - row_base, p.N - n0);
+              warp_load_tile(stg, lane, dg, hrow + p.F, p.ldh, p.M - row_base, p.N - n0);
             }
           }
         };
@@ -627,7 +612,10 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
       // release this accumulator stage back to the MMA warp
       tc_fence_before();
       __syncwarp();
-      if (lane == 0) mbar_arrive(&tempty[as]);
+      if (lane == 0) {
+        if (CL == 2) mbar_arrive_leader(&tempty[as]);
+        else mbar_arrive(&tempty[as]);
+      }
     }
   }
 
@@ -636,13 +624,14 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
   if (CL == 2) cluster_sync_all();  // the peer may still multicast into / arrive on this CTA's shared memory
   if (warp == 1) {
     tc_fence_after();
-    tmem_dealloc<Cfg::TMEM_COLS>(tmem_base);
+    if (CL == 2) tmem_dealloc2<Cfg::TMEM_COLS>(tmem_base);
+    else tmem_dealloc<Cfg::TMEM_COLS>(tmem_base);
   }
 }
 
 template <int BN, int EPI, int CL>
 static int launch_gemm_cl(const CUtensorMap& tmA, const CUtensorMap& tmB, const GemmParams& p, cudaStream_t stream) {
-  using Cfg = GemmCfg<BN>;
+  using Cfg = GemmCfg<BN, CL>;
   static bool configured = false;
   if (!configured) {
     DB1_CUDA(cudaFuncSetAttribute(gemm_kernel<BN, EPI, CL>, cudaFuncAttributeMaxDynamicSharedMemorySize,
@@ -671,8 +660,9 @@ static int launch_gemm_cl(const CUtensorMap& tmA, const CUtensorMap& tmB, const 
   return 0;
 }
 
-// Clusters of two CTAs (vertically adjacent tiles sharing the B tile through TMA multicast) cut the L2 -> SM operand
-// traffic per tile from 48 KB to 32 KB per k-block; used whenever both CTAs see the same k-range.
+// CTA pairs (cta_group::2: one 256 x BN MMA over two vertically adjacent 128-row tiles, each CTA staging half of the B
+// tile) cut both the L2 -> SM and the shared-memory operand traffic per tile from 48 KB to 32 KB per k-block; used
+// whenever both CTAs see the same k-range.
 template <int BN, int EPI>
 static int launch_gemm(const CUtensorMap& tmA, const CUtensorMap& tmB, const GemmParams& p, cudaStream_t stream) {
   const bool batched = p.Z1 * p.Z2 > 1;

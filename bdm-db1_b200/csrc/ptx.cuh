@@ -140,6 +140,52 @@ DEVI void umma_commit_mc(uint64_t* bar, uint16_t cta_mask) {
       ::"r"(smem_u32(bar)), "h"(cta_mask)
       : "memory");
 }
+// ---------------------------------------------------------------- CTA-pair (cta_group::2) variants
+// The two CTAs of a cluster (ranks 0/1, one TPC) run ONE M=256 MMA: each supplies 128 rows of A and N/2 rows of B from
+// the same shared-memory offsets and owns the accumulator rows of its own 128-lane TMEM. Per flop every SM then reads
+// and writes half as many B bytes of shared memory as with cta_group::1 (which is shared-memory-bandwidth bound:
+// 12 KB read + 12 KB TMA-written per 128-cycle 128x256x16 MMA against a 128 B/clk port).
+constexpr uint32_t PEER_BIT_MASK = 0xFEFFFFFFu;  // clears the bit that selects the odd CTA of the pair in a shared::cluster address
+
+template <int NCOLS>
+DEVI void tmem_alloc2(uint32_t* smem_slot) {
+  asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(smem_slot)),
+               "r"(NCOLS)
+               : "memory");
+  asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+}
+template <int NCOLS>
+DEVI void tmem_dealloc2(uint32_t taddr) {
+  asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(NCOLS) : "memory");
+}
+DEVI void umma_ss2(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+      ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+// arrive (once all prior cta_group::2 MMAs of this thread completed) on the barrier at this offset in both CTAs
+DEVI void umma_commit2_mc(uint64_t* bar, uint16_t cta_mask) {
+  asm volatile(
+      "tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
+      ::"r"(smem_u32(bar)), "h"(cta_mask)
+      : "memory");
+}
+// TMA load into this CTA's shared memory whose transaction bytes are counted on the LEADER (even) CTA's mbarrier
+DEVI void tma_load_4d_2sm(void* smem_dst, const CUtensorMap* m, uint64_t* bar, int c0, int c1, int c2, int c3) {
+  asm volatile(
+      "cp.async.bulk.tensor.4d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes"
+      " [%0], [%1, {%3, %4, %5, %6}], [%2];"
+      ::"r"(smem_u32(smem_dst)), "l"(m), "r"(smem_u32(bar) & PEER_BIT_MASK), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
+      : "memory");
+}
+// arrive on the barrier at this offset in the leader CTA's shared memory (works from either CTA of the pair)
+DEVI void mbar_arrive_leader(uint64_t* bar) {
+  asm volatile("mbarrier.arrive.shared::cluster.b64 _, [%0];" ::"r"(smem_u32(bar) & PEER_BIT_MASK) : "memory");
+}
+
 DEVI uint32_t cluster_ctarank() {
   uint32_t r;
   asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
@@ -232,6 +278,45 @@ DEVI uint32_t pack_half2(float a, float b) {
 DEVI float2 unpack_half2(uint32_t v) {
   __half2 h = *reinterpret_cast<__half2*>(&v);
   return __half22float2(h);
+}
+// Eight fp16 values moved as ONE 128-bit access. (A struct of four __half2 is copied member-wise by nvcc - four 32-bit
+// LDG/STG per "vector" access, i.e. 4x the memory instructions and quarter-sector writes - so the carrier is a uint4.)
+struct alignas(16) Half8 {
+  uint4 u;
+};
+DEVI Half8 ld_half8(const __half* p) {
+  Half8 v;
+  v.u = *reinterpret_cast<const uint4*>(p);
+  return v;
+}
+DEVI void st_half8(__half* p, const Half8& v) { *reinterpret_cast<uint4*>(p) = v.u; }
+DEVI Half8 lds_half8(uint32_t saddr) {
+  Half8 v;
+  asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(v.u.x), "=r"(v.u.y), "=r"(v.u.z), "=r"(v.u.w) : "r"(saddr));
+  return v;
+}
+DEVI void sts_half8(uint32_t saddr, const Half8& v) {
+  asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(saddr), "r"(v.u.x), "r"(v.u.y), "r"(v.u.z), "r"(v.u.w) : "memory");
+}
+DEVI void half8_to_float(const Half8& v, float (&f)[8]) {
+  float2 t;
+  t = unpack_half2(v.u.x); f[0] = t.x; f[1] = t.y;
+  t = unpack_half2(v.u.y); f[2] = t.x; f[3] = t.y;
+  t = unpack_half2(v.u.z); f[4] = t.x; f[5] = t.y;
+  t = unpack_half2(v.u.w); f[6] = t.x; f[7] = t.y;
+}
+DEVI Half8 float_to_half8(const float (&f)[8]) {
+  Half8 v;
+  v.u.x = pack_half2(f[0], f[1]);
+  v.u.y = pack_half2(f[2], f[3]);
+  v.u.z = pack_half2(f[4], f[5]);
+  v.u.w = pack_half2(f[6], f[7]);
+  return v;
+}
+DEVI Half8 half8_zero() {
+  Half8 v;
+  v.u = make_uint4(0u, 0u, 0u, 0u);
+  return v;
 }
 DEVI void named_bar_sync(int id, int nthreads) {
   asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
