@@ -5,6 +5,8 @@
 //   db1_build_rl_sample_idx     : src/data/helpers.cpp:82-115 semantics (trajectory window index)
 // Compiled with -ffp-contract=off: every float32 operation below is rounded exactly once, in the order the
 // reference's torch expression evaluates it.
+#include "../../include/db1_host.h"
+
 #include <math.h>
 #include <stdint.h>
 #include <string.h>

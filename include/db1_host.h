@@ -1,0 +1,34 @@
+/*
+ * db1_host.h — C ABI of libdb1_host.so: the host-side INTEGER paths of DB1's batch contract (plain C++, no CUDA).
+ * All pointers are HOST pointers. Results are bit-exact with the reference (tests/test_oracle_golden.py).
+ * Return 0 = ok, negative = argument error (db1_build_rl_sample_idx returns the row count).
+ */
+#ifndef DB1_HOST_H_
+#define DB1_HOST_H_
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+/* ContinuousScalarTokenizer.discretize (src/tokenizer/scalar_tokenizer.py:28-45): mu-law (observations only), clamp to
+ * [-1,1], uniform bins; float32 operations rounded once each in the reference's order (-ffp-contract=off). */
+int db1_discretize(const float* x, int32_t* out, long long n, int is_action, int num_bins, float mu, float M);
+/* ContinuousScalarTokenizer.decode (src/tokenizer/scalar_tokenizer.py:47-63). */
+int db1_decode(const int32_t* tok, float* out, long long n, int is_action, int num_bins, float mu, float M);
+/* One RL sample -> (tensor_seq, label, loss_mask, position_id), each seq_len long: action flags / local position ids
+ * (src/data/rl_dataset.py:44-71), join :683-697, pad/truncate to L+1 :711-716 + :865-872, shift :738-746.
+ * obs [T, obs_len] and act [T, act_len] hold vocabulary ids (-1 = image patch slot). */
+int db1_rl_layout(const long long* obs, const long long* act, int T, int obs_len, int act_len, long long sep_id,
+                  int seq_len, long long pad_id, int prepend_trans_num, long long* tensor_seq, long long* label,
+                  float* loss_mask, long long* position_id);
+/* build_rl_sample_idx (src/data/helpers.cpp:82-115): rows (i, j, min(j + transition_num, len_i)) for every trajectory
+ * i and start j in [0, len_i - 1). out == NULL counts only. Returns the number of rows, -2 if out_rows is too small. */
+long long db1_build_rl_sample_idx(const int32_t* path_lengths, long long n_paths, int transition_num, int32_t* out,
+                                  long long out_rows);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* DB1_HOST_H_ */
