@@ -139,22 +139,32 @@ DEVI void warp_store_tile(uint8_t* stg, int lane, const Half8 (&hv)[4], __half* 
 // Coalesced load of a warp's 32 x 32 fp16 tile (the mirror image of warp_store_tile): every load instruction covers
 // 8 rows x 64 contiguous bytes; the tile is handed to the row-owning threads through the staging buffer.
 // (Row-strided loads straight into the accumulator layout touch 32 different 128-byte lines per instruction.)
-DEVI void warp_load_tile(uint8_t* stg, int lane, Half8 (&hv)[4], const __half* base, long long ld, int rows_valid,
-                         int cols_valid) {
-  const uint32_t sbase = smem_u32(stg);
-  const int piece = lane & 3;
-  const int col = piece * 8;
+// Split so the global loads of the NEXT chunk can be in flight while the current one is processed:
+// tile_issue = 4 coalesced LDG.128 into registers; tile_finish = the transpose through the staging buffer.
+DEVI void tile_issue(int lane, Half8 (&v)[4], const __half* base, long long ld, int rows_valid, int cols_valid) {
+  const int col = (lane & 3) * 8;
 #pragma unroll
   for (int k = 0; k < 4; ++k) {
     const int rr = k * 8 + (lane >> 2);
-    Half8 v = half8_zero();
-    if (rr < rows_valid && col < cols_valid) v = ld_half8(base + (long long)rr * ld + col);
-    sts_half8(sbase + rr * 80 + piece * 16, v);
+    v[k] = half8_zero();
+    if (rr < rows_valid && col < cols_valid) v[k] = ld_half8(base + (long long)rr * ld + col);
   }
+}
+DEVI void tile_finish(uint8_t* stg, int lane, const Half8 (&v)[4], Half8 (&hv)[4]) {
+  const uint32_t sbase = smem_u32(stg);
+  const int piece = lane & 3;
+#pragma unroll
+  for (int k = 0; k < 4; ++k) sts_half8(sbase + (k * 8 + (lane >> 2)) * 80 + piece * 16, v[k]);
   __syncwarp();
 #pragma unroll
   for (int g = 0; g < 4; ++g) hv[g] = lds_half8(sbase + lane * 80 + g * 16);
   __syncwarp();
+}
+DEVI void warp_load_tile(uint8_t* stg, int lane, Half8 (&hv)[4], const __half* base, long long ld, int rows_valid,
+                         int cols_valid) {
+  Half8 v[4];
+  tile_issue(lane, v, base, ld, rows_valid, cols_valid);
+  tile_finish(stg, lane, v, hv);
 }
 
 struct TileCoord {
@@ -525,18 +535,16 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
         constexpr int NCH = (EPI == DB1_EPI_GEGLU ? HALF : BN) / 32;
         constexpr int CPW = NCH / 2;
         const int c_first = half * CPW;
-        Half8 ha[2][4], hg[2][4];
-        auto load_h = [&](int c, Half8 (&da)[4], Half8 (&dg)[4]) {
+        Half8 la[2][4], lg[2][4];  // saved pre-activations a | g of the chunk in flight (coalesced pieces)
+        auto issue_h = [&](int c, Half8 (&da)[4], Half8 (&dg)[4]) {
           if (EPI == DB1_EPI_DGEGLU) {
             const int n0 = nt * BN + c * 32;
-            if (n0 < p.N) {
-              const __half* hrow = p.H + (size_t)row_base * p.ldh + n0;
-              warp_load_tile(stg, lane, da, hrow, p.ldh, p.M - row_base, p.N - n0);
-              warp_load_tile(stg, lane, dg, hrow + p.F, p.ldh, p.M - row_base, p.N - n0);
-            }
+            const __half* hrow = p.H + (size_t)row_base * p.ldh + n0;
+            tile_issue(lane, da, hrow, p.ldh, p.M - row_base, p.N - n0);
+            tile_issue(lane, dg, hrow + p.F, p.ldh, p.M - row_base, p.N - n0);
           }
         };
-        load_h(c_first, ha[0], hg[0]);
+        issue_h(c_first, la[0], lg[0]);
         mbar_wait(&tfull[as], aph);
         tc_fence_after();
 #pragma unroll
@@ -581,7 +589,10 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
             warp_store_tile(stg, lane, xg, p.H + (size_t)row_base * p.ldh + p.F + n0, p.ldh, rows_valid, 32, false);
             warp_store_tile(stg, lane, xy, p.C + (size_t)row_base * p.ldc + n0, p.ldc, rows_valid, 32, false);
           } else {
-            if (ci + 1 < CPW) load_h(c + 1, ha[(ci + 1) & 1], hg[(ci + 1) & 1]);
+            if (ci + 1 < CPW) issue_h(c + 1, la[(ci + 1) & 1], lg[(ci + 1) & 1]);
+            Half8 ha[4], hg[4];
+            tile_finish(stg, lane, la[ci & 1], ha);
+            tile_finish(stg, lane, lg[ci & 1], hg);
             tmem_ld_wait();
             const int n0 = nt * BN + c * 32;
             if (n0 >= p.N) break;  // warp-uniform
@@ -591,8 +602,8 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
               float dy[8], a[8], gg[8], da[8], dg[8];
 #pragma unroll
               for (int i = 0; i < 8; ++i) dy[i] = __uint_as_float(ra[g * 8 + i]) * p.alpha;
-              half8_to_float(ha[ci & 1][g], a);
-              half8_to_float(hg[ci & 1][g], gg);
+              half8_to_float(ha[g], a);
+              half8_to_float(hg[g], gg);
 #pragma unroll
               for (int i = 0; i < 8; ++i) {
                 float gl, dgl;

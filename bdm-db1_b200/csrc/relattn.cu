@@ -38,6 +38,9 @@ struct AttnParams {
   float* lse2;
   __half* P;
   int mode;
+  __half* dS;          // mode 2
+  const float* Drow;   // mode 2: rowsum(dO * O) [B,H,L]
+  float scale;         // mode 2: softmax scale (natural domain) applied to dS
 };
 
 template <int D>
@@ -58,7 +61,8 @@ template <int D>
 __global__ void __launch_bounds__(AT_THREADS, 1)
 relattn_fwd_kernel(const __grid_constant__ CUtensorMap tmQu, const __grid_constant__ CUtensorMap tmQv,
                    const __grid_constant__ CUtensorMap tmK, const __grid_constant__ CUtensorMap tmV,
-                   const __grid_constant__ CUtensorMap tmR, const AttnParams p) {
+                   const __grid_constant__ CUtensorMap tmR, const __grid_constant__ CUtensorMap tmDO,
+                   const AttnParams p) {
   using SM = AttnSmem<D>;
   extern __shared__ __align__(1024) uint8_t smem[];
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + SM::BARS);
@@ -91,6 +95,7 @@ relattn_fwd_kernel(const __grid_constant__ CUtensorMap tmQu, const __grid_consta
     tma_prefetch_desc(&tmK);
     tma_prefetch_desc(&tmV);
     tma_prefetch_desc(&tmR);
+    if (p.mode == 2) tma_prefetch_desc(&tmDO);
   }
   if (warp == 1) {
     if (lane == 0) {
@@ -119,21 +124,23 @@ relattn_fwd_kernel(const __grid_constant__ CUtensorMap tmQu, const __grid_consta
   if (warp == 0) {
     // ------------------------------------------------------------------ TMA producer
     if (lane == 0) {
-      mbar_expect_tx(bar_q, 2 * SM::TILE);
+      mbar_expect_tx(bar_q, (p.mode == 2 ? 3 : 2) * SM::TILE);
 #pragma unroll
       for (int s = 0; s < NSLAB; ++s) {
         tma_load_4d(smem + SM::QU + s * 16384, &tmQu, bar_q, s * 64, I0, h, b);
         tma_load_4d(smem + SM::QV + s * 16384, &tmQv, bar_q, s * 64, I0, h, b);
+        if (p.mode == 2) tma_load_4d(smem + SM::PT + s * 16384, &tmDO, bar_q, s * 64, I0, h, b);  // dO_I lives where P would
       }
       for (int st = 0; st < nsteps; ++st) {
         const int J0 = (I - st) * 128;
         const int cb = p.L - 128 - I0 + J0;  // first row of the new chunk of r
         if (st > 0) mbar_wait(bar_kfree, (st - 1) & 1);
-        mbar_expect_tx(bar_k, 2 * SM::TILE);
+        mbar_expect_tx(bar_k, (p.mode == 2 ? 3 : 2) * SM::TILE);
 #pragma unroll
         for (int s = 0; s < NSLAB; ++s) {
           tma_load_4d(smem + SM::KT + s * 16384, &tmK, bar_k, s * 64, J0, h, b);
           tma_load_4d(smem + SM::RT + s * 16384, &tmR, bar_k, s * 64, cb, h, 0);
+          if (p.mode == 2) tma_load_4d(smem + SM::VT + s * 16384, &tmV, bar_k, s * 64, J0, h, b);
         }
         if (p.mode == 0) {
           if (st > 0) mbar_wait(bar_o, (st - 1) & 1);
@@ -163,6 +170,14 @@ relattn_fwd_kernel(const __grid_constant__ CUtensorMap tmQu, const __grid_consta
         for (int k = 0; k < D / 16; ++k) {
           const uint32_t off = (k >> 2) * 16384 + (k & 3) * 32;
           umma_ss(tbd, umma_smem_desc(qv + off, 16, 1024), umma_smem_desc(rt + off, 16, 1024), idesc_s, k ? 1u : 0u);
+        }
+        if (p.mode == 2) {
+          // dP = dO_I . V_J^T into the columns the forward uses for O (same K-major x K-major form as the scores)
+#pragma unroll
+          for (int k = 0; k < D / 16; ++k) {
+            const uint32_t off = (k >> 2) * 16384 + (k & 3) * 32;
+            umma_ss(T_O, umma_smem_desc(pt + off, 16, 1024), umma_smem_desc(vt + off, 16, 1024), idesc_s, k ? 1u : 0u);
+          }
         }
         umma_commit(bar_kfree);
         umma_commit(bar_s);
@@ -197,7 +212,9 @@ relattn_fwd_kernel(const __grid_constant__ CUtensorMap tmQu, const __grid_consta
     uint8_t* prow = smem + SM::PT + r * 128;
     float m_run = NEG_BIG, l_run = 0.f;
     float lse_row = 0.f;
-    if (p.mode == 1) lse_row = (i < p.L) ? p.lse2[((long long)b * p.H + h) * p.L + i] : 0.f;
+    float d_row = 0.f;
+    if (p.mode >= 1) lse_row = (i < p.L) ? p.lse2[((long long)b * p.H + h) * p.L + i] : 0.f;
+    if (p.mode == 2) d_row = (i < p.L) ? p.Drow[((long long)b * p.H + h) * p.L + i] : 0.f;
 
     for (int st = 0; st < nsteps; ++st) {
       const int J0 = (I - st) * 128;
@@ -284,12 +301,30 @@ relattn_fwd_kernel(const __grid_constant__ CUtensorMap tmQu, const __grid_consta
             const int chunk = ((cc & 1) * 4 + g) ^ (r & 7);
             *reinterpret_cast<uint4*>(dst + chunk * 16) = make_uint4(pk[4 * g], pk[4 * g + 1], pk[4 * g + 2], pk[4 * g + 3]);
           }
-        } else if (i < p.L) {
-          __half* dst = p.P + (((long long)b * p.H + h) * p.L + i) * p.L + J0 + cc * 32;
+        } else {
+          uint32_t dk[16];
+          if (p.mode == 2) {
+            // dS = P * (dP - D) * scale; masked entries have P == 0 exactly
+            uint32_t dp[32];
+            tmem_ld32(T_O + lane_off + cc * 32, dp);
+            tmem_ld_wait();
 #pragma unroll
-          for (int g = 0; g < 4; ++g)
-            if (J0 + cc * 32 + g * 8 < p.L)
-              *reinterpret_cast<uint4*>(dst + g * 8) = make_uint4(pk[4 * g], pk[4 * g + 1], pk[4 * g + 2], pk[4 * g + 3]);
+            for (int t = 0; t < 16; ++t) {
+              const float2 pp = unpack_half2(pk[t]);
+              dk[t] = pack_half2(pp.x * (__uint_as_float(dp[2 * t]) - d_row) * p.scale,
+                                 pp.y * (__uint_as_float(dp[2 * t + 1]) - d_row) * p.scale);
+            }
+          }
+          if (i < p.L) {
+            const long long off = (((long long)b * p.H + h) * p.L + i) * p.L + J0 + cc * 32;
+#pragma unroll
+            for (int g = 0; g < 4; ++g)
+              if (J0 + cc * 32 + g * 8 < p.L) {
+                *reinterpret_cast<uint4*>(p.P + off + g * 8) = make_uint4(pk[4 * g], pk[4 * g + 1], pk[4 * g + 2], pk[4 * g + 3]);
+                if (p.mode == 2)
+                  *reinterpret_cast<uint4*>(p.dS + off + g * 8) = make_uint4(dk[4 * g], dk[4 * g + 1], dk[4 * g + 2], dk[4 * g + 3]);
+              }
+          }
         }
       }
       l_run += sum;
@@ -354,7 +389,7 @@ static int launch_attn(const CUtensorMap* tm, const AttnParams& p, cudaStream_t 
     configured = true;
   }
   dim3 grid((p.L + 127) / 128, p.H, p.B);
-  relattn_fwd_kernel<D><<<grid, AT_THREADS, SM::TOTAL, stream>>>(tm[0], tm[1], tm[2], tm[3], tm[4], p);
+  relattn_fwd_kernel<D><<<grid, AT_THREADS, SM::TOTAL, stream>>>(tm[0], tm[1], tm[2], tm[3], tm[4], tm[5], p);
   DB1_CUDA(cudaGetLastError());
   return 0;
 }
@@ -363,29 +398,52 @@ static int launch_attn(const CUtensorMap* tm, const AttnParams& p, cudaStream_t 
 
 using namespace db1;
 
-extern "C" int db1_relattn_fwd(const void* qu, const void* qv, const void* k, const void* v, long long ld_qkv,
-                               const void* r, long long ld_r, void* out, long long ld_out, float* lse2, void* probs,
-                               int B, int L, int H, int dh, int window, float scale, int mode, void* stream_) {
-  cudaStream_t stream = (cudaStream_t)stream_;
+static int relattn_launch(const void* qu, const void* qv, const void* k, const void* v, long long ld_qkv,
+                          const void* r, long long ld_r, void* out, long long ld_out, float* lse2, void* probs,
+                          const void* dout, long long ld_do, const float* drow, void* ds, int B, int L, int H, int dh,
+                          int window, float scale, int mode, cudaStream_t stream) {
   DB1_CHECK_ARG(qu && qv && k && r && lse2, "relattn: null pointer");
-  DB1_CHECK_ARG(mode == 0 || mode == 1, "relattn: mode must be 0 (O, LSE) or 1 (P)");
-  DB1_CHECK_ARG((mode == 0 && v && out) || (mode == 1 && probs), "relattn: missing output for mode %d", mode);
   DB1_CHECK_ARG(B > 0 && L > 0 && H > 0, "relattn: bad shape B=%d L=%d H=%d", B, L, H);
   DB1_CHECK_ARG(dh % 8 == 0 && dh >= 8 && dh <= 128, "relattn: head dim %d unsupported (multiple of 8, <= 128)", dh);
   DB1_CHECK_ARG(L % 8 == 0, "relattn: sequence length %d must be a multiple of 8", L);
-  DB1_CHECK_ARG(ld_qkv % 8 == 0 && ld_r % 8 == 0 && ld_out % 8 == 0, "relattn: row strides must be multiples of 8");
+  DB1_CHECK_ARG(ld_qkv % 8 == 0 && ld_r % 8 == 0 && ld_out % 8 == 0 && ld_do % 8 == 0,
+                "relattn: row strides must be multiples of 8");
   DB1_CHECK_ARG(window > 0, "relattn: window (mem_len) must be > 0; mem_len == 0 masks every key");
   AttnParams p;
   p.L = L; p.H = H; p.B = B; p.dh = dh; p.window = window;
   p.scale_log2 = scale * 1.4426950408889634f;
   p.O = (__half*)out; p.ldo = ld_out; p.lse2 = lse2; p.P = (__half*)probs; p.mode = mode;
-  CUtensorMap tm[5];
+  p.dS = (__half*)ds; p.Drow = drow; p.scale = scale;
+  CUtensorMap tm[6];
   int e;
   if ((e = make_head_map(&tm[0], qu, dh, L, H, B, ld_qkv))) return e;
   if ((e = make_head_map(&tm[1], qv, dh, L, H, B, ld_qkv))) return e;
   if ((e = make_head_map(&tm[2], k, dh, L, H, B, ld_qkv))) return e;
-  if ((e = make_head_map(&tm[3], mode == 0 ? v : k, dh, L, H, B, ld_qkv))) return e;
+  if ((e = make_head_map(&tm[3], mode == 1 ? k : v, dh, L, H, B, ld_qkv))) return e;
   if ((e = make_head_map(&tm[4], r, dh, L, H, 1, ld_r))) return e;
+  if (mode == 2) {
+    if ((e = make_head_map(&tm[5], dout, dh, L, H, B, ld_do))) return e;
+  } else {
+    tm[5] = tm[2];
+  }
   if (dh <= 64) return launch_attn<64>(tm, p, stream);
   return launch_attn<128>(tm, p, stream);
+}
+
+extern "C" int db1_relattn_fwd(const void* qu, const void* qv, const void* k, const void* v, long long ld_qkv,
+                               const void* r, long long ld_r, void* out, long long ld_out, float* lse2, void* probs,
+                               int B, int L, int H, int dh, int window, float scale, int mode, void* stream_) {
+  DB1_CHECK_ARG(mode == 0 || mode == 1, "relattn: mode must be 0 (O, LSE) or 1 (P)");
+  DB1_CHECK_ARG((mode == 0 && v && out) || (mode == 1 && probs), "relattn: missing output for mode %d", mode);
+  return relattn_launch(qu, qv, k, v, ld_qkv, r, ld_r, out, ld_out, lse2, probs, nullptr, 0, nullptr, nullptr, B, L, H,
+                        dh, window, scale, mode, (cudaStream_t)stream_);
+}
+
+extern "C" int db1_relattn_bwd_ds(const void* qu, const void* qv, const void* k, const void* v, long long ld_qkv,
+                                  const void* r, long long ld_r, const void* dout, long long ld_do, const float* lse2,
+                                  const float* drow, void* probs, void* ds, int B, int L, int H, int dh, int window,
+                                  float scale, void* stream_) {
+  DB1_CHECK_ARG(v && dout && drow && probs && ds, "relattn_bwd_ds: null pointer");
+  return relattn_launch(qu, qv, k, v, ld_qkv, r, ld_r, nullptr, 0, const_cast<float*>(lse2), probs, dout, ld_do, drow,
+                        ds, B, L, H, dh, window, scale, 2, (cudaStream_t)stream_);
 }

@@ -116,16 +116,12 @@ class AttnBlockFn(torch.autograd.Function):
         P = _workspace("P", (B, H, L, L), f16, dev)
         dS = _workspace("dS", (B, H, L, L), f16, dev)
         dSr = _workspace("dSr", (B, H, L, L), f16, dev)
-        ops.relattn_fwd(qkv4, rk, None, lse2, B, L, H, dh, window, scale, probs=P)
+        ops.relattn_bwd_ds(qkv4, rk, do, lse2, Drow, P, dS, B, L, H, dh, window, scale)
         qu = qkv4[:, 0:d]
         qv = qkv4[:, d:2 * d]
         kk = qkv4[:, 2 * d:3 * d]
-        vv = qkv4[:, 3 * d:4 * d]
         LL = L * L
         sz = (LL, H * LL)
-        ops.gemm(do, vv, dS, L, L, dh, lda=d, ldb=4 * d, ldc=L, epilogue=ops.EPI_DS, alpha=scale, Z1=H, Z2=B,
-                 a_z=(dh, L * d), b_z=(dh, L * 4 * d), c_z=sz, skip_upper=True, P=P, Drow=Drow,
-                 window=window)
         ops.rel_unshift(dS, dSr, B * H, L)
         dqkv = torch.empty(rows, 3 * d, dtype=f16, device=dev)
         ops.gemm(P, do, dqkv[:, 2 * d:], L, dh, L, lda=L, ldb=d, ldc=3 * d, a_mn=True, b_mn=True, Z1=H, Z2=B,

@@ -141,6 +141,21 @@ def relattn_fwd(qkv4, r, out, lse2, B, L, H, dh, window, scale, probs=None):
         ptr(lse2), ptr(probs), B, L, H, dh, int(window), C.c_float(scale), mode, cur_stream()), "db1_relattn_fwd")
 
 
+def relattn_bwd_ds(qkv4, r, dout, lse2, drow, probs, ds, B, L, H, dh, window, scale):
+    """P and dS = P * (dO V^T - D) * scale for the attention backward; include/db1_sm100.h:db1_relattn_bwd_ds."""
+    _need_cuda_half(qkv4, r, dout, probs, ds)
+    d = H * dh
+    es = qkv4.element_size()
+    base = qkv4.data_ptr()
+    pairs = L * (L + 1) / 2.0 if window >= L else (window * (window + 1) / 2.0 + (L - window) * window)
+    with _Launch("relattn_bwd_ds", 1, B * H * pairs * dh * 6.0):
+      check(_lib.lib().db1_relattn_bwd_ds(
+        C.c_void_p(base), C.c_void_p(base + d * es), C.c_void_p(base + 2 * d * es), C.c_void_p(base + 3 * d * es),
+        C.c_longlong(qkv4.stride(0)), ptr(r), C.c_longlong(r.stride(0)), ptr(dout), C.c_longlong(dout.stride(0)),
+        _f32(lse2), _f32(drow), ptr(probs), ptr(ds), B, L, H, dh, int(window), C.c_float(scale), cur_stream()),
+        "db1_relattn_bwd_ds")
+
+
 def _f32(t):
     if t is not None and (not t.is_cuda or t.dtype != torch.float32):
         raise _lib.Db1Error("expected a CUDA fp32 tensor, got %s on %s" % (t.dtype, t.device))

@@ -104,6 +104,14 @@ int db1_relattn_fwd(const void* qu, const void* qv, const void* k, const void* v
                     long long ld_r, void* out, long long ld_out, float* lse2, void* probs, int B, int L, int H, int dh,
                     int window, float scale, int mode, void* stream);
 
+/* Attention backward, first half (same tiling as the forward): recomputes P = softmax(S) from the saved LSE, forms
+ * dP = dO . V^T on the tensor cores and writes both P and dS = P * (dP - D) * scale ([B,H,L,L] fp16, visited causal
+ * tiles only; D = rowsum(dO * O) from db1_rowdot). Adjoint of transformer_xl.py:173-225; the contractions that consume
+ * P / dS (dV, dK, dQ, dR) are db1_gemm_f16 calls. */
+int db1_relattn_bwd_ds(const void* qu, const void* qv, const void* k, const void* v, long long ld_qkv, const void* r,
+                       long long ld_r, const void* dout, long long ld_do, const float* lse2, const float* drow,
+                       void* probs, void* ds, int B, int L, int H, int dh, int window, float scale, void* stream);
+
 /* ------------------------------------------------------------------------------------------------------------------
  * HBM-bound kernels (single pass over the large operand, 16-byte vector accesses, fp32 math).
  * ------------------------------------------------------------------------------------------------------------------ */

@@ -52,3 +52,44 @@ def test_relattn_fwd_matches_oracle(cuda, B, L, H, dh, window):
     ops.relattn_fwd(qkv4, r, None, lse2, B, L, H, dh, window, scale, probs=probs)
     torch.cuda.synchronize()
     assert (probs.cpu().float() - p).abs().max().item() < 2e-3
+
+
+@pytest.mark.parametrize("B,L,H,dh,window", [(2, 256, 2, 128, 1 << 20), (1, 512, 2, 128, 200), (2, 256, 4, 32, 1 << 20),
+                                             (1, 200, 2, 64, 77), (1, 1024, 1, 128, 1024)])
+def test_relattn_bwd_ds_matches_autograd(cuda, B, L, H, dh, window):
+    """P and dS = dLoss/dS (pre-softmax scores, scale folded in) from the fused recompute kernel vs fp32 autograd of
+    the oracle's score/softmax/value restatement on the same fp16-rounded operands."""
+    from db1_sm100 import ops
+    from oracle import db1_oracle as orc
+    d = H * dh
+    g = torch.Generator().manual_seed(2)
+    qu = torch.randn(B, L, H, dh, generator=g).half()
+    qv = torch.randn(B, L, H, dh, generator=g).half()
+    k = torch.randn(B, L, H, dh, generator=g).half()
+    v = torch.randn(B, L, H, dh, generator=g).half()
+    rk = torch.randn(L, H, dh, generator=g).half()
+    do = torch.randn(B, L, H, dh, generator=g).half()
+    scale = 1.0 / math.sqrt(dh)
+    ok = orc.attention_mask_ok(L, L, window, True)
+    zero = torch.zeros(H, dh)
+    _, _, s_ac = orc.rel_attention_core(qu.float(), k.float(), v.float(), rk.float() * 0, zero, zero, ok, scale)
+    _, _, s_bd = orc.rel_attention_core(qv.float(), k.float() * 0, v.float(), rk.float(), zero, zero, ok, scale)
+    s = torch.where(ok[None, None], s_ac + s_bd, torch.full((), -1e30)).requires_grad_(True)  # already scaled
+    p = torch.softmax(s, -1)
+    o = torch.einsum("bhij,bjhd->bihd", p, v.float())
+    (o * do.float()).sum().backward()
+    ds_ref = s.grad * scale  # the kernel returns dLoss/d(unscaled score) = dLoss/dS * scale
+    qkv4 = torch.cat([x.reshape(B * L, d) for x in (qu, qv, k, v)], 1).contiguous().to(cuda)
+    r = rk.reshape(L, d).contiguous().to(cuda)
+    do_d = do.reshape(B * L, d).contiguous().to(cuda)
+    out = torch.zeros(B * L, d, dtype=torch.half, device=cuda)
+    lse2 = torch.zeros(B, H, L, dtype=torch.float32, device=cuda)
+    ops.relattn_fwd(qkv4, r, out, lse2, B, L, H, dh, window, scale)
+    drow = torch.empty(B, H, L, dtype=torch.float32, device=cuda)
+    ops.rowdot(do_d, out, drow, B, L, H, dh)
+    P = torch.zeros(B, H, L, L, dtype=torch.half, device=cuda)
+    dS = torch.zeros(B, H, L, L, dtype=torch.half, device=cuda)
+    ops.relattn_bwd_ds(qkv4, r, do_d, lse2, drow, P, dS, B, L, H, dh, window, scale)
+    torch.cuda.synchronize()
+    assert (P.cpu().float() - p.detach()).abs().max().item() < 2e-3
+    assert _rel(dS.cpu(), ds_ref) < 5e-3  # D comes from the fp16-rounded O; dS itself is stored in fp16
