@@ -73,6 +73,7 @@ relattn_fwd_kernel(const __grid_constant__ CUtensorMap tmQu, const __grid_consta
   uint64_t* bar_s = bars + 4;
   uint64_t* bar_p = bars + 5;
   uint64_t* bar_o = bars + 6;
+  uint64_t* bar_s1 = bars + 7;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 8);
 
   const int warp = threadIdx.x >> 5;
@@ -106,6 +107,7 @@ relattn_fwd_kernel(const __grid_constant__ CUtensorMap tmQu, const __grid_consta
       mbar_init(bar_s, 1);
       mbar_init(bar_p, 4);
       mbar_init(bar_o, 1);
+      mbar_init(bar_s1, 4);
       mbar_fence_init();
     }
     __syncwarp();
@@ -152,6 +154,8 @@ relattn_fwd_kernel(const __grid_constant__ CUtensorMap tmQu, const __grid_consta
     }
   } else if (warp == 1) {
     // ------------------------------------------------------------------ MMA issuer
+    // Step st's scores are issued as soon as the softmax warps have pulled step st-1's S / band out of TMEM (bar_s1),
+    // i.e. they run under step st-1's exponentials; P.V (or dP) follows when P has been published (bar_p).
     if (lane == 0) {
       const uint32_t idesc_s = umma_idesc(128, 128, 0, 0, 0);
       const uint32_t idesc_o = umma_idesc(128, D, 0, 1, 0);
@@ -171,24 +175,29 @@ relattn_fwd_kernel(const __grid_constant__ CUtensorMap tmQu, const __grid_consta
           const uint32_t off = (k >> 2) * 16384 + (k & 3) * 32;
           umma_ss(tbd, umma_smem_desc(qv + off, 16, 1024), umma_smem_desc(rt + off, 16, 1024), idesc_s, k ? 1u : 0u);
         }
-        if (p.mode == 2) {
-          // dP = dO_I . V_J^T into the columns the forward uses for O (same K-major x K-major form as the scores)
+        if (p.mode != 2) umma_commit(bar_kfree);  // mode 2: V_J (same load group) is still needed by dP
+        umma_commit(bar_s);
+      };
+      auto issue_dp = [&](int st) {
+        // dP = dO_I . V_J^T into the columns the forward uses for O (same K-major x K-major form as the scores)
 #pragma unroll
-          for (int k = 0; k < D / 16; ++k) {
-            const uint32_t off = (k >> 2) * 16384 + (k & 3) * 32;
-            umma_ss(T_O, umma_smem_desc(pt + off, 16, 1024), umma_smem_desc(vt + off, 16, 1024), idesc_s, k ? 1u : 0u);
-          }
+        for (int k = 0; k < D / 16; ++k) {
+          const uint32_t off = (k >> 2) * 16384 + (k & 3) * 32;
+          umma_ss(T_O, umma_smem_desc(pt + off, 16, 1024), umma_smem_desc(vt + off, 16, 1024), idesc_s, k ? 1u : 0u);
         }
         umma_commit(bar_kfree);
-        umma_commit(bar_s);
+        umma_commit(bar_o);
       };
       mbar_wait(bar_q, 0);
       tc_fence_after();
       issue_scores(0);
+      if (p.mode == 2) issue_dp(0);
       for (int st = 0; st < nsteps; ++st) {
-        mbar_wait(bar_p, st & 1);
+        mbar_wait(bar_s1, st & 1);
         tc_fence_after();
         if (st + 1 < nsteps) issue_scores(st + 1);
+        mbar_wait(bar_p, st & 1);
+        tc_fence_after();
         if (p.mode == 0) {
           mbar_wait(bar_v, st & 1);
           tc_fence_after();
@@ -198,8 +207,10 @@ relattn_fwd_kernel(const __grid_constant__ CUtensorMap tmQu, const __grid_consta
             const uint64_t bdesc = umma_smem_desc(vt + k * 2048, 16384, 1024);
             umma_ss(T_O, adesc, bdesc, idesc_o, (st | k) ? 1u : 0u);
           }
+          umma_commit(bar_o);
+        } else if (p.mode == 2) {
+          if (st + 1 < nsteps) issue_dp(st + 1);  // the softmax warps are done reading dP(st)
         }
-        umma_commit(bar_o);
       }
     }
   } else {
@@ -208,22 +219,27 @@ relattn_fwd_kernel(const __grid_constant__ CUtensorMap tmQu, const __grid_consta
     const int r = q * 32 + lane;
     const int i = I0 + r;
     const uint32_t lane_off = (uint32_t)(q * 32) << 16;
-    float* stg = reinterpret_cast<float*>(smem + SM::STG) + (warp - 2) * 32 * STG_PITCH + lane * STG_PITCH;
+    uint8_t* wstg = smem + SM::STG + (warp - 2) * 32 * STG_PITCH * 4;  // this warp's staging area (8704 B)
+    float* stg = reinterpret_cast<float*>(wstg) + lane * STG_PITCH;
     uint8_t* prow = smem + SM::PT + r * 128;
     float m_run = NEG_BIG, l_run = 0.f;
     float lse_row = 0.f;
     float d_row = 0.f;
     if (p.mode >= 1) lse_row = (i < p.L) ? p.lse2[((long long)b * p.H + h) * p.L + i] : 0.f;
     if (p.mode == 2) d_row = (i < p.L) ? p.Drow[((long long)b * p.H + h) * p.L + i] : 0.f;
+    const long long zrow0 = (((long long)b * p.H + h) * p.L + I0 + q * 32) * p.L;  // first row of this warp in P / dS
 
     for (int st = 0; st < nsteps; ++st) {
       const int J0 = (I - st) * 128;
       const uint32_t tnew = T_BD + (st & 1) * 128, tprev = T_BD + ((st + 1) & 1) * 128;
+      // interior tiles need no predicate: every (i, j) is causal, inside the window and inside the sequence
+      const bool need_mask = !(J0 + 127 <= I0 && I0 + 127 - J0 < p.window && I0 + 127 < p.L);
       mbar_wait(bar_s, st & 1);
       tc_fence_after();
-      // ---- pass 1: combine content + shifted position scores, mask, row max; write the result back over S
+      // ---- pass 1: content + shifted position scores -> registers (raw, unscaled), row max
+      float sc[4][32];
       float mx = NEG_BIG;
-#pragma unroll 1
+#pragma unroll
       for (int cc = 0; cc < 4; ++cc) {
         uint32_t s[32], w0[32], w1[32];
         const int blk = cc - q + 3;  // 32-column block of the 256-wide [new | prev] window
@@ -238,18 +254,28 @@ relattn_fwd_kernel(const __grid_constant__ CUtensorMap tmQu, const __grid_consta
         }
         __syncwarp();
         const float* rd = stg + (31 - lane);
+        if (need_mask) {
 #pragma unroll
-        for (int t = 0; t < 32; ++t) {
-          const int j = J0 + cc * 32 + t;
-          const bool ok = (j <= i) && (i - j < p.window) && (j < p.L);
-          const float sc = ok ? (__uint_as_float(s[t]) + rd[t]) * p.scale_log2 : NEG_BIG;
-          mx = fmaxf(mx, sc);
-          s[t] = __float_as_uint(sc);
+          for (int t = 0; t < 32; ++t) {
+            const int j = J0 + cc * 32 + t;
+            const bool ok = (j <= i) && (i - j < p.window) && (j < p.L);
+            sc[cc][t] = ok ? (__uint_as_float(s[t]) + rd[t]) : NEG_BIG;
+            mx = fmaxf(mx, sc[cc][t]);
+          }
+        } else {
+#pragma unroll
+          for (int t = 0; t < 32; ++t) {
+            sc[cc][t] = __uint_as_float(s[t]) + rd[t];
+            mx = fmaxf(mx, sc[cc][t]);
+          }
         }
         __syncwarp();
-        tmem_st32(T_S + lane_off + cc * 32, s);
       }
-      tmem_st_wait();
+      // S and the previous band chunk are consumed: the MMA warp may overwrite them with step st+1's scores
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(bar_s1);
+      mx *= p.scale_log2;  // scale > 0: max commutes with the scaling; masked entries stay hugely negative
 
       if (p.mode == 0) {
         // ---- online softmax bookkeeping with lazy rescale (rescale only when the max grew by more than 2^8)
@@ -276,20 +302,20 @@ relattn_fwd_kernel(const __grid_constant__ CUtensorMap tmQu, const __grid_consta
             tmem_st_wait();
           }
         }
+      } else if (p.mode == 2) {
+        mbar_wait(bar_o, st & 1);  // dP(st) is in TMEM
+        tc_fence_after();
       }
       const float m_use = (p.mode == 0) ? m_run : lse_row;
-      // ---- pass 2: probabilities
+      // ---- pass 2: probabilities from the registers, p = exp2(raw * scale_log2 - m)
       float sum = 0.f;
-#pragma unroll 1
+#pragma unroll
       for (int cc = 0; cc < 4; ++cc) {
-        uint32_t s[32];
-        tmem_ld32(T_S + lane_off + cc * 32, s);
-        tmem_ld_wait();
         uint32_t pk[16];
 #pragma unroll
         for (int t = 0; t < 16; ++t) {
-          const float p0 = exp2f(__uint_as_float(s[2 * t]) - m_use);
-          const float p1 = exp2f(__uint_as_float(s[2 * t + 1]) - m_use);
+          const float p0 = exp2f(fmaf(sc[cc][2 * t], p.scale_log2, -m_use));
+          const float p1 = exp2f(fmaf(sc[cc][2 * t + 1], p.scale_log2, -m_use));
           sum += p0 + p1;
           pk[t] = pack_half2(p0, p1);
         }
@@ -302,10 +328,31 @@ relattn_fwd_kernel(const __grid_constant__ CUtensorMap tmQu, const __grid_consta
             *reinterpret_cast<uint4*>(dst + chunk * 16) = make_uint4(pk[4 * g], pk[4 * g + 1], pk[4 * g + 2], pk[4 * g + 3]);
           }
         } else {
-          uint32_t dk[16];
+          // P (and dS) leave through the staging area so that every global store covers 8 rows x 64 contiguous bytes
+          const int rows_valid = p.L - (I0 + q * 32);
+          const int cols_valid = p.L - (J0 + cc * 32);
+          const uint32_t sbase = smem_u32(wstg);
+          const int piece = lane & 3;
+          auto store_tile = [&](const uint32_t (&v)[16], __half* base) {
+#pragma unroll
+            for (int g = 0; g < 4; ++g) {
+              Half8 h8;
+              h8.u = make_uint4(v[4 * g], v[4 * g + 1], v[4 * g + 2], v[4 * g + 3]);
+              sts_half8(sbase + lane * 80 + g * 16, h8);
+            }
+            __syncwarp();
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+              const int rr = k * 8 + (lane >> 2);
+              if (rr < rows_valid && piece * 8 < cols_valid)
+                st_half8(base + (long long)rr * p.L + piece * 8, lds_half8(sbase + rr * 80 + piece * 16));
+            }
+            __syncwarp();
+          };
+          store_tile(pk, p.P + zrow0 + J0 + cc * 32);
           if (p.mode == 2) {
             // dS = P * (dP - D) * scale; masked entries have P == 0 exactly
-            uint32_t dp[32];
+            uint32_t dp[32], dk[16];
             tmem_ld32(T_O + lane_off + cc * 32, dp);
             tmem_ld_wait();
 #pragma unroll
@@ -314,21 +361,12 @@ relattn_fwd_kernel(const __grid_constant__ CUtensorMap tmQu, const __grid_consta
               dk[t] = pack_half2(pp.x * (__uint_as_float(dp[2 * t]) - d_row) * p.scale,
                                  pp.y * (__uint_as_float(dp[2 * t + 1]) - d_row) * p.scale);
             }
-          }
-          if (i < p.L) {
-            const long long off = (((long long)b * p.H + h) * p.L + i) * p.L + J0 + cc * 32;
-#pragma unroll
-            for (int g = 0; g < 4; ++g)
-              if (J0 + cc * 32 + g * 8 < p.L) {
-                *reinterpret_cast<uint4*>(p.P + off + g * 8) = make_uint4(pk[4 * g], pk[4 * g + 1], pk[4 * g + 2], pk[4 * g + 3]);
-                if (p.mode == 2)
-                  *reinterpret_cast<uint4*>(p.dS + off + g * 8) = make_uint4(dk[4 * g], dk[4 * g + 1], dk[4 * g + 2], dk[4 * g + 3]);
-              }
+            store_tile(dk, p.dS + zrow0 + J0 + cc * 32);
           }
         }
       }
       l_run += sum;
-      // publish: P is in smem (generic proxy -> async proxy), S / BD TMEM reads are complete
+      // publish: P is in smem (generic proxy -> async proxy) / dP has been read
       fence_proxy_async_smem();
       tc_fence_before();
       __syncwarp();
