@@ -316,4 +316,6 @@ def patch_embed(module, pixel_values, pos_sum):
 
 
 def dropout_rows(x, p):
-    raise NotImplementedError("embedding dropout on image-caption patch embeddings is not built yet")
+    """Embedding dropout (transformer_xl.py:545) on the image-patch rows of an image-caption / VQA sequence."""
+    from . import vision
+    return vision.DropoutFn.apply(x, p, seeds.next())

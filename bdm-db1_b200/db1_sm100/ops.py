@@ -262,3 +262,47 @@ def rel_unshift(ds, dsr, Z, L):
     _need_cuda_half(ds, dsr)
     with _Launch("rel_unshift", 1, 0.0, 2.0 * Z * L * (L + 1)):
       check(_lib.lib().db1_rel_unshift(ptr(ds), ptr(dsr), Z, L, cur_stream()), "db1_rel_unshift")
+
+
+def transpose(x, out, batch, rows, cols):
+    """out[b][c][r] = x[b][r][c] (contiguous fp16)."""
+    _need_cuda_half(x, out)
+    with _Launch("transpose", 1):
+      check(_lib.lib().db1_transpose_f16(ptr(x), ptr(out), batch, rows, cols, cur_stream()), "db1_transpose_f16")
+    return out
+
+
+def patch_conv1_fwd(pixels, W1, b1, xs, y1):
+    _need_cuda_half(pixels, W1, b1, xs, y1)
+    N, Cc, Hh, Ww = pixels.shape
+    with _Launch("patch_conv1_fwd", 1):
+      check(_lib.lib().db1_patch_conv1_fwd(ptr(pixels), ptr(W1), ptr(b1), ptr(xs), ptr(y1), N, Cc, Hh, Ww, cur_stream()),
+          "db1_patch_conv1_fwd")
+
+
+def patch_conv1_bwd(xs, dy1, dW1, P, Cc):
+    _need_cuda_half(xs, dy1)
+    with _Launch("patch_conv1_bwd", 1):
+      check(_lib.lib().db1_patch_conv1_bwd(ptr(xs), ptr(dy1), _f32(dW1), P, Cc, cur_stream()), "db1_patch_conv1_bwd")
+
+
+def gn_gelu_im2col(x, gamma, beta, col, stats, P, eps):
+    _need_cuda_half(x, gamma, beta, col)
+    with _Launch("gn_gelu_im2col", 1, 0.0, P * 256 * (64 + 576) * 2.0):
+      check(_lib.lib().db1_gn_gelu_im2col(ptr(x), ptr(gamma), ptr(beta), ptr(col), _f32(stats), P, C.c_float(eps),
+                                        cur_stream()), "db1_gn_gelu_im2col")
+
+
+def col2im_gn_gelu_bwd(dcol, x, stats, gamma, beta, dres, dx, dgamma, dbeta, P):
+    _need_cuda_half(dcol, x, gamma, beta, dres, dx)
+    with _Launch("col2im_gn_gelu_bwd", 1, 0.0, P * 256 * (576 + 64 * 3) * 2.0):
+      check(_lib.lib().db1_col2im_gn_gelu_bwd(ptr(dcol), ptr(x), _f32(stats), ptr(gamma), ptr(beta), ptr(dres), ptr(dx),
+                                            _f32(dgamma), _f32(dbeta), P, cur_stream()), "db1_col2im_gn_gelu_bwd")
+
+
+def dropout(x, out, p, seed):
+    _need_cuda_half(x, out)
+    with _Launch("dropout", 1):
+      check(_lib.lib().db1_dropout_f16(ptr(x), ptr(out), C.c_longlong(x.numel()), C.c_float(p), C.c_uint64(seed),
+                                     cur_stream()), "db1_dropout_f16")
+    return out

@@ -159,6 +159,32 @@ int db1_posemb(void* out, const float* inv_freq, int klen, int d, int clamp_len,
 int db1_rel_unshift(const void* ds, void* dsr, int Z, int L, void* stream);
 int db1_f32_to_f16(const float* src, void* dst, long long n, int accumulate, void* stream);
 
+/* ------------------------------------------------------------------------------------------------------------------
+ * Image patch embedder (src/tokenizer/vision_embedding.py:36-86). Patches are the batch dimension; activations are
+ * [P, 256 pixels, 64 channels] fp16 (channels-last). The two conv3x3(64->64) layers and the 16x16/stride-16 projection
+ * run as db1_gemm_f16 on the matrices these kernels produce.
+ * ------------------------------------------------------------------------------------------------------------------ */
+/* out[b][c][r] = in[b][r][c]: weight re-layouts (conv [co][ci][9] <-> [co][9][ci]; projection [d][64][256] <-> [d][256][64]) */
+int db1_transpose_f16(const void* in, void* out, int batch, int rows, int cols, void* stream);
+/* einops patch split + per-(patch, channel) standardisation (x-mean)/(1e-6+std_unbiased)/4 (:67-79) + conv1 3x3 (C->64)
+ * (:80). pixels [N,C,H,W] fp16; xs [P,C,256] (standardised pixels, kept for the weight gradient); y1 [P,256,64]. */
+int db1_patch_conv1_fwd(const void* pixels, const void* W1, const void* b1, void* xs, void* y1, int N, int C, int Himg,
+                        int Wimg, void* stream);
+/* dW1 [64, C*9] fp32 += sum over patches and pixels of dy1 (x) shifted xs (weight gradient of conv1). */
+int db1_patch_conv1_bwd(const void* xs, const void* dy1, float* dW1, int P, int C, void* stream);
+/* GroupNorm(32 groups of 2 channels, eps) -> exact GELU -> im2col: col [P*256, 576], col[q][tap*64+ci] = a[q+tap][ci]
+ * with per-patch zero padding (:57-62 residual_path.{0,1} / {3,4} and the unfold of the following conv3x3).
+ * stats [P,32,2] = (mean, rstd) per group for the backward. */
+int db1_gn_gelu_im2col(const void* x, const void* gamma, const void* beta, void* col, float* stats, int P, float eps,
+                       void* stream);
+/* Adjoint of the above: col2im of dcol [P*256,576], GELU', GroupNorm backward; dx [P,256,64] (+ dres if not NULL),
+ * dgamma / dbeta [64] fp32 accumulated. */
+int db1_col2im_gn_gelu_bwd(const void* dcol, const void* x, const float* stats, const void* gamma, const void* beta,
+                           const void* dres, void* dx, float* dgamma, float* dbeta, int P, void* stream);
+/* out = x * keep(seed, element index) / (1 - p): embedding dropout on image-patch rows (transformer_xl.py:545);
+ * applying it to a gradient with the same seed is its adjoint. n % 8 == 0. */
+int db1_dropout_f16(const void* x, void* out, long long n, float drop_p, uint64_t seed, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -20,7 +20,7 @@ def _build(cfg, seed, cuda):
     return model.half().to(cuda), sd
 
 
-@pytest.mark.parametrize("name", ["tiny_text_rl", "tiny_window_clamp"])
+@pytest.mark.parametrize("name", ["tiny_text_rl", "tiny_window_clamp", "tiny_mixed_images"])
 def test_tiny_forward_backward_matches_oracle_and_golden(cuda, name):
     from oracle import db1_oracle as orc
     g = util.load_golden(name)
