@@ -704,6 +704,25 @@ __global__ void f32_to_f16_kernel(const float* __restrict__ src, __half* __restr
   dst[i] = __float2half_rn(v);
 }
 
+// up to 8 independent (fp32 slice -> fp16 destination) conversions in one launch: blockIdx.y = segment
+struct CvtSegs {
+  __half* dst[8];
+  long long off[8];
+  long long n[8];
+  int acc[8];
+};
+__global__ void f32_to_f16_multi_kernel(const float* __restrict__ src, const CvtSegs sg) {
+  const int k = blockIdx.y;
+  const long long n = sg.n[k];
+  const float* sp = src + sg.off[k];
+  __half* dp = sg.dst[k];
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+    float v = sp[i];
+    if (sg.acc[k]) v += __half2float(dp[i]);
+    dp[i] = __float2half_rn(v);
+  }
+}
+
 static inline uint32_t thr16(float p) { return (uint32_t)(p * 65536.0f + 0.5f); }
 static inline float dscale(uint32_t t) { return t ? 65536.0f / (65536.0f - (float)t) : 1.0f; }
 
@@ -869,6 +888,26 @@ extern "C" int db1_rel_unshift(const void* ds, void* dsr, int Z, int L, void* st
 extern "C" int db1_f32_to_f16(const float* src, void* dst, long long n, int accumulate, void* stream) {
   DB1_CHECK_ARG(src && dst && n > 0, "f32_to_f16: bad arguments");
   f32_to_f16_kernel<<<(unsigned)((n + 255) / 256), 256, 0, (cudaStream_t)stream>>>(src, (__half*)dst, n, accumulate);
+  DB1_CUDA(cudaGetLastError());
+  return 0;
+}
+
+extern "C" int db1_f32_to_f16_multi(const float* src, int nseg, void* const* dst, const long long* off, const long long* n,
+                                    const int* accumulate, void* stream) {
+  DB1_CHECK_ARG(src && dst && off && n && accumulate && nseg > 0 && nseg <= 8, "f32_to_f16_multi: bad arguments");
+  CvtSegs sg;
+  long long mx = 0;
+  for (int k = 0; k < nseg; ++k) {
+    DB1_CHECK_ARG(dst[k] != nullptr && n[k] > 0 && off[k] >= 0, "f32_to_f16_multi: bad segment %d", k);
+    sg.dst[k] = (__half*)dst[k];
+    sg.off[k] = off[k];
+    sg.n[k] = n[k];
+    sg.acc[k] = accumulate[k];
+    if (n[k] > mx) mx = n[k];
+  }
+  long long bx = (mx + 255) / 256;
+  if (bx > 1024) bx = 1024;
+  f32_to_f16_multi_kernel<<<dim3((unsigned)bx, nseg), 256, 0, (cudaStream_t)stream>>>(src, sg);
   DB1_CUDA(cudaGetLastError());
   return 0;
 }

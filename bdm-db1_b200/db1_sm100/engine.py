@@ -45,7 +45,7 @@ class _Bucket:
 
 class DB1Engine:
     def __init__(self, model, optimizer=None, lr_scheduler=None, mpu=None, gradient_accumulation_steps=1,
-                 loss_scale=4096.0, clip_grad=0.0, bucket_of=_default_bucket_of, overlap_comm=True):
+                 loss_scale=4096.0, clip_grad=0.0, bucket_of=_default_bucket_of, overlap_comm=True, direct_grads=True):
         self.module = model
         self.optimizer = optimizer
         self.lr_scheduler = lr_scheduler
@@ -74,6 +74,13 @@ class DB1Engine:
         self._hooks = []
         if self._world > 1:
             self._install_hooks()
+        # gradient sink (db1_sm100.functions): weight-gradient kernels write into the bucket views directly
+        self._written = set()    # ids of parameters whose bucket view already holds this window's gradient
+        self._sink_seen = set()  # ids of parameters that have ever been written through the sink
+        self._param_by_id = {id(p): p for b in self.buckets for p in b.params}
+        if self._cuda and direct_grads:
+            from . import functions
+            functions.set_grad_sink(self)
 
     # ------------------------------------------------------------------------------------------ buckets
     def _build_buckets(self, bucket_of):
@@ -113,6 +120,30 @@ class DB1Engine:
                 self._launch_allreduce(bucket)
         return hook
 
+    # ------------------------------------------------------------------------------------------ gradient sink protocol
+    def target(self, param):
+        """(bucket view, accumulate) for a parameter this engine owns, else None. The first write of an accumulation
+        window overwrites (so the buckets never need a zero-fill), later ones accumulate."""
+        pid = id(param)
+        if pid not in self._param_by_id:
+            return None
+        acc = pid in self._written
+        self._written.add(pid)
+        return param.grad, acc
+
+    def done(self, param):
+        """A kernel finished writing one contribution to param's gradient. Parameters of a decoder-layer bucket are used
+        once per forward, so this completes them; the shared 'rest' bucket (embeddings, u/v, vision) is launched after
+        backward returns."""
+        b = self._bucket_of_param.get(id(param))
+        if b is None or b.key == "rest" or self._world == 1:
+            return
+        if not self._is_boundary() or not self.enable_backward_allreduce:
+            return
+        b.pending -= 1
+        if b.pending == 0:
+            self._launch_allreduce(b)
+
     def _launch_allreduce(self, bucket):
         if bucket.work is not None or self._world == 1:
             return
@@ -151,8 +182,22 @@ class DB1Engine:
         return self._is_boundary()
 
     def zero_grad(self):
+        """Start of an accumulation window. Gradients that arrive through the sink overwrite their views, so only
+        parameters that come through autograd's own accumulation (never seen by the sink) are zero-filled."""
+        self._written.clear()
         for b in self.buckets:
-            b.flat.zero_()
+            unseen = [p for p in b.params if id(p) not in self._sink_seen]
+            if len(unseen) == len(b.params):
+                b.flat.zero_()
+            else:
+                for p in unseen:
+                    p.grad.zero_()
+
+    def _zero_unwritten(self):
+        """Sink-fed parameters that received nothing in this window (e.g. unused this step) must read as zero."""
+        for pid in self._sink_seen - self._written:
+            self._param_by_id[pid].grad.zero_()
+        self._sink_seen |= self._written
 
     def backward(self, loss):
         """Scale, back-propagate; on the boundary micro-step the bucket all-reduces start as their gradients complete."""
@@ -164,6 +209,10 @@ class DB1Engine:
             b.post_scale = None
         scaled = loss * (self.loss_scale / self._ga)
         scaled.backward()
+        if self._is_boundary():
+            self._zero_unwritten()
+        else:
+            self._sink_seen |= self._written
         if self._world > 1 and self._is_boundary() and self.enable_backward_allreduce:
             # buckets whose parameters got no gradient at all this step still take part (zero contribution)
             for b in self.buckets:

@@ -46,6 +46,56 @@ class _Seeds:
 seeds = _Seeds()
 
 
+# ---------------------------------------------------------------------------------------------------------------------
+# Gradient sink: when a training engine registers one (DB1Engine does), weight-gradient kernels write straight into the
+# engine's flat all-reduce buckets (first write of an accumulation window overwrites, later ones accumulate) and the
+# engine is told when a parameter's gradient is complete - no autograd `.grad +=` kernels, no bucket zero-fill.
+# Without a sink (plain module use, parity tests) the Functions return gradients to autograd as usual.
+# ---------------------------------------------------------------------------------------------------------------------
+_sink = None
+
+
+def set_grad_sink(sink):
+    """sink.target(param) -> (fp16 view shaped like param, accumulate: bool) or None;  sink.done(param)."""
+    global _sink
+    _sink = sink
+
+
+class _Grad:
+    """Destination of one parameter gradient inside a backward: the sink's bucket view, or a fresh tensor for autograd."""
+    __slots__ = ("param", "buf", "acc", "direct")
+
+    def __init__(self, param, shape=None, zero=False):
+        t = _sink.target(param) if (_sink is not None and param is not None) else None
+        self.param = param
+        if t is not None:
+            self.buf, self.acc = t
+            self.direct = True
+        else:
+            shape = tuple(param.shape) if shape is None else shape
+            mk = torch.zeros if zero else torch.empty
+            self.buf, self.acc, self.direct = mk(shape, dtype=torch.float16, device=param.device), False, False
+
+    def ret(self):
+        """Value to hand back to autograd (None when the gradient already sits in the engine's bucket)."""
+        if self.direct:
+            _sink.done(self.param)
+            return None
+        return self.buf
+
+
+def _scatter_small(small, plan):
+    """plan: list of (param, offset, n). Converts slices of the fp32 accumulator `small` to fp16 gradients with one
+    launch per 8 parameters; returns the autograd return values in plan order."""
+    grads = [_Grad(p, (n,)) for p, _o, n in plan]
+    ops.f32_to_f16_multi(small, [(g.buf, o, n, g.acc) for g, (_p, o, n) in zip(grads, plan)])
+    out = []
+    for g, (p, _o, _n) in zip(grads, plan):
+        r = g.ret()
+        out.append(r.view(p.shape) if r is not None else None)
+    return out
+
+
 def _f32zeros(n, dev):
     return torch.zeros(n, dtype=torch.float32, device=dev)
 
@@ -87,6 +137,7 @@ class AttnBlockFn(torch.autograd.Function):
         ops.layernorm_fwd(y, gamma, beta, out, stats, eps)
         ctx.save_for_backward(x2, r, Wqkv, Wr, Wo, gamma, qkv4, rk, o, lse2, y, stats)
         ctx.cfg = (B, L, d, H, dh, drop_p, seed, window, scale)
+        ctx.params = (Wqkv, Wr, Wo, u, v, gamma, beta)
         return out.view(B, L, d)
 
     @staticmethod
@@ -105,9 +156,10 @@ class AttnBlockFn(torch.autograd.Function):
         dz = torch.empty(rows, d, dtype=f16, device=dev) if drop_p > 0 else None
         ops.layernorm_bwd(dout2, y, gamma, stats, dy, dz, dgamma, dbeta, None, drop_p, seed)
         dzz = dz if dz is not None else dy
+        pWqkv, pWr, pWo, pu, pv, pgamma, pbeta = ctx.params
         # o_net
-        dWo = torch.empty(d, d, dtype=f16, device=dev)
-        ops.gemm(dzz, o, dWo, d, d, rows, lda=d, ldb=d, ldc=d, a_mn=True, b_mn=True)
+        gWo = _Grad(pWo)
+        ops.gemm(dzz, o, gWo.buf, d, d, rows, lda=d, ldb=d, ldc=d, a_mn=True, b_mn=True, accumulate=gWo.acc)
         do = torch.empty(rows, d, dtype=f16, device=dev)
         ops.gemm(dzz, Wo, do, rows, d, d, lda=d, ldb=d, ldc=d, b_mn=True)
         # attention core: recompute P, then the causal contractions on tensor cores
@@ -139,15 +191,15 @@ class AttnBlockFn(torch.autograd.Function):
                  a_z=sz, b_z=(dh, L * 4 * d), c_z=(dh, 0), reduce_z2=True, k_mode=ops.K_BEGIN_REV)
         ops.dq_finalize(dqu, dqv, dqkv[:, 0:d], du, dv, rows, d)
         # r_net / qkv_net
-        dWr = torch.empty(d, d, dtype=f16, device=dev)
-        ops.gemm(drk, r, dWr, d, d, L, lda=d, ldb=d, ldc=d, a_mn=True, b_mn=True)
-        dWqkv = torch.empty(3 * d, d, dtype=f16, device=dev)
-        ops.gemm(dqkv, x2, dWqkv, 3 * d, d, rows, lda=3 * d, ldb=d, ldc=d, a_mn=True, b_mn=True)
+        gWr = _Grad(pWr)
+        ops.gemm(drk, r, gWr.buf, d, d, L, lda=d, ldb=d, ldc=d, a_mn=True, b_mn=True, accumulate=gWr.acc)
+        gWqkv = _Grad(pWqkv)
+        ops.gemm(dqkv, x2, gWqkv.buf, 3 * d, d, rows, lda=3 * d, ldb=d, ldc=d, a_mn=True, b_mn=True,
+                 accumulate=gWqkv.acc)
         dx = torch.empty(rows, d, dtype=f16, device=dev)
         ops.gemm(dqkv, Wqkv, dx, rows, d, 3 * d, lda=3 * d, ldb=d, ldc=d, b_mn=True, resid=dy, ldr=d)
-        sh = _to_half(small, (4 * d,))
-        return (dx.view(B, L, d), None, dWqkv, dWr, dWo, sh[0:d].view(H, dh), sh[d:2 * d].view(H, dh),
-                sh[2 * d:3 * d], sh[3 * d:4 * d], None, None, None, None)
+        gu, gv, gg, gb = _scatter_small(small, [(pu, 0, d), (pv, d, d), (pgamma, 2 * d, d), (pbeta, 3 * d, d)])
+        return (dx.view(B, L, d), None, gWqkv.ret(), gWr.ret(), gWo.ret(), gu, gv, gg, gb, None, None, None, None)
 
 
 class FFBlockFn(torch.autograd.Function):
@@ -175,6 +227,7 @@ class FFBlockFn(torch.autograd.Function):
         ops.layernorm_fwd(y, gamma, beta, out, stats, eps)
         ctx.save_for_backward(x2, W1, W2, gamma, Hb, g, y, stats)
         ctx.cfg = (B, L, d, F, drop_p, seed)
+        ctx.params = (W1, b1, W2, b2, gamma, beta)
         return out.view(B, L, d)
 
     @staticmethod
@@ -193,18 +246,19 @@ class FFBlockFn(torch.autograd.Function):
         dz = torch.empty(rows, d, dtype=f16, device=dev) if drop_p > 0 else None
         ops.layernorm_bwd(dout2, y, gamma, stats, dy, dz, dgamma, dbeta, db2, drop_p, seed)
         dzz = dz if dz is not None else dy
-        dW2 = torch.empty(d, F, dtype=f16, device=dev)
-        ops.gemm(dzz, g, dW2, d, F, rows, lda=d, ldb=F, ldc=F, a_mn=True, b_mn=True)
+        pW1, pb1, pW2, pb2, pgamma, pbeta = ctx.params
+        gW2 = _Grad(pW2)
+        ops.gemm(dzz, g, gW2.buf, d, F, rows, lda=d, ldb=F, ldc=F, a_mn=True, b_mn=True, accumulate=gW2.acc)
         dH = torch.empty(rows, 2 * F, dtype=f16, device=dev)
         ops.gemm(dzz, W2, dH, rows, F, d, lda=d, ldb=F, ldc=2 * F, b_mn=True, epilogue=ops.EPI_DGEGLU, H=Hb,
                  ldh=2 * F, F=F)
         ops.colsum(dH, db1, rows, 2 * F)
-        dW1 = torch.empty(2 * F, d, dtype=f16, device=dev)
-        ops.gemm(dH, x2, dW1, 2 * F, d, rows, lda=2 * F, ldb=d, ldc=d, a_mn=True, b_mn=True)
+        gW1 = _Grad(pW1)
+        ops.gemm(dH, x2, gW1.buf, 2 * F, d, rows, lda=2 * F, ldb=d, ldc=d, a_mn=True, b_mn=True, accumulate=gW1.acc)
         dx = torch.empty(rows, d, dtype=f16, device=dev)
         ops.gemm(dH, W1, dx, rows, d, 2 * F, lda=2 * F, ldb=d, ldc=d, b_mn=True, resid=dy, ldr=d)
-        sh = _to_half(small, (3 * d + 2 * F,))
-        return (dx.view(B, L, d), dW1, sh[3 * d:], dW2, sh[2 * d:3 * d], sh[0:d], sh[d:2 * d], None, None)
+        gg, gb, gb2, gb1 = _scatter_small(small, [(pgamma, 0, d), (pbeta, d, d), (pb2, 2 * d, d), (pb1, 3 * d, 2 * F)])
+        return (dx.view(B, L, d), gW1.ret(), gb1, gW2.ret(), gb2, gg, gb, None, None)
 
 
 def _pad8(n):
@@ -235,6 +289,7 @@ class HeadLossFn(torch.autograd.Function):
         logits = buf.view(B, L, Vp)[:, :, :V]
         ctx.save_for_backward(h2, W, buf, lab, msk, row_lse, loss2)
         ctx.cfg = (B, L, d, V, Vp)
+        ctx.params = (W,)
         ctx.mark_non_differentiable(logits)
         return logits, loss2[0]
 
@@ -247,11 +302,11 @@ class HeadLossFn(torch.autograd.Function):
         gs = dloss.reshape(1).to(torch.float32)
         dl = _workspace("dlogits", (rows, Vp), torch.float16, dev)
         ops.ce_bwd(buf, lab, msk, row_lse, loss2, gs, dl, V)
-        dW = torch.empty(V, d, dtype=torch.float16, device=dev)
-        ops.gemm(dl, h2, dW, V, d, rows, lda=Vp, ldb=d, ldc=d, a_mn=True, b_mn=True)
+        gW = _Grad(ctx.params[0])
+        ops.gemm(dl, h2, gW.buf, V, d, rows, lda=Vp, ldb=d, ldc=d, a_mn=True, b_mn=True, accumulate=gW.acc)
         dh = torch.empty(rows, d, dtype=torch.float16, device=dev)
         ops.gemm(dl, W, dh, rows, d, V, lda=Vp, ldb=d, ldc=d, b_mn=True)
-        return dh.view(B, L, d), dW, None, None
+        return dh.view(B, L, d), gW.ret(), None, None
 
 
 def head_logits(hidden, W):
@@ -286,6 +341,7 @@ class EmbedFn(torch.autograd.Function):
         ctx.save_for_backward(tok, pos, slot)
         ctx.cfg = (B, L, d, V, drop_p, seed, T.shape[0] if T is not None else 0,
                    tuple(vis.shape) if vis is not None else None)
+        ctx.params = (W, T if pos is not None else None)
         return out
 
     @staticmethod
@@ -294,11 +350,20 @@ class EmbedFn(torch.autograd.Function):
         B, L, d, V, drop_p, seed, nT, vshape = ctx.cfg
         dev = dout.device
         dout = dout.contiguous()
-        dW = torch.zeros(V, d, dtype=torch.float16, device=dev)
-        dT = torch.zeros(nT, d, dtype=torch.float16, device=dev) if pos is not None else None
+        # scatter-adds: straight into the gradient bucket when it already holds this window's gradient, else into zeros
+        pW, pT = ctx.params
+        gW = _Grad(pW, zero=True)
+        if gW.direct and not gW.acc:
+            gW.buf.zero_()
+        gT = None
+        if pos is not None:
+            gT = _Grad(pT, zero=True)
+            if gT.direct and not gT.acc:
+                gT.buf.zero_()
         dvis = torch.zeros(vshape, dtype=torch.float16, device=dev) if vshape is not None else None
-        ops.embed_bwd(tok, pos, slot, dout, L * d, dW, dT, dvis, B, L, d, V, drop_p, seed, 0)
-        return None, None, dW, dT, dvis, None
+        ops.embed_bwd(tok, pos, slot, dout, L * d, gW.buf, gT.buf if gT is not None else None, dvis, B, L, d, V, drop_p,
+                      seed, 0)
+        return None, None, gW.ret(), gT.ret() if gT is not None else None, dvis, None
 
 
 def positional_rows(inv_freq, klen, d, clamp_len, drop_p):

@@ -306,3 +306,17 @@ def dropout(x, out, p, seed):
       check(_lib.lib().db1_dropout_f16(ptr(x), ptr(out), C.c_longlong(x.numel()), C.c_float(p), C.c_uint64(seed),
                                      cur_stream()), "db1_dropout_f16")
     return out
+
+
+def f32_to_f16_multi(src, segs):
+    """segs: list of (dst fp16 tensor (contiguous), src offset, n, accumulate) - at most 8 per launch."""
+    for i in range(0, len(segs), 8):
+        part = segs[i:i + 8]
+        k = len(part)
+        _need_cuda_half(*[sg[0] for sg in part])
+        dst = (C.c_void_p * k)(*[sg[0].data_ptr() for sg in part])
+        off = (C.c_longlong * k)(*[sg[1] for sg in part])
+        n = (C.c_longlong * k)(*[sg[2] for sg in part])
+        acc = (C.c_int * k)(*[int(sg[3]) for sg in part])
+        with _Launch("f32_to_f16", 1):
+          check(_lib.lib().db1_f32_to_f16_multi(_f32(src), k, dst, off, n, acc, cur_stream()), "db1_f32_to_f16_multi")

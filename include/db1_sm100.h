@@ -158,6 +158,10 @@ int db1_posemb(void* out, const float* inv_freq, int klen, int d, int clamp_len,
 /* dsr[z][i][c] = ds[z][i][c-(L-1-i)] for c >= L-1-i, else 0: adjoint of _rel_shift (transformer_xl.py:98-110) */
 int db1_rel_unshift(const void* ds, void* dsr, int Z, int L, void* stream);
 int db1_f32_to_f16(const float* src, void* dst, long long n, int accumulate, void* stream);
+/* nseg <= 8 conversions in one launch: dst[k][0..n[k]) (+)= fp16(src[off[k] .. off[k]+n[k])). dst / off / n / accumulate
+ * are HOST arrays. Used to drop a block's small fp32 gradient accumulators straight into the gradient buckets. */
+int db1_f32_to_f16_multi(const float* src, int nseg, void* const* dst, const long long* off, const long long* n,
+                         const int* accumulate, void* stream);
 
 /* ------------------------------------------------------------------------------------------------------------------
  * Image patch embedder (src/tokenizer/vision_embedding.py:36-86). Patches are the batch dimension; activations are

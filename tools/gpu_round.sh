@@ -9,8 +9,8 @@ if has tests; then timeout 900 python -m pytest tests -m gpu -x -q 2>&1 | tail -
 if has gemm; then timeout 300 python tools/bench_gemm.py 2>&1 | tee gpurun_out/bench_gemm_$TAG.log; fi
 if has bench; then timeout 600 python bench.py --steps 10 --warmup 3 > gpurun_out/bench_$TAG.json 2> gpurun_out/bench_$TAG.err; tail -c 1500 gpurun_out/bench_$TAG.json; cp gpurun_out/bench_breakdown_n1.json gpurun_out/breakdown_$TAG.json; fi
 if has ncu; then
-  timeout 900 ncu --metrics gpu__time_duration.sum,dram__bytes_read.sum,dram__bytes_write.sum --clock-control none -c 3000 --csv --log-file gpurun_out/launches_$TAG.csv \
-      python bench.py --steps 1 --warmup 1 --profile-only > gpurun_out/ncu_list_$TAG.log 2>&1
+  timeout 900 ncu --metrics gpu__time_duration.sum,dram__bytes_read.sum,dram__bytes_write.sum --clock-control none --profile-from-start off -c 3000 --csv --log-file gpurun_out/launches_$TAG.csv \
+      python bench.py --steps 1 --warmup 2 --profile-only > gpurun_out/ncu_list_$TAG.log 2>&1
   tail -2 gpurun_out/ncu_list_$TAG.log
 fi
 if has ncufull; then
