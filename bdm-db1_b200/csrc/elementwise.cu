@@ -618,32 +618,70 @@ colsum_kernel(const __half* __restrict__ in, long long ld, float* __restrict__ o
   }
 }
 
-// dq = dqu + dqv (fp16 out, written into the fused dQKV buffer) and du += colsum(dqu), dv += colsum(dqv)
+// dq = dqu + dqv (fp16 out, written into the fused dQKV buffer) and du += colsum(dqu), dv += colsum(dqv).
+// Same strip decomposition as colsum_kernel: a CTA owns 64 columns x CS_ROWS_PER_CTA rows, a warp touches 4 rows x 128
+// contiguous bytes per access, 4 row-iterations in flight; one atomic per column per CTA.
 __global__ void __launch_bounds__(256)
 dq_finalize_kernel(const __half* __restrict__ dqu, const __half* __restrict__ dqv, long long ld_in,
                    __half* __restrict__ dq, long long ld_out, float* __restrict__ du, float* __restrict__ dv, int rows,
                    int n) {
-  const int ch = blockIdx.x * blockDim.x + threadIdx.x;
-  if (ch * 8 >= n) return;
+  __shared__ float red[2][32][65];
+  const int cx = threadIdx.x & 7, ry = threadIdx.x >> 3;
+  const int col = blockIdx.x * 64 + cx * 8;
+  const int r_begin = blockIdx.y * CS_ROWS_PER_CTA;
+  const int r_end = min(rows, r_begin + CS_ROWS_PER_CTA);
   float au[8], av[8];
 #pragma unroll
   for (int i = 0; i < 8; ++i) au[i] = av[i] = 0.f;
-  for (int r = blockIdx.y; r < rows; r += gridDim.y) {
-    float a[8], b[8], o[8];
-    h8_to_f(*reinterpret_cast<const H8*>(dqu + (size_t)r * ld_in + ch * 8), a);
-    h8_to_f(*reinterpret_cast<const H8*>(dqv + (size_t)r * ld_in + ch * 8), b);
+  if (col < n) {
+    int r = r_begin + ry;
+    for (; r + 3 * 32 < r_end; r += 4 * 32) {
+      H8 a[4], b[4];
 #pragma unroll
-    for (int i = 0; i < 8; ++i) {
-      o[i] = a[i] + b[i];
-      au[i] += a[i];
-      av[i] += b[i];
+      for (int u = 0; u < 4; ++u) {
+        a[u] = *reinterpret_cast<const H8*>(dqu + (size_t)(r + u * 32) * ld_in + col);
+        b[u] = *reinterpret_cast<const H8*>(dqv + (size_t)(r + u * 32) * ld_in + col);
+      }
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        float fa[8], fb[8], o[8];
+        h8_to_f(a[u], fa);
+        h8_to_f(b[u], fb);
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          o[i] = fa[i] + fb[i];
+          au[i] += fa[i];
+          av[i] += fb[i];
+        }
+        *reinterpret_cast<H8*>(dq + (size_t)(r + u * 32) * ld_out + col) = f_to_h8(o);
+      }
     }
-    *reinterpret_cast<H8*>(dq + (size_t)r * ld_out + ch * 8) = f_to_h8(o);
+    for (; r < r_end; r += 32) {
+      float fa[8], fb[8], o[8];
+      h8_to_f(*reinterpret_cast<const H8*>(dqu + (size_t)r * ld_in + col), fa);
+      h8_to_f(*reinterpret_cast<const H8*>(dqv + (size_t)r * ld_in + col), fb);
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        o[i] = fa[i] + fb[i];
+        au[i] += fa[i];
+        av[i] += fb[i];
+      }
+      *reinterpret_cast<H8*>(dq + (size_t)r * ld_out + col) = f_to_h8(o);
+    }
   }
 #pragma unroll
   for (int i = 0; i < 8; ++i) {
-    atomicAdd(du + ch * 8 + i, au[i]);
-    atomicAdd(dv + ch * 8 + i, av[i]);
+    red[0][ry][cx * 8 + i] = au[i];
+    red[1][ry][cx * 8 + i] = av[i];
+  }
+  __syncthreads();
+  if (threadIdx.x < 128) {
+    const int which = threadIdx.x >> 6, c = threadIdx.x & 63;
+    float t = 0.f;
+#pragma unroll
+    for (int k = 0; k < 32; ++k) t += red[which][k][c];
+    const int gc = blockIdx.x * 64 + c;
+    if (gc < n) atomicAdd((which ? dv : du) + gc, t);
   }
 }
 
@@ -849,7 +887,7 @@ extern "C" int db1_dq_finalize(const void* dqu, const void* dqv, long long ld_in
                                float* dv, int rows, int n, void* stream) {
   DB1_CHECK_ARG(dqu && dqv && dq && du && dv && rows > 0 && n % 8 == 0 && ld_in % 8 == 0 && ld_out % 8 == 0,
                 "dq_finalize: bad arguments");
-  dim3 grid((n / 8 + 255) / 256, rows < 296 ? rows : 296);
+  dim3 grid((n + 63) / 64, (rows + CS_ROWS_PER_CTA - 1) / CS_ROWS_PER_CTA);
   dq_finalize_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>((const __half*)dqu, (const __half*)dqv, ld_in, (__half*)dq,
                                                            ld_out, du, dv, rows, n);
   DB1_CUDA(cudaGetLastError());

@@ -126,10 +126,16 @@ DEVI void warp_store_tile(uint8_t* stg, int lane, const Half8 (&hv)[4], __half* 
         }
         st_half8(dst, v);
       } else {
-        // ragged last group (N not a multiple of 8): scalar tail
-        const __half* hs = reinterpret_cast<const __half*>(&v);
-        for (int i = 0; i < cols_valid - col; ++i)
-          dst[i] = accumulate ? __float2half_rn(__half2float(hs[i]) + __half2float(dst[i])) : hs[i];
+        // ragged last group (N not a multiple of 8): scalar tail, kept in registers (taking the address of `v`
+        // would push every tile through local memory)
+        const uint32_t w[4] = {v.u.x, v.u.y, v.u.z, v.u.w};
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          if (i < cols_valid - col) {
+            const __half hv = __ushort_as_half((unsigned short)((i & 1) ? (w[i >> 1] >> 16) : (w[i >> 1] & 0xffffu)));
+            dst[i] = accumulate ? __float2half_rn(__half2float(hv) + __half2float(dst[i])) : hv;
+          }
+        }
       }
     }
   }
@@ -544,6 +550,23 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
             tile_issue(lane, dg, hrow + p.F, p.ldh, p.M - row_base, p.N - n0);
           }
         };
+        if (EPI == DB1_EPI_DGEGLU) {
+          // The saved pre-activations were written a whole forward pass ago (DRAM-resident): pull this warp's
+          // 32 rows x 128 columns of a and g into L2 while the tile's main loop is still running, so the LDGs below
+          // (issued only one chunk ahead - registers) see L2 latency instead of DRAM latency.
+          const int r = row_base + lane;
+          const int n0 = nt * BN + c_first * 32;
+          if (r < p.M && n0 < p.N) {
+            const __half* hp = p.H + (size_t)r * p.ldh + n0;
+#pragma unroll
+            for (int j = 0; j < 2; ++j) {
+              if (n0 + j * 64 < p.N) {
+                asm volatile("prefetch.global.L2 [%0];" ::"l"(hp + j * 64));
+                asm volatile("prefetch.global.L2 [%0];" ::"l"(hp + p.F + j * 64));
+              }
+            }
+          }
+        }
         issue_h(c_first, la[0], lg[0]);
         mbar_wait(&tfull[as], aph);
         tc_fence_after();

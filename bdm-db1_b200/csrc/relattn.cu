@@ -74,19 +74,40 @@ relattn_fwd_kernel(const __grid_constant__ CUtensorMap tmQu, const __grid_consta
   uint64_t* bar_p = bars + 5;
   uint64_t* bar_o = bars + 6;
   uint64_t* bar_s1 = bars + 7;
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 8);
+  uint64_t* bar_qfree = bars + 8;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 10);
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
+  // Persistent: one CTA per SM walks a static, balanced list of (query tile, head, sequence) items. Items are ordered
+  // heaviest first (descending query tile = descending number of key steps) and dealt to the CTAs in snake order
+  // (pass 0: CTA c takes item c, pass 1: item 2G-1-c, ...), so every CTA gets the same number of key steps +-1 tile.
+  // TMEM, barriers and the smem ring live across items; barrier phases are tracked by global step / item counters.
   const int nq = (p.L + 127) / 128;
-  const int I = nq - 1 - blockIdx.x;  // heaviest tiles first
-  const int h = blockIdx.y, b = blockIdx.z;
-  const int I0 = I * 128;
-  // oldest key any row of this tile may attend: j >= I0 - window + 1
-  int jlo = I0 - p.window + 1;
-  if (jlo < 0) jlo = 0;
-  const int Jmin = jlo / 128;
-  const int nsteps = I - Jmin + 1;
+  const int HB = p.H * p.B;
+  const int n_items = nq * HB;
+  const int G = gridDim.x;
+  auto item_of = [&](int pass) -> int {
+    const int c = (pass & 1) ? (G - 1 - (int)blockIdx.x) : (int)blockIdx.x;
+    const int k = pass * G + c;
+    return k < n_items ? k : -1;
+  };
+  const int n_pass = (n_items + G - 1) / G;
+  struct Item {
+    int I, h, b, I0, nsteps;
+  };
+  auto decode = [&](int k) -> Item {
+    Item t;
+    t.I = nq - 1 - k / HB;
+    const int hb = k % HB;
+    t.h = hb % p.H;
+    t.b = hb / p.H;
+    t.I0 = t.I * 128;
+    int jlo = t.I0 - p.window + 1;  // oldest key any row of this tile may attend
+    if (jlo < 0) jlo = 0;
+    t.nsteps = t.I - jlo / 128 + 1;
+    return t;
+  };
 
   if ((smem_u32(smem) & 1023u) != 0) __trap();
 
@@ -108,6 +129,7 @@ relattn_fwd_kernel(const __grid_constant__ CUtensorMap tmQu, const __grid_consta
       mbar_init(bar_p, 4);
       mbar_init(bar_o, 1);
       mbar_init(bar_s1, 4);
+      mbar_init(bar_qfree, 1);
       mbar_fence_init();
     }
     __syncwarp();
@@ -126,30 +148,39 @@ relattn_fwd_kernel(const __grid_constant__ CUtensorMap tmQu, const __grid_consta
   if (warp == 0) {
     // ------------------------------------------------------------------ TMA producer
     if (lane == 0) {
-      mbar_expect_tx(bar_q, (p.mode == 2 ? 3 : 2) * SM::TILE);
-#pragma unroll
-      for (int s = 0; s < NSLAB; ++s) {
-        tma_load_4d(smem + SM::QU + s * 16384, &tmQu, bar_q, s * 64, I0, h, b);
-        tma_load_4d(smem + SM::QV + s * 16384, &tmQv, bar_q, s * 64, I0, h, b);
-        if (p.mode == 2) tma_load_4d(smem + SM::PT + s * 16384, &tmDO, bar_q, s * 64, I0, h, b);  // dO_I lives where P would
-      }
-      for (int st = 0; st < nsteps; ++st) {
-        const int J0 = (I - st) * 128;
-        const int cb = p.L - 128 - I0 + J0;  // first row of the new chunk of r
-        if (st > 0) mbar_wait(bar_kfree, (st - 1) & 1);
-        mbar_expect_tx(bar_k, (p.mode == 2 ? 3 : 2) * SM::TILE);
+      int gs = 0, ti = 0;  // global key-step / item counters (barrier phases)
+      for (int pass = 0; pass < n_pass; ++pass) {
+        const int k = item_of(pass);
+        if (k < 0) continue;
+        const Item t = decode(k);
+        if (ti > 0) mbar_wait(bar_qfree, (ti - 1) & 1);  // the previous item's last score (and dP) MMAs have read Q / dO
+        mbar_expect_tx(bar_q, (p.mode == 2 ? 3 : 2) * SM::TILE);
 #pragma unroll
         for (int s = 0; s < NSLAB; ++s) {
-          tma_load_4d(smem + SM::KT + s * 16384, &tmK, bar_k, s * 64, J0, h, b);
-          tma_load_4d(smem + SM::RT + s * 16384, &tmR, bar_k, s * 64, cb, h, 0);
-          if (p.mode == 2) tma_load_4d(smem + SM::VT + s * 16384, &tmV, bar_k, s * 64, J0, h, b);
+          tma_load_4d(smem + SM::QU + s * 16384, &tmQu, bar_q, s * 64, t.I0, t.h, t.b);
+          tma_load_4d(smem + SM::QV + s * 16384, &tmQv, bar_q, s * 64, t.I0, t.h, t.b);
+          if (p.mode == 2)  // dO_I lives where P would
+            tma_load_4d(smem + SM::PT + s * 16384, &tmDO, bar_q, s * 64, t.I0, t.h, t.b);
         }
-        if (p.mode == 0) {
-          if (st > 0) mbar_wait(bar_o, (st - 1) & 1);
-          mbar_expect_tx(bar_v, SM::TILE);
+        for (int st = 0; st < t.nsteps; ++st, ++gs) {
+          const int J0 = (t.I - st) * 128;
+          const int cb = p.L - 128 - t.I0 + J0;  // first row of the new chunk of r
+          if (gs > 0) mbar_wait(bar_kfree, (gs - 1) & 1);
+          mbar_expect_tx(bar_k, (p.mode == 2 ? 3 : 2) * SM::TILE);
 #pragma unroll
-          for (int s = 0; s < NSLAB; ++s) tma_load_4d(smem + SM::VT + s * 16384, &tmV, bar_v, s * 64, J0, h, b);
+          for (int s = 0; s < NSLAB; ++s) {
+            tma_load_4d(smem + SM::KT + s * 16384, &tmK, bar_k, s * 64, J0, t.h, t.b);
+            tma_load_4d(smem + SM::RT + s * 16384, &tmR, bar_k, s * 64, cb, t.h, 0);
+            if (p.mode == 2) tma_load_4d(smem + SM::VT + s * 16384, &tmV, bar_k, s * 64, J0, t.h, t.b);
+          }
+          if (p.mode == 0) {
+            if (gs > 0) mbar_wait(bar_o, (gs - 1) & 1);
+            mbar_expect_tx(bar_v, SM::TILE);
+#pragma unroll
+            for (int s = 0; s < NSLAB; ++s) tma_load_4d(smem + SM::VT + s * 16384, &tmV, bar_v, s * 64, J0, t.h, t.b);
+          }
         }
+        ++ti;
       }
     }
   } else if (warp == 1) {
@@ -161,10 +192,10 @@ relattn_fwd_kernel(const __grid_constant__ CUtensorMap tmQu, const __grid_consta
       const uint32_t idesc_o = umma_idesc(128, D, 0, 1, 0);
       const uint32_t qu = smem_u32(smem + SM::QU), qv = smem_u32(smem + SM::QV), kt = smem_u32(smem + SM::KT),
                      vt = smem_u32(smem + SM::VT), rt = smem_u32(smem + SM::RT), pt = smem_u32(smem + SM::PT);
-      auto issue_scores = [&](int st) {
-        mbar_wait(bar_k, st & 1);
+      auto issue_scores = [&](int gs) {
+        mbar_wait(bar_k, gs & 1);
         tc_fence_after();
-        const uint32_t tbd = T_BD + (st & 1) * 128;
+        const uint32_t tbd = T_BD + (gs & 1) * 128;
 #pragma unroll
         for (int k = 0; k < D / 16; ++k) {
           const uint32_t off = (k >> 2) * 16384 + (k & 3) * 32;
@@ -178,7 +209,7 @@ relattn_fwd_kernel(const __grid_constant__ CUtensorMap tmQu, const __grid_consta
         if (p.mode != 2) umma_commit(bar_kfree);  // mode 2: V_J (same load group) is still needed by dP
         umma_commit(bar_s);
       };
-      auto issue_dp = [&](int st) {
+      auto issue_dp = [&]() {
         // dP = dO_I . V_J^T into the columns the forward uses for O (same K-major x K-major form as the scores)
 #pragma unroll
         for (int k = 0; k < D / 16; ++k) {
@@ -188,40 +219,61 @@ relattn_fwd_kernel(const __grid_constant__ CUtensorMap tmQu, const __grid_consta
         umma_commit(bar_kfree);
         umma_commit(bar_o);
       };
-      mbar_wait(bar_q, 0);
-      tc_fence_after();
-      issue_scores(0);
-      if (p.mode == 2) issue_dp(0);
-      for (int st = 0; st < nsteps; ++st) {
-        mbar_wait(bar_s1, st & 1);
+      int gs = 0, ti = 0;
+      for (int pass = 0; pass < n_pass; ++pass) {
+        const int kk = item_of(pass);
+        if (kk < 0) continue;
+        const Item t = decode(kk);
+        mbar_wait(bar_q, ti & 1);
         tc_fence_after();
-        if (st + 1 < nsteps) issue_scores(st + 1);
-        mbar_wait(bar_p, st & 1);
-        tc_fence_after();
-        if (p.mode == 0) {
-          mbar_wait(bar_v, st & 1);
+        // T_S / the band slot are free: bar_s1 of the previous item's last step was waited for below
+        issue_scores(gs);
+        if (p.mode == 2) issue_dp();
+        if (t.nsteps == 1) umma_commit(bar_qfree);
+        for (int st = 0; st < t.nsteps; ++st, ++gs) {
+          mbar_wait(bar_s1, gs & 1);
           tc_fence_after();
-#pragma unroll
-          for (int k = 0; k < 8; ++k) {  // 128 keys / 16
-            const uint64_t adesc = umma_smem_desc(pt + (k >> 2) * 16384 + (k & 3) * 32, 16, 1024);
-            const uint64_t bdesc = umma_smem_desc(vt + k * 2048, 16384, 1024);
-            umma_ss(T_O, adesc, bdesc, idesc_o, (st | k) ? 1u : 0u);
+          if (st + 1 < t.nsteps) {
+            issue_scores(gs + 1);
+            if (p.mode != 2 && st + 2 == t.nsteps) umma_commit(bar_qfree);  // last scores of this item issued
           }
-          umma_commit(bar_o);
-        } else if (p.mode == 2) {
-          if (st + 1 < nsteps) issue_dp(st + 1);  // the softmax warps are done reading dP(st)
+          mbar_wait(bar_p, gs & 1);
+          tc_fence_after();
+          if (p.mode == 0) {
+            mbar_wait(bar_v, gs & 1);
+            tc_fence_after();
+#pragma unroll
+            for (int k = 0; k < 8; ++k) {  // 128 keys / 16
+              const uint64_t adesc = umma_smem_desc(pt + (k >> 2) * 16384 + (k & 3) * 32, 16, 1024);
+              const uint64_t bdesc = umma_smem_desc(vt + k * 2048, 16384, 1024);
+              umma_ss(T_O, adesc, bdesc, idesc_o, (st | k) ? 1u : 0u);
+            }
+            umma_commit(bar_o);
+          } else if (p.mode == 2) {
+            if (st + 1 < t.nsteps) {
+              issue_dp();  // the softmax warps are done reading dP(st)
+              if (st + 2 == t.nsteps) umma_commit(bar_qfree);  // last dP of this item issued: Q / dO may be replaced
+            }
+          }
         }
+        ++ti;
       }
     }
   } else {
     // ------------------------------------------------------------------ softmax warps: one query row per thread
     const int q = warp & 3;
     const int r = q * 32 + lane;
-    const int i = I0 + r;
     const uint32_t lane_off = (uint32_t)(q * 32) << 16;
     uint8_t* wstg = smem + SM::STG + (warp - 2) * 32 * STG_PITCH * 4;  // this warp's staging area (8704 B)
     float* stg = reinterpret_cast<float*>(wstg) + lane * STG_PITCH;
     uint8_t* prow = smem + SM::PT + r * 128;
+    int gs = 0;
+    for (int pass = 0; pass < n_pass; ++pass) {
+    const int kk = item_of(pass);
+    if (kk < 0) continue;
+    const Item it = decode(kk);
+    const int I = it.I, I0 = it.I0, h = it.h, b = it.b, nsteps = it.nsteps;
+    const int i = I0 + r;
     float m_run = NEG_BIG, l_run = 0.f;
     float lse_row = 0.f;
     float d_row = 0.f;
@@ -229,12 +281,12 @@ relattn_fwd_kernel(const __grid_constant__ CUtensorMap tmQu, const __grid_consta
     if (p.mode == 2) d_row = (i < p.L) ? p.Drow[((long long)b * p.H + h) * p.L + i] : 0.f;
     const long long zrow0 = (((long long)b * p.H + h) * p.L + I0 + q * 32) * p.L;  // first row of this warp in P / dS
 
-    for (int st = 0; st < nsteps; ++st) {
+    for (int st = 0; st < nsteps; ++st, ++gs) {
       const int J0 = (I - st) * 128;
-      const uint32_t tnew = T_BD + (st & 1) * 128, tprev = T_BD + ((st + 1) & 1) * 128;
+      const uint32_t tnew = T_BD + (gs & 1) * 128, tprev = T_BD + ((gs + 1) & 1) * 128;
       // interior tiles need no predicate: every (i, j) is causal, inside the window and inside the sequence
       const bool need_mask = !(J0 + 127 <= I0 && I0 + 127 - J0 < p.window && I0 + 127 < p.L);
-      mbar_wait(bar_s, st & 1);
+      mbar_wait(bar_s, gs & 1);
       tc_fence_after();
       // ---- pass 1: content + shifted position scores -> registers (raw, unscaled), row max
       float sc[4][32];
@@ -280,7 +332,7 @@ relattn_fwd_kernel(const __grid_constant__ CUtensorMap tmQu, const __grid_consta
       if (p.mode == 0) {
         // ---- online softmax bookkeeping with lazy rescale (rescale only when the max grew by more than 2^8)
         if (st > 0) {
-          mbar_wait(bar_o, (st - 1) & 1);  // O accumulated, P smem free
+          mbar_wait(bar_o, (gs - 1) & 1);  // O accumulated, P smem free
           tc_fence_after();
         }
         const bool grow = (st == 0) || (mx > m_run + 8.0f);
@@ -303,7 +355,7 @@ relattn_fwd_kernel(const __grid_constant__ CUtensorMap tmQu, const __grid_consta
           }
         }
       } else if (p.mode == 2) {
-        mbar_wait(bar_o, st & 1);  // dP(st) is in TMEM
+        mbar_wait(bar_o, gs & 1);  // dP(st) is in TMEM
         tc_fence_after();
       }
       const float m_use = (p.mode == 0) ? m_run : lse_row;
@@ -374,7 +426,7 @@ relattn_fwd_kernel(const __grid_constant__ CUtensorMap tmQu, const __grid_consta
     }
 
     if (p.mode == 0) {
-      mbar_wait(bar_o, (nsteps - 1) & 1);
+      mbar_wait(bar_o, (gs - 1) & 1);
       tc_fence_after();
       const float inv = 1.0f / l_run;
       if (i < p.L) p.lse2[((long long)b * p.H + h) * p.L + i] = m_run + log2f(l_run);
@@ -399,7 +451,11 @@ relattn_fwd_kernel(const __grid_constant__ CUtensorMap tmQu, const __grid_consta
           }
         }
       }
+      // the next item's first P.V (accumulate = 0) must not start before every row of O has been read: it is issued
+      // only after bar_p of that step, which these warps arrive on after this point
+      tc_fence_before();
     }
+    }  // items
   }
 
   tc_fence_before();
@@ -426,7 +482,8 @@ static int launch_attn(const CUtensorMap* tm, const AttnParams& p, cudaStream_t 
     DB1_CUDA(cudaFuncSetAttribute(relattn_fwd_kernel<D>, cudaFuncAttributeMaxDynamicSharedMemorySize, SM::TOTAL));
     configured = true;
   }
-  dim3 grid((p.L + 127) / 128, p.H, p.B);
+  const int n_items = ((p.L + 127) / 128) * p.H * p.B;
+  const int grid = n_items < sm_count() ? n_items : sm_count();
   relattn_fwd_kernel<D><<<grid, AT_THREADS, SM::TOTAL, stream>>>(tm[0], tm[1], tm[2], tm[3], tm[4], tm[5], p);
   DB1_CUDA(cudaGetLastError());
   return 0;
