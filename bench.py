@@ -60,7 +60,7 @@ class ClockSampler:
     def start(self):
         try:
             self.proc = subprocess.Popen(["nvidia-smi", "--query-gpu=" + self.Q, "--format=csv,noheader,nounits",
-                                          "-lms", "200"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+                                          "-lms", "50"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             threading.Thread(target=self._read, daemon=True).start()
         except OSError:
             self.proc = None
@@ -69,18 +69,20 @@ class ClockSampler:
         for line in self.proc.stdout:
             parts = [x.strip() for x in line.split(",")]
             if len(parts) >= 7 and parts[0] == self.idx:
-                self.rows.append(parts)
+                self.rows.append((time.time(), parts))
 
-    def stop(self):
+    def stop(self, t0=None, t1=None):
+        """Summary of the samples received between host times t0 and t1 (the timed region)."""
         if self.proc is None:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
         self.proc.terminate()
-        sm = sorted(int(r[1]) for r in self.rows if r[1].isdigit())
-        mx = [int(r[2]) for r in self.rows if r[2].isdigit()]
+        rows = [r for t, r in self.rows if (t0 is None or t >= t0) and (t1 is None or t <= t1 + 0.05)]
+        sm = sorted(int(r[1]) for r in rows if r[1].isdigit())
+        mx = [int(r[2]) for r in rows if r[2].isdigit()]
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        reasons = [n for i, n in enumerate(names) if any(r[3 + i].lower().startswith("active") for r in self.rows)]
+        reasons = [n for i, n in enumerate(names) if any(r[3 + i].lower().startswith("active") for r in rows)]
         return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": max(mx) if mx else None, "reasons": reasons,
-                "samples": len(self.rows)}
+                "samples": len(rows)}
 
 
 def make_config(fp16=True, **kw):
@@ -190,6 +192,9 @@ def run_ours(args):
             dist.barrier()
         torch.cuda.synchronize()
 
+    sampler = ClockSampler(torch.cuda.current_device() if "CUDA_VISIBLE_DEVICES" not in os.environ else local)
+    if not args.profile_only:
+        sampler.start()  # nvidia-smi needs a moment to start: launched before the warm-up, filtered to the timed region
     n_warm = args.warmup if args.profile_only else max(args.warmup, 3)
     for _ in range(n_warm):
         step(resident)
@@ -203,17 +208,16 @@ def run_ours(args):
         return
 
     # ---- timed region 1: inputs resident in HBM; per-launch CUDA events on the launching stream
-    sampler = ClockSampler(torch.cuda.current_device() if "CUDA_VISIBLE_DEVICES" not in os.environ else local)
     count = ops.set_profile(ops.Profile(timing=False))  # launch counter only: no events inside the headline region
-    sampler.start()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     barrier()
+    t_host0 = time.time()
     e0.record()
     for _ in range(args.steps):
         step(resident)
     e1.record()
     barrier()
-    clocks = sampler.stop()
+    t_host1 = time.time()
     ops.set_profile(None)
     # same steps again with one CUDA-event pair per launch (on the launching stream) for the per-kernel roofline
     prof = ops.set_profile(ops.Profile(timing=True))
@@ -243,6 +247,7 @@ def run_ours(args):
     if world > 1:
         dist.all_reduce(ms2, op=dist.ReduceOp.MAX)
     e2e_value = tokens_per_step * args.steps / (ms2.item() / 1e3)
+    clocks = sampler.stop(t_host0, time.time())  # samples under load: the resident, per-kernel and end-to-end regions
 
     if rank == 0:
         pk = peaks()
@@ -301,7 +306,7 @@ def run_ours(args):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")

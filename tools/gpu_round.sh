@@ -14,9 +14,13 @@ if has ncu; then
   tail -2 gpurun_out/ncu_list_$TAG.log
 fi
 if has ncufull; then
-  timeout 900 ncu --set full --clock-control none --import-source on -k regex:gemm_kernel -s 4 -c 2 -o gpurun_out/prof_gemm_$TAG -f \
+  timeout 600 ncu --set full --clock-control none --import-source on -k regex:gemm_kernel -s 4 -c 1 -o gpurun_out/prof_gemm_$TAG -f \
       python tools/bench_gemm.py "ff2" > gpurun_out/ncu_gemm_$TAG.log 2>&1
-  timeout 900 ncu --set full --clock-control none --import-source on -k regex:relattn -s 2 -c 1 -o gpurun_out/prof_attn_$TAG -f \
-      python tools/bench_attn.py > gpurun_out/ncu_attn_$TAG.log 2>&1
-  ls -la gpurun_out/*.ncu-rep
+  timeout 600 ncu --set full --clock-control none --import-source on -k regex:relattn -s 3 -c 1 -o gpurun_out/prof_attn_$TAG -f \
+      python tools/bench_attn.py 1024 > gpurun_out/ncu_attn_$TAG.log 2>&1
+  timeout 600 ncu --set full --clock-control none --import-source on -k regex:relattn -s 4 -c 1 -o gpurun_out/prof_attnbwd_$TAG -f \
+      python tools/bench_attn_bwd.py 1024 > gpurun_out/ncu_attnbwd_$TAG.log 2>&1
+  timeout 600 ncu --set full --clock-control none -k regex:ln_bwd_fused -s 2 -c 1 -o gpurun_out/prof_lnbwd_$TAG -f \
+      python bench.py --steps 1 --warmup 1 --profile-only > gpurun_out/ncu_lnbwd_$TAG.log 2>&1
+  ls -la gpurun_out/*_$TAG.ncu-rep
 fi
