@@ -25,7 +25,7 @@
 
 namespace db1 {
 
-constexpr int AT_THREADS = 192;
+constexpr int AT_THREADS = 320;  // TMA warp + MMA warp + 8 softmax warps
 constexpr float NEG_BIG = -1e30f;
 constexpr int STG_PITCH = 68;  // floats per staged row (64 + 4): 16-byte stores and odd-stride reads are conflict-free
 
@@ -126,9 +126,9 @@ relattn_fwd_kernel(const __grid_constant__ CUtensorMap tmQu, const __grid_consta
       mbar_init(bar_v, 1);
       mbar_init(bar_kfree, 1);
       mbar_init(bar_s, 1);
-      mbar_init(bar_p, 4);
+      mbar_init(bar_p, 8);
       mbar_init(bar_o, 1);
-      mbar_init(bar_s1, 4);
+      mbar_init(bar_s1, 8);
       mbar_init(bar_qfree, 1);
       mbar_fence_init();
     }
@@ -260,13 +260,20 @@ relattn_fwd_kernel(const __grid_constant__ CUtensorMap tmQu, const __grid_consta
       }
     }
   } else {
-    // ------------------------------------------------------------------ softmax warps: one query row per thread
+    // ------------------------------------------------------------------ softmax warps
+    // Eight warps, two per TMEM lane quadrant: thread = one query row x HALF of the tile's 128 key columns. The
+    // per-row shift of the position band (_rel_shift) is a 5-stage barrel shifter on registers (shift = 31 - lane),
+    // fed by two 32-column TMEM loads; the two halves of a row exchange their row maximum through shared memory.
     const int q = warp & 3;
+    const int half = (warp - 2) >> 2;
     const int r = q * 32 + lane;
     const uint32_t lane_off = (uint32_t)(q * 32) << 16;
-    uint8_t* wstg = smem + SM::STG + (warp - 2) * 32 * STG_PITCH * 4;  // this warp's staging area (8704 B)
-    float* stg = reinterpret_cast<float*>(wstg) + lane * STG_PITCH;
+    uint8_t* wstg = smem + SM::STG + (warp - 2) * 2560;                     // per-warp 32 x 80 B transpose area for P / dS stores
+    float* xmax = reinterpret_cast<float*>(smem + SM::STG + 8 * 2560);      // [2 parity][2 half][128]
+    float* xsum = xmax + 2 * 2 * 128;                                       // [2 half][128]
     uint8_t* prow = smem + SM::PT + r * 128;
+    const int sh = 31 - lane;
+    const bool b16 = sh & 16, b8 = sh & 8, b4 = sh & 4, b2 = sh & 2, b1 = sh & 1;
     int gs = 0;
     for (int pass = 0; pass < n_pass; ++pass) {
     const int kk = item_of(pass);
@@ -288,45 +295,59 @@ relattn_fwd_kernel(const __grid_constant__ CUtensorMap tmQu, const __grid_consta
       const bool need_mask = !(J0 + 127 <= I0 && I0 + 127 - J0 < p.window && I0 + 127 < p.L);
       mbar_wait(bar_s, gs & 1);
       tc_fence_after();
-      // ---- pass 1: content + shifted position scores -> registers (raw, unscaled), row max
-      float sc[4][32];
+      // ---- pass 1: content + shifted position scores -> registers (raw, unscaled), row max over this half
+      float sc[2][32];
       float mx = NEG_BIG;
 #pragma unroll
-      for (int cc = 0; cc < 4; ++cc) {
+      for (int c2 = 0; c2 < 2; ++c2) {
+        const int cc = half * 2 + c2;
         uint32_t s[32], w0[32], w1[32];
         const int blk = cc - q + 3;  // 32-column block of the 256-wide [new | prev] window
-        tmem_ld32(T_S + lane_off + cc * 32, s);
         tmem_ld32(((blk < 4) ? tnew + blk * 32 : tprev + (blk - 4) * 32) + lane_off, w0);
         tmem_ld32(((blk + 1 < 4) ? tnew + (blk + 1) * 32 : tprev + (blk - 3) * 32) + lane_off, w1);
+        tmem_ld32(T_S + lane_off + cc * 32, s);
         tmem_ld_wait();
+        // x[t] <- window[t + sh], t < 32: stages 16, 8, 4, 2, 1 (in place, ascending t reads not-yet-written slots)
+        float x[64];
 #pragma unroll
-        for (int k = 0; k < 8; ++k) {
-          reinterpret_cast<uint4*>(stg)[k] = make_uint4(w0[4 * k], w0[4 * k + 1], w0[4 * k + 2], w0[4 * k + 3]);
-          reinterpret_cast<uint4*>(stg)[8 + k] = make_uint4(w1[4 * k], w1[4 * k + 1], w1[4 * k + 2], w1[4 * k + 3]);
+        for (int t = 0; t < 32; ++t) {
+          x[t] = __uint_as_float(w0[t]);
+          x[32 + t] = __uint_as_float(w1[t]);
         }
-        __syncwarp();
-        const float* rd = stg + (31 - lane);
+#pragma unroll
+        for (int t = 0; t < 47; ++t) x[t] = b16 ? x[t + 16] : x[t];
+#pragma unroll
+        for (int t = 0; t < 39; ++t) x[t] = b8 ? x[t + 8] : x[t];
+#pragma unroll
+        for (int t = 0; t < 35; ++t) x[t] = b4 ? x[t + 4] : x[t];
+#pragma unroll
+        for (int t = 0; t < 33; ++t) x[t] = b2 ? x[t + 2] : x[t];
+#pragma unroll
+        for (int t = 0; t < 32; ++t) x[t] = b1 ? x[t + 1] : x[t];
         if (need_mask) {
 #pragma unroll
           for (int t = 0; t < 32; ++t) {
             const int j = J0 + cc * 32 + t;
             const bool ok = (j <= i) && (i - j < p.window) && (j < p.L);
-            sc[cc][t] = ok ? (__uint_as_float(s[t]) + rd[t]) : NEG_BIG;
-            mx = fmaxf(mx, sc[cc][t]);
+            sc[c2][t] = ok ? (__uint_as_float(s[t]) + x[t]) : NEG_BIG;
+            mx = fmaxf(mx, sc[c2][t]);
           }
         } else {
 #pragma unroll
           for (int t = 0; t < 32; ++t) {
-            sc[cc][t] = __uint_as_float(s[t]) + rd[t];
-            mx = fmaxf(mx, sc[cc][t]);
+            sc[c2][t] = __uint_as_float(s[t]) + x[t];
+            mx = fmaxf(mx, sc[c2][t]);
           }
         }
-        __syncwarp();
       }
       // S and the previous band chunk are consumed: the MMA warp may overwrite them with step st+1's scores
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(bar_s1);
+      // row maximum over both halves (double-buffered slot, one 64-thread named barrier per quadrant and step)
+      xmax[((gs & 1) * 2 + half) * 128 + r] = mx;
+      named_bar_sync(1 + q, 64);
+      mx = fmaxf(mx, xmax[((gs & 1) * 2 + (half ^ 1)) * 128 + r]);
       mx *= p.scale_log2;  // scale > 0: max commutes with the scaling; masked entries stay hugely negative
 
       if (p.mode == 0) {
@@ -343,7 +364,7 @@ relattn_fwd_kernel(const __grid_constant__ CUtensorMap tmQu, const __grid_consta
           m_run = m_new;
           if (st > 0) {
 #pragma unroll 1
-            for (int c = 0; c < D / 32; ++c) {
+            for (int c = half * (D / 64); c < (half + 1) * (D / 64); ++c) {  // this half's columns of O
               uint32_t o[32];
               tmem_ld32(T_O + lane_off + c * 32, o);
               tmem_ld_wait();
@@ -362,12 +383,13 @@ relattn_fwd_kernel(const __grid_constant__ CUtensorMap tmQu, const __grid_consta
       // ---- pass 2: probabilities from the registers, p = exp2(raw * scale_log2 - m)
       float sum = 0.f;
 #pragma unroll
-      for (int cc = 0; cc < 4; ++cc) {
+      for (int c2 = 0; c2 < 2; ++c2) {
+        const int cc = half * 2 + c2;
         uint32_t pk[16];
 #pragma unroll
         for (int t = 0; t < 16; ++t) {
-          const float p0 = exp2f(fmaf(sc[cc][2 * t], p.scale_log2, -m_use));
-          const float p1 = exp2f(fmaf(sc[cc][2 * t + 1], p.scale_log2, -m_use));
+          const float p0 = exp2f(fmaf(sc[c2][2 * t], p.scale_log2, -m_use));
+          const float p1 = exp2f(fmaf(sc[c2][2 * t + 1], p.scale_log2, -m_use));
           sum += p0 + p1;
           pk[t] = pack_half2(p0, p1);
         }
@@ -426,13 +448,17 @@ relattn_fwd_kernel(const __grid_constant__ CUtensorMap tmQu, const __grid_consta
     }
 
     if (p.mode == 0) {
+      // total row sum over both halves, then each half normalises and writes its D/2 columns of O
+      xsum[half * 128 + r] = l_run;
       mbar_wait(bar_o, (gs - 1) & 1);
       tc_fence_after();
-      const float inv = 1.0f / l_run;
-      if (i < p.L) p.lse2[((long long)b * p.H + h) * p.L + i] = m_run + log2f(l_run);
+      named_bar_sync(1 + q, 64);
+      const float l_tot = l_run + xsum[(half ^ 1) * 128 + r];
+      const float inv = 1.0f / l_tot;
+      if (half == 0 && i < p.L) p.lse2[((long long)b * p.H + h) * p.L + i] = m_run + log2f(l_tot);
       __half* orow = p.O + ((long long)b * p.L + i) * p.ldo + (long long)h * p.dh;
 #pragma unroll 1
-      for (int c = 0; c < D / 32; ++c) {
+      for (int c = half * (D / 64); c < (half + 1) * (D / 64); ++c) {
         uint32_t o[32];
         tmem_ld32(T_O + lane_off + c * 32, o);
         tmem_ld_wait();
@@ -452,8 +478,10 @@ relattn_fwd_kernel(const __grid_constant__ CUtensorMap tmQu, const __grid_consta
         }
       }
       // the next item's first P.V (accumulate = 0) must not start before every row of O has been read: it is issued
-      // only after bar_p of that step, which these warps arrive on after this point
+      // only after bar_p of that step, which these warps arrive on after this point. The second named barrier keeps
+      // a fast half from overwriting xsum (next item) before its partner has read it.
       tc_fence_before();
+      named_bar_sync(1 + q, 64);
     }
     }  // items
   }
