@@ -15,8 +15,9 @@ from ._lib import (EPI_DGEGLU, EPI_DS, EPI_GEGLU, EPI_PLAIN, EPI_QKV, K_BEGIN_BY
 class Profile:
     """Launch accounting and optional per-launch CUDA-event timing (events are recorded on the launching stream)."""
 
-    def __init__(self, timing=False):
+    def __init__(self, timing=False, by_shape=False):
         self.timing = timing
+        self.by_shape = by_shape  # GEMM records are keyed by shape as well (development view)
         self.launches = 0
         self.records = []  # (name, algorithmic flops, algorithmic bytes, start event, end event)
 
@@ -117,7 +118,10 @@ def gemm(A, B, C_out, M, N, K, *, lda, ldb, ldc, a_mn=False, b_mn=False, epilogu
     flops = 2.0 * M * N * K * Z1 * Z2
     if k_mode != K_FULL or skip_upper:
         flops *= (M + 1) / (2.0 * M)  # causal: only unmasked (i, j) pairs are algorithmic work
-    with _Launch("gemm_" + _EPI_NAMES[epilogue] + ("_batched" if Z1 * Z2 > 1 else ""), 1, flops):
+    name = "gemm_" + _EPI_NAMES[epilogue] + ("_batched" if Z1 * Z2 > 1 else "")
+    if _active is not None and _active.timing and _active.by_shape:
+        name += "_%dx%dx%d%s%s" % (M, N, K, "_Amn" if a_mn else "", "_Bmn" if b_mn else "")
+    with _Launch(name, 1, flops):
         check(_lib.lib().db1_gemm_f16(C.byref(d), cur_stream()), "db1_gemm_f16")
     return C_out
 

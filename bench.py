@@ -220,7 +220,7 @@ def run_ours(args):
     t_host1 = time.time()
     ops.set_profile(None)
     # same steps again with one CUDA-event pair per launch (on the launching stream) for the per-kernel roofline
-    prof = ops.set_profile(ops.Profile(timing=True))
+    prof = ops.set_profile(ops.Profile(timing=True, by_shape=args.by_shape))
     n_prof = min(args.steps, 3)
     for _ in range(n_prof):
         step(resident)
@@ -313,6 +313,7 @@ def main():
     ap.add_argument("--workload", default="rl", choices=["rl", "atari", "mixed"],
                     help="rl = BASELINE config 2 (headline, default); atari = config 3; mixed = config 4's per-rank batch")
     ap.add_argument("--profile-only", action="store_true", help="warm-up + steps only (for runs under ncu)")
+    ap.add_argument("--by-shape", action="store_true", help="per-kernel breakdown keyed by GEMM shape (development)")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)
