@@ -764,8 +764,8 @@ extern "C" int db1_gemm_f16(const db1_gemm_desc* d, void* stream_) {
   int BNsel = 256;
   if (epilogue == DB1_EPI_PLAIN || epilogue == DB1_EPI_DGEGLU) {
     if (d->bn_hint == 128 || (d->bn_hint == 0 && N <= 128)) BNsel = 128;
-    // small problems: if 128 x 256 tiles cannot give every SM a tile, halve the tile width (twice the CTAs in flight)
-    if (d->bn_hint == 0 && !batched && (long long)cdiv(M, BM) * cdiv(N, 256) < sm_count()) BNsel = 128;
+    // small problems: if 128 x 256 tiles leave at least half of the SMs idle, halve the tile width (twice the CTAs)
+    if (d->bn_hint == 0 && !batched && 2LL * cdiv(M, BM) * cdiv(N, 256) <= sm_count()) BNsel = 128;
   }
   if (epilogue == DB1_EPI_QKV) {
     DB1_CHECK_ARG(d->u && d->v && d->d_model > 0 && N == 3 * d->d_model, "gemm(qkv): need u, v and N == 3*d_model");
