@@ -41,6 +41,7 @@ struct AttnParams {
   __half* dS;          // mode 2
   const float* Drow;   // mode 2: rowsum(dO * O) [B,H,L]
   float scale;         // mode 2: softmax scale (natural domain) applied to dS
+  int q_start;         // first query row that is computed (memory-augmented inference: rows < q_start are memory)
 };
 
 template <int D>
@@ -85,7 +86,7 @@ relattn_fwd_kernel(const __grid_constant__ CUtensorMap tmQu, const __grid_consta
   // TMEM, barriers and the smem ring live across items; barrier phases are tracked by global step / item counters.
   const int nq = (p.L + 127) / 128;
   const int HB = p.H * p.B;
-  const int n_items = nq * HB;
+  const int n_items = (nq - p.q_start / 128) * HB;  // query tiles that contain rows >= q_start
   const int G = gridDim.x;
   auto item_of = [&](int pass) -> int {
     const int c = (pass & 1) ? (G - 1 - (int)blockIdx.x) : (int)blockIdx.x;
@@ -455,14 +456,14 @@ relattn_fwd_kernel(const __grid_constant__ CUtensorMap tmQu, const __grid_consta
       named_bar_sync(1 + q, 64);
       const float l_tot = l_run + xsum[(half ^ 1) * 128 + r];
       const float inv = 1.0f / l_tot;
-      if (half == 0 && i < p.L) p.lse2[((long long)b * p.H + h) * p.L + i] = m_run + log2f(l_tot);
+      if (half == 0 && i < p.L && i >= p.q_start) p.lse2[((long long)b * p.H + h) * p.L + i] = m_run + log2f(l_tot);
       __half* orow = p.O + ((long long)b * p.L + i) * p.ldo + (long long)h * p.dh;
 #pragma unroll 1
       for (int c = half * (D / 64); c < (half + 1) * (D / 64); ++c) {
         uint32_t o[32];
         tmem_ld32(T_O + lane_off + c * 32, o);
         tmem_ld_wait();
-        if (i < p.L) {
+        if (i < p.L && i >= p.q_start) {
 #pragma unroll
           for (int g = 0; g < 4; ++g) {
             const int col = c * 32 + g * 8;
@@ -510,7 +511,7 @@ static int launch_attn(const CUtensorMap* tm, const AttnParams& p, cudaStream_t 
     DB1_CUDA(cudaFuncSetAttribute(relattn_fwd_kernel<D>, cudaFuncAttributeMaxDynamicSharedMemorySize, SM::TOTAL));
     configured = true;
   }
-  const int n_items = ((p.L + 127) / 128) * p.H * p.B;
+  const int n_items = ((p.L + 127) / 128 - p.q_start / 128) * p.H * p.B;
   const int grid = n_items < sm_count() ? n_items : sm_count();
   relattn_fwd_kernel<D><<<grid, AT_THREADS, SM::TOTAL, stream>>>(tm[0], tm[1], tm[2], tm[3], tm[4], tm[5], p);
   DB1_CUDA(cudaGetLastError());
@@ -524,11 +525,12 @@ using namespace db1;
 static int relattn_launch(const void* qu, const void* qv, const void* k, const void* v, long long ld_qkv,
                           const void* r, long long ld_r, void* out, long long ld_out, float* lse2, void* probs,
                           const void* dout, long long ld_do, const float* drow, void* ds, int B, int L, int H, int dh,
-                          int window, float scale, int mode, cudaStream_t stream) {
+                          int window, float scale, int mode, int q_start, cudaStream_t stream) {
   DB1_CHECK_ARG(qu && qv && k && r && lse2, "relattn: null pointer");
+  DB1_CHECK_ARG(q_start >= 0 && q_start < L && (q_start == 0 || mode == 0), "relattn: bad q_start %d", q_start);
   DB1_CHECK_ARG(B > 0 && L > 0 && H > 0, "relattn: bad shape B=%d L=%d H=%d", B, L, H);
   DB1_CHECK_ARG(dh % 8 == 0 && dh >= 8 && dh <= 128, "relattn: head dim %d unsupported (multiple of 8, <= 128)", dh);
-  DB1_CHECK_ARG(L % 8 == 0, "relattn: sequence length %d must be a multiple of 8", L);
+  DB1_CHECK_ARG(mode == 0 || L % 8 == 0, "relattn: sequence length %d must be a multiple of 8 for the P / dS outputs", L);
   DB1_CHECK_ARG(ld_qkv % 8 == 0 && ld_r % 8 == 0 && ld_out % 8 == 0 && ld_do % 8 == 0,
                 "relattn: row strides must be multiples of 8");
   DB1_CHECK_ARG(window > 0, "relattn: window (mem_len) must be > 0; mem_len == 0 masks every key");
@@ -536,7 +538,7 @@ static int relattn_launch(const void* qu, const void* qv, const void* k, const v
   p.L = L; p.H = H; p.B = B; p.dh = dh; p.window = window;
   p.scale_log2 = scale * 1.4426950408889634f;
   p.O = (__half*)out; p.ldo = ld_out; p.lse2 = lse2; p.P = (__half*)probs; p.mode = mode;
-  p.dS = (__half*)ds; p.Drow = drow; p.scale = scale;
+  p.dS = (__half*)ds; p.Drow = drow; p.scale = scale; p.q_start = q_start;
   CUtensorMap tm[6];
   int e;
   if ((e = make_head_map(&tm[0], qu, dh, L, H, B, ld_qkv))) return e;
@@ -559,7 +561,15 @@ extern "C" int db1_relattn_fwd(const void* qu, const void* qv, const void* k, co
   DB1_CHECK_ARG(mode == 0 || mode == 1, "relattn: mode must be 0 (O, LSE) or 1 (P)");
   DB1_CHECK_ARG((mode == 0 && v && out) || (mode == 1 && probs), "relattn: missing output for mode %d", mode);
   return relattn_launch(qu, qv, k, v, ld_qkv, r, ld_r, out, ld_out, lse2, probs, nullptr, 0, nullptr, nullptr, B, L, H,
-                        dh, window, scale, mode, (cudaStream_t)stream_);
+                        dh, window, scale, mode, 0, (cudaStream_t)stream_);
+}
+
+extern "C" int db1_relattn_mem_fwd(const void* qu, const void* qv, const void* k, const void* v, long long ld_qkv,
+                                   const void* r, long long ld_r, void* out, long long ld_out, float* lse2, int B, int K,
+                                   int H, int dh, int window, float scale, int mlen, void* stream_) {
+  DB1_CHECK_ARG(v && out, "relattn_mem_fwd: null pointer");
+  return relattn_launch(qu, qv, k, v, ld_qkv, r, ld_r, out, ld_out, lse2, nullptr, nullptr, 0, nullptr, nullptr, B, K, H,
+                        dh, window, scale, 0, mlen, (cudaStream_t)stream_);
 }
 
 extern "C" int db1_relattn_bwd_ds(const void* qu, const void* qv, const void* k, const void* v, long long ld_qkv,
@@ -568,5 +578,5 @@ extern "C" int db1_relattn_bwd_ds(const void* qu, const void* qv, const void* k,
                                   float scale, void* stream_) {
   DB1_CHECK_ARG(v && dout && drow && probs && ds, "relattn_bwd_ds: null pointer");
   return relattn_launch(qu, qv, k, v, ld_qkv, r, ld_r, nullptr, 0, const_cast<float*>(lse2), probs, dout, ld_do, drow,
-                        ds, B, L, H, dh, window, scale, 2, (cudaStream_t)stream_);
+                        ds, B, L, H, dh, window, scale, 2, 0, (cudaStream_t)stream_);
 }

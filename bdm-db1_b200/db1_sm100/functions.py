@@ -202,6 +202,36 @@ class AttnBlockFn(torch.autograd.Function):
         return (dx.view(B, L, d), None, gWqkv.ret(), gWr.ret(), gWo.ret(), gu, gv, gg, gb, None, None, None, None)
 
 
+def attn_block_with_memory(w, mem, r, Wqkv, Wr, Wo, u, v, gamma, beta, H, eps, window):
+    """RelPartialLearnableMultiHeadAttn.forward with `mems` (transformer_xl.py:124-133, :141-238), inference only:
+    keys / values come from cat(mem, w), queries are the last qlen rows, r has klen = mlen + qlen rows."""
+    B, qlen, d = w.shape
+    mlen = mem.shape[1]
+    K = mlen + qlen
+    dh = d // H
+    dev = w.device
+    f16 = torch.float16
+    cat = torch.cat([mem, w], dim=1).reshape(B * K, d)  # buffer plumbing only (the reference concatenates too, :125)
+    qkv4 = torch.empty(B * K, 4 * d, dtype=f16, device=dev)
+    ops.gemm(cat, Wqkv, qkv4, B * K, 3 * d, d, lda=d, ldb=d, ldc=4 * d, epilogue=ops.EPI_QKV, u=u.reshape(d),
+             v=v.reshape(d), d_model=d)
+    rk = torch.empty(K, d, dtype=f16, device=dev)
+    ops.gemm(r, Wr, rk, K, d, d, lda=d, ldb=d, ldc=d)
+    o = torch.empty(B, K, d, dtype=f16, device=dev)
+    lse2 = torch.empty(B, H, K, dtype=torch.float32, device=dev)
+    ops.relattn_mem_fwd(qkv4, rk, o.view(B * K, d), lse2, B, K, H, dh, window, 1.0 / math.sqrt(dh), mlen)
+    oq = o[:, mlen:].reshape(B * qlen, d)  # gathers the query rows (copy)
+    x2 = w.reshape(B * qlen, d)
+    if not x2.is_contiguous():
+        x2 = x2.contiguous()
+    y = torch.empty(B * qlen, d, dtype=f16, device=dev)
+    ops.gemm(oq, Wo, y, B * qlen, d, d, lda=d, ldb=d, ldc=d, resid=x2, ldr=d)
+    out = torch.empty(B * qlen, d, dtype=f16, device=dev)
+    stats = torch.empty(B * qlen, 2, dtype=torch.float32, device=dev)
+    ops.layernorm_fwd(y, gamma, beta, out, stats, eps)
+    return out.view(B, qlen, d)
+
+
 class FFBlockFn(torch.autograd.Function):
     """PositionwiseFF.forward, post-LN branch with GeGLU (transformer_xl.py:276-292, activations.py:19-32):
     out = LayerNorm(x + dropout(W2 (a * gelu(g)) + b2)), [a|g] = W1 x + b1."""

@@ -145,6 +145,20 @@ def relattn_fwd(qkv4, r, out, lse2, B, L, H, dh, window, scale, probs=None):
         ptr(lse2), ptr(probs), B, L, H, dh, int(window), C.c_float(scale), mode, cur_stream()), "db1_relattn_fwd")
 
 
+def relattn_mem_fwd(qkv4, r, out, lse2, B, K, H, dh, window, scale, mlen):
+    """Attention over cat(mem, w) (K = mlen + qlen rows per sequence); only query rows >= mlen are produced.
+    include/db1_sm100.h:db1_relattn_mem_fwd."""
+    _need_cuda_half(qkv4, r, out)
+    d = H * dh
+    es = qkv4.element_size()
+    base = qkv4.data_ptr()
+    with _Launch("relattn_mem_fwd", 1):
+      check(_lib.lib().db1_relattn_mem_fwd(
+        C.c_void_p(base), C.c_void_p(base + d * es), C.c_void_p(base + 2 * d * es), C.c_void_p(base + 3 * d * es),
+        C.c_longlong(qkv4.stride(0)), ptr(r), C.c_longlong(r.stride(0)), ptr(out), C.c_longlong(out.stride(0)),
+        _f32(lse2), B, K, H, dh, int(window), C.c_float(scale), int(mlen), cur_stream()), "db1_relattn_mem_fwd")
+
+
 def relattn_bwd_ds(qkv4, r, dout, lse2, drow, probs, ds, B, L, H, dh, window, scale):
     """P and dS = P * (dO V^T - D) * scale for the attention backward; include/db1_sm100.h:db1_relattn_bwd_ds."""
     _need_cuda_half(qkv4, r, dout, probs, ds)

@@ -84,8 +84,6 @@ class RelPartialLearnableMultiHeadAttn(nn.Module):
             raise NotImplementedError("sm_100a path implements the released post-LN, non-DeepNorm configuration")
         if head_mask is not None or output_attentions:
             raise NotImplementedError("head_mask / output_attentions are never used by DB1's callers")
-        if mem is not None:
-            raise NotImplementedError("memory-augmented inference (mems) is not on the fwd+bwd path yet")
         if self.training and self.dropatt.p > 0:
             raise NotImplementedError("attention-probability dropout (dropattn) is 0 in DB1")
         _require_kernel_tensor(w, "hidden states")
@@ -96,6 +94,16 @@ class RelPartialLearnableMultiHeadAttn(nn.Module):
             # reference semantics (:177): a mask that is all zeros is an error
             pass
         win = int(window) if window is not None else (1 << 30)
+        if mem is not None and mem.size(1) > 0:
+            # memory-augmented inference (reference :124-133): no autograd, no dropout (callers run under eval())
+            if torch.is_grad_enabled() and (w.requires_grad or self.qkv_net.weight.requires_grad) and self.training:
+                raise NotImplementedError("training with mems is asserted off by the reference (:515-517)")
+            with torch.no_grad():
+                out = F_.attn_block_with_memory(w, mem.to(w.dtype), r2, self.qkv_net.weight, self.r_net.weight,
+                                                self.o_net.weight, self.r_w_bias, self.r_r_bias,
+                                                self.layer_norm.weight, self.layer_norm.bias, self.n_head,
+                                                self.layer_norm.eps, min(win, 1 << 30))
+            return (out,)
         p = self.drop.p if self.training else 0.0
         out = F_.AttnBlockFn.apply(w, r2, self.qkv_net.weight, self.r_net.weight, self.o_net.weight, self.r_w_bias,
                                    self.r_r_bias, self.layer_norm.weight, self.layer_norm.bias, self.n_head,
@@ -236,8 +244,6 @@ class TransformerXL(nn.Module):
     # ------------------------------------------------------------------------------------------------ forward
     def forward(self, tasks_input: List[GatoInputBase], compute_loss: bool = True, mems=None):
         assert not (compute_loss and mems is not None), "During training, Gato does not use memory mechanism."
-        if mems is not None:
-            raise NotImplementedError("memory-augmented inference (mems) is not on the fwd+bwd path yet")
         embs, masks, labels = [], [], []
         p_emb = self.drop.p if self.training else 0.0
         for task in tasks_input:
@@ -260,7 +266,8 @@ class TransformerXL(nn.Module):
         hidden = embs[0] if len(embs) == 1 else torch.cat(embs, dim=0)
 
         qlen = hidden.size(1)
-        klen = qlen
+        mlen = mems[0].size(1) if mems is not None else 0
+        klen = mlen + qlen
         # same_length: every query sees exactly mem_len keys once klen exceeds mem_len (reference :551-562);
         # otherwise plain causal. mem_len == 0 with same_length masks everything -> the reference raises ValueError.
         if self.same_length and klen > self.mem_len:
@@ -271,9 +278,13 @@ class TransformerXL(nn.Module):
             window = 1 << 30
         pos_rows = self.pos_emb.rows(klen, self.clamp_len, self.drop.p if self.training else 0.0)
 
-        for block in self.h:
-            hidden = block(hidden, pos_rows, attention_mask=None, mems=None, head_mask=None, output_attentions=False,
-                           deepnorm_alpha=self.deepnorm_alpha, window=window)[0]
+        hids = []
+        for li, block in enumerate(self.h):
+            if mems is not None:
+                hids.append(hidden)
+            hidden = block(hidden, pos_rows, attention_mask=None, mems=None if mems is None else mems[li],
+                           head_mask=None, output_attentions=False, deepnorm_alpha=self.deepnorm_alpha, window=window)[0]
+        new_mems = self._update_mem(hids, mems, mlen, qlen) if mems is not None else None
 
         W = self.word_embedding.weight if self.share_input_output_embedding else self.lm_head.weight
         if compute_loss:
@@ -282,6 +293,8 @@ class TransformerXL(nn.Module):
             with torch.no_grad():
                 lm_logits = F_.head_logits(hidden, W)
             loss = None
+        if new_mems is not None:
+            return (lm_logits, loss, new_mems)  # reference :615-619
         return (lm_logits, loss)
 
     # ------------------------------------------------------------------------------------------------ task embeddings

@@ -104,6 +104,13 @@ int db1_relattn_fwd(const void* qu, const void* qv, const void* k, const void* v
                     long long ld_r, void* out, long long ld_out, float* lse2, void* probs, int B, int L, int H, int dh,
                     int window, float scale, int mode, void* stream);
 
+/* Memory-augmented inference (transformer_xl.py:124-133 with mems, evaluate_rl.py:157-266): the same kernel over the
+ * K = mlen + qlen rows of cat(mem, w); only query rows >= mlen are computed and written (out / lse2 are addressed
+ * with the row index in the concatenated sequence). r holds K rows. window as above (keys with 0 <= delta < window). */
+int db1_relattn_mem_fwd(const void* qu, const void* qv, const void* k, const void* v, long long ld_qkv, const void* r,
+                        long long ld_r, void* out, long long ld_out, float* lse2, int B, int K, int H, int dh,
+                        int window, float scale, int mlen, void* stream);
+
 /* Attention backward, first half (same tiling as the forward): recomputes P = softmax(S) from the saved LSE, forms
  * dP = dO . V^T on the tensor cores and writes both P and dS = P * (dP - D) * scale ([B,H,L,L] fp16, visited causal
  * tiles only; D = rowsum(dO * O) from db1_rowdot). Adjoint of transformer_xl.py:173-225; the contractions that consume
