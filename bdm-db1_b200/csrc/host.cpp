@@ -3,6 +3,7 @@
 //   db1_rl_layout               : src/data/rl_dataset.py:44-71 (action flag / local position ids),
 //                                 :683-697 (join), :711-716 + :865-872 (pad/truncate to L+1), :738-746 (shift)
 //   db1_build_rl_sample_idx     : src/data/helpers.cpp:82-115 semantics (trajectory window index)
+//   db1_build_sample_idx        : src/data/helpers.cpp:117-203 semantics (GPT packed-sample index)
 // Compiled with -ffp-contract=off: every float32 operation below is rounded exactly once, in the order the
 // reference's torch expression evaluates it.
 #include "../../include/db1_host.h"
@@ -112,6 +113,32 @@ long long db1_build_rl_sample_idx(const int32_t* path_lengths, long long n_paths
     }
   }
   return r;
+}
+
+// GPT sample index (src/data/helpers.cpp:117-203 semantics, Megatron packing): documents doc_idx[0..n_doc_idx) are laid
+// end to end; sample k covers seq_length + 1 tokens starting at flattened token k * seq_length (one token of overlap),
+// so its start is the (document slot, offset) that holds that token. out: [num_samples + 1, 2] int32 with
+// num_samples = (num_epochs * tokens_per_epoch - 1) / seq_length. out == NULL: returns the row count only.
+// Returns the number of rows, -1 on bad arguments, -2 if out_rows is too small, -3 if the documents run out.
+long long db1_build_sample_idx(const int32_t* sizes, const int32_t* doc_idx, long long n_doc_idx, int seq_length,
+                               int num_epochs, long long tokens_per_epoch, int32_t* out, long long out_rows) {
+  if (!sizes || !doc_idx || n_doc_idx <= 0 || seq_length <= 1 || num_epochs <= 0 || tokens_per_epoch <= 1) return -1;
+  const long long num_samples = ((long long)num_epochs * tokens_per_epoch - 1) / seq_length;
+  const long long rows = num_samples + 1;
+  if (!out) return rows;
+  if (out_rows < rows) return -2;
+  long long slot = 0;       // index into doc_idx of the document holding the current start token
+  long long slot_begin = 0; // flattened index of that document's first token
+  for (long long k = 0; k < rows; ++k) {
+    const long long start = k * (long long)seq_length;
+    while (start >= slot_begin + sizes[doc_idx[slot]]) {
+      slot_begin += sizes[doc_idx[slot]];
+      if (++slot >= n_doc_idx) return -3;
+    }
+    out[2 * k] = (int32_t)slot;
+    out[2 * k + 1] = (int32_t)(start - slot_begin);
+  }
+  return rows;
 }
 
 }  // extern "C"

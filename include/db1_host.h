@@ -28,6 +28,13 @@ int db1_rl_layout(const long long* obs, const long long* act, int T, int obs_len
 long long db1_build_rl_sample_idx(const int32_t* path_lengths, long long n_paths, int transition_num, int32_t* out,
                                   long long out_rows);
 
+/* build_sample_idx (src/data/helpers.cpp:117-203, used by gpt_dataset.py:283-289): packed GPT samples of
+ * seq_length + 1 tokens over the documents doc_idx[0..n_doc_idx) laid end to end; row k = (index into doc_idx, offset in
+ * that document) of flattened token k * seq_length. Rows = (num_epochs * tokens_per_epoch - 1) / seq_length + 1.
+ * out == NULL counts only. Returns rows, -2 if out_rows is too small, -3 if the documents run out. */
+long long db1_build_sample_idx(const int32_t* sizes, const int32_t* doc_idx, long long n_doc_idx, int seq_length,
+                               int num_epochs, long long tokens_per_epoch, int32_t* out, long long out_rows);
+
 #ifdef __cplusplus
 }
 #endif

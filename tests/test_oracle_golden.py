@@ -164,3 +164,69 @@ def test_oracle_model_forward_backward_matches_reference(name):
         assert abs(p.grad.double().norm().item() - g["gradnorm:" + k[5:]][0]) < 1e-4 * g["gradnorm:" + k[5:]][0] + 1e-9
         checked += 1
     assert checked >= 8
+
+
+def _rl_idx(lens, T):
+    import ctypes as C
+    from db1_sm100 import _lib
+    f = _lib.hostlib().db1_build_rl_sample_idx
+    f.restype = C.c_longlong
+    n = f(lens.ctypes.data_as(C.c_void_p), C.c_longlong(len(lens)), int(T), None, C.c_longlong(0))
+    out = np.empty((n, 3), dtype=np.int32)
+    assert f(lens.ctypes.data_as(C.c_void_p), C.c_longlong(len(lens)), int(T), out.ctypes.data_as(C.c_void_p), C.c_longlong(n)) == n
+    return out
+
+
+def _gpt_idx(sizes, doc_idx, seq, ep, tpe):
+    import ctypes as C
+    from db1_sm100 import _lib
+    f = _lib.hostlib().db1_build_sample_idx
+    f.restype = C.c_longlong
+    args = (sizes.ctypes.data_as(C.c_void_p), doc_idx.ctypes.data_as(C.c_void_p), C.c_longlong(len(doc_idx)), int(seq),
+            int(ep), C.c_longlong(int(tpe)))
+    n = f(*args, None, C.c_longlong(0))
+    out = np.empty((n, 2), dtype=np.int32)
+    assert f(*args, out.ctypes.data_as(C.c_void_p), C.c_longlong(n)) == n
+    return out
+
+
+def test_host_index_builders_match_reference_golden():
+    """libdb1_host.so vs vectors produced by the reference's compiled helpers.cpp (tools/make_golden_index.py): bit-exact."""
+    g = _load("index_builders")
+    i = 0
+    while "rl%d:lens" % i in g:
+        assert np.array_equal(_rl_idx(g["rl%d:lens" % i], g["rl%d:T" % i][0]), g["rl%d:idx" % i]), i
+        i += 1
+    assert i >= 5
+    i = 0
+    while "gpt%d:sizes" % i in g:
+        seq, ep, tpe = g["gpt%d:args" % i]
+        assert np.array_equal(_gpt_idx(g["gpt%d:sizes" % i], g["gpt%d:doc_idx" % i], seq, ep, tpe), g["gpt%d:idx" % i]), i
+        i += 1
+    assert i >= 5
+
+
+def test_host_index_builders_match_live_reference_when_built():
+    """Randomised comparison against oracle/_ref (the reference's helpers.cpp compiled in the build container)."""
+    import contextlib
+    import glob
+    import io
+    import sys
+    ref_dir = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "oracle", "_ref")
+    if not glob.glob(os.path.join(ref_dir, "helpers*.so")):
+        pytest.skip("oracle/_ref not built (make -C oracle; needs /root/reference)")
+    sys.path.insert(0, ref_dir)
+    import helpers
+    rng = np.random.default_rng(5)
+    for _ in range(20):
+        lens = rng.integers(1, 60, size=int(rng.integers(1, 40))).astype(np.int32)
+        T = int(rng.integers(1, 50))
+        assert np.array_equal(_rl_idx(lens, T), np.asarray(helpers.build_rl_sample_idx(lens, T)))
+        ndoc, ep, seq = int(rng.integers(1, 50)), int(rng.integers(1, 4)), int(rng.integers(2, 300))
+        sizes = rng.integers(1, 400, size=ndoc).astype(np.int32)
+        doc_idx = np.concatenate([rng.permutation(ndoc) for _ in range(ep)]).astype(np.int32)
+        if ep * int(sizes.sum()) - 1 < seq:
+            continue
+        with contextlib.redirect_stdout(io.StringIO()):
+            ref = np.asarray(helpers.build_sample_idx(sizes, doc_idx, seq, ep, int(sizes.sum())))
+        assert np.array_equal(_gpt_idx(sizes, doc_idx, seq, ep, int(sizes.sum())), ref)
