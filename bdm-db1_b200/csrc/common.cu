@@ -2,6 +2,7 @@
 #include "common.cuh"
 
 #include <stdarg.h>
+#include <stdlib.h>
 
 namespace db1 {
 
@@ -59,6 +60,12 @@ int make_tmap_f16(CUtensorMap* out, const void* base, int rank, const uint64_t* 
                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) return set_err(-3, "cuTensorMapEncodeTiled failed with CUresult %d", (int)r);
   return 0;
+}
+
+bool pdl_enabled() {
+  static int v = -1;
+  if (v < 0) v = getenv("DB1_NO_PDL") ? 0 : 1;
+  return v != 0;
 }
 
 int sm_count() {

@@ -195,6 +195,8 @@ template <int CH>
 __global__ void __launch_bounds__(256)
 ln_fwd_warp_kernel(const __half* __restrict__ y, const __half* __restrict__ gamma, const __half* __restrict__ beta,
                    __half* __restrict__ out, float* __restrict__ stats, int rows, float eps) {
+  pdl_launch_dependents();
+  pdl_wait();
   constexpr int d = 256 * CH;
   const int lane = threadIdx.x & 31;
   const int row = blockIdx.x * 8 + (threadIdx.x >> 5);
@@ -249,6 +251,8 @@ ln_bwd_fused_kernel(const __half* __restrict__ dout, const __half* __restrict__ 
                     const float* __restrict__ stats, __half* __restrict__ dy, __half* __restrict__ dz,
                     float* __restrict__ dgamma, float* __restrict__ dbeta, float* __restrict__ dbias, int rows,
                     uint32_t drop_thr16, float drop_scale, uint64_t seed) {
+  pdl_launch_dependents();
+  pdl_wait();
   constexpr int d = THREADS * 8;
   constexpr int NW = THREADS / 32;
   __shared__ float red[NW][2 * LNB_ROWS];
@@ -358,6 +362,8 @@ ln_bwd_fused_kernel(const __half* __restrict__ dout, const __half* __restrict__ 
 // of dSr are 16-byte aligned and fully coalesced.
 __global__ void __launch_bounds__(128)
 rel_unshift_kernel(const __half* __restrict__ ds, __half* __restrict__ dsr, int L) {
+  pdl_launch_dependents();
+  pdl_wait();
   extern __shared__ __half rowbuf[];
   const int i = blockIdx.x;
   const size_t zrow = ((size_t)blockIdx.y * L + i) * (size_t)L;
@@ -577,6 +583,8 @@ embed_bwd_kernel(const long long* __restrict__ tok, const long long* __restrict_
 constexpr int CS_ROWS_PER_CTA = 512;
 __global__ void __launch_bounds__(256)
 colsum_kernel(const __half* __restrict__ in, long long ld, float* __restrict__ out, int rows, int n) {
+  pdl_launch_dependents();
+  pdl_wait();
   __shared__ float red[32][65];
   const int cx = threadIdx.x & 7, ry = threadIdx.x >> 3;
   const int col = blockIdx.x * 64 + cx * 8;
@@ -625,6 +633,8 @@ __global__ void __launch_bounds__(256)
 dq_finalize_kernel(const __half* __restrict__ dqu, const __half* __restrict__ dqv, long long ld_in,
                    __half* __restrict__ dq, long long ld_out, float* __restrict__ du, float* __restrict__ dv, int rows,
                    int n) {
+  pdl_launch_dependents();
+  pdl_wait();
   __shared__ float red[2][32][65];
   const int cx = threadIdx.x & 7, ry = threadIdx.x >> 3;
   const int col = blockIdx.x * 64 + cx * 8;
@@ -689,6 +699,8 @@ dq_finalize_kernel(const __half* __restrict__ dqu, const __half* __restrict__ dq
 __global__ void __launch_bounds__(256)
 rowdot_kernel(const __half* __restrict__ a, const __half* __restrict__ b, long long ld, float* __restrict__ out, int B,
               int L, int H, int dh) {
+  pdl_launch_dependents();
+  pdl_wait();
   const int w = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   const int lane = threadIdx.x & 31;
   if (w >= B * L * H) return;
@@ -750,6 +762,8 @@ struct CvtSegs {
   int acc[8];
 };
 __global__ void f32_to_f16_multi_kernel(const float* __restrict__ src, const CvtSegs sg) {
+  pdl_launch_dependents();
+  pdl_wait();
   const int k = blockIdx.y;
   const long long n = sg.n[k];
   const float* sp = src + sg.off[k];
@@ -775,10 +789,10 @@ extern "C" int db1_layernorm_fwd(const void* y, const void* gamma, const void* b
   cudaStream_t st = (cudaStream_t)stream;
   const __half *yy = (const __half*)y, *gg = (const __half*)gamma, *bb = (const __half*)beta;
   const int g8 = (rows + 7) / 8;
-  if (d == 2048) ln_fwd_warp_kernel<8><<<g8, 256, 0, st>>>(yy, gg, bb, (__half*)out, stats, rows, eps);
-  else if (d == 1024) ln_fwd_warp_kernel<4><<<g8, 256, 0, st>>>(yy, gg, bb, (__half*)out, stats, rows, eps);
-  else if (d == 512) ln_fwd_warp_kernel<2><<<g8, 256, 0, st>>>(yy, gg, bb, (__half*)out, stats, rows, eps);
-  else if (d == 256) ln_fwd_warp_kernel<1><<<g8, 256, 0, st>>>(yy, gg, bb, (__half*)out, stats, rows, eps);
+  if (d == 2048) DB1_CUDA(launch_pdl(ln_fwd_warp_kernel<8>, dim3(g8), dim3(256), 0, st, 1, yy, gg, bb, (__half*)out, stats, rows, eps));
+  else if (d == 1024) DB1_CUDA(launch_pdl(ln_fwd_warp_kernel<4>, dim3(g8), dim3(256), 0, st, 1, yy, gg, bb, (__half*)out, stats, rows, eps));
+  else if (d == 512) DB1_CUDA(launch_pdl(ln_fwd_warp_kernel<2>, dim3(g8), dim3(256), 0, st, 1, yy, gg, bb, (__half*)out, stats, rows, eps));
+  else if (d == 256) DB1_CUDA(launch_pdl(ln_fwd_warp_kernel<1>, dim3(g8), dim3(256), 0, st, 1, yy, gg, bb, (__half*)out, stats, rows, eps));
   else {
     const int grid = rows < 148 * 8 ? rows : 148 * 8;
     ln_fwd_kernel<<<grid, LN_THREADS, 0, st>>>(yy, gg, bb, (__half*)out, stats, rows, d, eps);
@@ -806,7 +820,7 @@ extern "C" int db1_layernorm_bwd(const void* dout, const void* y, const void* ga
     // whole waves of equally loaded CTAs: ceil(ngroups / k) CTAs with k groups each
     const int k = (ngroups + slots - 1) / slots;
     const int grid = (ngroups + k - 1) / k;
-#define DB1_LNB(T) ln_bwd_fused_kernel<T><<<grid, T, 0, st>>>(go, yy, gg, stats, o1, o2, dgamma, dbeta, dbias, rows, t, dscale(t), seed)
+#define DB1_LNB(T) DB1_CUDA(launch_pdl(ln_bwd_fused_kernel<T>, dim3(grid), dim3(T), 0, st, 1, go, yy, gg, stats, o1, o2, dgamma, dbeta, dbias, rows, t, dscale(t), seed))
     if (d == 4096) DB1_LNB(512);
     else if (d == 2048) DB1_LNB(256);
     else if (d == 1024) DB1_LNB(128);
@@ -878,7 +892,7 @@ extern "C" int db1_embed_bwd(const long long* tok, const long long* pos, const i
 extern "C" int db1_colsum(const void* in, long long ld, float* out, int rows, int n, void* stream) {
   DB1_CHECK_ARG(in && out && rows > 0 && n > 0 && n % 8 == 0 && ld % 8 == 0, "colsum: bad arguments");
   dim3 grid((n + 63) / 64, (rows + CS_ROWS_PER_CTA - 1) / CS_ROWS_PER_CTA);
-  colsum_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>((const __half*)in, ld, out, rows, n);
+  DB1_CUDA(launch_pdl(colsum_kernel, grid, dim3(256), 0, (cudaStream_t)stream, 1, (const __half*)in, ld, out, rows, n));
   DB1_CUDA(cudaGetLastError());
   return 0;
 }
@@ -888,8 +902,8 @@ extern "C" int db1_dq_finalize(const void* dqu, const void* dqv, long long ld_in
   DB1_CHECK_ARG(dqu && dqv && dq && du && dv && rows > 0 && n % 8 == 0 && ld_in % 8 == 0 && ld_out % 8 == 0,
                 "dq_finalize: bad arguments");
   dim3 grid((n + 63) / 64, (rows + CS_ROWS_PER_CTA - 1) / CS_ROWS_PER_CTA);
-  dq_finalize_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>((const __half*)dqu, (const __half*)dqv, ld_in, (__half*)dq,
-                                                           ld_out, du, dv, rows, n);
+  DB1_CUDA(launch_pdl(dq_finalize_kernel, grid, dim3(256), 0, (cudaStream_t)stream, 1, (const __half*)dqu,
+                      (const __half*)dqv, ld_in, (__half*)dq, ld_out, du, dv, rows, n));
   DB1_CUDA(cudaGetLastError());
   return 0;
 }
@@ -898,8 +912,8 @@ extern "C" int db1_rowdot(const void* a, const void* b, long long ld, float* out
                           void* stream) {
   DB1_CHECK_ARG(a && b && out && B > 0 && L > 0 && H > 0 && dh % 8 == 0 && ld % 8 == 0, "rowdot: bad arguments");
   const long long nthreads = (long long)B * L * H * 32;
-  rowdot_kernel<<<(unsigned)((nthreads + 255) / 256), 256, 0, (cudaStream_t)stream>>>((const __half*)a, (const __half*)b,
-                                                                                     ld, out, B, L, H, dh);
+  DB1_CUDA(launch_pdl(rowdot_kernel, dim3((unsigned)((nthreads + 255) / 256)), dim3(256), 0, (cudaStream_t)stream, 1,
+                      (const __half*)a, (const __half*)b, ld, out, B, L, H, dh));
   DB1_CUDA(cudaGetLastError());
   return 0;
 }
@@ -918,7 +932,8 @@ extern "C" int db1_posemb(void* out, const float* inv_freq, int klen, int d, int
 extern "C" int db1_rel_unshift(const void* ds, void* dsr, int Z, int L, void* stream) {
   DB1_CHECK_ARG(ds && dsr && Z > 0 && L > 0 && L % 8 == 0 && L <= 16384, "rel_unshift: bad arguments");
   dim3 grid(L, Z);
-  rel_unshift_kernel<<<grid, 128, (size_t)L * 2 + 16, (cudaStream_t)stream>>>((const __half*)ds, (__half*)dsr, L);
+  DB1_CUDA(launch_pdl(rel_unshift_kernel, grid, dim3(128), (size_t)L * 2 + 16, (cudaStream_t)stream, 1, (const __half*)ds,
+                      (__half*)dsr, L));
   DB1_CUDA(cudaGetLastError());
   return 0;
 }
@@ -945,7 +960,7 @@ extern "C" int db1_f32_to_f16_multi(const float* src, int nseg, void* const* dst
   }
   long long bx = (mx + 255) / 256;
   if (bx > 1024) bx = 1024;
-  f32_to_f16_multi_kernel<<<dim3((unsigned)bx, nseg), 256, 0, (cudaStream_t)stream>>>(src, sg);
+  DB1_CUDA(launch_pdl(f32_to_f16_multi_kernel, dim3((unsigned)bx, nseg), dim3(256), 0, (cudaStream_t)stream, 1, src, sg));
   DB1_CUDA(cudaGetLastError());
   return 0;
 }

@@ -265,6 +265,9 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
   if (CL == 2) cluster_sync_all();  // barriers of both CTAs are initialised before any remote arrive / multicast
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  // everything above overlapped the previous kernel's tail; from here on global memory is touched
+  pdl_launch_dependents();
+  pdl_wait();
 
   if (warp == 0) {
     // ------------------------------------------------------------ TMA producer
@@ -677,20 +680,7 @@ static int launch_gemm_cl(const CUtensorMap& tmA, const CUtensorMap& tmB, const 
   long long tiles = (CL == 2 ? (MT + 1) / 2 : MT) * NT * p.Z1 * (p.reduce_z2 ? 1 : p.Z2);
   const int slots = sm_count() / CL;
   int grid = (int)(tiles > slots ? slots : tiles) * CL;
-  cudaLaunchConfig_t cfg;
-  memset(&cfg, 0, sizeof(cfg));
-  cfg.gridDim = dim3(grid);
-  cfg.blockDim = dim3(GEMM_THREADS);
-  cfg.dynamicSmemBytes = Cfg::SMEM_BYTES;
-  cfg.stream = stream;
-  cudaLaunchAttribute attr[1];
-  attr[0].id = cudaLaunchAttributeClusterDimension;
-  attr[0].val.clusterDim.x = CL;
-  attr[0].val.clusterDim.y = 1;
-  attr[0].val.clusterDim.z = 1;
-  cfg.attrs = attr;
-  cfg.numAttrs = 1;
-  DB1_CUDA(cudaLaunchKernelEx(&cfg, gemm_kernel<BN, EPI, CL>, tmA, tmB, p));
+  DB1_CUDA(launch_pdl(gemm_kernel<BN, EPI, CL>, dim3(grid), dim3(GEMM_THREADS), Cfg::SMEM_BYTES, stream, CL, tmA, tmB, p));
   return 0;
 }
 

@@ -270,6 +270,15 @@ __host__ __device__ constexpr uint32_t umma_idesc(int M, int N, int a_mn_major, 
          ((uint32_t)b_mn_major << 16) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
 }
 
+// ---------------------------------------------------------------- programmatic dependent launch
+// Kernels are launched with cudaLaunchAttributeProgrammaticStreamSerialization (common.cuh: launch_pdl): the grid may
+// become resident while its predecessor in the stream is still draining, so its prologue (barrier init, TMEM
+// allocation, descriptor prefetch) and the launch latency overlap the predecessor's tail. pdl_wait() must precede the
+// first access to global memory (it returns once every prerequisite grid has completed and its writes are visible);
+// pdl_launch_dependents() lets the NEXT kernel in the stream start being scheduled.
+DEVI void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+DEVI void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+
 // ---------------------------------------------------------------- misc
 DEVI uint32_t pack_half2(float a, float b) {
   __half2 h = __floats2half2_rn(a, b);

@@ -140,6 +140,8 @@ relattn_fwd_kernel(const __grid_constant__ CUtensorMap tmQu, const __grid_consta
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  pdl_launch_dependents();  // prologue done: from here on global memory is read / written
+  pdl_wait();
   const uint32_t T_S = tmem_base;          // 128 columns
   const uint32_t T_BD = tmem_base + 128;   // 2 x 128 columns
   const uint32_t T_O = tmem_base + 384;    // D columns
@@ -513,8 +515,8 @@ static int launch_attn(const CUtensorMap* tm, const AttnParams& p, cudaStream_t 
   }
   const int n_items = ((p.L + 127) / 128 - p.q_start / 128) * p.H * p.B;
   const int grid = n_items < sm_count() ? n_items : sm_count();
-  relattn_fwd_kernel<D><<<grid, AT_THREADS, SM::TOTAL, stream>>>(tm[0], tm[1], tm[2], tm[3], tm[4], tm[5], p);
-  DB1_CUDA(cudaGetLastError());
+  DB1_CUDA(launch_pdl(relattn_fwd_kernel<D>, dim3(grid), dim3(AT_THREADS), SM::TOTAL, stream, 1, tm[0], tm[1], tm[2], tm[3],
+                      tm[4], tm[5], p));
   return 0;
 }
 
