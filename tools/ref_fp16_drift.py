@@ -1,0 +1,43 @@
+"""How far does the REFERENCE's own fp16 mode (module.half(), what DeepSpeed fp16 runs) drift from its fp32 mode at
+DB1-1.3B depth/width with random-init weights? Build container only (imports /root/reference). CPU, takes minutes.
+    python tools/ref_fp16_drift.py [n_layer] [L]"""
+import os
+import sys
+import time
+
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+from oracle import db1_oracle as orc  # noqa: E402
+
+sys.path.insert(0, "/root/reference")
+import types  # noqa: E402
+for m in ("gym", "d4rl", "tree"):
+    sys.modules.setdefault(m, types.ModuleType(m))
+from src.model import TransformerXL  # noqa: E402  (the reference's)
+from src.data.input_specs import NLPTaskInput  # noqa: E402
+
+nl = int(sys.argv[1]) if len(sys.argv) > 1 else 24
+L = int(sys.argv[2]) if len(sys.argv) > 2 else 128
+cfg = orc.default_config(n_layer=nl)
+ns = types.SimpleNamespace(**vars(cfg))
+torch.manual_seed(0)
+model = TransformerXL(ns).eval()
+sd = orc.synth_state_dict(cfg, seed=21)
+sd = {k: (v.half().float() if v.is_floating_point() and k != "pos_emb.inv_freq" else v) for k, v in sd.items()}
+model.load_state_dict(sd, strict=False)
+tok = torch.randint(0, 32000, (1, L), generator=torch.Generator().manual_seed(3))
+mk = lambda: NLPTaskInput(position_id=None, attention_mask=None, loss_mask=torch.ones(1, L), label=tok.clone(),  # noqa: E731
+                          text_seq=tok.clone(), text_len=None)
+with torch.no_grad():
+    t0 = time.time()
+    l32, _ = model([mk()])
+    print("fp32 forward %.1f s" % (time.time() - t0), flush=True)
+    model.half()
+    t0 = time.time()
+    l16, _ = model([mk()])
+    print("fp16 forward %.1f s" % (time.time() - t0), flush=True)
+d = (l16.float() - l32)
+print("reference fp16 vs reference fp32, %d layers, L=%d: max-norm rel %.3e, rms rel %.3e" %
+      (nl, L, (d.abs().max() / l32.abs().max()).item(), (d.pow(2).mean().sqrt() / l32.pow(2).mean().sqrt()).item()))
