@@ -45,7 +45,8 @@ class _Bucket:
 
 class DB1Engine:
     def __init__(self, model, optimizer=None, lr_scheduler=None, mpu=None, gradient_accumulation_steps=1,
-                 loss_scale=4096.0, clip_grad=0.0, bucket_of=_default_bucket_of, overlap_comm=True, direct_grads=True):
+                 loss_scale=4096.0, clip_grad=0.0, bucket_of=_default_bucket_of, overlap_comm=True, direct_grads=True,
+                 fused_adam=None, loss_scale_window=1000, min_loss_scale=1.0):
         self.module = model
         self.optimizer = optimizer
         self.lr_scheduler = lr_scheduler
@@ -74,6 +75,16 @@ class DB1Engine:
         self._hooks = []
         if self._world > 1:
             self._install_hooks()
+        # fused optimizer (db1_adam_step over the flat buckets): fp16 parameters become views of a flat buffer per bucket,
+        # with fp32 master weights and Adam moments beside it
+        self._fused = None
+        self._good_steps = 0
+        self._scale_window = int(loss_scale_window)
+        self._min_scale = float(min_loss_scale)
+        if fused_adam is not None:
+            if not self._cuda:
+                raise ValueError("fused_adam needs CUDA fp16 parameters")
+            self._setup_fused_adam(dict(fused_adam))
         # gradient sink (db1_sm100.functions): weight-gradient kernels write into the bucket views directly
         self._written = set()    # ids of parameters whose bucket view already holds this window's gradient
         self._sink_seen = set()  # ids of parameters that have ever been written through the sink
@@ -105,6 +116,30 @@ class DB1Engine:
                 off += (p.numel() + 7) // 8 * 8
                 self._bucket_of_param[id(p)] = b
             self.buckets.append(b)
+
+    def _setup_fused_adam(self, cfg):
+        betas = cfg.get("betas", (0.9, 0.999))
+        self._fused = FusedAdamState(lr=float(cfg.get("lr", 1e-4)), beta1=float(betas[0]), beta2=float(betas[1]),
+                                     eps=float(cfg.get("eps", 1e-8)), weight_decay=float(cfg.get("weight_decay", 0.0)),
+                                     adamw=bool(cfg.get("adamw", True)))
+        if self.optimizer is None:
+            self.optimizer = self._fused  # exposes param_groups[0]["lr"] to LR schedulers (OptimizerParamScheduler)
+        for b in self.buckets:
+            b.pflat = torch.zeros_like(b.flat)
+            off = 0
+            with torch.no_grad():
+                for p in b.params:
+                    n = p.numel()
+                    b.pflat[off:off + n].copy_(p.data.reshape(-1))
+                    p.data = b.pflat[off:off + n].view_as(p)
+                    off += (n + 7) // 8 * 8
+            b.master = b.pflat.float()
+            b.m = torch.zeros_like(b.master)
+            b.v = torch.zeros_like(b.master)
+        dev = self.device
+        self._sumsq = torch.zeros(1, dtype=torch.float32, device=dev)
+        self._gcoef = torch.zeros(2, dtype=torch.float32, device=dev)
+        self._oflag = torch.zeros(1, dtype=torch.int32, device=dev)
 
     def _install_hooks(self):
         for b in self.buckets:
@@ -236,6 +271,8 @@ class DB1Engine:
         if self.micro_steps % self._ga != 0:
             return
         self.global_steps += 1
+        if self._fused is not None:
+            return self._fused_step()
         if self.optimizer is None:
             return
         inv = 1.0 / self.loss_scale
@@ -256,6 +293,37 @@ class DB1Engine:
         if self.lr_scheduler is not None:
             self.lr_scheduler.step()
 
+    def _fused_step(self):
+        """Unscale, global-norm clip, overflow check and Adam(W) on fp32 masters: two passes over the flat buckets
+        (db1_grad_sumsq, db1_adam_step), one 4-byte host read for the overflow flag (as DeepSpeed's has_overflow)."""
+        from . import ops
+        st = self._fused
+        self._sumsq.zero_()
+        for b in self.buckets:
+            ops.grad_sumsq(b.flat, self._sumsq)
+        ops.clip_coef(self._sumsq, 1.0 / self.loss_scale, self.clip_grad, self._gcoef, self._oflag)
+        if int(self._oflag.item()) != 0:  # inf / nan in the gradients: skip the step, halve the loss scale
+            self.loss_scale = max(self.loss_scale / 2.0, self._min_scale)
+            self._good_steps = 0
+            self.skipped_steps = getattr(self, "skipped_steps", 0) + 1
+            return False
+        st.step += 1
+        lr = float(st.param_groups[0]["lr"])
+        wd = float(st.param_groups[0].get("weight_decay", st.weight_decay))
+        for b in self.buckets:
+            ops.adam_step(b.flat, b.pflat, b.master, b.m, b.v, self._gcoef, lr, st.beta1, st.beta2, st.eps, wd, st.step,
+                          st.adamw)
+        if self.lr_scheduler is not None:
+            self.lr_scheduler.step()
+        self._good_steps += 1
+        if self._scale_window > 0 and self._good_steps % self._scale_window == 0:
+            self.loss_scale *= 2.0
+        return True
+
+    def grad_norm(self):
+        """Unscaled global gradient norm of the last fused step (device scalar)."""
+        return self._gcoef[1]
+
     # ------------------------------------------------------------------------------------------ checkpoints
     def save_checkpoint(self, save_dir, tag=None, client_state=None):
         tag = tag if tag is not None else "global_step%d" % self.global_steps
@@ -265,7 +333,11 @@ class DB1Engine:
             os.makedirs(path, exist_ok=True)
             state = {"module": self.module.state_dict(), "global_steps": self.global_steps,
                      "micro_steps": self.micro_steps, "loss_scale": self.loss_scale}
-            if self.optimizer is not None:
+            if self._fused is not None:
+                state["optimizer"] = {"fused_adam": self._fused.state_dict(),
+                                      "buckets": [{"key": b.key, "master": b.master.cpu(), "m": b.m.cpu(), "v": b.v.cpu()}
+                                                  for b in self.buckets]}
+            elif self.optimizer is not None:
                 state["optimizer"] = self.optimizer.state_dict()
             state.update(client_state or {})
             torch.save(state, os.path.join(path, "mp_rank_00_model_states.pt"))
@@ -285,10 +357,38 @@ class DB1Engine:
         self.global_steps = state.get("global_steps", 0)
         self.micro_steps = state.get("micro_steps", 0)
         self.loss_scale = state.get("loss_scale", self.loss_scale)
-        if load_optimizer_states and self.optimizer is not None and "optimizer" in state:
+        if self._fused is not None:
+            # parameters are views of the flat buffers: load_state_dict above copied into them in place
+            if load_optimizer_states and "optimizer" in state and "buckets" in state["optimizer"]:
+                self._fused.load_state_dict(state["optimizer"]["fused_adam"])
+                for b, sb in zip(self.buckets, state["optimizer"]["buckets"]):
+                    b.master.copy_(sb["master"]); b.m.copy_(sb["m"]); b.v.copy_(sb["v"])
+            else:
+                for b in self.buckets:
+                    b.master.copy_(b.pflat.float())
+        elif load_optimizer_states and self.optimizer is not None and "optimizer" in state:
             self.optimizer.load_state_dict(state["optimizer"])
         known = {"module", "global_steps", "micro_steps", "loss_scale", "optimizer"}
         return path, {k: v for k, v in state.items() if k not in known}
+
+
+class FusedAdamState:
+    """Hyper-parameters + step counter of the fused optimizer; looks enough like a torch optimizer (param_groups,
+    state_dict) for the reference's OptimizerParamScheduler (optimizer_param_scheduler.py:100-142) to drive lr / wd."""
+
+    def __init__(self, lr, beta1, beta2, eps, weight_decay, adamw):
+        self.beta1, self.beta2, self.eps, self.weight_decay, self.adamw = beta1, beta2, eps, weight_decay, adamw
+        self.step = 0
+        self.param_groups = [{"lr": lr, "weight_decay": weight_decay}]
+
+    def state_dict(self):
+        return {"step": self.step, "param_groups": [dict(g) for g in self.param_groups], "beta1": self.beta1,
+                "beta2": self.beta2, "eps": self.eps, "adamw": self.adamw}
+
+    def load_state_dict(self, sd):
+        self.step = sd["step"]
+        self.param_groups = [dict(g) for g in sd["param_groups"]]
+        self.beta1, self.beta2, self.eps, self.adamw = sd["beta1"], sd["beta2"], sd["eps"], sd["adamw"]
 
 
 def initialize(args=None, model=None, optimizer=None, lr_scheduler=None, mpu=None, **kw):

@@ -338,3 +338,23 @@ def f32_to_f16_multi(src, segs):
         acc = (C.c_int * k)(*[int(sg[3]) for sg in part])
         with _Launch("f32_to_f16", 1):
           check(_lib.lib().db1_f32_to_f16_multi(_f32(src), k, dst, off, n, acc, cur_stream()), "db1_f32_to_f16_multi")
+
+
+def grad_sumsq(g16, out):
+    _need_cuda_half(g16)
+    with _Launch("grad_sumsq", 1, 0.0, 2.0 * g16.numel()):
+      check(_lib.lib().db1_grad_sumsq(ptr(g16), C.c_longlong(g16.numel()), _f32(out), cur_stream()), "db1_grad_sumsq")
+
+
+def clip_coef(sumsq, inv_scale, clip, gcoef2, flag):
+    with _Launch("clip_coef", 1):
+      check(_lib.lib().db1_clip_coef(_f32(sumsq), C.c_float(inv_scale), C.c_float(clip), _f32(gcoef2), ptr(flag),
+                                   cur_stream()), "db1_clip_coef")
+
+
+def adam_step(g16, p16, master, m, v, gcoef, lr, beta1, beta2, eps, weight_decay, step, adamw=True):
+    _need_cuda_half(g16, p16)
+    with _Launch("adam_step", 1, 0.0, 28.0 * g16.numel()):
+      check(_lib.lib().db1_adam_step(ptr(g16), ptr(p16), _f32(master), _f32(m), _f32(v), C.c_longlong(g16.numel()),
+                                   _f32(gcoef), C.c_float(lr), C.c_float(beta1), C.c_float(beta2), C.c_float(eps),
+                                   C.c_float(weight_decay), int(step), int(adamw), cur_stream()), "db1_adam_step")

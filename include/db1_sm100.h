@@ -196,6 +196,20 @@ int db1_col2im_gn_gelu_bwd(const void* dcol, const void* x, const float* stats, 
  * applying it to a gradient with the same seed is its adjoint. n % 8 == 0. */
 int db1_dropout_f16(const void* x, void* out, long long n, float drop_p, uint64_t seed, void* stream);
 
+/* ------------------------------------------------------------------------------------------------------------------
+ * Fused optimizer step over flat buckets (what DeepSpeed's fp16 optimizer + FusedAdam do in the reference's loop,
+ * src/train_utils/train.py:231-232; flags train_config.py:212-235). HBM-bound: 28 bytes per parameter.
+ * ------------------------------------------------------------------------------------------------------------------ */
+/* out[0] += sum(g^2) over an fp16 bucket (n % 8 == 0); inf / nan propagate (overflow detection). */
+int db1_grad_sumsq(const void* g16, long long n, float* out, void* stream);
+/* gcoef2[0] = inv_scale * min(1, clip / (global norm + 1e-6)) (0 on overflow), gcoef2[1] = unscaled global gradient norm,
+ * overflow_flag[0] = 1 iff sumsq is inf/nan. All device scalars: no host sync. clip <= 0 disables clipping. */
+int db1_clip_coef(const float* sumsq, float inv_scale, float clip, float* gcoef2, int* overflow_flag, void* stream);
+/* Adam / AdamW on fp32 master weights from an fp16 gradient bucket scaled by gcoef[0] (device scalar); refreshes the
+ * fp16 parameters. step >= 1 (bias correction). */
+int db1_adam_step(const void* g16, void* p16, float* master, float* m, float* v, long long n, const float* gcoef,
+                  float lr, float beta1, float beta2, float eps, float weight_decay, int step, int adamw, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

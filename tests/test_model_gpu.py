@@ -164,3 +164,51 @@ def test_full_depth_1p3b_logits_match_oracle(cuda):
     print("1.3B logits, chained: max-norm rel err %.3e, rms rel err %.3e, loss %.6f vs %.6f" % (err, rms, loss.item(), oloss.item()))
     assert err <= 3.8e-2 and rms <= 2.6e-2  # the reference's own fp16-vs-fp32 drift on these weights
     assert abs(loss.item() - oloss.item()) <= 2e-3 * abs(oloss.item())
+
+
+def test_fused_adam_step_matches_torch_adamw_and_skips_on_overflow(cuda):
+    """DB1Engine(fused_adam=...): db1_grad_sumsq + db1_clip_coef + db1_adam_step on the flat buckets vs torch.optim.AdamW on
+    fp32 copies fed the same unscaled, clipped gradients; overflow (inf in a gradient) skips the step and halves the scale."""
+    from db1_sm100 import functions as F_
+    from db1_sm100.engine import DB1Engine
+    g = util.load_golden("tiny_text_rl")
+    cfg = util.golden_cfg(g)
+    tasks = util.tasks_from_golden(g)
+    model, _sd = _build(cfg, 6, cuda)
+    model.train()
+    hp = dict(lr=3e-3, betas=(0.9, 0.95), eps=1e-8, weight_decay=0.1)
+    CLIP, SCALE = 0.5, 1024.0
+    try:
+        eng = DB1Engine(model, loss_scale=SCALE, clip_grad=CLIP, fused_adam=hp, loss_scale_window=0)
+        ref_params = [p.detach().float().clone().requires_grad_(True) for p in model.parameters()]
+        ref_opt = torch.optim.AdamW(ref_params, lr=hp["lr"], betas=hp["betas"], eps=hp["eps"], weight_decay=hp["weight_decay"])
+        for step in range(3):
+            _, loss = eng(util.to_model_inputs(tasks, cuda))
+            eng.backward(loss)
+            grads = [p.grad.float() / SCALE for p in model.parameters()]
+            norm = torch.sqrt(sum((x * x).sum() for x in grads))
+            coef = min(1.0, CLIP / (norm.item() + 1e-6))
+            assert eng.step() is True
+            assert abs(eng.grad_norm().item() - norm.item()) <= 1e-3 * norm.item()
+            for rp, gr in zip(ref_params, grads):
+                rp.grad = gr * coef
+            ref_opt.step()
+            flat_master = {id(p): None for p in model.parameters()}
+            for b in eng.buckets:
+                off = 0
+                for p in b.params:
+                    flat_master[id(p)] = b.master[off:off + p.numel()].view_as(p)
+                    off += (p.numel() + 7) // 8 * 8
+            worst = max(util.rel_l2(flat_master[id(p)], rp) for p, rp in zip(model.parameters(), ref_params))
+            assert worst <= 2e-5, (step, worst)
+            for p in model.parameters():  # fp16 parameters = rounded masters
+                assert torch.equal(p.data, flat_master[id(p)].half())
+        # overflow: poison one gradient
+        _, loss = eng(util.to_model_inputs(tasks, cuda))
+        eng.backward(loss)
+        eng.buckets[1].flat[3] = float("inf")
+        before = eng.buckets[1].master.clone()
+        assert eng.step() is False and eng.loss_scale == SCALE / 2
+        assert torch.equal(eng.buckets[1].master, before)
+    finally:
+        F_.set_grad_sink(None)
