@@ -147,8 +147,12 @@ class DB1Engine:
                 self._hooks.append(p.register_post_accumulate_grad_hook(self._make_hook(b)))
 
     def _make_hook(self, bucket):
-        def hook(_param):
+        def hook(param):
             if not self._is_boundary() or not self.enable_backward_allreduce:
+                return
+            if id(param) in self._written:
+                # autograd runs AccumulateGrad (and this hook) even when the Function returned None because its kernel
+                # already wrote the bucket view; those parameters are accounted for by done()
                 return
             bucket.pending -= 1
             if bucket.pending == 0:

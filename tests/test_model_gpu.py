@@ -212,3 +212,31 @@ def test_fused_adam_step_matches_torch_adamw_and_skips_on_overflow(cuda):
         assert torch.equal(eng.buckets[1].master, before)
     finally:
         F_.set_grad_sink(None)
+
+
+def test_reference_error_behaviour_is_kept(cuda):
+    """AssertionError for compute_loss with mems (:515-517), ValueError when same_length with mem_len == 0 masks every key
+    (:205-206), in-place label[label == -1] = 0 on RL batches with images (:645), Db1Error (no fallback) off the GPU."""
+    from db1_sm100._lib import Db1Error
+    from oracle import db1_oracle as orc
+    from src.model import TransformerXL
+    g = util.load_golden("tiny_mixed_images")
+    cfg = util.golden_cfg(g)
+    tasks = util.tasks_from_golden(g)
+    model, sd = _build(cfg, 5, cuda)
+    model.eval()
+    inputs = util.to_model_inputs(tasks, cuda)
+    with pytest.raises(AssertionError):
+        model(inputs, compute_loss=True, mems=model.init_mem(1))
+    rl_img = [t for t in inputs if getattr(t, "vision_seq", None) is not None][0]
+    assert (rl_img.label == -1).any()
+    with torch.no_grad():
+        model(inputs)
+    assert not (rl_img.label == -1).any()
+    cfg0 = orc.tiny_config(text_vocab_size=480, mem_len=0)
+    m0 = TransformerXL(cfg0).half().to(cuda).eval()
+    with pytest.raises(ValueError):
+        m0(util.to_model_inputs(tasks[1:2], cuda))
+    cpu_model = TransformerXL(cfg)
+    with pytest.raises(Db1Error):
+        cpu_model(util.to_model_inputs(tasks[1:2], torch.device("cpu"), half=False))
