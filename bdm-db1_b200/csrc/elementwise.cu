@@ -360,26 +360,31 @@ ln_bwd_fused_kernel(const __half* __restrict__ dout, const __half* __restrict__ 
 // dSr[z][i][c] = dS[z][i][c - (L-1-i)] for c >= L-1-i, 0 below: the adjoint of _rel_shift (transformer_xl.py:98-110)
 // as a pure re-layout. One CTA per row; the row is staged in shared memory so that both the read of dS and the write
 // of dSr are 16-byte aligned and fully coalesced.
+constexpr int UNSHIFT_ROWS = 8;  // rows per CTA (one row moves only ~2 KB: amortise the CTA launch)
 __global__ void __launch_bounds__(128)
 rel_unshift_kernel(const __half* __restrict__ ds, __half* __restrict__ dsr, int L) {
   pdl_launch_dependents();
   pdl_wait();
   extern __shared__ __half rowbuf[];
-  const int i = blockIdx.x;
-  const size_t zrow = ((size_t)blockIdx.y * L + i) * (size_t)L;
-  const int n8 = (i + 8) / 8 * 8;  // elements 0..i, rounded up to a multiple of 8 (the tail is zero in dS)
-  for (int j = threadIdx.x * 8; j < n8; j += 128 * 8)
-    *reinterpret_cast<H8*>(rowbuf + j) = *reinterpret_cast<const H8*>(ds + zrow + j);
-  __syncthreads();
-  const int c_lo = L - 1 - i;
-  for (int c8 = (c_lo / 8) * 8 + threadIdx.x * 8; c8 < L; c8 += 128 * 8) {
-    __half v[8];
+  for (int rr = 0; rr < UNSHIFT_ROWS; ++rr) {
+    const int i = blockIdx.x * UNSHIFT_ROWS + rr;
+    if (i >= L) break;
+    const size_t zrow = ((size_t)blockIdx.y * L + i) * (size_t)L;
+    const int n8 = (i + 8) / 8 * 8;  // elements 0..i, rounded up to a multiple of 8 (the tail is zero in dS)
+    __syncthreads();                 // the previous row's readers are done with rowbuf
+    for (int j = threadIdx.x * 8; j < n8; j += 128 * 8)
+      *reinterpret_cast<H8*>(rowbuf + j) = *reinterpret_cast<const H8*>(ds + zrow + j);
+    __syncthreads();
+    const int c_lo = L - 1 - i;
+    for (int c8 = (c_lo / 8) * 8 + threadIdx.x * 8; c8 < L; c8 += 128 * 8) {
+      __half v[8];
 #pragma unroll
-    for (int t = 0; t < 8; ++t) {
-      const int j = c8 + t - c_lo;
-      v[t] = (j >= 0 && j <= i) ? rowbuf[j] : __float2half_rn(0.f);
+      for (int t = 0; t < 8; ++t) {
+        const int j = c8 + t - c_lo;
+        v[t] = (j >= 0 && j <= i) ? rowbuf[j] : __float2half_rn(0.f);
+      }
+      *reinterpret_cast<H8*>(dsr + zrow + c8) = *reinterpret_cast<const H8*>(v);
     }
-    *reinterpret_cast<H8*>(dsr + zrow + c8) = *reinterpret_cast<const H8*>(v);
   }
 }
 
@@ -723,6 +728,34 @@ rowdot_kernel(const __half* __restrict__ a, const __half* __restrict__ b, long l
   }
 }
 
+// Same, one warp per (b, i) row covering all heads: lanes read consecutive 16-byte chunks (fully coalesced), a head's
+// dh / 8 chunks sit in CPH consecutive lanes and are folded with xor-shuffles. d % 256 == 0, CPH = dh / 8 in {1..32} pow2.
+template <int CPH>
+__global__ void __launch_bounds__(256)
+rowdot_rows_kernel(const __half* __restrict__ a, const __half* __restrict__ b, long long ld, float* __restrict__ out,
+                   int B, int L, int H, int d) {
+  pdl_launch_dependents();
+  pdl_wait();
+  const int row = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int lane = threadIdx.x & 31;
+  if (row >= B * L) return;
+  const __half* pa = a + (size_t)row * ld;
+  const __half* pb = b + (size_t)row * ld;
+  const int bb = row / L, i = row % L;
+  for (int c0 = 0; c0 < d / 8; c0 += 32) {
+    const int c = c0 + lane;
+    float x[8], y[8];
+    h8_to_f(*reinterpret_cast<const H8*>(pa + c * 8), x);
+    h8_to_f(*reinterpret_cast<const H8*>(pb + c * 8), y);
+    float s = 0.f;
+#pragma unroll
+    for (int k = 0; k < 8; ++k) s = fmaf(x[k], y[k], s);
+#pragma unroll
+    for (int o = 1; o < CPH; o <<= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+    if ((lane & (CPH - 1)) == 0) out[((size_t)bb * H + c / CPH) * L + i] = s;
+  }
+}
+
 // sinusoid rows in the reference order: row c <-> distance min(klen-1-c, clamp); [sin | cos]; fp32 math -> fp16, dropout
 __global__ void posemb_kernel(__half* __restrict__ out, const float* __restrict__ inv_freq, int klen, int d,
                               int clamp_len, uint32_t drop_thr16, float drop_scale, uint64_t seed) {
@@ -911,6 +944,23 @@ extern "C" int db1_dq_finalize(const void* dqu, const void* dqv, long long ld_in
 extern "C" int db1_rowdot(const void* a, const void* b, long long ld, float* out, int B, int L, int H, int dh,
                           void* stream) {
   DB1_CHECK_ARG(a && b && out && B > 0 && L > 0 && H > 0 && dh % 8 == 0 && ld % 8 == 0, "rowdot: bad arguments");
+  const int cph = dh / 8, dd = H * dh;
+  if (dd % 256 == 0 && cph <= 32 && (cph & (cph - 1)) == 0) {
+    const dim3 grid((unsigned)(((long long)B * L * 32 + 255) / 256));
+    const __half *pa = (const __half*)a, *pb = (const __half*)b;
+    cudaStream_t st = (cudaStream_t)stream;
+#define DB1_RD(C) DB1_CUDA(launch_pdl(rowdot_rows_kernel<C>, grid, dim3(256), 0, st, 1, pa, pb, ld, out, B, L, H, dd))
+    switch (cph) {
+      case 1: DB1_RD(1); break;
+      case 2: DB1_RD(2); break;
+      case 4: DB1_RD(4); break;
+      case 8: DB1_RD(8); break;
+      case 16: DB1_RD(16); break;
+      default: DB1_RD(32); break;
+    }
+#undef DB1_RD
+    return 0;
+  }
   const long long nthreads = (long long)B * L * H * 32;
   DB1_CUDA(launch_pdl(rowdot_kernel, dim3((unsigned)((nthreads + 255) / 256)), dim3(256), 0, (cudaStream_t)stream, 1,
                       (const __half*)a, (const __half*)b, ld, out, B, L, H, dh));
@@ -931,7 +981,7 @@ extern "C" int db1_posemb(void* out, const float* inv_freq, int klen, int d, int
 
 extern "C" int db1_rel_unshift(const void* ds, void* dsr, int Z, int L, void* stream) {
   DB1_CHECK_ARG(ds && dsr && Z > 0 && L > 0 && L % 8 == 0 && L <= 16384, "rel_unshift: bad arguments");
-  dim3 grid(L, Z);
+  dim3 grid((L + UNSHIFT_ROWS - 1) / UNSHIFT_ROWS, Z);
   DB1_CUDA(launch_pdl(rel_unshift_kernel, grid, dim3(128), (size_t)L * 2 + 16, (cudaStream_t)stream, 1, (const __half*)ds,
                       (__half*)dsr, L));
   DB1_CUDA(cudaGetLastError());
