@@ -145,6 +145,8 @@ def run_reference(args):
 
 # ------------------------------------------------------------------------------------------------------------------
 def run_ours(args):
+    global B_MICRO, SEQ
+    B_MICRO, SEQ = args.micro_batch, args.seq_len  # defaults = BASELINE config 2 (4 x 1024); others are sweep points
     import torch
     import torch.distributed as dist
     from db1_sm100 import engine as eng_mod, ops, synth
@@ -265,9 +267,10 @@ def run_ours(args):
         if os.path.exists(tpath):
             with open(tpath) as f:
                 traffic = json.load(f).get("gemm_dram_bytes_per_launch")
-        step_flops = algorithmic_flops(B_MICRO, SEQ)
+        step_flops = algorithmic_flops(B_MICRO, SEQ, window=cfg.mem_len)
         line = {
-            "metric": METRIC, "value": value, "unit": "tokens/s", "n_gpus": world, "steps": args.steps,
+            "metric": METRIC.replace("seq1024", "seq%d" % SEQ), "value": value, "unit": "tokens/s", "n_gpus": world,
+            "steps": args.steps,
             "warmup": max(args.warmup, 3), "ms_per_step": ms_total / args.steps, "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "f16", "data": "synthetic",
             "config": {"workload": "DB1-1.3B (24 layers, d 2048, 16 heads, GeGLU 8192, vocab 33025) fwd+bwd, "
@@ -317,6 +320,9 @@ def main():
     ap.add_argument("--workload", default="rl", choices=["rl", "atari", "mixed"],
                     help="rl = BASELINE config 2 (headline, default); atari = config 3; mixed = config 4's per-rank batch")
     ap.add_argument("--profile-only", action="store_true", help="warm-up + steps only (for runs under ncu)")
+    ap.add_argument("--seq-len", type=int, default=1024, help="sequence length (default 1024 = the headline config; "
+                    "beyond n_position = mem_len = 1024 the same_length sliding window and the distance clamp are active)")
+    ap.add_argument("--micro-batch", type=int, default=4, help="sequences per GPU per step (default 4)")
     ap.add_argument("--optimizer", action="store_true",
                     help="also run the fused loss-scale / clip / AdamW step every iteration (whole training step)")
     ap.add_argument("--by-shape", action="store_true", help="per-kernel breakdown keyed by GEMM shape (development)")
