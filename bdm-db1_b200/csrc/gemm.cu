@@ -59,6 +59,11 @@ struct GemmParams {
   const float* Drow;
   int window;
   int dbg;  // development switches (DB1_GEMM_DBG): 1 = epilogue skips global stores, 2 = epilogue skips TMEM loads too
+  // stream-K tail (CTA-pair launches only; 0 = off): the last sk_tiles pair-tiles are cut along K into sk_pairs
+  // contiguous, equally long k-block ranges, one per CTA pair; see SkSched below
+  int sk_tiles, sk_pairs;
+  float* sk_ws;         // partial accumulators, one slot per contributing CTA pair: [pair][crank][128 x BN] fp32
+  unsigned int* sk_cnt; // [2 * pairs]: arrivals per owner pair | owner warps that consumed them (self-resetting)
 };
 
 // CL == 2: the CTA pair of a cluster runs cta_group::2 MMAs (M = 256 across the pair); each CTA stages its own 128
@@ -212,6 +217,155 @@ DEVI TileCoord decode_tile(const GemmParams& p, int tile, int MT, int NT, int KB
   return t;
 }
 
+// ---------------------------------------------------------------------------------------------------------------------
+// Work list of one CTA (pair). Without stream-K: tiles pair, pair + G, ... (data parallel, "DP"). With stream-K the
+// tile count T is not a multiple of the G pairs, so instead of a last wave that keeps only T mod G pairs busy, the
+// R = sk_tiles trailing tiles are treated as one strip of R * KB k-blocks that is cut into sk_pairs equal ranges
+// [b(g), b(g+1)), b(g) = g * R * KB / sk_pairs. A range is shorter than a tile, so it touches at most two tiles:
+//   * the tail [kb0, KB) of a tile whose head belongs to a lower-numbered pair  -> CONTRIB: the fp32 accumulator goes to
+//     this pair's workspace slot and the owner's arrival counter is bumped;
+//   * the head [0, kb1) of the next tile                                        -> OWNER: waits for the contributors
+//     (pairs g+1 ...), adds their partials in pair order (deterministic) and runs the normal fused epilogue.
+// Every pair works through its stream-K range FIRST (contribution before owned head), then its DP tiles: a
+// contribution an owner waits for was the first thing its producer did, and the fix-up hides under the DP tiles.
+// ---------------------------------------------------------------------------------------------------------------------
+enum { SK_FULL = 0, SK_CONTRIB = 1, SK_OWNER = 2 };
+// One CTA's work list, computed once by one thread and kept in shared memory (the role loops only keep a counter live:
+// the fused epilogues have no registers to spare).
+struct SkPlan {
+  int nseg;   // stream-K segments of this pair (0, 1 or 2), processed before the DP tiles
+  int T_dp;   // tiles [0, T_dp) are data parallel: pair, pair + G, ...
+  int tile[2], kb0[2], kb1[2];
+  int role[2];   // SK_*
+  int peer[2];   // CONTRIB: owner pair; OWNER: first contributing pair
+  int npeer[2];  // OWNER: number of contributing pairs (consecutive)
+};
+__host__ __device__ inline void sk_plan_build(SkPlan* pl, int R, int GS, int pair, int num_tiles, int KB) {
+  auto bound = [&](int g) { return (int)(((long long)g * R * KB) / GS); };
+  pl->nseg = 0;
+  pl->T_dp = num_tiles - R;
+  if (R <= 0 || pair >= GS) return;
+  int u = bound(pair);
+  const int u1 = bound(pair + 1);
+  int n = 0;
+  while (u < u1 && n < 2) {
+    const int s = u / KB;
+    const int e = u1 < (s + 1) * KB ? u1 : (s + 1) * KB;
+    const int kb0 = u - s * KB, kb1 = e - s * KB;
+    pl->tile[n] = pl->T_dp + s;
+    pl->kb0[n] = kb0;
+    pl->kb1[n] = kb1;
+    pl->peer[n] = 0;
+    pl->npeer[n] = 0;
+    if (kb0 == 0 && kb1 == KB) {
+      pl->role[n] = SK_FULL;
+    } else if (kb0 == 0) {
+      int g = pair + 1;
+      while (g < GS && bound(g) < (s + 1) * KB) ++g;
+      pl->role[n] = SK_OWNER;
+      pl->peer[n] = pair + 1;
+      pl->npeer[n] = g - (pair + 1);
+    } else {
+      int g = pair - 1;
+      while (g > 0 && bound(g) > s * KB) --g;
+      pl->role[n] = SK_CONTRIB;
+      pl->peer[n] = g;
+    }
+    ++n;
+    u = e;
+  }
+  pl->nseg = n;
+}
+// n-th work item of this pair: returns false when the list is exhausted. kb1 < 0 = the tile's own k-range.
+DEVI bool sk_item(const volatile SkPlan* pl, int n, int pair, int G, int& tile, int& kb0, int& kb1) {
+  const int nseg = pl->nseg;
+  if (n < nseg) {
+    tile = pl->tile[n];
+    kb0 = pl->kb0[n];
+    kb1 = pl->kb1[n];
+    return true;
+  }
+  tile = pair + (n - nseg) * G;
+  kb0 = 0;
+  kb1 = -1;
+  return tile < pl->T_dp;
+}
+
+DEVI unsigned int ld_acquire_gpu(const unsigned int* p) {
+  unsigned int v;
+  asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+  return v;
+}
+
+// ---- stream-K fix-up. Every epilogue warp owns the same 32 lanes x BN/2 accumulator columns in both roles, so a
+// partial is stored / fetched in "register order": [chunk][8 x (32 lanes x float4)] - fully coalesced 512-byte rows.
+// Kept out of line: they run at most twice per CTA and must not add register pressure to the fused epilogues.
+template <int BN>
+DEVI void sk_store_partial(const GemmParams& p, uint32_t tacc, int pair, int owner, int crank, int ew,
+                                              int half, int lane) {
+  constexpr int CPW = BN / 64;
+  float* ws = p.sk_ws + (size_t)pair * (2 * BM * BN) + (size_t)crank * (BM * BN) + (size_t)ew * (CPW * 8 * 128) +
+              (size_t)lane * 4;
+#pragma unroll 1
+  for (int ci = 0; ci < CPW; ++ci) {
+    uint32_t r[32];
+    tmem_ld32(tacc + (half * CPW + ci) * 32, r);
+    tmem_ld_wait();
+#pragma unroll
+    for (int j = 0; j < 8; ++j)
+      __stcg(reinterpret_cast<float4*>(ws + (ci * 8 + j) * 128),
+             make_float4(__uint_as_float(r[4 * j]), __uint_as_float(r[4 * j + 1]), __uint_as_float(r[4 * j + 2]),
+                         __uint_as_float(r[4 * j + 3])));
+  }
+  __threadfence();  // the partial is visible device-wide before the arrival is
+  __syncwarp();
+  if (lane == 0) atomicAdd(p.sk_cnt + owner, 1u);
+}
+
+template <int BN>
+DEVI void sk_reduce_partials(const GemmParams& p, uint32_t tacc, int pair, int npairs, int first,
+                                                int npeer, int crank, int ew, int half, int lane) {
+  constexpr int CPW = BN / 64;
+  // all 16 epilogue warps (8 per CTA of the pair) of every contributing pair have arrived?
+  if (lane == 0) {
+    const unsigned int want = (unsigned int)(16 * npeer);
+    while (ld_acquire_gpu(p.sk_cnt + pair) < want) __nanosleep(40);
+  }
+  __syncwarp();
+  __threadfence();
+  const size_t my_off = (size_t)crank * (BM * BN) + (size_t)ew * (CPW * 8 * 128) + (size_t)lane * 4;
+#pragma unroll 1
+  for (int ci = 0; ci < CPW; ++ci) {
+    uint32_t r[32];
+    tmem_ld32(tacc + (half * CPW + ci) * 32, r);
+    tmem_ld_wait();
+#pragma unroll 1
+    for (int q = 0; q < npeer; ++q) {  // fixed order: deterministic sums
+      const float* ws = p.sk_ws + (size_t)(first + q) * (2 * BM * BN) + my_off;
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        const float4 v = __ldcg(reinterpret_cast<const float4*>(ws + (ci * 8 + j) * 128));
+        r[4 * j] = __float_as_uint(__uint_as_float(r[4 * j]) + v.x);
+        r[4 * j + 1] = __float_as_uint(__uint_as_float(r[4 * j + 1]) + v.y);
+        r[4 * j + 2] = __float_as_uint(__uint_as_float(r[4 * j + 2]) + v.z);
+        r[4 * j + 3] = __float_as_uint(__uint_as_float(r[4 * j + 3]) + v.w);
+      }
+    }
+    tmem_st32(tacc + (half * CPW + ci) * 32, r);
+  }
+  tmem_st_wait();
+  tc_fence_before();
+  __syncwarp();
+  if (lane == 0) {
+    // the last of the pair's 16 owner warps to get here re-arms both counters for the next launch
+    const unsigned int done = atomicAdd(p.sk_cnt + npairs + pair, 1u);
+    if (done == 15u) {
+      p.sk_cnt[pair] = 0u;
+      p.sk_cnt[npairs + pair] = 0u;
+    }
+  }
+}
+
 template <int BN, int EPI, int CL>
 __global__ void __launch_bounds__(GEMM_THREADS, 1)
 gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const GemmParams p) {
@@ -226,6 +380,8 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
   uint64_t* tfull = bars + 2 * STAGES;
   uint64_t* tempty = bars + 2 * STAGES + 2;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * STAGES + 4);
+  SkPlan* plan = reinterpret_cast<SkPlan*>(bars + 2 * STAGES + 6);
+  static_assert((2 * STAGES + 6) * 8 + sizeof(SkPlan) <= 256, "barrier area too small");
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -255,6 +411,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
         mbar_init(&tempty[i], 8 * CL);  // CL == 2: the epilogue warps of BOTH CTAs arrive on the leader's barrier
       }
       mbar_fence_init();
+      sk_plan_build(plan, p.sk_tiles, p.sk_pairs, tile0, num_tiles, KB);
     }
     __syncwarp();
     if (CL == 2) tmem_alloc2<Cfg::TMEM_COLS>(tmem_slot);
@@ -274,9 +431,12 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
     if (lane == 0) {
       int s = 0;
       uint32_t ph = 0;
-      for (int tile = tile0; tile < num_tiles; tile += tstep) {
-        const TileCoord t = decode_tile<BN, EPI, CL>(p, tile, MT, NT, KB, crank);
+      for (int wn = 0;; ++wn) {
+        int tile, skb0, skb1;
+        if (!sk_item(plan, wn, tile0, tstep, tile, skb0, skb1)) break;
+        TileCoord t = decode_tile<BN, EPI, CL>(p, tile, MT, NT, KB, crank);
         if (t.skip) continue;
+        if (skb1 >= 0) { t.kb0 = skb0; t.kb1 = skb1; }
         const int m0 = t.mt * BM;
         for (int kz = 0; kz < KZ; ++kz) {
           const int z2 = p.reduce_z2 ? kz : t.z2;
@@ -350,9 +510,12 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
       int s = 0;
       uint32_t ph = 0;
       int it = 0;
-      for (int tile = tile0; tile < num_tiles; tile += tstep) {
-        const TileCoord t = decode_tile<BN, EPI, CL>(p, tile, MT, NT, KB, crank);
+      for (int wn = 0;; ++wn) {
+        int tile, skb0, skb1;
+        if (!sk_item(plan, wn, tile0, tstep, tile, skb0, skb1)) break;
+        TileCoord t = decode_tile<BN, EPI, CL>(p, tile, MT, NT, KB, crank);
         if (t.skip) continue;
+        if (skb1 >= 0) { t.kb0 = skb0; t.kb1 = skb1; }
         const int as = it & 1;
         const uint32_t aph = (it >> 1) & 1;
         ++it;
@@ -394,7 +557,9 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
     const int quad = warp & 3;
     const int half = ew >> 2;
     int it = 0;
-    for (int tile = tile0; tile < num_tiles; tile += tstep) {
+    for (int wn = 0;; ++wn) {
+      int tile, skb0, skb1;
+      if (!sk_item(plan, wn, tile0, tstep, tile, skb0, skb1)) break;
       const TileCoord t = decode_tile<BN, EPI, CL>(p, tile, MT, NT, KB, crank);
       if (t.skip) continue;
       const int mt = t.mt, nt = t.nt;
@@ -407,6 +572,26 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
       const uint32_t tacc = tmem_base + as * BN + ((uint32_t)(quad * 32) << 16);
       uint8_t* stg = staging + ew * (32 * 80);
       const int row_base = mt * BM + quad * 32;
+
+      if (CL == 2 && wn < 2 && skb1 >= 0) {
+        const volatile SkPlan* vp = plan;
+        const int role = vp->role[wn];
+        if (role != SK_FULL) {
+          mbar_wait(&tfull[as], aph);
+          tc_fence_after();
+          if (role == SK_CONTRIB) {
+            sk_store_partial<BN>(p, tacc, tile0, vp->peer[wn], crank, ew, half, lane);
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive_leader(&tempty[as]);
+            continue;
+          }
+          sk_reduce_partials<BN>(p, tacc, tile0, tstep, vp->peer[wn], vp->npeer[wn], crank, ew, half, lane);
+          // the regular epilogue below may read columns that the other warp of this lane quadrant has just patched
+          named_bar_sync(1 + quad, 64);
+          tc_fence_after();
+        }
+      }
 
       if (EPI == DB1_EPI_PLAIN || EPI == DB1_EPI_QKV) {
         constexpr int CPW = BN / 64;  // chunks per warp
@@ -666,8 +851,34 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
   }
 }
 
+// Stream-K workspace registered by the caller (db1_gemm_set_workspace): counters first, then the partial-tile slots.
+struct SkWorkspace {
+  void* base = nullptr;
+  long long bytes = 0;
+  int device = -1;
+};
+static SkWorkspace g_sk_ws;
+constexpr long long SK_CNT_BYTES = 4096;
+constexpr int SK_MAX_SPLIT = 4;     // a tile is cut into at most this many k-ranges ...
+constexpr int SK_MIN_KB = 4;        // ... of at least this many 64-wide k-blocks
+
+// Stream-K tail: worth it when the last data-parallel wave would leave a visible share of the pairs idle.
+static bool sk_choose(long long tiles, int slots, int KB, int* R_out, int* GS_out) {
+  const int R = (int)(tiles % slots);
+  if (R == 0) return false;
+  const long long waves = (tiles + slots - 1) / slots;
+  const double idle = 1.0 - (double)tiles / (double)(waves * slots);  // share of the data-parallel schedule wasted
+  int split = KB / SK_MIN_KB;
+  if (split > SK_MAX_SPLIT) split = SK_MAX_SPLIT;
+  if (idle < 0.04 || split < 2) return false;
+  const long long gs = (long long)R * split;
+  *R_out = R;
+  *GS_out = (int)(gs < slots ? gs : slots);
+  return true;
+}
+
 template <int BN, int EPI, int CL>
-static int launch_gemm_cl(const CUtensorMap& tmA, const CUtensorMap& tmB, const GemmParams& p, cudaStream_t stream) {
+static int launch_gemm_cl(const CUtensorMap& tmA, const CUtensorMap& tmB, const GemmParams& p_in, cudaStream_t stream) {
   using Cfg = GemmCfg<BN, CL>;
   static bool configured = false;
   if (!configured) {
@@ -675,11 +886,26 @@ static int launch_gemm_cl(const CUtensorMap& tmA, const CUtensorMap& tmB, const 
                                   Cfg::SMEM_BYTES));
     configured = true;
   }
+  GemmParams p = p_in;
   const long long MT = cdiv(p.M, BM);
   const long long NT = (EPI == DB1_EPI_GEGLU) ? p.F / (BN / 2) : cdiv(p.N, BN);
   long long tiles = (CL == 2 ? (MT + 1) / 2 : MT) * NT * p.Z1 * (p.reduce_z2 ? 1 : p.Z2);
   const int slots = sm_count() / CL;
   int grid = (int)(tiles > slots ? slots : tiles) * CL;
+  if (CL == 2 && g_sk_ws.base != nullptr && !getenv("DB1_GEMM_NO_SK")) {
+    int dev = -1;
+    cudaGetDevice(&dev);
+    const long long need = SK_CNT_BYTES + (long long)slots * CL * BM * BN * 4;
+    int R = 0, GS = 0;
+    if (dev == g_sk_ws.device && g_sk_ws.bytes >= need && 2 * slots * (long long)sizeof(unsigned int) <= SK_CNT_BYTES &&
+        sk_choose(tiles, slots, cdiv(p.K, BK), &R, &GS)) {
+      p.sk_tiles = R;
+      p.sk_pairs = GS;
+      p.sk_cnt = reinterpret_cast<unsigned int*>(g_sk_ws.base);
+      p.sk_ws = reinterpret_cast<float*>(reinterpret_cast<char*>(g_sk_ws.base) + SK_CNT_BYTES);
+      grid = slots * CL;  // every pair takes part, also when there are fewer tiles than pairs
+    }
+  }
   DB1_CUDA(launch_pdl(gemm_kernel<BN, EPI, CL>, dim3(grid), dim3(GEMM_THREADS), Cfg::SMEM_BYTES, stream, CL, tmA, tmB, p));
   return 0;
 }
@@ -717,6 +943,41 @@ static int make_operand_map(CUtensorMap* tm, const void* base, int mn_major, lon
 }  // namespace db1
 
 using namespace db1;
+
+extern "C" int db1_gemm_set_workspace(void* ws, long long bytes) {
+  if (ws == nullptr || bytes <= 0) {
+    g_sk_ws = SkWorkspace();
+    return 0;
+  }
+  DB1_CHECK_ARG(((uintptr_t)ws & 15) == 0, "gemm workspace %p not 16-byte aligned", ws);
+  int dev = -1;
+  DB1_CUDA(cudaGetDevice(&dev));
+  g_sk_ws.base = ws;
+  g_sk_ws.bytes = bytes;
+  g_sk_ws.device = dev;
+  return 0;
+}
+
+// Host-side view of the stream-K schedule (tests / tooling): the decision for a tile count and the work list of one pair.
+extern "C" int db1_gemm_sk_choose(long long tiles, int pairs, int KB, int* sk_tiles, int* sk_pairs) {
+  DB1_CHECK_ARG(tiles > 0 && pairs > 0 && KB > 0 && sk_tiles && sk_pairs, "sk_choose: bad argument");
+  *sk_tiles = 0;
+  *sk_pairs = 0;
+  return sk_choose(tiles, pairs, KB, sk_tiles, sk_pairs) ? 1 : 0;
+}
+/* out[14] = nseg, T_dp, tile[2], kb0[2], kb1[2], role[2], peer[2], npeer[2] */
+extern "C" int db1_gemm_sk_plan(int pair, long long tiles, int KB, int sk_tiles, int sk_pairs, int* out) {
+  DB1_CHECK_ARG(out && pair >= 0 && tiles > 0 && KB > 0, "sk_plan: bad argument");
+  SkPlan pl;
+  memset(&pl, 0, sizeof(pl));
+  sk_plan_build(&pl, sk_tiles, sk_pairs, pair, (int)tiles, KB);
+  memcpy(out, &pl, sizeof(pl));
+  return 0;
+}
+
+extern "C" long long db1_gemm_workspace_bytes(void) {
+  return SK_CNT_BYTES + (long long)(sm_count() / 2) * 2 * BM * 256 * 4;
+}
 
 extern "C" int db1_gemm_f16(const db1_gemm_desc* d, void* stream_) {
   cudaStream_t stream = (cudaStream_t)stream_;

@@ -78,12 +78,35 @@ def _need_cuda_half(*ts):
             raise _lib.Db1Error("DB1 sm_100a kernels need CUDA fp16 tensors, got %s on %s" % (t.dtype, t.device))
 
 
+_gemm_ws = {}  # device index -> (tensor, registered)
+
+
+def _ensure_gemm_workspace(device):
+    """Scratch for the GEMM's stream-K tail (include/db1_sm100.h:db1_gemm_set_workspace): allocated by torch once per
+    device, zero-filled, kept alive for the life of the process. The library is bound to one device per process (one
+    process per GPU); a second device simply runs without the stream-K tail."""
+    idx = device.index if device.index is not None else torch.cuda.current_device()
+    if idx in _gemm_ws:
+        return
+    l = _lib.lib()
+    l.db1_gemm_workspace_bytes.restype = C.c_longlong
+    if _gemm_ws:  # already bound to another device
+        _gemm_ws[idx] = None
+        return
+    with torch.cuda.device(idx):
+        n = int(l.db1_gemm_workspace_bytes())
+        ws = torch.zeros(n, dtype=torch.uint8, device=device)
+        check(l.db1_gemm_set_workspace(ptr(ws), C.c_longlong(n)), "db1_gemm_set_workspace")
+    _gemm_ws[idx] = ws
+
+
 def gemm(A, B, C_out, M, N, K, *, lda, ldb, ldc, a_mn=False, b_mn=False, epilogue=EPI_PLAIN, alpha=1.0,
          accumulate=False, bias=None, resid=None, ldr=0, drop_p=0.0, seed=0, u=None, v=None, d_model=0, H=None,
          ldh=0, F=0, Z1=1, Z2=1, a_z=(0, 0), b_z=(0, 0), c_z=(0, 0), reduce_z2=False, k_mode=K_FULL,
          skip_upper=False, P=None, C2=None, Drow=None, window=0, bn_hint=0):
     """C[M,N] (+)= epilogue(alpha * A[M,K] @ B[N,K]^T) per batch index; see include/db1_sm100.h:db1_gemm_f16."""
     _need_cuda_half(A, B, C_out, bias, resid, u, v, H, P, C2)
+    _ensure_gemm_workspace(A.device)
     d = GemmDesc()
     d.epilogue = epilogue
     d.M, d.N, d.K = M, N, K

@@ -88,6 +88,22 @@ typedef struct db1_gemm_desc {
 
 int db1_gemm_f16(const db1_gemm_desc* d, void* stream);
 
+/* Optional scratch for the GEMM's stream-K tail (the library never allocates): when the tile count of a large GEMM is
+ * not a multiple of the CTA pairs, the last partial wave is cut along K across all pairs; partial fp32 accumulators
+ * and their arrival counters live here. `ws` = db1_gemm_workspace_bytes() bytes of device memory, ZERO-FILLED once by
+ * the caller, 16-byte aligned, owned by the caller for as long as GEMMs are launched; GEMM launches that share it must
+ * be stream-ordered (one compute stream). Without a workspace (or ws == NULL) every GEMM uses the plain data-parallel
+ * tile schedule - same results up to fp32 summation order. Registration is per process and bound to the current device. */
+int db1_gemm_set_workspace(void* ws, long long bytes);
+long long db1_gemm_workspace_bytes(void);
+/* Host-side view of that schedule (tests, tooling; no device work). db1_gemm_sk_choose: returns 1 and the number of
+ * trailing pair-tiles / participating pairs if a GEMM with `tiles` 256 x 256 pair-tiles of KB 64-wide k-blocks would
+ * use the stream-K tail on `pairs` CTA pairs, else 0. db1_gemm_sk_plan: work list of CTA pair `pair`:
+ * out[14] = { nseg, T_dp, tile[2], kb0[2], kb1[2], role[2] (0 full, 1 contributor, 2 owner), peer[2], npeer[2] };
+ * the pair then walks the data-parallel tiles pair, pair + pairs, ... < T_dp. */
+int db1_gemm_sk_choose(long long tiles, int pairs, int KB, int* sk_tiles, int* sk_pairs);
+int db1_gemm_sk_plan(int pair, long long tiles, int KB, int sk_tiles, int sk_pairs, int* out);
+
 /* ------------------------------------------------------------------------------------------------------------------
  * Fused relative-position causal attention, forward (tcgen05 QK^T / QR^T / PV on TMEM, online softmax, in-kernel
  * _rel_shift, causal + sliding-window predicate from indices).

@@ -184,3 +184,91 @@ def test_gemm_ds_epilogue_and_causal_kmodes(cuda, L, dh, window):
              a_z=(L * L, Hh * L * L), b_z=(dh, L * d), c_z=(dh, 0), reduce_z2=True, k_mode=ops.K_BEGIN_REV)
     refR = torch.einsum("bhic,bihd->chd", dSr.float(), dO.float())
     assert _rel(dR, refR) < 3e-3
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# Stream-K tail (CTA-pair launches whose pair-tile count is not a multiple of 74): same results as the data-parallel
+# schedule up to fp32 summation order; repeated launches must re-arm the arrival counters.
+# ---------------------------------------------------------------------------------------------------------------------
+def _sk_expected(M, N, K):
+    import ctypes as C
+    from db1_sm100 import _lib
+    R, GS = C.c_int(0), C.c_int(0)
+    tiles = ((M + 127) // 128 + 1) // 2 * ((N + 255) // 256)
+    return _lib.lib().db1_gemm_sk_choose(C.c_longlong(tiles), 74, (K + 63) // 64, C.byref(R), C.byref(GS)), R.value, GS.value
+
+
+@pytest.mark.parametrize("M,N,K,a_mn,b_mn", [
+    (4096, 2048, 2048, 0, 0),   # o_net: 128 pair-tiles, 54 in the tail, every pair both contributes and owns
+    (4096, 2048, 4096, 0, 1),   # dgrad layout
+    (2048, 2048, 4096, 1, 1),   # wgrad: 64 tiles on 74 pairs (no data-parallel part at all)
+    (6144, 2048, 4096, 1, 1),   # 192 tiles: 2 DP waves + 44-tile tail
+    (4096, 2048, 6144, 0, 1),   # KB = 96
+    (2560, 2048, 512, 0, 0),    # 80 tiles, KB = 8: the 6 tail tiles are cut in two, most pairs only do their DP tile
+    (4000, 2040, 1096, 0, 0),   # ragged M / N / K
+])
+def test_gemm_stream_k_tail(cuda, M, N, K, a_mn, b_mn):
+    from db1_sm100 import ops
+    on, R, GS = _sk_expected(M, N, K)
+    assert on == 1, "shape does not exercise the stream-K tail"
+    A = _mk((M, K), cuda, 1.0, 31)
+    B = _mk((N, K), cuda, 1.0, 32)
+    As = A.t().contiguous() if a_mn else A
+    Bs = B.t().contiguous() if b_mn else B
+    ref = A.float() @ B.float().t()
+    outs = []
+    for _rep in range(3):  # back-to-back launches: the counters re-arm themselves
+        Cc = torch.empty(M, N, dtype=torch.half, device=cuda)
+        ops.gemm(As, Bs, Cc, M, N, K, lda=As.stride(0), ldb=Bs.stride(0), ldc=N, a_mn=a_mn, b_mn=b_mn)
+        outs.append(Cc)
+    torch.cuda.synchronize()
+    for Cc in outs:
+        assert _rel(Cc, ref) < 2e-3
+        assert torch.equal(Cc, outs[0]), "stream-K sums must be deterministic"
+    ws = ops._gemm_ws[cuda.index if cuda.index is not None else 0]
+    assert ws[:4096].view(torch.int32).abs().max().item() == 0, "arrival counters not re-armed"
+
+
+def test_gemm_stream_k_fused_epilogues(cuda):
+    """Owner tiles run the normal fused epilogues after the fix-up: bias + dropout + residual, QKV, GeGLU backward."""
+    from db1_sm100 import ops
+    M, N, K = 4096, 2048, 2048
+    assert _sk_expected(M, N, K)[0] == 1
+    A = _mk((M, K), cuda, 1.0, 33)
+    B = _mk((N, K), cuda, 0.05, 34)
+    bias = _mk((N,), cuda, 1.0, 35)
+    resid = _mk((M, N), cuda, 1.0, 36)
+    C1 = torch.empty(M, N, dtype=torch.half, device=cuda)
+    ops.gemm(A, B, C1, M, N, K, lda=K, ldb=K, ldc=N, bias=bias, resid=resid, ldr=N)
+    ref = A.float() @ B.float().t() + bias.float() + resid.float()
+    assert _rel(C1, ref) < 2e-3
+    C2 = torch.empty_like(C1)
+    ops.gemm(A, B, C2, M, N, K, lda=K, ldb=K, ldc=N, bias=bias, resid=resid, ldr=N, drop_p=0.1, seed=77)
+    keep = (C2 != resid)
+    assert abs(keep.float().mean().item() - 0.9) < 0.01
+    refd = (A.float() @ B.float().t() + bias.float()) / 0.9 + resid.float()
+    assert _rel(C2[keep], refd[keep]) < 2e-3
+    # QKV epilogue: 3*d columns, d = 1024 -> 16 x 12 = 192 pair-tiles
+    d = 1024
+    assert _sk_expected(M, 3 * d, d)[0] == 1
+    X = _mk((M, d), cuda, 1.0, 37)
+    W = _mk((3 * d, d), cuda, 0.05, 38)
+    u = _mk((d,), cuda, 1.0, 39)
+    v = _mk((d,), cuda, 1.0, 40)
+    Q = torch.empty(M, 4 * d, dtype=torch.half, device=cuda)
+    ops.gemm(X, W, Q, M, 3 * d, d, lda=d, ldb=d, ldc=4 * d, epilogue=ops.EPI_QKV, u=u, v=v, d_model=d)
+    r = X.float() @ W.float().t()
+    refq = torch.cat([r[:, :d] + u.float(), r[:, :d] + v.float(), r[:, d:2 * d], r[:, 2 * d:]], 1)
+    assert _rel(Q, refq) < 2e-3
+    # GeGLU backward epilogue: M x F accumulator, F = 4096 -> 256 pair-tiles (34-tile tail)
+    F, N2 = 4096, 1024
+    assert _sk_expected(M, F, N2)[0] == 1
+    Hs = _mk((M, 2 * F), cuda, 1.0, 41)
+    G = _mk((M, N2), cuda, 1.0, 42)
+    W2 = _mk((N2, F), cuda, 0.05, 43)
+    dH = torch.empty(M, 2 * F, dtype=torch.half, device=cuda)
+    ops.gemm(G, W2, dH, M, F, N2, lda=N2, ldb=F, ldc=2 * F, b_mn=True, epilogue=ops.EPI_DGEGLU, H=Hs, ldh=2 * F, F=F)
+    dY = G.float() @ W2.float()
+    hh = Hs.float().requires_grad_(True)
+    (hh[:, :F] * torch.nn.functional.gelu(hh[:, F:])).backward(dY)
+    assert _rel(dH, hh.grad) < 3e-3
