@@ -37,7 +37,7 @@ static EncodeTiledFn encode_fn() {
 }
 
 int make_tmap_f16(CUtensorMap* out, const void* base, int rank, const uint64_t* dims, const uint64_t* strides_bytes,
-                  const uint32_t* box) {
+                  const uint32_t* box, int swizzle_bytes) {
   EncodeTiledFn fn = encode_fn();
   if (!fn) return set_err(-2, "cuTensorMapEncodeTiled unavailable (no CUDA driver?)");
   if (((uintptr_t)base & 15) != 0) return set_err(-1, "tensor map base %p not 16-byte aligned", base);
@@ -56,7 +56,9 @@ int make_tmap_f16(CUtensorMap* out, const void* base, int rank, const uint64_t* 
     }
   }
   CUresult r = fn(out, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, (cuuint32_t)rank, const_cast<void*>(base), gdim, gstr, bx, es,
-                  CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                  CU_TENSOR_MAP_INTERLEAVE_NONE,
+                  swizzle_bytes == 64 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_128B,
+                  CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) return set_err(-3, "cuTensorMapEncodeTiled failed with CUresult %d", (int)r);
   return 0;

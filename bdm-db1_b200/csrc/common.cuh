@@ -28,7 +28,7 @@ int set_err(int code, const char* fmt, ...);
 // Encode a 2-D/3-D fp16 tensor map with 128-byte swizzle. dims/strides innermost first; strides in BYTES for
 // dims 1.. (dim 0 is contiguous). Returns 0 or a negative error after set_err().
 int make_tmap_f16(CUtensorMap* out, const void* base, int rank, const uint64_t* dims, const uint64_t* strides_bytes,
-                  const uint32_t* box);
+                  const uint32_t* box, int swizzle_bytes = 128);
 
 int sm_count();
 bool pdl_enabled();  // programmatic dependent launch on (default) unless DB1_NO_PDL is set

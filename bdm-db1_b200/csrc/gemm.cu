@@ -64,17 +64,23 @@ struct GemmParams {
   int sk_tiles, sk_pairs;
   float* sk_ws;         // partial accumulators, one slot per contributing CTA pair: [pair][crank][128 x BN] fp32
   unsigned int* sk_cnt; // [2 * pairs]: arrivals per owner pair | owner warps that consumed them (self-resetting)
+  // TMA epilogue (PLAIN, CTA pairs): C leaves through shared memory and cp.async.bulk.tensor stores; the optional
+  // addend (residual, or C itself when accumulating) arrives the same way
+  int tma_epi;
+  int tma_in;  // 0 = no addend, 1 = residual / old C through tmIn
 };
 
 // CL == 2: the CTA pair of a cluster runs cta_group::2 MMAs (M = 256 across the pair); each CTA stages its own 128
 // rows of A and HALF of the B tile, so a stage is 32 KB instead of 48 KB and the ring gets deeper.
 template <int BN, int CL = 1>
 struct GemmCfg {
-  static constexpr int STAGES = (BN == 256) ? (CL == 2 ? 6 : 4) : 6;
+  static constexpr int STAGES = (BN == 256) ? (CL == 2 ? 5 : 4) : 6;
   static constexpr int B_STAGE_BYTES = BN / CL * BK * 2;
   static constexpr int STAGE_BYTES = A_STAGE_BYTES + B_STAGE_BYTES;
-  static constexpr int STAGING_BYTES = 8 * 32 * 80;  // DS epilogue: per-warp 32 rows x (64 B + 16 B pad)
-  static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + STAGING_BYTES + 1024 /*align*/ + 256 /*barriers*/;
+  // per-warp 32 rows x (64 B + 16 B pad) transpose areas; CTA-pair kernels: four 8 KB in/out tiles of the TMA epilogue
+  static constexpr int EPI_NB = 4;  // in/out tiles per column half of the TMA epilogue
+  static constexpr int STAGING_BYTES = (CL == 2) ? 2 * EPI_NB * 8192 : 8 * 32 * 80;
+  static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + STAGING_BYTES + 1024 /*align*/ + 384 /*barriers*/;
   static constexpr int TMEM_COLS = 2 * BN;  // 512 or 256
 };
 
@@ -366,9 +372,56 @@ DEVI void sk_reduce_partials(const GemmParams& p, uint32_t tacc, int pair, int n
   }
 }
 
+// One 32-column chunk of the TMA epilogue for one thread (= one output row): accumulator registers -> fused math ->
+// four 16-byte pieces of the row in the [128][32] fp16 shared-memory tile (64-byte swizzle). Specialised at compile time:
+// with run-time flags every piece carries ~60 predicated-off or branch instructions and a handful of constant-bank
+// reloads, which with two epilogue warps per scheduler were most of the epilogue's time.
+template <bool FULL, bool IN>
+DEVI void epi_chunk(const uint32_t (&r)[32], uint32_t rowp, uint32_t swz, int row, int col0, int N, float alpha,
+                    const __half* bias, uint32_t thr, float dscale, uint64_t seed) {
+  Half8 bv[4];
+  if (FULL) {
+#pragma unroll
+    for (int g = 0; g < 4; ++g) {
+      bv[g] = half8_zero();
+      if (bias && col0 + g * 8 < N) bv[g] = ld_half8(bias + col0 + g * 8);
+    }
+  }
+#pragma unroll
+  for (int g = 0; g < 4; ++g) {
+    float f[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) f[i] = __uint_as_float(r[g * 8 + i]);
+    if (FULL) {
+      float bb[8];
+      half8_to_float(bv[g], bb);
+#pragma unroll
+      for (int i = 0; i < 8; ++i) f[i] = fmaf(f[i], alpha, bb[i]);
+      if (thr) {
+        const uint64_t e = (uint64_t)row * (uint64_t)N + (uint64_t)(col0 + g * 8);
+        const uint64_t b0 = rng64(seed, e >> 2), b1 = rng64(seed, (e >> 2) + 1);
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          f[i] = dropout_keep(b0, i, thr) ? f[i] * dscale : 0.f;
+          f[4 + i] = dropout_keep(b1, i, thr) ? f[4 + i] * dscale : 0.f;
+        }
+      }
+    }
+    const uint32_t sa = rowp + (((uint32_t)g ^ swz) << 4);
+    if (IN) {
+      float bb[8];
+      half8_to_float(lds_half8(sa), bb);
+#pragma unroll
+      for (int i = 0; i < 8; ++i) f[i] += bb[i];
+    }
+    sts_half8(sa, float_to_half8(f));
+  }
+}
+
 template <int BN, int EPI, int CL>
 __global__ void __launch_bounds__(GEMM_THREADS, 1)
-gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const GemmParams p) {
+gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
+            const __grid_constant__ CUtensorMap tmC, const __grid_constant__ CUtensorMap tmIn, const GemmParams p) {
   using Cfg = GemmCfg<BN, CL>;
   constexpr int STAGES = Cfg::STAGES;
   extern __shared__ uint8_t smem_raw[];
@@ -380,8 +433,9 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
   uint64_t* tfull = bars + 2 * STAGES;
   uint64_t* tempty = bars + 2 * STAGES + 2;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * STAGES + 4);
-  SkPlan* plan = reinterpret_cast<SkPlan*>(bars + 2 * STAGES + 6);
-  static_assert((2 * STAGES + 6) * 8 + sizeof(SkPlan) <= 256, "barrier area too small");
+  uint64_t* ebar = bars + 2 * STAGES + 6;  // TMA epilogue: "in/out tile ready" per (column half, buffer)
+  SkPlan* plan = reinterpret_cast<SkPlan*>(bars + 2 * STAGES + 6 + 2 * Cfg::EPI_NB);
+  static_assert((2 * STAGES + 6 + 2 * Cfg::EPI_NB) * 8 + sizeof(SkPlan) <= 384, "barrier area too small");
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -399,6 +453,10 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&tmA);
     tma_prefetch_desc(&tmB);
+    if (p.tma_epi) {
+      tma_prefetch_desc(&tmC);
+      if (p.tma_in) tma_prefetch_desc(&tmIn);
+    }
   }
   if (warp == 1) {
     if (lane == 0) {
@@ -410,6 +468,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
         mbar_init(&tfull[i], 1);
         mbar_init(&tempty[i], 8 * CL);  // CL == 2: the epilogue warps of BOTH CTAs arrive on the leader's barrier
       }
+      for (int i = 0; i < 2 * Cfg::EPI_NB; ++i) mbar_init(&ebar[i], 1);
       mbar_fence_init();
       sk_plan_build(plan, p.sk_tiles, p.sk_pairs, tile0, num_tiles, KB);
     }
@@ -425,6 +484,9 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
   // everything above overlapped the previous kernel's tail; from here on global memory is touched
   pdl_launch_dependents();
   pdl_wait();
+  // development timeline (DB1_GEMM_DBG & 8): clock64 stamps per CTA into the registered workspace
+  unsigned long long* tl = (p.dbg & 8) ? reinterpret_cast<unsigned long long*>(p.sk_ws) + (size_t)blockIdx.x * 64 : nullptr;
+  if (tl && threadIdx.x == 64) tl[0] = clock64();
 
   if (warp == 0) {
     // ------------------------------------------------------------ TMA producer
@@ -449,7 +511,9 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
             const int k0 = kb * BK;
             if (CL == 2) {
               // both CTAs' boxes are counted on the leader's barrier (the MMA issuer lives there)
-              if (crank == 0) mbar_expect_tx(&full[s], 2 * Cfg::STAGE_BYTES);
+              // (dbg & 4: experiment - every other k-block reuses the stale B tile, i.e. 25 % less L2 -> SM traffic)
+              const bool skip_b = (p.dbg & 4) && (kb & 1);
+              if (crank == 0) mbar_expect_tx(&full[s], skip_b ? 2 * A_STAGE_BYTES : 2 * Cfg::STAGE_BYTES);
               if (!p.a_mn) {
                 tma_load_4d_2sm(sa, &tmA, &full[s], k0, m0, az1, az2);
               } else {
@@ -457,7 +521,8 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
                 tma_load_4d_2sm(sa + 8192, &tmA, &full[s], m0 + 64, k0, az1, az2);
               }
               // this CTA's half of the B tile: rows (K-major) / columns (MN-major) [crank * BN/2, +BN/2)
-              if (!p.b_mn) {
+              if (skip_b) {
+              } else if (!p.b_mn) {
 #pragma unroll
                 for (int j = 0; j < BN / 256; ++j) {
                   int row0;
@@ -527,6 +592,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
           for (int kb = t.kb0; kb < t.kb1; ++kb) {
             mbar_wait(&full[s], ph);
             tc_fence_after();
+            if (tl && kb == t.kb0 && it <= 15) tl[4 + 4 * (it - 1)] = clock64();
             const uint32_t sa = smem_u32(smem + s * Cfg::STAGE_BYTES);
             const uint64_t adesc = umma_smem_desc(sa, a_lbo, 1024);
             const uint64_t bdesc = umma_smem_desc(sa + A_STAGE_BYTES, b_lbo, 1024);
@@ -546,6 +612,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
         }
         if (CL == 2) umma_commit2_mc(&tfull[as], (uint16_t)3);
         else umma_commit(&tfull[as]);
+        if (tl && it <= 15) tl[4 + 4 * (it - 1) + 1] = clock64();
       }
     }
   } else {
@@ -557,6 +624,18 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
     const int quad = warp & 3;
     const int half = ew >> 2;
     int it = 0;
+    unsigned int eseq = 0;  // TMA epilogue: chunks this column half has processed (buffer = eseq % NB)
+    // Epilogue parameters as locals: every inline-asm statement here clobbers "memory", after which the compiler
+    // re-reads kernel parameters from the constant bank (LDC / LDCU + a dependent uniform branch, ~100 cycles each);
+    // measured: 1000 of the 1450 cycles per 32-column chunk were spent on those reloads.
+    const float e_alpha = p.alpha;
+    const __half* const e_bias = p.bias;
+    const uint32_t e_thr = p.drop_thr16;
+    const float e_dscale = p.drop_scale;
+    const uint64_t e_seed = p.seed;
+    const int e_in = p.tma_in;
+    const int e_N = p.N;
+    const bool e_full = e_alpha != 1.0f || e_bias != nullptr || e_thr != 0u;
     for (int wn = 0;; ++wn) {
       int tile, skb0, skb1;
       if (!sk_item(plan, wn, tile0, tstep, tile, skb0, skb1)) break;
@@ -593,7 +672,92 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
         }
       }
 
-      if (EPI == DB1_EPI_PLAIN || EPI == DB1_EPI_QKV) {
+      if constexpr (CL == 2 && EPI == DB1_EPI_PLAIN) {
+        {
+          // ---- TMA epilogue. The four warps of a column half (one per TMEM lane quadrant) own 128 rows x 128 columns
+          // and work through them in 32-column chunks: tcgen05.ld (next chunk's load in flight) -> fused math -> the
+          // chunk as a [128][32] fp16 tile in shared memory (64-byte swizzle, conflict-free 16-byte accesses) -> one
+          // cp.async.bulk.tensor store by the half's leader thread. The addend (residual / old C) is fetched into
+          // the same buffer by TMA one chunk ahead and overwritten in place. Two buffers per half; nothing in this
+          // path waits on a global load or store round trip except through the mbarrier / bulk-group machinery.
+          constexpr int CPW = BN / 64;
+          constexpr int NB = Cfg::EPI_NB;
+          static_assert(NB == 4 && CPW <= NB, "buffer ring sized for one tile's chunks");
+          const int c_first = half * CPW;
+          uint8_t* ebuf = staging + half * (NB * 8192);
+          uint64_t* ebh = ebar + half * NB;
+          const bool eleader = ((ew & 3) == 0) && lane == 0;
+          const int trow = quad * 32 + lane;
+          const uint32_t swz = (uint32_t)((trow >> 1) & 3);
+          const int row0 = mt * BM;
+          const int colh = nt * BN + c_first * 32;  // first column of this half
+          int nch = (e_N - colh + 31) / 32;         // chunks of this half that hold valid columns (ragged N)
+          nch = nch < 0 ? 0 : (nch > CPW ? CPW : nch);
+          if (p.dbg & 2) nch = 0;
+          // leader: make buffer seq % NB ready for chunk `seq` (its previous user, chunk seq - NB, has been stored:
+          // callers keep at most ONE store group pending before arming)
+          auto arm = [&](unsigned int seq, int col0) {
+            const unsigned int b = seq & (NB - 1);
+            if (e_in) {
+              mbar_expect_tx(&ebh[b], 8192);
+              tma_load_2d(ebuf + b * 8192, &tmIn, &ebh[b], col0, row0);
+            } else {
+              mbar_arrive(&ebh[b]);
+            }
+          };
+          if (eleader && nch > 0) {  // under the tail of this tile's main loop: the first NB - 1 chunks
+            bulk_wait_group_read<1>();
+            for (int k = 0; k < nch && k < NB - 1; ++k) arm(eseq + k, colh + k * 32);
+          }
+          mbar_wait(&tfull[as], aph);
+          tc_fence_after();
+          if (tl && ew == 0 && lane == 0 && it <= 15) tl[4 + 4 * (it - 1) + 2] = clock64();
+          uint32_t r[2][32];
+          if (nch > 0) tmem_ld32(tacc + c_first * 32, r[0]);
+#pragma unroll
+          for (int ci = 0; ci < CPW; ++ci) {
+            if (ci < nch) {
+              const bool stamp = tl && ew == 0 && lane == 0 && it == 1;
+              if (stamp) tl[32 + ci * 6 + 0] = clock64();
+              tmem_ld_wait();
+              if (stamp) tl[32 + ci * 6 + 1] = clock64();
+              if (ci + 1 < nch) tmem_ld32(tacc + (c_first + ci + 1) * 32, r[(ci + 1) & 1]);
+              const int col0 = colh + ci * 32;
+              const unsigned int b = eseq & (NB - 1);
+              mbar_wait(&ebh[b], (eseq / NB) & 1u);
+              if (stamp) tl[32 + ci * 6 + 2] = clock64();
+              const uint32_t rowp = smem_u32(ebuf + b * 8192 + trow * 64);
+              if (e_full) {
+                if (e_in) epi_chunk<true, true>(r[ci & 1], rowp, swz, row, col0, e_N, e_alpha, e_bias, e_thr, e_dscale, e_seed);
+                else epi_chunk<true, false>(r[ci & 1], rowp, swz, row, col0, e_N, e_alpha, e_bias, e_thr, e_dscale, e_seed);
+              } else {
+                if (e_in) epi_chunk<false, true>(r[ci & 1], rowp, swz, row, col0, e_N, 1.f, nullptr, 0u, 1.f, 0ull);
+                else epi_chunk<false, false>(r[ci & 1], rowp, swz, row, col0, e_N, 1.f, nullptr, 0u, 1.f, 0ull);
+              }
+              if (stamp) tl[32 + ci * 6 + 3] = clock64();
+              fence_proxy_async_smem();
+              if (stamp) tl[32 + ci * 6 + 4] = clock64();
+              named_bar_sync(5 + half, 128);
+              if (stamp) tl[32 + ci * 6 + 5] = clock64();
+              if (eleader) {
+                if (!(p.dbg & 1)) tma_store_2d(&tmC, ebuf + b * 8192, col0, row0);
+                bulk_commit_group();
+                if (ci + NB - 1 < nch) {  // the ring's last buffer: free once the previous chunk's store has read it
+                  bulk_wait_group_read<1>();
+                  arm(eseq + NB - 1, col0 + (NB - 1) * 32);
+                }
+              }
+              ++eseq;
+            }
+          }
+          if (tl && ew == 0 && lane == 0 && it <= 15) tl[4 + 4 * (it - 1) + 3] = clock64();
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) mbar_arrive_leader(&tempty[as]);
+          continue;
+        }
+      }
+      if constexpr ((EPI == DB1_EPI_PLAIN && CL == 1) || EPI == DB1_EPI_QKV) {
         constexpr int CPW = BN / 64;  // chunks per warp
         const int c_first = half * CPW;
         Half8 rs[CPW][4];
@@ -608,6 +772,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
         }
         mbar_wait(&tfull[as], aph);
         tc_fence_after();
+        if (tl && ew == 0 && lane == 0 && it <= 15) tl[4 + 4 * (it - 1) + 2] = clock64();
 #pragma unroll
         for (int ci = 0; ci < CPW; ++ci) {
           const int c = c_first + ci;
@@ -832,6 +997,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
         }
       }
       // release this accumulator stage back to the MMA warp
+      if (tl && ew == 0 && lane == 0 && it <= 15) tl[4 + 4 * (it - 1) + 3] = clock64();
       tc_fence_before();
       __syncwarp();
       if (lane == 0) {
@@ -841,6 +1007,9 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
     }
   }
 
+  if (CL == 2 && p.tma_epi && warp >= 2 && ((warp - 2) & 3) == 0 && lane == 0)
+    bulk_wait_group_read<0>();  // shared memory must outlive the last tile stores
+  if (tl && threadIdx.x == 64) tl[1] = clock64();
   tc_fence_before();
   __syncthreads();
   if (CL == 2) cluster_sync_all();  // the peer may still multicast into / arrive on this CTA's shared memory
@@ -862,6 +1031,14 @@ constexpr long long SK_CNT_BYTES = 4096;
 constexpr int SK_MAX_SPLIT = 4;     // a tile is cut into at most this many k-ranges ...
 constexpr int SK_MIN_KB = 4;        // ... of at least this many 64-wide k-blocks
 
+// 2-D map of a row-major [rows, cols] fp16 matrix for the TMA epilogue: box = 32 columns x 128 rows, 64-byte swizzle.
+static int make_tile_map(CUtensorMap* tm, const void* base, long long rows, long long cols, long long ld) {
+  uint64_t dims[2] = {(uint64_t)cols, (uint64_t)rows};
+  uint64_t str[1] = {(uint64_t)ld * 2};
+  uint32_t box[2] = {32, 128};
+  return make_tmap_f16(tm, base, 2, dims, str, box, 64);
+}
+
 // Stream-K tail: worth it when the last data-parallel wave would leave a visible share of the pairs idle.
 static bool sk_choose(long long tiles, int slots, int KB, int* R_out, int* GS_out) {
   const int R = (int)(tiles % slots);
@@ -878,7 +1055,8 @@ static bool sk_choose(long long tiles, int slots, int KB, int* R_out, int* GS_ou
 }
 
 template <int BN, int EPI, int CL>
-static int launch_gemm_cl(const CUtensorMap& tmA, const CUtensorMap& tmB, const GemmParams& p_in, cudaStream_t stream) {
+static int launch_gemm_cl(const CUtensorMap& tmA, const CUtensorMap& tmB, const GemmParams& p_in, cudaStream_t stream,
+                          const db1_gemm_desc* d) {
   using Cfg = GemmCfg<BN, CL>;
   static bool configured = false;
   if (!configured) {
@@ -892,7 +1070,7 @@ static int launch_gemm_cl(const CUtensorMap& tmA, const CUtensorMap& tmB, const 
   long long tiles = (CL == 2 ? (MT + 1) / 2 : MT) * NT * p.Z1 * (p.reduce_z2 ? 1 : p.Z2);
   const int slots = sm_count() / CL;
   int grid = (int)(tiles > slots ? slots : tiles) * CL;
-  if (CL == 2 && g_sk_ws.base != nullptr && !getenv("DB1_GEMM_NO_SK")) {
+  if (CL == 2 && g_sk_ws.base != nullptr && getenv("DB1_GEMM_SK")) {
     int dev = -1;
     cudaGetDevice(&dev);
     const long long need = SK_CNT_BYTES + (long long)slots * CL * BM * BN * 4;
@@ -906,20 +1084,46 @@ static int launch_gemm_cl(const CUtensorMap& tmA, const CUtensorMap& tmB, const 
       grid = slots * CL;  // every pair takes part, also when there are fewer tiles than pairs
     }
   }
-  DB1_CUDA(launch_pdl(gemm_kernel<BN, EPI, CL>, dim3(grid), dim3(GEMM_THREADS), Cfg::SMEM_BYTES, stream, CL, tmA, tmB, p));
+  CUtensorMap tmC = tmA, tmIn = tmA;  // placeholders unless the TMA epilogue is used
+  if (CL == 2 && EPI == DB1_EPI_PLAIN) {  // launch_gemm has checked tma_epilogue_ok()
+    const void* in = p.resid ? (const void*)p.resid : (p.accumulate ? (const void*)p.C : nullptr);
+    const long long ldin = p.resid ? p.ldr : p.ldc;
+    int e = make_tile_map(&tmC, p.C, p.M, p.N, p.ldc);
+    if (e) return e;
+    if (in && (e = make_tile_map(&tmIn, in, p.M, p.N, ldin))) return e;
+    p.tma_epi = 1;
+    p.tma_in = in ? 1 : 0;
+  }
+  (void)d;
+  if ((p.dbg & 8) && g_sk_ws.base != nullptr && p.sk_tiles == 0)
+    p.sk_ws = reinterpret_cast<float*>(reinterpret_cast<char*>(g_sk_ws.base) + SK_CNT_BYTES);
+  else
+    p.dbg &= ~8;
+  DB1_CUDA(launch_pdl(gemm_kernel<BN, EPI, CL>, dim3(grid), dim3(GEMM_THREADS), Cfg::SMEM_BYTES, stream, CL, tmA, tmB, tmC,
+                      tmIn, p));
   return 0;
 }
 
 // CTA pairs (cta_group::2: one 256 x BN MMA over two vertically adjacent 128-row tiles, each CTA staging half of the B
 // tile) cut both the L2 -> SM and the shared-memory operand traffic per tile from 48 KB to 32 KB per k-block; used
 // whenever both CTAs see the same k-range.
+// The CTA-pair PLAIN kernel has only the TMA epilogue: C (and the addend) must be addressable by a tensor map, and
+// "residual + accumulate" (two addends) stays on the single-CTA kernel.
+static bool tma_epilogue_ok(const GemmParams& p) {
+  if (p.resid && p.accumulate) return false;
+  if (((uintptr_t)p.C & 15) != 0) return false;
+  if (p.resid && (((uintptr_t)p.resid & 15) != 0 || p.ldr % 8 != 0)) return false;
+  return true;
+}
+
 template <int BN, int EPI>
 static int launch_gemm(const CUtensorMap& tmA, const CUtensorMap& tmB, const GemmParams& p, cudaStream_t stream) {
+  const db1_gemm_desc* d = nullptr;
   const bool batched = p.Z1 * p.Z2 > 1;
   if (BN == 256 && EPI != DB1_EPI_DS && !batched && p.k_mode == DB1_K_FULL && !p.skip_upper && p.M > BM &&
-      !getenv("DB1_GEMM_NO_CLUSTER"))
-    return launch_gemm_cl<BN, EPI, (BN == 256 && EPI != DB1_EPI_DS) ? 2 : 1>(tmA, tmB, p, stream);
-  return launch_gemm_cl<BN, EPI, 1>(tmA, tmB, p, stream);
+      (EPI != DB1_EPI_PLAIN || tma_epilogue_ok(p)) && !getenv("DB1_GEMM_NO_CLUSTER"))
+    return launch_gemm_cl<BN, EPI, (BN == 256 && EPI != DB1_EPI_DS) ? 2 : 1>(tmA, tmB, p, stream, d);
+  return launch_gemm_cl<BN, EPI, 1>(tmA, tmB, p, stream, d);
 }
 
 // 4-D map (inner, rows, z1, z2). A broadcast batch dim (stride 0) is encoded as a dim of size 1.

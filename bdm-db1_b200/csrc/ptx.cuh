@@ -96,6 +96,19 @@ DEVI void tma_load_3d(void* smem_dst, const CUtensorMap* m, uint64_t* bar, int c
       : "memory");
 }
 
+// shared -> global tile store (bulk async-group completion); out-of-bounds parts of the box are clipped
+DEVI void tma_store_2d(const CUtensorMap* m, const void* smem_src, int c0, int c1) {
+  asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%2, %3}], [%1];"
+               ::"l"(m), "r"(smem_u32(smem_src)), "r"(c0), "r"(c1)
+               : "memory");
+}
+DEVI void bulk_commit_group() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+// wait until at most N of this thread's bulk groups still have to READ their shared-memory source
+template <int N>
+DEVI void bulk_wait_group_read() {
+  asm volatile("cp.async.bulk.wait_group.read %0;" ::"n"(N) : "memory");
+}
+
 // ---------------------------------------------------------------- TMEM
 template <int NCOLS>
 DEVI void tmem_alloc(uint32_t* smem_slot) {
