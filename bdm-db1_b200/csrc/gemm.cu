@@ -68,18 +68,19 @@ struct GemmParams {
   // addend (residual, or C itself when accumulating) arrives the same way
   int tma_epi;
   int tma_in;  // 0 = no addend, 1 = residual / old C through tmIn
+  int snake;   // causal k-ranges: tiles are visited heaviest first in alternating direction (see sk_item)
 };
 
 // CL == 2: the CTA pair of a cluster runs cta_group::2 MMAs (M = 256 across the pair); each CTA stages its own 128
 // rows of A and HALF of the B tile, so a stage is 32 KB instead of 48 KB and the ring gets deeper.
 template <int BN, int CL = 1>
 struct GemmCfg {
-  static constexpr int STAGES = (BN == 256) ? (CL == 2 ? 5 : 4) : 6;
-  static constexpr int B_STAGE_BYTES = BN / CL * BK * 2;
+  static constexpr int STAGES = (BN == 256) ? (CL >= 2 ? 5 : 4) : 6;
+  static constexpr int B_STAGE_BYTES = BN / (CL >= 2 ? 2 : 1) * BK * 2;  // CTA pairs: half of the B tile per CTA
   static constexpr int STAGE_BYTES = A_STAGE_BYTES + B_STAGE_BYTES;
   // per-warp 32 rows x (64 B + 16 B pad) transpose areas; CTA-pair kernels: four 8 KB in/out tiles of the TMA epilogue
   static constexpr int EPI_NB = 4;  // in/out tiles per column half of the TMA epilogue
-  static constexpr int STAGING_BYTES = (CL == 2) ? 2 * EPI_NB * 8192 : 8 * 32 * 80;
+  static constexpr int STAGING_BYTES = (CL >= 2) ? 2 * EPI_NB * 8192 : 8 * 32 * 80;
   static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + STAGING_BYTES + 1024 /*align*/ + 384 /*barriers*/;
   static constexpr int TMEM_COLS = 2 * BN;  // 512 or 256
 };
@@ -194,11 +195,19 @@ template <int BN, int EPI, int CL>
 DEVI TileCoord decode_tile(const GemmParams& p, int tile, int MT, int NT, int KB, int crank) {
   TileCoord t;
   int r;
-  if (CL == 2) {
-    // `tile` indexes pairs of vertically adjacent tiles: one cta_group::2 MMA tile of 256 rows
-    const int MT2 = (MT + 1) / 2;
-    t.mt = 2 * (tile % MT2) + crank;
-    r = tile / MT2;
+  if (CL >= 2) {
+    // `tile` indexes groups of CL vertically adjacent tiles: CL == 2: one cta_group::2 MMA tile of 256 rows;
+    // CL == 4: two such pairs (512 rows) that share - and multicast - the B tile
+    const int MTG = (MT + CL - 1) / CL;
+    t.mt = CL * (tile % MTG) + crank;
+    r = tile / MTG;
+  } else if (p.snake) {
+    // position in cost order: all tiles of the heaviest row block first. Rows get heavier with mt for the k-ranges that
+    // END at the row (or begin K-(mt+1)*128 from the end), lighter for the one that BEGINS at the row.
+    const int per = NT * p.Z1 * (p.reduce_z2 ? 1 : p.Z2);
+    const int g = tile / per;
+    t.mt = (p.k_mode == DB1_K_BEGIN_BY_ROW) ? g : MT - 1 - g;
+    r = tile % per;
   } else {
     t.mt = tile % MT;
     r = tile / MT;
@@ -283,7 +292,10 @@ __host__ __device__ inline void sk_plan_build(SkPlan* pl, int R, int GS, int pai
   pl->nseg = n;
 }
 // n-th work item of this pair: returns false when the list is exhausted. kb1 < 0 = the tile's own k-range.
-DEVI bool sk_item(const volatile SkPlan* pl, int n, int pair, int G, int& tile, int& kb0, int& kb1) {
+// snake != 0 (causal k-ranges: tile cost falls with the tile index, decode_tile sorts heaviest first): passes alternate
+// direction - pass 0: CTA c takes position c, pass 1: 2G-1-c, ... - so every CTA gets the same load within one tile;
+// a position past the end is reported as tile = -1 (skip).
+DEVI bool sk_item(const volatile SkPlan* pl, int n, int pair, int G, int snake, int& tile, int& kb0, int& kb1) {
   const int nseg = pl->nseg;
   if (n < nseg) {
     tile = pl->tile[n];
@@ -291,10 +303,17 @@ DEVI bool sk_item(const volatile SkPlan* pl, int n, int pair, int G, int& tile, 
     kb1 = pl->kb1[n];
     return true;
   }
-  tile = pair + (n - nseg) * G;
   kb0 = 0;
   kb1 = -1;
-  return tile < pl->T_dp;
+  const int T = pl->T_dp;
+  if (snake) {
+    if (n * G >= T) return false;
+    tile = (n & 1) ? (n + 1) * G - 1 - pair : n * G + pair;
+    if (tile >= T) tile = -1;
+    return true;
+  }
+  tile = pair + (n - nseg) * G;
+  return tile < T;
 }
 
 DEVI unsigned int ld_acquire_gpu(const unsigned int* p) {
@@ -421,7 +440,8 @@ DEVI void epi_chunk(const uint32_t (&r)[32], uint32_t rowp, uint32_t swz, int ro
 template <int BN, int EPI, int CL>
 __global__ void __launch_bounds__(GEMM_THREADS, 1)
 gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
-            const __grid_constant__ CUtensorMap tmC, const __grid_constant__ CUtensorMap tmIn, const GemmParams p) {
+            const __grid_constant__ CUtensorMap tmB64, const __grid_constant__ CUtensorMap tmC,
+            const __grid_constant__ CUtensorMap tmIn, const GemmParams p) {
   using Cfg = GemmCfg<BN, CL>;
   constexpr int STAGES = Cfg::STAGES;
   extern __shared__ uint8_t smem_raw[];
@@ -443,11 +463,13 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
   const int MT = (p.M + BM - 1) / BM;
   const int NT = (EPI == DB1_EPI_GEGLU) ? (p.F / (BN / 2)) : (p.N + BN - 1) / BN;
   const int ZO = p.reduce_z2 ? 1 : p.Z2;
-  const int num_tiles = (CL == 2 ? (MT + 1) / 2 : MT) * NT * p.Z1 * ZO;  // tile pairs when clustered
+  const int num_tiles = (CL >= 2 ? (MT + CL - 1) / CL : MT) * NT * p.Z1 * ZO;  // tile groups when clustered
   const int KB = (p.K + BK - 1) / BK;
-  const int crank = (CL == 2) ? (int)cluster_ctarank() : 0;
-  const int tile0 = (CL == 2) ? (int)(blockIdx.x >> 1) : (int)blockIdx.x;
-  const int tstep = (CL == 2) ? (int)(gridDim.x >> 1) : (int)gridDim.x;
+  const int crank = (CL >= 2) ? (int)cluster_ctarank() : 0;
+  const int prank = crank & 1;   // rank within the CTA pair (0 = leader: expects the bytes, issues the MMAs)
+  const int pairi = crank >> 1;  // pair within the cluster (CL == 4)
+  const int tile0 = (CL >= 2) ? (int)(blockIdx.x / CL) : (int)blockIdx.x;
+  const int tstep = (CL >= 2) ? (int)(gridDim.x / CL) : (int)gridDim.x;
   const int KZ = p.reduce_z2 ? p.Z2 : 1;  // extra contraction loop over z2
 
   if (warp == 0 && lane == 0) {
@@ -462,23 +484,23 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
     if (lane == 0) {
       for (int i = 0; i < STAGES; ++i) {
         mbar_init(&full[i], 1);   // CL == 2: only the leader's is used; it counts the bytes of both CTAs' loads
-        mbar_init(&empty[i], 1);  // CL == 2: released in both CTAs by the leader's multicast commit
+        mbar_init(&empty[i], CL == 4 ? 2 : 1);  // CL >= 2: released in every CTA of the cluster by each pair leader's multicast commit
       }
       for (int i = 0; i < 2; ++i) {
         mbar_init(&tfull[i], 1);
-        mbar_init(&tempty[i], 8 * CL);  // CL == 2: the epilogue warps of BOTH CTAs arrive on the leader's barrier
+        mbar_init(&tempty[i], CL >= 2 ? 16 : 8);  // CL >= 2: the epilogue warps of BOTH CTAs of a pair arrive on its leader's barrier
       }
       for (int i = 0; i < 2 * Cfg::EPI_NB; ++i) mbar_init(&ebar[i], 1);
       mbar_fence_init();
       sk_plan_build(plan, p.sk_tiles, p.sk_pairs, tile0, num_tiles, KB);
     }
     __syncwarp();
-    if (CL == 2) tmem_alloc2<Cfg::TMEM_COLS>(tmem_slot);
+    if (CL >= 2) tmem_alloc2<Cfg::TMEM_COLS>(tmem_slot);
     else tmem_alloc<Cfg::TMEM_COLS>(tmem_slot);
   }
   tc_fence_before();
   __syncthreads();
-  if (CL == 2) cluster_sync_all();  // barriers of both CTAs are initialised before any remote arrive / multicast
+  if (CL >= 2) cluster_sync_all();  // barriers of all CTAs are initialised before any remote arrive / multicast
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
   // everything above overlapped the previous kernel's tail; from here on global memory is touched
@@ -495,7 +517,8 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
       uint32_t ph = 0;
       for (int wn = 0;; ++wn) {
         int tile, skb0, skb1;
-        if (!sk_item(plan, wn, tile0, tstep, tile, skb0, skb1)) break;
+        if (!sk_item(plan, wn, tile0, tstep, p.snake, tile, skb0, skb1)) break;
+        if (tile < 0) continue;
         TileCoord t = decode_tile<BN, EPI, CL>(p, tile, MT, NT, KB, crank);
         if (t.skip) continue;
         if (skb1 >= 0) { t.kb0 = skb0; t.kb1 = skb1; }
@@ -509,31 +532,40 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
             uint8_t* sa = smem + s * Cfg::STAGE_BYTES;
             uint8_t* sb = sa + A_STAGE_BYTES;
             const int k0 = kb * BK;
-            if (CL == 2) {
-              // both CTAs' boxes are counted on the leader's barrier (the MMA issuer lives there)
+            if (CL >= 2) {
+              // both CTAs' boxes are counted on the pair leader's barrier (the MMA issuer lives there)
               // (dbg & 4: experiment - every other k-block reuses the stale B tile, i.e. 25 % less L2 -> SM traffic)
               const bool skip_b = (p.dbg & 4) && (kb & 1);
-              if (crank == 0) mbar_expect_tx(&full[s], skip_b ? 2 * A_STAGE_BYTES : 2 * Cfg::STAGE_BYTES);
+              if (prank == 0) mbar_expect_tx(&full[s], skip_b ? 2 * A_STAGE_BYTES : 2 * Cfg::STAGE_BYTES);
               if (!p.a_mn) {
                 tma_load_4d_2sm(sa, &tmA, &full[s], k0, m0, az1, az2);
               } else {
                 tma_load_4d_2sm(sa, &tmA, &full[s], m0, k0, az1, az2);
                 tma_load_4d_2sm(sa + 8192, &tmA, &full[s], m0 + 64, k0, az1, az2);
               }
-              // this CTA's half of the B tile: rows (K-major) / columns (MN-major) [crank * BN/2, +BN/2)
+              // this CTA's half of the B tile: rows (K-major) / columns (MN-major) [prank * BN/2, +BN/2)
               if (skip_b) {
+              } else if (CL == 4) {
+                // The two pairs of the cluster need the same B halves: the half is two 8 KB boxes (64 rows / columns
+                // each); pair i fetches box i and multicasts it to the CTAs of equal pair rank in both pairs, so the
+                // cluster reads every B byte from L2 once instead of twice.
+                const uint16_t mask = (uint16_t)(0x5u << prank);
+                uint8_t* dst = sb + pairi * 8192;
+                const int n0 = t.nt * BN + prank * (BN / 2) + pairi * 64;
+                if (!p.b_mn) tma_load_4d_2sm_mc(dst, &tmB64, &full[s], k0, n0, bz1, bz2, mask);
+                else tma_load_4d_2sm_mc(dst, &tmB, &full[s], n0, k0, bz1, bz2, mask);
               } else if (!p.b_mn) {
 #pragma unroll
                 for (int j = 0; j < BN / 256; ++j) {
                   int row0;
-                  if (EPI == DB1_EPI_GEGLU) row0 = crank * p.F + t.nt * (BN / 2);
-                  else row0 = t.nt * BN + crank * (BN / 2);
+                  if (EPI == DB1_EPI_GEGLU) row0 = prank * p.F + t.nt * (BN / 2);
+                  else row0 = t.nt * BN + prank * (BN / 2);
                   tma_load_4d_2sm(sb + j * 16384, &tmB, &full[s], k0, row0 + j * 128, bz1, bz2);
                 }
               } else {
 #pragma unroll
                 for (int j = 0; j < BN / 128; ++j)
-                  tma_load_4d_2sm(sb + j * 8192, &tmB, &full[s], t.nt * BN + crank * (BN / 2) + j * 64, k0, bz1, bz2);
+                  tma_load_4d_2sm(sb + j * 8192, &tmB, &full[s], t.nt * BN + prank * (BN / 2) + j * 64, k0, bz1, bz2);
               }
             } else {
               mbar_expect_tx(&full[s], Cfg::STAGE_BYTES);
@@ -567,8 +599,8 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
     }
   } else if (warp == 1) {
     // ------------------------------------------------------------ MMA issuer
-    if (lane == 0 && crank == 0) {  // CL == 2: the leader issues for the pair
-      const uint32_t idesc = umma_idesc(BM * CL, BN, p.a_mn, p.b_mn, 0);
+    if (lane == 0 && prank == 0) {  // CL >= 2: the pair leader issues for its pair
+      const uint32_t idesc = umma_idesc(CL >= 2 ? 2 * BM : BM, BN, p.a_mn, p.b_mn, 0);
       const uint32_t a_lbo = p.a_mn ? 8192u : 16u, b_lbo = p.b_mn ? 8192u : 16u;
       const uint32_t a_kadv = p.a_mn ? (2048u >> 4) : (32u >> 4);  // descriptor start-address units of 16 B
       const uint32_t b_kadv = p.b_mn ? (2048u >> 4) : (32u >> 4);
@@ -577,7 +609,8 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
       int it = 0;
       for (int wn = 0;; ++wn) {
         int tile, skb0, skb1;
-        if (!sk_item(plan, wn, tile0, tstep, tile, skb0, skb1)) break;
+        if (!sk_item(plan, wn, tile0, tstep, p.snake, tile, skb0, skb1)) break;
+        if (tile < 0) continue;
         TileCoord t = decode_tile<BN, EPI, CL>(p, tile, MT, NT, KB, crank);
         if (t.skip) continue;
         if (skb1 >= 0) { t.kb0 = skb0; t.kb1 = skb1; }
@@ -598,11 +631,11 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
             const uint64_t bdesc = umma_smem_desc(sa + A_STAGE_BYTES, b_lbo, 1024);
 #pragma unroll
             for (int k = 0; k < BK / 16; ++k) {
-              if (CL == 2) umma_ss2(tacc, adesc + (uint64_t)(k * a_kadv), bdesc + (uint64_t)(k * b_kadv), idesc, acc);
+              if (CL >= 2) umma_ss2(tacc, adesc + (uint64_t)(k * a_kadv), bdesc + (uint64_t)(k * b_kadv), idesc, acc);
               else umma_ss(tacc, adesc + (uint64_t)(k * a_kadv), bdesc + (uint64_t)(k * b_kadv), idesc, acc);
               acc = 1;
             }
-            if (CL == 2) umma_commit2_mc(&empty[s], (uint16_t)3);
+            if (CL >= 2) umma_commit2_mc(&empty[s], (uint16_t)(CL == 4 ? 0xF : 3));
             else umma_commit(&empty[s]);
             if (++s == STAGES) {
               s = 0;
@@ -610,7 +643,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
             }
           }
         }
-        if (CL == 2) umma_commit2_mc(&tfull[as], (uint16_t)3);
+        if (CL >= 2) umma_commit2_mc(&tfull[as], (uint16_t)(3u << (crank & 2)));
         else umma_commit(&tfull[as]);
         if (tl && it <= 15) tl[4 + 4 * (it - 1) + 1] = clock64();
       }
@@ -636,9 +669,12 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
     const int e_in = p.tma_in;
     const int e_N = p.N;
     const bool e_full = e_alpha != 1.0f || e_bias != nullptr || e_thr != 0u;
+    // register-direct epilogues: 256-bit row accesses need 32-byte aligned rows of C and H
+    const bool e_al32 = (((uintptr_t)p.C | (uintptr_t)p.H) & 31) == 0 && ((p.ldc | p.ldh | p.F) & 15) == 0;
     for (int wn = 0;; ++wn) {
       int tile, skb0, skb1;
-      if (!sk_item(plan, wn, tile0, tstep, tile, skb0, skb1)) break;
+      if (!sk_item(plan, wn, tile0, tstep, p.snake, tile, skb0, skb1)) break;
+        if (tile < 0) continue;
       const TileCoord t = decode_tile<BN, EPI, CL>(p, tile, MT, NT, KB, crank);
       if (t.skip) continue;
       const int mt = t.mt, nt = t.nt;
@@ -659,20 +695,20 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
           mbar_wait(&tfull[as], aph);
           tc_fence_after();
           if (role == SK_CONTRIB) {
-            sk_store_partial<BN>(p, tacc, tile0, vp->peer[wn], crank, ew, half, lane);
+            sk_store_partial<BN>(p, tacc, tile0, vp->peer[wn], prank, ew, half, lane);
             tc_fence_before();
             __syncwarp();
             if (lane == 0) mbar_arrive_leader(&tempty[as]);
             continue;
           }
-          sk_reduce_partials<BN>(p, tacc, tile0, tstep, vp->peer[wn], vp->npeer[wn], crank, ew, half, lane);
+          sk_reduce_partials<BN>(p, tacc, tile0, tstep, vp->peer[wn], vp->npeer[wn], prank, ew, half, lane);
           // the regular epilogue below may read columns that the other warp of this lane quadrant has just patched
           named_bar_sync(1 + quad, 64);
           tc_fence_after();
         }
       }
 
-      if constexpr (CL == 2 && EPI == DB1_EPI_PLAIN) {
+      if constexpr (CL >= 2 && EPI == DB1_EPI_PLAIN) {
         {
           // ---- TMA epilogue. The four warps of a column half (one per TMEM lane quadrant) own 128 rows x 128 columns
           // and work through them in 32-column chunks: tcgen05.ld (next chunk's load in flight) -> fused math -> the
@@ -756,6 +792,76 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
           if (lane == 0) mbar_arrive_leader(&tempty[as]);
           continue;
         }
+      }
+      if constexpr (CL >= 2 && EPI == DB1_EPI_DGEGLU) {
+        // ---- GeGLU backward, register-direct: a thread owns one output row; per 32-column chunk it pulls its 64 bytes
+        // of a and of g with 256-bit loads (next chunk's in flight), turns the accumulator chunk into dY * gelu(g) and
+        // dY * a * gelu'(g) and writes both with 256-bit stores (full sectors). No shared memory: the staged variants
+        // of this epilogue (transposes or TMA tiles) cost the main loop 25-45 % through the shared-memory port.
+        constexpr int CPW = BN / 64;
+        const int c_first = half * CPW;
+        const int colh = nt * BN + c_first * 32;
+        const __half* hrow = p.H + (size_t)row * p.ldh;
+        __half* crow = p.C + (size_t)row * p.ldc;
+        const bool al32 = e_al32;
+        {  // the saved pre-activations were written a forward pass ago: start them towards L2 under the main loop
+          if (row_ok && colh < e_N) {
+#pragma unroll
+            for (int j = 0; j < 2; ++j) {
+              if (colh + j * 64 < e_N) {
+                asm volatile("prefetch.global.L2 [%0];" ::"l"(hrow + colh + j * 64));
+                asm volatile("prefetch.global.L2 [%0];" ::"l"(hrow + p.F + colh + j * 64));
+              }
+            }
+          }
+        }
+        uint32_t va[2][16], vg[2][16];
+        auto fetch = [&](int ci, uint32_t (&da)[16], uint32_t (&dg)[16]) {
+          const int col0 = colh + ci * 32;
+          int n = e_N - col0;
+          n = n > 32 ? 32 : n;
+          if (row_ok && n > 0) {
+            ldg_row32(hrow + col0, da, n, al32);
+            ldg_row32(hrow + p.F + col0, dg, n, al32);
+          }
+        };
+        fetch(0, va[0], vg[0]);
+        mbar_wait(&tfull[as], aph);
+        tc_fence_after();
+        if (tl && ew == 0 && lane == 0 && it <= 15) tl[4 + 4 * (it - 1) + 2] = clock64();
+#pragma unroll
+        for (int ci = 0; ci < CPW; ++ci) {
+          const int col0 = colh + ci * 32;
+          if (col0 < e_N) {  // warp-uniform
+            uint32_t r[32];
+            tmem_ld32(tacc + (c_first + ci) * 32, r);
+            if (ci + 1 < CPW) fetch(ci + 1, va[(ci + 1) & 1], vg[(ci + 1) & 1]);
+            tmem_ld_wait();
+            uint32_t oa[16], og[16];
+#pragma unroll
+            for (int k = 0; k < 16; ++k) {
+              const float2 a2 = unpack_half2(va[ci & 1][k]);
+              const float2 g2 = unpack_half2(vg[ci & 1][k]);
+              const float dy0 = __uint_as_float(r[2 * k]) * e_alpha, dy1 = __uint_as_float(r[2 * k + 1]) * e_alpha;
+              float gl0, dgl0, gl1, dgl1;
+              gelu_erf_both(g2.x, gl0, dgl0);
+              gelu_erf_both(g2.y, gl1, dgl1);
+              oa[k] = pack_half2(dy0 * gl0, dy1 * gl1);
+              og[k] = pack_half2(dy0 * a2.x * dgl0, dy1 * a2.y * dgl1);
+            }
+            if (row_ok) {
+              int n = e_N - col0;
+              n = n > 32 ? 32 : n;
+              stg_row32(crow + col0, oa, n, al32);
+              stg_row32(crow + p.F + col0, og, n, al32);
+            }
+          }
+        }
+        if (tl && ew == 0 && lane == 0 && it <= 15) tl[4 + 4 * (it - 1) + 3] = clock64();
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive_leader(&tempty[as]);
+        continue;
       }
       if constexpr ((EPI == DB1_EPI_PLAIN && CL == 1) || EPI == DB1_EPI_QKV) {
         constexpr int CPW = BN / 64;  // chunks per warp
@@ -1001,21 +1107,21 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
       tc_fence_before();
       __syncwarp();
       if (lane == 0) {
-        if (CL == 2) mbar_arrive_leader(&tempty[as]);
+        if (CL >= 2) mbar_arrive_leader(&tempty[as]);
         else mbar_arrive(&tempty[as]);
       }
     }
   }
 
-  if (CL == 2 && p.tma_epi && warp >= 2 && ((warp - 2) & 3) == 0 && lane == 0)
+  if (CL >= 2 && p.tma_epi && warp >= 2 && ((warp - 2) & 3) == 0 && lane == 0)
     bulk_wait_group_read<0>();  // shared memory must outlive the last tile stores
   if (tl && threadIdx.x == 64) tl[1] = clock64();
   tc_fence_before();
   __syncthreads();
-  if (CL == 2) cluster_sync_all();  // the peer may still multicast into / arrive on this CTA's shared memory
+  if (CL >= 2) cluster_sync_all();  // peers may still multicast into / arrive on this CTA's shared memory
   if (warp == 1) {
     tc_fence_after();
-    if (CL == 2) tmem_dealloc2<Cfg::TMEM_COLS>(tmem_base);
+    if (CL >= 2) tmem_dealloc2<Cfg::TMEM_COLS>(tmem_base);
     else tmem_dealloc<Cfg::TMEM_COLS>(tmem_base);
   }
 }
@@ -1039,6 +1145,15 @@ static int make_tile_map(CUtensorMap* tm, const void* base, long long rows, long
   return make_tmap_f16(tm, base, 2, dims, str, box, 64);
 }
 
+// 3-D map (column, part, row) over a row-major [rows, 2F] matrix seen as two [rows, F] halves (GeGLU's [a | g]): the
+// column dimension is clipped at F, so a ragged last chunk never spills into the other half.
+static int make_part_map(CUtensorMap* tm, const void* base, long long rows, long long F, long long ld) {
+  uint64_t dims[3] = {(uint64_t)F, 2, (uint64_t)rows};
+  uint64_t str[2] = {(uint64_t)F * 2, (uint64_t)ld * 2};
+  uint32_t box[3] = {32, 1, 128};
+  return make_tmap_f16(tm, base, 3, dims, str, box, 64);
+}
+
 // Stream-K tail: worth it when the last data-parallel wave would leave a visible share of the pairs idle.
 static bool sk_choose(long long tiles, int slots, int KB, int* R_out, int* GS_out) {
   const int R = (int)(tiles % slots);
@@ -1055,8 +1170,8 @@ static bool sk_choose(long long tiles, int slots, int KB, int* R_out, int* GS_ou
 }
 
 template <int BN, int EPI, int CL>
-static int launch_gemm_cl(const CUtensorMap& tmA, const CUtensorMap& tmB, const GemmParams& p_in, cudaStream_t stream,
-                          const db1_gemm_desc* d) {
+static int launch_gemm_cl(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensorMap& tmB64, const GemmParams& p_in,
+                          cudaStream_t stream, int max_groups) {
   using Cfg = GemmCfg<BN, CL>;
   static bool configured = false;
   if (!configured) {
@@ -1067,8 +1182,8 @@ static int launch_gemm_cl(const CUtensorMap& tmA, const CUtensorMap& tmB, const 
   GemmParams p = p_in;
   const long long MT = cdiv(p.M, BM);
   const long long NT = (EPI == DB1_EPI_GEGLU) ? p.F / (BN / 2) : cdiv(p.N, BN);
-  long long tiles = (CL == 2 ? (MT + 1) / 2 : MT) * NT * p.Z1 * (p.reduce_z2 ? 1 : p.Z2);
-  const int slots = sm_count() / CL;
+  long long tiles = (CL >= 2 ? (MT + CL - 1) / CL : MT) * NT * p.Z1 * (p.reduce_z2 ? 1 : p.Z2);
+  const int slots = max_groups > 0 ? max_groups : sm_count() / CL;
   int grid = (int)(tiles > slots ? slots : tiles) * CL;
   if (CL == 2 && g_sk_ws.base != nullptr && getenv("DB1_GEMM_SK")) {
     int dev = -1;
@@ -1085,7 +1200,7 @@ static int launch_gemm_cl(const CUtensorMap& tmA, const CUtensorMap& tmB, const 
     }
   }
   CUtensorMap tmC = tmA, tmIn = tmA;  // placeholders unless the TMA epilogue is used
-  if (CL == 2 && EPI == DB1_EPI_PLAIN) {  // launch_gemm has checked tma_epilogue_ok()
+  if (CL >= 2 && EPI == DB1_EPI_PLAIN) {  // launch_gemm has checked tma_epilogue_ok()
     const void* in = p.resid ? (const void*)p.resid : (p.accumulate ? (const void*)p.C : nullptr);
     const long long ldin = p.resid ? p.ldr : p.ldc;
     int e = make_tile_map(&tmC, p.C, p.M, p.N, p.ldc);
@@ -1094,36 +1209,77 @@ static int launch_gemm_cl(const CUtensorMap& tmA, const CUtensorMap& tmB, const 
     p.tma_epi = 1;
     p.tma_in = in ? 1 : 0;
   }
-  (void)d;
   if ((p.dbg & 8) && g_sk_ws.base != nullptr && p.sk_tiles == 0)
     p.sk_ws = reinterpret_cast<float*>(reinterpret_cast<char*>(g_sk_ws.base) + SK_CNT_BYTES);
   else
     p.dbg &= ~8;
-  DB1_CUDA(launch_pdl(gemm_kernel<BN, EPI, CL>, dim3(grid), dim3(GEMM_THREADS), Cfg::SMEM_BYTES, stream, CL, tmA, tmB, tmC,
-                      tmIn, p));
+  DB1_CUDA(launch_pdl(gemm_kernel<BN, EPI, CL>, dim3(grid), dim3(GEMM_THREADS), Cfg::SMEM_BYTES, stream, CL, tmA, tmB, tmB64,
+                      tmC, tmIn, p));
   return 0;
 }
 
-// CTA pairs (cta_group::2: one 256 x BN MMA over two vertically adjacent 128-row tiles, each CTA staging half of the B
-// tile) cut both the L2 -> SM and the shared-memory operand traffic per tile from 48 KB to 32 KB per k-block; used
-// whenever both CTAs see the same k-range.
 // The CTA-pair PLAIN kernel has only the TMA epilogue: C (and the addend) must be addressable by a tensor map, and
 // "residual + accumulate" (two addends) stays on the single-CTA kernel.
-static bool tma_epilogue_ok(const GemmParams& p) {
+static bool tma_epilogue_ok(const GemmParams& p, int epi) {
+  if (epi != DB1_EPI_PLAIN) return true;
   if (p.resid && p.accumulate) return false;
   if (((uintptr_t)p.C & 15) != 0) return false;
   if (p.resid && (((uintptr_t)p.resid & 15) != 0 || p.ldr % 8 != 0)) return false;
   return true;
 }
 
+// How many 4-CTA clusters of this kernel the device can hold at once (GPC granularity: fewer than SMs / 4).
 template <int BN, int EPI>
-static int launch_gemm(const CUtensorMap& tmA, const CUtensorMap& tmB, const GemmParams& p, cudaStream_t stream) {
-  const db1_gemm_desc* d = nullptr;
+static int max_clusters4() {
+  static int n = -1;
+  if (n < 0) {
+    using Cfg = GemmCfg<BN, 4>;
+    n = 0;
+    if (cudaFuncSetAttribute(gemm_kernel<BN, EPI, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES) ==
+        cudaSuccess) {
+      cudaLaunchConfig_t cfg;
+      memset(&cfg, 0, sizeof(cfg));
+      cfg.gridDim = dim3(sm_count() / 4 * 4);
+      cfg.blockDim = dim3(GEMM_THREADS);
+      cfg.dynamicSmemBytes = Cfg::SMEM_BYTES;
+      cudaLaunchAttribute attr[1];
+      attr[0].id = cudaLaunchAttributeClusterDimension;
+      attr[0].val.clusterDim.x = 4;
+      attr[0].val.clusterDim.y = 1;
+      attr[0].val.clusterDim.z = 1;
+      cfg.attrs = attr;
+      cfg.numAttrs = 1;
+      int k = 0;
+      if (cudaOccupancyMaxActiveClusters(&k, gemm_kernel<BN, EPI, 4>, &cfg) == cudaSuccess) n = k;
+    }
+    cudaGetLastError();
+    if (getenv("DB1_GEMM_VERBOSE")) fprintf(stderr, "[db1] gemm<%d,%d>: %d resident 4-CTA clusters\n", BN, EPI, n);
+  }
+  return n;
+}
+
+// CTA pairs (cta_group::2: one 256 x BN MMA over two vertically adjacent 128-row tiles, each CTA staging half of the B
+// tile) cut both the L2 -> SM and the shared-memory operand traffic per tile from 48 KB to 32 KB per k-block; used
+// whenever both CTAs see the same k-range. Two pairs in one 4-CTA cluster (512 x BN) additionally share the B tile by
+// TMA multicast (24 KB per CTA and k-block): the main loops are L2-throughput bound (lts sectors / cycle within 15 % of
+// the chip cap, ncu), so fewer L2 reads per flop is the remaining lever.
+template <int BN, int EPI>
+static int launch_gemm(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensorMap& tmB64, const GemmParams& p,
+                       cudaStream_t stream) {
   const bool batched = p.Z1 * p.Z2 > 1;
   if (BN == 256 && EPI != DB1_EPI_DS && !batched && p.k_mode == DB1_K_FULL && !p.skip_upper && p.M > BM &&
-      (EPI != DB1_EPI_PLAIN || tma_epilogue_ok(p)) && !getenv("DB1_GEMM_NO_CLUSTER"))
-    return launch_gemm_cl<BN, EPI, (BN == 256 && EPI != DB1_EPI_DS) ? 2 : 1>(tmA, tmB, p, stream, d);
-  return launch_gemm_cl<BN, EPI, 1>(tmA, tmB, p, stream, d);
+      ((EPI != DB1_EPI_PLAIN && EPI != DB1_EPI_DGEGLU) || tma_epilogue_ok(p, EPI)) && !getenv("DB1_GEMM_NO_CLUSTER")) {
+    constexpr bool HAS4 = (BN == 256 && EPI == DB1_EPI_PLAIN);
+    if (HAS4 && p.M > 3 * BM) {
+      const char* e = getenv("DB1_GEMM_CL");
+      const int want = e ? atoi(e) : 2;  // opt-in: measured equal to CTA pairs (33 clusters = 132 of 148 SMs)
+      const int nc = max_clusters4<BN, HAS4 ? EPI : DB1_EPI_PLAIN>();
+      if (want == 4 && nc >= 30)
+        return launch_gemm_cl<BN, EPI, HAS4 ? 4 : 2>(tmA, tmB, tmB64, p, stream, nc);
+    }
+    return launch_gemm_cl<BN, EPI, (BN == 256 && EPI != DB1_EPI_DS) ? 2 : 1>(tmA, tmB, tmB64, p, stream, 0);
+  }
+  return launch_gemm_cl<BN, EPI, 1>(tmA, tmB, tmB64, p, stream, 0);
 }
 
 // 4-D map (inner, rows, z1, z2). A broadcast batch dim (stride 0) is encoded as a dim of size 1.
@@ -1213,6 +1369,7 @@ extern "C" int db1_gemm_f16(const db1_gemm_desc* d, void* stream_) {
   p.seed = d->seed; p.u = (const __half*)d->u; p.v = (const __half*)d->v; p.d_model = d->d_model;
   p.H = (__half*)d->H; p.ldh = d->ldh; p.F = d->F;
   p.P = (const __half*)d->P; p.C2 = (__half*)d->C2; p.Drow = d->Drow; p.window = d->window;
+  p.snake = (d->k_mode != DB1_K_FULL && !d->skip_upper && !getenv("DB1_GEMM_NO_SNAKE")) ? 1 : 0;
   { const char* e = getenv("DB1_GEMM_DBG"); p.dbg = e ? atoi(e) : 0; }
   if (p.reduce_z2) DB1_CHECK_ARG(d->c_z2 == 0, "gemm: reduce_z2 needs c_z2 == 0");
 
@@ -1251,21 +1408,23 @@ extern "C" int db1_gemm_f16(const db1_gemm_desc* d, void* stream_) {
   // EPI_GEGLU addresses rows up to 2F; the tensor's row count is N in every case
   e = make_operand_map(&tmB, d->B, p.b_mn, N, K, d->ldb, Z1, d->b_z1, Z2, d->b_z2, 128);
   if (e) return e;
+  CUtensorMap tmB64 = tmB;  // K-major B in 64-row boxes: the quarter tiles the 4-CTA clusters multicast
+  if (!p.b_mn && (e = make_operand_map(&tmB64, d->B, 0, N, K, d->ldb, Z1, d->b_z1, Z2, d->b_z2, 64))) return e;
 
   switch (epilogue) {
     case DB1_EPI_PLAIN:
-      return BNsel == 256 ? launch_gemm<256, DB1_EPI_PLAIN>(tmA, tmB, p, stream)
-                          : launch_gemm<128, DB1_EPI_PLAIN>(tmA, tmB, p, stream);
+      return BNsel == 256 ? launch_gemm<256, DB1_EPI_PLAIN>(tmA, tmB, tmB64, p, stream)
+                          : launch_gemm<128, DB1_EPI_PLAIN>(tmA, tmB, tmB64, p, stream);
     case DB1_EPI_QKV:
-      return BNsel == 256 ? launch_gemm<256, DB1_EPI_QKV>(tmA, tmB, p, stream)
-                          : launch_gemm<128, DB1_EPI_QKV>(tmA, tmB, p, stream);
+      return BNsel == 256 ? launch_gemm<256, DB1_EPI_QKV>(tmA, tmB, tmB64, p, stream)
+                          : launch_gemm<128, DB1_EPI_QKV>(tmA, tmB, tmB64, p, stream);
     case DB1_EPI_GEGLU:
-      return launch_gemm<256, DB1_EPI_GEGLU>(tmA, tmB, p, stream);
+      return launch_gemm<256, DB1_EPI_GEGLU>(tmA, tmB, tmB64, p, stream);
     case DB1_EPI_DGEGLU:
-      return BNsel == 256 ? launch_gemm<256, DB1_EPI_DGEGLU>(tmA, tmB, p, stream)
-                          : launch_gemm<128, DB1_EPI_DGEGLU>(tmA, tmB, p, stream);
+      return BNsel == 256 ? launch_gemm<256, DB1_EPI_DGEGLU>(tmA, tmB, tmB64, p, stream)
+                          : launch_gemm<128, DB1_EPI_DGEGLU>(tmA, tmB, tmB64, p, stream);
     case DB1_EPI_DS:
-      return launch_gemm<128, DB1_EPI_DS>(tmA, tmB, p, stream);
+      return launch_gemm<128, DB1_EPI_DS>(tmA, tmB, tmB64, p, stream);
   }
   return set_err(-1, "gemm: unreachable");
 }

@@ -102,6 +102,11 @@ DEVI void tma_store_2d(const CUtensorMap* m, const void* smem_src, int c0, int c
                ::"l"(m), "r"(smem_u32(smem_src)), "r"(c0), "r"(c1)
                : "memory");
 }
+DEVI void tma_store_3d(const CUtensorMap* m, const void* smem_src, int c0, int c1, int c2) {
+  asm volatile("cp.async.bulk.tensor.3d.global.shared::cta.bulk_group [%0, {%2, %3, %4}], [%1];"
+               ::"l"(m), "r"(smem_u32(smem_src)), "r"(c0), "r"(c1), "r"(c2)
+               : "memory");
+}
 DEVI void bulk_commit_group() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
 // wait until at most N of this thread's bulk groups still have to READ their shared-memory source
 template <int N>
@@ -192,6 +197,17 @@ DEVI void tma_load_4d_2sm(void* smem_dst, const CUtensorMap* m, uint64_t* bar, i
       "cp.async.bulk.tensor.4d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes"
       " [%0], [%1, {%3, %4, %5, %6}], [%2];"
       ::"r"(smem_u32(smem_dst)), "l"(m), "r"(smem_u32(bar) & PEER_BIT_MASK), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
+      : "memory");
+}
+// same, delivered to the same shared-memory offset of every CTA in cta_mask; each destination's bytes are counted on
+// the barrier at `bar`'s offset in the leader (even) CTA of THAT destination's pair
+DEVI void tma_load_4d_2sm_mc(void* smem_dst, const CUtensorMap* m, uint64_t* bar, int c0, int c1, int c2, int c3,
+                             uint16_t cta_mask) {
+  asm volatile(
+      "cp.async.bulk.tensor.4d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes.multicast::cluster"
+      " [%0], [%1, {%3, %4, %5, %6}], [%2], %7;"
+      ::"r"(smem_u32(smem_dst)), "l"(m), "r"(smem_u32(bar) & PEER_BIT_MASK), "r"(c0), "r"(c1), "r"(c2), "r"(c3),
+        "h"(cta_mask)
       : "memory");
 }
 // arrive on the barrier at this offset in the leader CTA's shared memory (works from either CTA of the pair)
@@ -335,6 +351,56 @@ DEVI Half8 float_to_half8(const float (&f)[8]) {
   v.u.w = pack_half2(f[6], f[7]);
   return v;
 }
+// 32 consecutive fp16 of one row (16 packed words) straight between registers and global memory: two 256-bit accesses
+// (sm_100: LDG / STG.256 = one full 32-byte sector per thread and instruction), or four 128-bit ones when the row is
+// only 16-byte aligned; `n` = valid elements (multiple of 8, <= 32), the rest is skipped / zero.
+DEVI void ldg_row32(const __half* p, uint32_t (&v)[16], int n, bool al32) {
+#pragma unroll
+  for (int i = 0; i < 16; ++i) v[i] = 0u;
+  if (al32) {
+#pragma unroll
+    for (int h = 0; h < 2; ++h) {
+      if (n >= 16 * (h + 1)) {
+        asm volatile("ld.global.v8.b32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+                     : "=r"(v[8 * h]), "=r"(v[8 * h + 1]), "=r"(v[8 * h + 2]), "=r"(v[8 * h + 3]), "=r"(v[8 * h + 4]),
+                       "=r"(v[8 * h + 5]), "=r"(v[8 * h + 6]), "=r"(v[8 * h + 7])
+                     : "l"(p + 16 * h));
+      } else if (n > 16 * h) {
+        const uint4 t = *reinterpret_cast<const uint4*>(p + 16 * h);
+        v[8 * h] = t.x; v[8 * h + 1] = t.y; v[8 * h + 2] = t.z; v[8 * h + 3] = t.w;
+      }
+    }
+  } else {
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+      if (n >= 8 * (q + 1)) {
+        const uint4 t = *reinterpret_cast<const uint4*>(p + 8 * q);
+        v[4 * q] = t.x; v[4 * q + 1] = t.y; v[4 * q + 2] = t.z; v[4 * q + 3] = t.w;
+      }
+    }
+  }
+}
+DEVI void stg_row32(__half* p, const uint32_t (&v)[16], int n, bool al32) {
+  if (al32) {
+#pragma unroll
+    for (int h = 0; h < 2; ++h) {
+      if (n >= 16 * (h + 1)) {
+        asm volatile("st.global.v8.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};"
+                     ::"l"(p + 16 * h), "r"(v[8 * h]), "r"(v[8 * h + 1]), "r"(v[8 * h + 2]), "r"(v[8 * h + 3]),
+                       "r"(v[8 * h + 4]), "r"(v[8 * h + 5]), "r"(v[8 * h + 6]), "r"(v[8 * h + 7])
+                     : "memory");
+      } else if (n > 16 * h) {
+        *reinterpret_cast<uint4*>(p + 16 * h) = make_uint4(v[8 * h], v[8 * h + 1], v[8 * h + 2], v[8 * h + 3]);
+      }
+    }
+  } else {
+#pragma unroll
+    for (int q = 0; q < 4; ++q)
+      if (n >= 8 * (q + 1))
+        *reinterpret_cast<uint4*>(p + 8 * q) = make_uint4(v[4 * q], v[4 * q + 1], v[4 * q + 2], v[4 * q + 3]);
+  }
+}
+
 DEVI Half8 half8_zero() {
   Half8 v;
   v.u = make_uint4(0u, 0u, 0u, 0u);

@@ -207,8 +207,9 @@ def _sk_expected(M, N, K):
     (2560, 2048, 512, 0, 0),    # 80 tiles, KB = 8: the 6 tail tiles are cut in two, most pairs only do their DP tile
     (4000, 2040, 1096, 0, 0),   # ragged M / N / K
 ])
-def test_gemm_stream_k_tail(cuda, M, N, K, a_mn, b_mn):
+def test_gemm_stream_k_tail(cuda, M, N, K, a_mn, b_mn, monkeypatch):
     from db1_sm100 import ops
+    monkeypatch.setenv("DB1_GEMM_SK", "1")  # opt-in: measured slower than the data-parallel schedule on B200
     on, R, GS = _sk_expected(M, N, K)
     assert on == 1, "shape does not exercise the stream-K tail"
     A = _mk((M, K), cuda, 1.0, 31)
@@ -229,9 +230,13 @@ def test_gemm_stream_k_tail(cuda, M, N, K, a_mn, b_mn):
     assert ws[:4096].view(torch.int32).abs().max().item() == 0, "arrival counters not re-armed"
 
 
-def test_gemm_stream_k_fused_epilogues(cuda):
-    """Owner tiles run the normal fused epilogues after the fix-up: bias + dropout + residual, QKV, GeGLU backward."""
+@pytest.mark.parametrize("sk", [0, 1])
+def test_gemm_stream_k_fused_epilogues(cuda, sk, monkeypatch):
+    """CTA-pair kernels at model size, with and without the stream-K tail (owner tiles run the normal fused epilogues
+    after the fix-up): bias + dropout + residual (TMA epilogue), QKV, GeGLU backward (TMA epilogue)."""
     from db1_sm100 import ops
+    if sk:
+        monkeypatch.setenv("DB1_GEMM_SK", "1")
     M, N, K = 4096, 2048, 2048
     assert _sk_expected(M, N, K)[0] == 1
     A = _mk((M, K), cuda, 1.0, 33)
@@ -268,6 +273,37 @@ def test_gemm_stream_k_fused_epilogues(cuda):
     W2 = _mk((N2, F), cuda, 0.05, 43)
     dH = torch.empty(M, 2 * F, dtype=torch.half, device=cuda)
     ops.gemm(G, W2, dH, M, F, N2, lda=N2, ldb=F, ldc=2 * F, b_mn=True, epilogue=ops.EPI_DGEGLU, H=Hs, ldh=2 * F, F=F)
+    dY = G.float() @ W2.float()
+    hh = Hs.float().requires_grad_(True)
+    (hh[:, :F] * torch.nn.functional.gelu(hh[:, F:])).backward(dY)
+    assert _rel(dH, hh.grad) < 3e-3
+
+
+def test_gemm_tma_epilogue_ragged_and_accumulate(cuda):
+    """CTA-pair PLAIN / GeGLU-backward kernels (TMA epilogue) on shapes whose last tiles are ragged in M, N and K, and
+    the C += path (old C fetched by TMA)."""
+    from db1_sm100 import ops
+    M, N, K = 2000, 2072, 520
+    A = _mk((M, K), cuda, 1.0, 51)
+    B = _mk((N, K), cuda, 0.05, 52)
+    C0 = _mk((M, N), cuda, 1.0, 53)
+    Cc = C0.clone()
+    ops.gemm(A, B, Cc, M, N, K, lda=K, ldb=K, ldc=N, accumulate=True)
+    assert _rel(Cc, A.float() @ B.float().t() + C0.float()) < 2e-3
+    # odd N (no 16-byte row alignment of the logical width; ldc padded): the head shape in miniature
+    N2, ld2 = 2057, 2064
+    B2 = _mk((N2, K), cuda, 0.05, 54)
+    C2 = torch.zeros(M, ld2, dtype=torch.half, device=cuda)
+    ops.gemm(A, B2, C2, M, N2, K, lda=K, ldb=K, ldc=ld2)
+    assert _rel(C2[:, :N2], A.float() @ B2.float().t()) < 2e-3
+    assert C2[:, N2:].abs().max().item() == 0
+    # GeGLU backward, F not a multiple of 32
+    F, N3 = 2072, 328
+    Hs = _mk((M, 2 * F), cuda, 1.0, 55)
+    G = _mk((M, N3), cuda, 1.0, 56)
+    W2 = _mk((N3, F), cuda, 0.05, 57)
+    dH = torch.full((M, 2 * F), 7.0, dtype=torch.half, device=cuda)
+    ops.gemm(G, W2, dH, M, F, N3, lda=N3, ldb=F, ldc=2 * F, b_mn=True, epilogue=ops.EPI_DGEGLU, H=Hs, ldh=2 * F, F=F)
     dY = G.float() @ W2.float()
     hh = Hs.float().requires_grad_(True)
     (hh[:, :F] * torch.nn.functional.gelu(hh[:, F:])).backward(dY)

@@ -14,12 +14,19 @@ M, N, K = (int(x) for x in sys.argv[1:4])
 resid = "resid" in sys.argv
 drop = 0.1 if "drop" in sys.argv else 0.0
 bmn = "bmn" in sys.argv
+dgeglu = "dgeglu" in sys.argv
 A = (torch.randn(M, K, device=dev) * 0.05).half()
 B = (torch.randn(K, N, device=dev) * 0.05).half() if bmn else (torch.randn(N, K, device=dev) * 0.05).half()
 Cc = torch.empty(M, N, dtype=torch.half, device=dev)
 R = torch.randn(M, N, device=dev).half() if resid else None
+if dgeglu:
+    Hs = torch.randn(M, 2 * N, device=dev).half()
+    Cc = torch.empty(M, 2 * N, dtype=torch.half, device=dev)
 for _ in range(3):
-    ops.gemm(A, B, Cc, M, N, K, lda=K, ldb=B.stride(0), ldc=N, b_mn=bmn, resid=R, ldr=N if resid else 0, drop_p=drop, seed=5)
+    if dgeglu:
+        ops.gemm(A, B, Cc, M, N, K, lda=K, ldb=B.stride(0), ldc=2 * N, b_mn=bmn, epilogue=ops.EPI_DGEGLU, H=Hs, ldh=2 * N, F=N)
+    else:
+        ops.gemm(A, B, Cc, M, N, K, lda=K, ldb=B.stride(0), ldc=N, b_mn=bmn, resid=R, ldr=N if resid else 0, drop_p=drop, seed=5)
 torch.cuda.synchronize()
 ws = ops._gemm_ws[0]
 tl = ws[4096:4096 + 148 * 64 * 8].view(torch.int64).view(148, 64).cpu()
@@ -27,7 +34,7 @@ print("cta  total | per item: mma_first_full->issue_end  tfull_seen  epi_end (cl
 for c in list(range(0, 8)) + list(range(140, 148)):
     t0 = tl[c, 0].item()
     row = ["%3d %7d |" % (c, tl[c, 1].item() - t0)]
-    for i in range(3):
+    for i in range(5):
         v = [tl[c, 4 + 4 * i + j].item() for j in range(4)]
         if v[0] == 0:
             break
