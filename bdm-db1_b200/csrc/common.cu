@@ -84,4 +84,4 @@ int sm_count() {
 }  // namespace db1
 
 extern "C" const char* db1_last_error() { return db1::err_buf(); }
-extern "C" int db1_abi_version() { return 1; }
+extern "C" int db1_abi_version() { return 2; }

@@ -69,6 +69,10 @@ struct GemmParams {
   int tma_epi;
   int tma_in;  // 0 = no addend, 1 = residual / old C through tmIn
   int snake;   // causal k-ranges: tiles are visited heaviest first in alternating direction (see sk_item)
+  // row-dot side output of the TMA epilogue: dot_out[(b * dot_H + h) * dot_L + i] = sum over head h's 128 columns of
+  // acc[row = b * dot_L + i, :] * X[row, :], X arriving through tmIn (attention backward: D = rowsum(dO * O))
+  float* dot_out;
+  int dot_L, dot_H;
 };
 
 // CL == 2: the CTA pair of a cluster runs cta_group::2 MMAs (M = 256 across the pair); each CTA stages its own 128
@@ -395,9 +399,9 @@ DEVI void sk_reduce_partials(const GemmParams& p, uint32_t tacc, int pair, int n
 // four 16-byte pieces of the row in the [128][32] fp16 shared-memory tile (64-byte swizzle). Specialised at compile time:
 // with run-time flags every piece carries ~60 predicated-off or branch instructions and a handful of constant-bank
 // reloads, which with two epilogue warps per scheduler were most of the epilogue's time.
-template <bool FULL, bool IN>
+template <bool FULL, int IN>  // IN: 0 = no second operand, 1 = add it (residual / old C), 2 = dot it with the result (dacc)
 DEVI void epi_chunk(const uint32_t (&r)[32], uint32_t rowp, uint32_t swz, int row, int col0, int N, float alpha,
-                    const __half* bias, uint32_t thr, float dscale, uint64_t seed) {
+                    const __half* bias, uint32_t thr, float dscale, uint64_t seed, float& dacc) {
   Half8 bv[4];
   if (FULL) {
 #pragma unroll
@@ -427,11 +431,17 @@ DEVI void epi_chunk(const uint32_t (&r)[32], uint32_t rowp, uint32_t swz, int ro
       }
     }
     const uint32_t sa = rowp + (((uint32_t)g ^ swz) << 4);
-    if (IN) {
+    if (IN == 1) {
       float bb[8];
       half8_to_float(lds_half8(sa), bb);
 #pragma unroll
       for (int i = 0; i < 8; ++i) f[i] += bb[i];
+    }
+    if (IN == 2) {
+      float bb[8];
+      half8_to_float(lds_half8(sa), bb);
+#pragma unroll
+      for (int i = 0; i < 8; ++i) dacc = fmaf(f[i], bb[i], dacc);
     }
     sts_half8(sa, float_to_half8(f));
   }
@@ -669,6 +679,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
     const int e_in = p.tma_in;
     const int e_N = p.N;
     const bool e_full = e_alpha != 1.0f || e_bias != nullptr || e_thr != 0u;
+    const bool e_dot = p.dot_out != nullptr;
     // register-direct epilogues: 256-bit row accesses need 32-byte aligned rows of C and H
     const bool e_al32 = (((uintptr_t)p.C | (uintptr_t)p.H) & 31) == 0 && ((p.ldc | p.ldh | p.F) & 15) == 0;
     for (int wn = 0;; ++wn) {
@@ -749,6 +760,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
           tc_fence_after();
           if (tl && ew == 0 && lane == 0 && it <= 15) tl[4 + 4 * (it - 1) + 2] = clock64();
           uint32_t r[2][32];
+          float dacc = 0.f;
           if (nch > 0) tmem_ld32(tacc + c_first * 32, r[0]);
 #pragma unroll
           for (int ci = 0; ci < CPW; ++ci) {
@@ -763,12 +775,14 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
               mbar_wait(&ebh[b], (eseq / NB) & 1u);
               if (stamp) tl[32 + ci * 6 + 2] = clock64();
               const uint32_t rowp = smem_u32(ebuf + b * 8192 + trow * 64);
-              if (e_full) {
-                if (e_in) epi_chunk<true, true>(r[ci & 1], rowp, swz, row, col0, e_N, e_alpha, e_bias, e_thr, e_dscale, e_seed);
-                else epi_chunk<true, false>(r[ci & 1], rowp, swz, row, col0, e_N, e_alpha, e_bias, e_thr, e_dscale, e_seed);
+              if (e_dot) {
+                epi_chunk<false, 2>(r[ci & 1], rowp, swz, row, col0, e_N, 1.f, nullptr, 0u, 1.f, 0ull, dacc);
+              } else if (e_full) {
+                if (e_in) epi_chunk<true, 1>(r[ci & 1], rowp, swz, row, col0, e_N, e_alpha, e_bias, e_thr, e_dscale, e_seed, dacc);
+                else epi_chunk<true, 0>(r[ci & 1], rowp, swz, row, col0, e_N, e_alpha, e_bias, e_thr, e_dscale, e_seed, dacc);
               } else {
-                if (e_in) epi_chunk<false, true>(r[ci & 1], rowp, swz, row, col0, e_N, 1.f, nullptr, 0u, 1.f, 0ull);
-                else epi_chunk<false, false>(r[ci & 1], rowp, swz, row, col0, e_N, 1.f, nullptr, 0u, 1.f, 0ull);
+                if (e_in) epi_chunk<false, 1>(r[ci & 1], rowp, swz, row, col0, e_N, 1.f, nullptr, 0u, 1.f, 0ull, dacc);
+                else epi_chunk<false, 0>(r[ci & 1], rowp, swz, row, col0, e_N, 1.f, nullptr, 0u, 1.f, 0ull, dacc);
               }
               if (stamp) tl[32 + ci * 6 + 3] = clock64();
               fence_proxy_async_smem();
@@ -785,6 +799,11 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
               }
               ++eseq;
             }
+          }
+          if (e_dot && row_ok && nch == CPW) {
+            // this column half = one 128-wide head: dacc is the complete row-dot for (row, head)
+            const int hh = (colh >> 7), bb = row / p.dot_L, ii = row - bb * p.dot_L;
+            p.dot_out[((size_t)bb * p.dot_H + hh) * p.dot_L + ii] = dacc;
           }
           if (tl && ew == 0 && lane == 0 && it <= 15) tl[4 + 4 * (it - 1) + 3] = clock64();
           tc_fence_before();
@@ -1180,6 +1199,8 @@ static int launch_gemm_cl(const CUtensorMap& tmA, const CUtensorMap& tmB, const 
     configured = true;
   }
   GemmParams p = p_in;
+  if (CL == 1 && p.dot_out != nullptr)
+    return set_err(-1, "gemm(dot): the row-dot side output needs the CTA-pair kernel (unset DB1_GEMM_NO_CLUSTER)");
   const long long MT = cdiv(p.M, BM);
   const long long NT = (EPI == DB1_EPI_GEGLU) ? p.F / (BN / 2) : cdiv(p.N, BN);
   long long tiles = (CL >= 2 ? (MT + CL - 1) / CL : MT) * NT * p.Z1 * (p.reduce_z2 ? 1 : p.Z2);
@@ -1201,7 +1222,7 @@ static int launch_gemm_cl(const CUtensorMap& tmA, const CUtensorMap& tmB, const 
   }
   CUtensorMap tmC = tmA, tmIn = tmA;  // placeholders unless the TMA epilogue is used
   if (CL >= 2 && EPI == DB1_EPI_PLAIN) {  // launch_gemm has checked tma_epilogue_ok()
-    const void* in = p.resid ? (const void*)p.resid : (p.accumulate ? (const void*)p.C : nullptr);
+    const void* in = p.resid ? (const void*)p.resid : (p.accumulate ? (const void*)p.C : nullptr);  // dot: resid = X
     const long long ldin = p.resid ? p.ldr : p.ldc;
     int e = make_tile_map(&tmC, p.C, p.M, p.N, p.ldc);
     if (e) return e;
@@ -1370,6 +1391,18 @@ extern "C" int db1_gemm_f16(const db1_gemm_desc* d, void* stream_) {
   p.H = (__half*)d->H; p.ldh = d->ldh; p.F = d->F;
   p.P = (const __half*)d->P; p.C2 = (__half*)d->C2; p.Drow = d->Drow; p.window = d->window;
   p.snake = (d->k_mode != DB1_K_FULL && !d->skip_upper && !getenv("DB1_GEMM_NO_SNAKE")) ? 1 : 0;
+  if (d->dot_out != nullptr) {
+    DB1_CHECK_ARG(epilogue == DB1_EPI_PLAIN && d->dot_with && !d->resid && !d->accumulate && !d->bias && d->drop_p == 0.f &&
+                      d->alpha == 1.0f && !batched && d->dot_H > 0 && d->dot_L > 0 && N == d->dot_H * 128 &&
+                      M % d->dot_L == 0 && d->ld_dot % 8 == 0 && M > 3 * 128 && d->bn_hint != 128 &&
+                      2LL * cdiv(M, BM) * cdiv(N, 256) > sm_count(),
+                  "gemm(dot): plain un-batched GEMM at CTA-pair size with N == dot_H * 128 (head dim 128) required");
+    p.resid = (const __half*)d->dot_with;  // travels through the epilogue's TMA addend path
+    p.ldr = d->ld_dot;
+    p.dot_out = d->dot_out;
+    p.dot_L = d->dot_L;
+    p.dot_H = d->dot_H;
+  }
   { const char* e = getenv("DB1_GEMM_DBG"); p.dbg = e ? atoi(e) : 0; }
   if (p.reduce_z2) DB1_CHECK_ARG(d->c_z2 == 0, "gemm: reduce_z2 needs c_z2 == 0");
 

@@ -39,7 +39,10 @@ struct AttnParams {
   __half* P;
   int mode;
   __half* dS;          // mode 2
-  const float* Drow;   // mode 2: rowsum(dO * O) [B,H,L]
+  const float* Drow;   // mode 2: rowsum(dO * O) [B,H,L], or NULL: computed here from dOp / Op at the start of every item
+  const __half* dOp;   // mode 2 without Drow: dO and O as plain row-major [B*L, ld] matrices (head h at column h*dh)
+  const __half* Op;
+  long long lddo, ldop;
   float scale;         // mode 2: softmax scale (natural domain) applied to dS
   int q_start;         // first query row that is computed (memory-augmented inference: rows < q_start are memory)
 };
@@ -58,7 +61,7 @@ struct AttnSmem {
   static constexpr int TOTAL = BARS + 128;
 };
 
-template <int D>
+template <int D, int MODE>
 __global__ void __launch_bounds__(AT_THREADS, 1)
 relattn_fwd_kernel(const __grid_constant__ CUtensorMap tmQu, const __grid_constant__ CUtensorMap tmQv,
                    const __grid_constant__ CUtensorMap tmK, const __grid_constant__ CUtensorMap tmV,
@@ -118,7 +121,7 @@ relattn_fwd_kernel(const __grid_constant__ CUtensorMap tmQu, const __grid_consta
     tma_prefetch_desc(&tmK);
     tma_prefetch_desc(&tmV);
     tma_prefetch_desc(&tmR);
-    if (p.mode == 2) tma_prefetch_desc(&tmDO);
+    if (MODE == 2) tma_prefetch_desc(&tmDO);
   }
   if (warp == 1) {
     if (lane == 0) {
@@ -157,26 +160,26 @@ relattn_fwd_kernel(const __grid_constant__ CUtensorMap tmQu, const __grid_consta
         if (k < 0) continue;
         const Item t = decode(k);
         if (ti > 0) mbar_wait(bar_qfree, (ti - 1) & 1);  // the previous item's last score (and dP) MMAs have read Q / dO
-        mbar_expect_tx(bar_q, (p.mode == 2 ? 3 : 2) * SM::TILE);
+        mbar_expect_tx(bar_q, (MODE == 2 ? 3 : 2) * SM::TILE);
 #pragma unroll
         for (int s = 0; s < NSLAB; ++s) {
           tma_load_4d(smem + SM::QU + s * 16384, &tmQu, bar_q, s * 64, t.I0, t.h, t.b);
           tma_load_4d(smem + SM::QV + s * 16384, &tmQv, bar_q, s * 64, t.I0, t.h, t.b);
-          if (p.mode == 2)  // dO_I lives where P would
+          if (MODE == 2)  // dO_I lives where P would
             tma_load_4d(smem + SM::PT + s * 16384, &tmDO, bar_q, s * 64, t.I0, t.h, t.b);
         }
         for (int st = 0; st < t.nsteps; ++st, ++gs) {
           const int J0 = (t.I - st) * 128;
           const int cb = p.L - 128 - t.I0 + J0;  // first row of the new chunk of r
           if (gs > 0) mbar_wait(bar_kfree, (gs - 1) & 1);
-          mbar_expect_tx(bar_k, (p.mode == 2 ? 3 : 2) * SM::TILE);
+          mbar_expect_tx(bar_k, (MODE == 2 ? 3 : 2) * SM::TILE);
 #pragma unroll
           for (int s = 0; s < NSLAB; ++s) {
             tma_load_4d(smem + SM::KT + s * 16384, &tmK, bar_k, s * 64, J0, t.h, t.b);
             tma_load_4d(smem + SM::RT + s * 16384, &tmR, bar_k, s * 64, cb, t.h, 0);
-            if (p.mode == 2) tma_load_4d(smem + SM::VT + s * 16384, &tmV, bar_k, s * 64, J0, t.h, t.b);
+            if (MODE == 2) tma_load_4d(smem + SM::VT + s * 16384, &tmV, bar_k, s * 64, J0, t.h, t.b);
           }
-          if (p.mode == 0) {
+          if (MODE == 0) {
             if (gs > 0) mbar_wait(bar_o, (gs - 1) & 1);
             mbar_expect_tx(bar_v, SM::TILE);
 #pragma unroll
@@ -209,7 +212,7 @@ relattn_fwd_kernel(const __grid_constant__ CUtensorMap tmQu, const __grid_consta
           const uint32_t off = (k >> 2) * 16384 + (k & 3) * 32;
           umma_ss(tbd, umma_smem_desc(qv + off, 16, 1024), umma_smem_desc(rt + off, 16, 1024), idesc_s, k ? 1u : 0u);
         }
-        if (p.mode != 2) umma_commit(bar_kfree);  // mode 2: V_J (same load group) is still needed by dP
+        if (MODE != 2) umma_commit(bar_kfree);  // mode 2: V_J (same load group) is still needed by dP
         umma_commit(bar_s);
       };
       auto issue_dp = [&]() {
@@ -231,18 +234,18 @@ relattn_fwd_kernel(const __grid_constant__ CUtensorMap tmQu, const __grid_consta
         tc_fence_after();
         // T_S / the band slot are free: bar_s1 of the previous item's last step was waited for below
         issue_scores(gs);
-        if (p.mode == 2) issue_dp();
+        if (MODE == 2) issue_dp();
         if (t.nsteps == 1) umma_commit(bar_qfree);
         for (int st = 0; st < t.nsteps; ++st, ++gs) {
           mbar_wait(bar_s1, gs & 1);
           tc_fence_after();
           if (st + 1 < t.nsteps) {
             issue_scores(gs + 1);
-            if (p.mode != 2 && st + 2 == t.nsteps) umma_commit(bar_qfree);  // last scores of this item issued
+            if (MODE != 2 && st + 2 == t.nsteps) umma_commit(bar_qfree);  // last scores of this item issued
           }
           mbar_wait(bar_p, gs & 1);
           tc_fence_after();
-          if (p.mode == 0) {
+          if (MODE == 0) {
             mbar_wait(bar_v, gs & 1);
             tc_fence_after();
 #pragma unroll
@@ -252,7 +255,7 @@ relattn_fwd_kernel(const __grid_constant__ CUtensorMap tmQu, const __grid_consta
               umma_ss(T_O, adesc, bdesc, idesc_o, (st | k) ? 1u : 0u);
             }
             umma_commit(bar_o);
-          } else if (p.mode == 2) {
+          } else if (MODE == 2) {
             if (st + 1 < t.nsteps) {
               issue_dp();  // the softmax warps are done reading dP(st)
               if (st + 2 == t.nsteps) umma_commit(bar_qfree);  // last dP of this item issued: Q / dO may be replaced
@@ -287,8 +290,35 @@ relattn_fwd_kernel(const __grid_constant__ CUtensorMap tmQu, const __grid_consta
     float m_run = NEG_BIG, l_run = 0.f;
     float lse_row = 0.f;
     float d_row = 0.f;
-    if (p.mode >= 1) lse_row = (i < p.L) ? p.lse2[((long long)b * p.H + h) * p.L + i] : 0.f;
-    if (p.mode == 2) d_row = (i < p.L) ? p.Drow[((long long)b * p.H + h) * p.L + i] : 0.f;
+    if (MODE >= 1) lse_row = (i < p.L) ? p.lse2[((long long)b * p.H + h) * p.L + i] : 0.f;
+    if (MODE == 2) {
+      if (p.Drow != nullptr) {
+        d_row = (i < p.L) ? p.Drow[((long long)b * p.H + h) * p.L + i] : 0.f;
+      } else {
+        // D_i = sum_d dO[i,d] * O[i,d] over this head (the softmax-backward row term): each half of the row's thread
+        // pair takes half of the head dimension; the loads fly under the wait for the item's first scores
+        float acc = 0.f;
+        if (i < p.L) {
+          const long long ro = (long long)b * p.L + i;
+          const __half* pa = p.dOp + ro * p.lddo + (long long)h * p.dh + half * (D / 2);
+          const __half* po = p.Op + ro * p.ldop + (long long)h * p.dh + half * (D / 2);
+#pragma unroll
+          for (int c = 0; c < D / 2; c += 8) {
+            if (half * (D / 2) + c < p.dh) {
+              float xa[8], xo[8];
+              half8_to_float(ld_half8(pa + c), xa);
+              half8_to_float(ld_half8(po + c), xo);
+#pragma unroll
+              for (int e = 0; e < 8; ++e) acc = fmaf(xa[e], xo[e], acc);
+            }
+          }
+        }
+        xsum[half * 128 + r] = acc;
+        named_bar_sync(1 + q, 64);
+        d_row = acc + xsum[(half ^ 1) * 128 + r];
+        named_bar_sync(1 + q, 64);  // xsum is written again by the next item
+      }
+    }
     const long long zrow0 = (((long long)b * p.H + h) * p.L + I0 + q * 32) * p.L;  // first row of this warp in P / dS
 
     for (int st = 0; st < nsteps; ++st, ++gs) {
@@ -347,13 +377,16 @@ relattn_fwd_kernel(const __grid_constant__ CUtensorMap tmQu, const __grid_consta
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(bar_s1);
-      // row maximum over both halves (double-buffered slot, one 64-thread named barrier per quadrant and step)
-      xmax[((gs & 1) * 2 + half) * 128 + r] = mx;
-      named_bar_sync(1 + q, 64);
-      mx = fmaxf(mx, xmax[((gs & 1) * 2 + (half ^ 1)) * 128 + r]);
-      mx *= p.scale_log2;  // scale > 0: max commutes with the scaling; masked entries stay hugely negative
+      if (MODE == 0) {
+        // row maximum over both halves (double-buffered slot, one 64-thread named barrier per quadrant and step);
+        // the recompute modes take the saved log-sum-exp instead and need neither the maximum nor the exchange
+        xmax[((gs & 1) * 2 + half) * 128 + r] = mx;
+        named_bar_sync(1 + q, 64);
+        mx = fmaxf(mx, xmax[((gs & 1) * 2 + (half ^ 1)) * 128 + r]);
+        mx *= p.scale_log2;  // scale > 0: max commutes with the scaling; masked entries stay hugely negative
+      }
 
-      if (p.mode == 0) {
+      if (MODE == 0) {
         // ---- online softmax bookkeeping with lazy rescale (rescale only when the max grew by more than 2^8)
         if (st > 0) {
           mbar_wait(bar_o, (gs - 1) & 1);  // O accumulated, P smem free
@@ -378,11 +411,11 @@ relattn_fwd_kernel(const __grid_constant__ CUtensorMap tmQu, const __grid_consta
             tmem_st_wait();
           }
         }
-      } else if (p.mode == 2) {
+      } else if (MODE == 2) {
         mbar_wait(bar_o, gs & 1);  // dP(st) is in TMEM
         tc_fence_after();
       }
-      const float m_use = (p.mode == 0) ? m_run : lse_row;
+      const float m_use = (MODE == 0) ? m_run : lse_row;
       // ---- pass 2: probabilities from the registers, p = exp2(raw * scale_log2 - m)
       float sum = 0.f;
 #pragma unroll
@@ -396,7 +429,7 @@ relattn_fwd_kernel(const __grid_constant__ CUtensorMap tmQu, const __grid_consta
           sum += p0 + p1;
           pk[t] = pack_half2(p0, p1);
         }
-        if (p.mode == 0) {
+        if (MODE == 0) {
           // K-major SW128 tile: slab = cc/2 (64 keys each), 16-byte chunk index within the row = (cc&1)*4 + g
           uint8_t* dst = prow + (cc >> 1) * 16384;
 #pragma unroll
@@ -427,7 +460,7 @@ relattn_fwd_kernel(const __grid_constant__ CUtensorMap tmQu, const __grid_consta
             __syncwarp();
           };
           store_tile(pk, p.P + zrow0 + J0 + cc * 32);
-          if (p.mode == 2) {
+          if (MODE == 2) {
             // dS = P * (dP - D) * scale; masked entries have P == 0 exactly
             uint32_t dp[32], dk[16];
             tmem_ld32(T_O + lane_off + cc * 32, dp);
@@ -450,7 +483,7 @@ relattn_fwd_kernel(const __grid_constant__ CUtensorMap tmQu, const __grid_consta
       if (lane == 0) mbar_arrive(bar_p);
     }
 
-    if (p.mode == 0) {
+    if (MODE == 0) {
       // total row sum over both halves, then each half normalises and writes its D/2 columns of O
       xsum[half * 128 + r] = l_run;
       mbar_wait(bar_o, (gs - 1) & 1);
@@ -505,19 +538,27 @@ static int make_head_map(CUtensorMap* tm, const void* base, int dh, int L, int H
   return make_tmap_f16(tm, base, 4, dims, str, box);
 }
 
-template <int D>
-static int launch_attn(const CUtensorMap* tm, const AttnParams& p, cudaStream_t stream) {
+template <int D, int MODE>
+static int launch_attn_m(const CUtensorMap* tm, const AttnParams& p, cudaStream_t stream) {
   using SM = AttnSmem<D>;
   static bool configured = false;
   if (!configured) {
-    DB1_CUDA(cudaFuncSetAttribute(relattn_fwd_kernel<D>, cudaFuncAttributeMaxDynamicSharedMemorySize, SM::TOTAL));
+    DB1_CUDA(cudaFuncSetAttribute(relattn_fwd_kernel<D, MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, SM::TOTAL));
     configured = true;
   }
   const int n_items = ((p.L + 127) / 128 - p.q_start / 128) * p.H * p.B;
   const int grid = n_items < sm_count() ? n_items : sm_count();
-  DB1_CUDA(launch_pdl(relattn_fwd_kernel<D>, dim3(grid), dim3(AT_THREADS), SM::TOTAL, stream, 1, tm[0], tm[1], tm[2], tm[3],
-                      tm[4], tm[5], p));
+  DB1_CUDA(launch_pdl(relattn_fwd_kernel<D, MODE>, dim3(grid), dim3(AT_THREADS), SM::TOTAL, stream, 1, tm[0], tm[1], tm[2],
+                      tm[3], tm[4], tm[5], p));
   return 0;
+}
+
+// the mode (0: O + LSE, 1: P, 2: P + dS) is a compile-time parameter: every per-step branch on it disappears
+template <int D>
+static int launch_attn(const CUtensorMap* tm, const AttnParams& p, cudaStream_t stream) {
+  if (p.mode == 0) return launch_attn_m<D, 0>(tm, p, stream);
+  if (p.mode == 1) return launch_attn_m<D, 1>(tm, p, stream);
+  return launch_attn_m<D, 2>(tm, p, stream);
 }
 
 }  // namespace db1
@@ -527,7 +568,8 @@ using namespace db1;
 static int relattn_launch(const void* qu, const void* qv, const void* k, const void* v, long long ld_qkv,
                           const void* r, long long ld_r, void* out, long long ld_out, float* lse2, void* probs,
                           const void* dout, long long ld_do, const float* drow, void* ds, int B, int L, int H, int dh,
-                          int window, float scale, int mode, int q_start, cudaStream_t stream) {
+                          int window, float scale, int mode, int q_start, cudaStream_t stream,
+                          const void* o_for_d = nullptr, long long ld_o_for_d = 0) {
   DB1_CHECK_ARG(qu && qv && k && r && lse2, "relattn: null pointer");
   DB1_CHECK_ARG(q_start >= 0 && q_start < L && (q_start == 0 || mode == 0), "relattn: bad q_start %d", q_start);
   DB1_CHECK_ARG(B > 0 && L > 0 && H > 0, "relattn: bad shape B=%d L=%d H=%d", B, L, H);
@@ -541,6 +583,7 @@ static int relattn_launch(const void* qu, const void* qv, const void* k, const v
   p.scale_log2 = scale * 1.4426950408889634f;
   p.O = (__half*)out; p.ldo = ld_out; p.lse2 = lse2; p.P = (__half*)probs; p.mode = mode;
   p.dS = (__half*)ds; p.Drow = drow; p.scale = scale; p.q_start = q_start;
+  p.dOp = (const __half*)dout; p.lddo = ld_do; p.Op = (const __half*)o_for_d; p.ldop = ld_o_for_d;
   CUtensorMap tm[6];
   int e;
   if ((e = make_head_map(&tm[0], qu, dh, L, H, B, ld_qkv))) return e;
@@ -581,4 +624,16 @@ extern "C" int db1_relattn_bwd_ds(const void* qu, const void* qv, const void* k,
   DB1_CHECK_ARG(v && dout && drow && probs && ds, "relattn_bwd_ds: null pointer");
   return relattn_launch(qu, qv, k, v, ld_qkv, r, ld_r, nullptr, 0, const_cast<float*>(lse2), probs, dout, ld_do, drow,
                         ds, B, L, H, dh, window, scale, 2, 0, (cudaStream_t)stream_);
+}
+
+/* Same, with D = rowsum(dO * O) computed inside the kernel from `o` (the forward output, [B*L, ld_o], head h at column
+ * h*dh) instead of being read from a db1_rowdot result: one launch and one pass over dO / O less per layer. */
+extern "C" int db1_relattn_bwd_ds_o(const void* qu, const void* qv, const void* k, const void* v, long long ld_qkv,
+                                    const void* r, long long ld_r, const void* dout, long long ld_do, const void* o,
+                                    long long ld_o, const float* lse2, void* probs, void* ds, int B, int L, int H, int dh,
+                                    int window, float scale, void* stream_) {
+  DB1_CHECK_ARG(v && dout && o && probs && ds, "relattn_bwd_ds_o: null pointer");
+  DB1_CHECK_ARG(ld_o % 8 == 0 && (((uintptr_t)o | (uintptr_t)dout) & 15) == 0, "relattn_bwd_ds_o: o / dout must be 16-byte aligned rows");
+  return relattn_launch(qu, qv, k, v, ld_qkv, r, ld_r, nullptr, 0, const_cast<float*>(lse2), probs, dout, ld_do, nullptr,
+                        ds, B, L, H, dh, window, scale, 2, 0, (cudaStream_t)stream_, o, ld_o);
 }

@@ -33,6 +33,8 @@ class GemmDesc(C.Structure):
         ("H", C.c_void_p), ("ldh", C.c_int64), ("F", C.c_int32),
         ("P", C.c_void_p), ("C2", C.c_void_p), ("Drow", C.c_void_p),
         ("window", C.c_int32), ("bn_hint", C.c_int32),
+        ("dot_with", C.c_void_p), ("ld_dot", C.c_int64), ("dot_out", C.c_void_p),
+        ("dot_L", C.c_int32), ("dot_H", C.c_int32),
     ]
 
 

@@ -161,14 +161,19 @@ class AttnBlockFn(torch.autograd.Function):
         gWo = _Grad(pWo)
         ops.gemm(dzz, o, gWo.buf, d, d, rows, lda=d, ldb=d, ldc=d, a_mn=True, b_mn=True, accumulate=gWo.acc)
         do = torch.empty(rows, d, dtype=f16, device=dev)
-        ops.gemm(dzz, Wo, do, rows, d, d, lda=d, ldb=d, ldc=d, b_mn=True)
+        # D = rowsum(dO * O), the softmax-backward row term: from the dO GEMM's own epilogue at model size (head dim 128),
+        # else inside the recompute kernel; no separate db1_rowdot pass over dO / O either way
+        Drow = None
+        if ops.gemm_dot_supported(rows, d, H, dh):
+            Drow = torch.empty(B, H, L, dtype=torch.float32, device=dev)
+            ops.gemm(dzz, Wo, do, rows, d, d, lda=d, ldb=d, ldc=d, b_mn=True, dot=(o, Drow, L, H))
+        else:
+            ops.gemm(dzz, Wo, do, rows, d, d, lda=d, ldb=d, ldc=d, b_mn=True)
         # attention core: recompute P, then the causal contractions on tensor cores
-        Drow = torch.empty(B, H, L, dtype=torch.float32, device=dev)
-        ops.rowdot(do, o, Drow, B, L, H, dh)
         P = _workspace("P", (B, H, L, L), f16, dev)
         dS = _workspace("dS", (B, H, L, L), f16, dev)
         dSr = _workspace("dSr", (B, H, L, L), f16, dev)
-        ops.relattn_bwd_ds(qkv4, rk, do, lse2, Drow, P, dS, B, L, H, dh, window, scale)
+        ops.relattn_bwd_ds(qkv4, rk, do, lse2, Drow, P, dS, B, L, H, dh, window, scale, o=o)
         qu = qkv4[:, 0:d]
         qv = qkv4[:, d:2 * d]
         kk = qkv4[:, 2 * d:3 * d]

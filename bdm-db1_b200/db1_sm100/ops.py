@@ -103,7 +103,7 @@ def _ensure_gemm_workspace(device):
 def gemm(A, B, C_out, M, N, K, *, lda, ldb, ldc, a_mn=False, b_mn=False, epilogue=EPI_PLAIN, alpha=1.0,
          accumulate=False, bias=None, resid=None, ldr=0, drop_p=0.0, seed=0, u=None, v=None, d_model=0, H=None,
          ldh=0, F=0, Z1=1, Z2=1, a_z=(0, 0), b_z=(0, 0), c_z=(0, 0), reduce_z2=False, k_mode=K_FULL,
-         skip_upper=False, P=None, C2=None, Drow=None, window=0, bn_hint=0):
+         skip_upper=False, P=None, C2=None, Drow=None, window=0, bn_hint=0, dot=None):
     """C[M,N] (+)= epilogue(alpha * A[M,K] @ B[N,K]^T) per batch index; see include/db1_sm100.h:db1_gemm_f16."""
     _need_cuda_half(A, B, C_out, bias, resid, u, v, H, P, C2)
     _ensure_gemm_workspace(A.device)
@@ -138,6 +138,10 @@ def gemm(A, B, C_out, M, N, K, *, lda, ldb, ldc, a_mn=False, b_mn=False, epilogu
     d.Drow = Drow.data_ptr() if Drow is not None else None
     d.window = window
     d.bn_hint = bn_hint
+    if dot is not None:  # (X fp16 [M, ld], out fp32 [M / L, H, L], L, H): out = per-head rowsum(C * X), head dim 128
+        X, dout_t, dL, dH = dot
+        _need_cuda_half(X)
+        d.dot_with, d.ld_dot, d.dot_out, d.dot_L, d.dot_H = X.data_ptr(), X.stride(0), _f32(dout_t), dL, dH
     flops = 2.0 * M * N * K * Z1 * Z2
     if k_mode != K_FULL or skip_upper:
         flops *= (M + 1) / (2.0 * M)  # causal: only unmasked (i, j) pairs are algorithmic work
@@ -147,6 +151,11 @@ def gemm(A, B, C_out, M, N, K, *, lda, ldb, ldc, a_mn=False, b_mn=False, epilogu
     with _Launch(name, 1, flops):
         check(_lib.lib().db1_gemm_f16(C.byref(d), cur_stream()), "db1_gemm_f16")
     return C_out
+
+
+def gemm_dot_supported(M, N, H, dh):
+    """Whether db1_gemm_f16 can emit the per-head row-dot next to C (include/db1_sm100.h: dot_with / dot_out)."""
+    return dh == 128 and N == H * dh and M > 384 and 2 * ((M + 127) // 128) * ((N + 255) // 256) > 148
 
 
 def relattn_fwd(qkv4, r, out, lse2, B, L, H, dh, window, scale, probs=None):
@@ -182,13 +191,22 @@ def relattn_mem_fwd(qkv4, r, out, lse2, B, K, H, dh, window, scale, mlen):
         _f32(lse2), B, K, H, dh, int(window), C.c_float(scale), int(mlen), cur_stream()), "db1_relattn_mem_fwd")
 
 
-def relattn_bwd_ds(qkv4, r, dout, lse2, drow, probs, ds, B, L, H, dh, window, scale):
-    """P and dS = P * (dO V^T - D) * scale for the attention backward; include/db1_sm100.h:db1_relattn_bwd_ds."""
-    _need_cuda_half(qkv4, r, dout, probs, ds)
+def relattn_bwd_ds(qkv4, r, dout, lse2, drow, probs, ds, B, L, H, dh, window, scale, o=None):
+    """P and dS = P * (dO V^T - D) * scale for the attention backward; include/db1_sm100.h:db1_relattn_bwd_ds.
+    D = rowsum(dO * O) comes from `drow` (db1_rowdot) or, with drow=None, is formed in the kernel from `o`."""
+    _need_cuda_half(qkv4, r, dout, probs, ds, o)
     d = H * dh
     es = qkv4.element_size()
     base = qkv4.data_ptr()
     pairs = L * (L + 1) / 2.0 if window >= L else (window * (window + 1) / 2.0 + (L - window) * window)
+    if drow is None:
+        with _Launch("relattn_bwd_ds", 1, B * H * pairs * dh * 6.0):
+          check(_lib.lib().db1_relattn_bwd_ds_o(
+            C.c_void_p(base), C.c_void_p(base + d * es), C.c_void_p(base + 2 * d * es), C.c_void_p(base + 3 * d * es),
+            C.c_longlong(qkv4.stride(0)), ptr(r), C.c_longlong(r.stride(0)), ptr(dout), C.c_longlong(dout.stride(0)),
+            ptr(o), C.c_longlong(o.stride(0)), _f32(lse2), ptr(probs), ptr(ds), B, L, H, dh, int(window),
+            C.c_float(scale), cur_stream()), "db1_relattn_bwd_ds_o")
+        return
     with _Launch("relattn_bwd_ds", 1, B * H * pairs * dh * 6.0):
       check(_lib.lib().db1_relattn_bwd_ds(
         C.c_void_p(base), C.c_void_p(base + d * es), C.c_void_p(base + 2 * d * es), C.c_void_p(base + 3 * d * es),

@@ -84,6 +84,13 @@ typedef struct db1_gemm_desc {
   const float* Drow;  /* fp32 [Z2][Z1][M] contiguous */
   int32_t window;     /* attend iff 0 <= i-j < window */
   int32_t bn_hint;    /* 0 = auto, 128 or 256 */
+  /* Row-dot side output (plain, un-batched GEMMs with N == dot_H * 128 at CTA-pair size; ABI version 2):
+   * dot_out[(b * dot_H + h) * dot_L + i] = sum_{c in head h} acc[b * dot_L + i, c] * dot_with[b * dot_L + i, c].
+   * Attention backward: C = dO = dZ . W_o and D = rowsum(dO * O) (softmax-backward row term) from the same epilogue. */
+  const void* dot_with; /* fp16 [M, ld_dot] or NULL */
+  int64_t ld_dot;
+  float* dot_out;       /* fp32 [M / dot_L, dot_H, dot_L] */
+  int32_t dot_L, dot_H;
 } db1_gemm_desc;
 
 int db1_gemm_f16(const db1_gemm_desc* d, void* stream);
@@ -134,6 +141,12 @@ int db1_relattn_mem_fwd(const void* qu, const void* qv, const void* k, const voi
 int db1_relattn_bwd_ds(const void* qu, const void* qv, const void* k, const void* v, long long ld_qkv, const void* r,
                        long long ld_r, const void* dout, long long ld_do, const float* lse2, const float* drow,
                        void* probs, void* ds, int B, int L, int H, int dh, int window, float scale, void* stream);
+/* Same, with D = rowsum(dO * O) formed inside the kernel from the forward output `o` ([B*L, ld_o] fp16, head h at column
+ * h*dh) instead of a db1_rowdot result. */
+int db1_relattn_bwd_ds_o(const void* qu, const void* qv, const void* k, const void* v, long long ld_qkv, const void* r,
+                         long long ld_r, const void* dout, long long ld_do, const void* o, long long ld_o,
+                         const float* lse2, void* probs, void* ds, int B, int L, int H, int dh, int window, float scale,
+                         void* stream);
 
 /* ------------------------------------------------------------------------------------------------------------------
  * HBM-bound kernels (single pass over the large operand, 16-byte vector accesses, fp32 math).

@@ -308,3 +308,21 @@ def test_gemm_tma_epilogue_ragged_and_accumulate(cuda):
     hh = Hs.float().requires_grad_(True)
     (hh[:, :F] * torch.nn.functional.gelu(hh[:, F:])).backward(dY)
     assert _rel(dH, hh.grad) < 3e-3
+
+
+def test_gemm_rowdot_side_output(cuda):
+    """dO = dZ . W_o with D[b,h,i] = sum over head h of dO[b*L+i, :] * O[b*L+i, :] from the same (TMA) epilogue."""
+    from db1_sm100 import ops
+    Bq, L, Hh, dh, K = 4, 512, 16, 128, 320
+    M, N = Bq * L, Hh * dh
+    assert ops.gemm_dot_supported(M, N, Hh, dh)
+    A = _mk((M, K), cuda, 1.0, 61)
+    W = _mk((K, N), cuda, 0.1, 62)  # stored [K][N]: MN-major B, as W_o is in the dgrad
+    O = _mk((M, N), cuda, 1.0, 63)
+    Cc = torch.empty(M, N, dtype=torch.half, device=cuda)
+    D = torch.full((Bq, Hh, L), float("nan"), dtype=torch.float32, device=cuda)
+    ops.gemm(A, W, Cc, M, N, K, lda=K, ldb=N, ldc=N, b_mn=True, dot=(O, D, L, Hh))
+    ref = A.float() @ W.float()
+    assert _rel(Cc, ref) < 2e-3
+    refD = (ref * O.float()).view(Bq, L, Hh, dh).sum(-1).permute(0, 2, 1)
+    assert _rel(D, refD) < 2e-3

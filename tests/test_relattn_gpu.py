@@ -93,3 +93,11 @@ def test_relattn_bwd_ds_matches_autograd(cuda, B, L, H, dh, window):
     torch.cuda.synchronize()
     assert (P.cpu().float() - p.detach()).abs().max().item() < 2e-3
     assert _rel(dS.cpu(), ds_ref) < 5e-3  # D comes from the fp16-rounded O; dS itself is stored in fp16
+    # same with D = rowsum(dO * O) formed inside the kernel (the path the model uses): identical inputs -> same dS
+    P2 = torch.zeros_like(P)
+    dS2 = torch.zeros_like(dS)
+    ops.relattn_bwd_ds(qkv4, r, do_d, lse2, None, P2, dS2, B, L, H, dh, window, scale, o=out)
+    torch.cuda.synchronize()
+    assert torch.equal(P2, P)
+    assert _rel(dS2.cpu(), ds_ref) < 5e-3
+    assert (dS2.float() - dS.float()).abs().max().item() <= 2e-3 * dS.float().abs().max().item()

@@ -27,7 +27,7 @@ e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=Tr
 for it in range(6):
     if it == 3:
         e0.record()
-    ops.relattn_bwd_ds(qkv4, r, do, lse2, drow, P, dS, B, L, H, dh, L, scale)
+    ops.relattn_bwd_ds(qkv4, r, do, lse2, None, P, dS, B, L, H, dh, L, scale, o=o)
 e1.record()
 torch.cuda.synchronize()
 us = e0.elapsed_time(e1) / 3 * 1e3
