@@ -459,7 +459,11 @@ relattn_fwd_kernel(const __grid_constant__ CUtensorMap tmQu, const __grid_consta
             }
             __syncwarp();
           };
-          store_tile(pk, p.P + zrow0 + J0 + cc * 32);
+          const bool direct = (p.L & 15) == 0;  // rows 32-byte aligned: 256-bit stores straight from the row's owner
+          const long long zme = zrow0 + (long long)lane * p.L + J0 + cc * 32;
+          const int nvalid = (lane < rows_valid) ? (cols_valid > 32 ? 32 : (cols_valid < 0 ? 0 : cols_valid)) : 0;
+          if (direct) stg_row32(p.P + zme, pk, nvalid, true);
+          else store_tile(pk, p.P + zrow0 + J0 + cc * 32);
           if (MODE == 2) {
             // dS = P * (dP - D) * scale; masked entries have P == 0 exactly
             uint32_t dp[32], dk[16];
@@ -471,7 +475,8 @@ relattn_fwd_kernel(const __grid_constant__ CUtensorMap tmQu, const __grid_consta
               dk[t] = pack_half2(pp.x * (__uint_as_float(dp[2 * t]) - d_row) * p.scale,
                                  pp.y * (__uint_as_float(dp[2 * t + 1]) - d_row) * p.scale);
             }
-            store_tile(dk, p.dS + zrow0 + J0 + cc * 32);
+            if (direct) stg_row32(p.dS + zme, dk, nvalid, true);
+            else store_tile(dk, p.dS + zrow0 + J0 + cc * 32);
           }
         }
       }

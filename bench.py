@@ -243,12 +243,16 @@ def run_ours(args):
     e2, e3 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     barrier()
     e2.record()
-    last = 0.0
-    for _ in range(args.steps):
+    # every step: inputs from pinned host buffers (async H2D on the compute stream) and the step's loss read back into
+    # pinned host memory (4-byte async D2H on the same stream); the host synchronises once, inside the timed region,
+    # after the last read-back has been enqueued - what a training loop that logs its losses does
+    loss_host = torch.empty(args.steps, dtype=torch.float32, pin_memory=True)
+    for i in range(args.steps):
         inputs = [synth.to_device(t, dev, non_blocking=True) for t in host]
-        last = step(inputs).item()  # 4-byte device->host read of the step's loss
+        loss_host[i:i + 1].copy_(step(inputs).detach().reshape(1).float(), non_blocking=True)
     e3.record()
     barrier()
+    last = float(loss_host[-1])
     ms2 = torch.tensor([e2.elapsed_time(e3)], device=dev)
     if world > 1:
         dist.all_reduce(ms2, op=dist.ReduceOp.MAX)
@@ -278,7 +282,10 @@ def run_ours(args):
                        "micro_batch_per_gpu": B_MICRO, "seq_len": SEQ, "global_batch": B_MICRO * world,
                        "parallelism": "dp%d" % world,
                        "cache": "no L2 flush needed: 2.4 GB of weights + 6 GB of saved activations stream per step (>> 126 MB L2)"},
-            "e2e": {"value": e2e_value, "unit": "tokens/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 4},
+            "e2e": {"value": e2e_value, "unit": "tokens/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 4,
+                    "how": "engine(inputs) / engine.backward(loss) per step; inputs copied from pinned host memory and the "
+                           "loss copied back to pinned host memory every step (both async on the compute stream), one "
+                           "host synchronisation at the end of the timed region"},
             "gpu_launches": count.launches,
             "clocks": clocks,
             "roofline": {"bound": "tensor", "achieved": achieved, "peak": pk["tflops"], "unit": "TFLOP/s",

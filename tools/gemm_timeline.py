@@ -15,6 +15,7 @@ resid = "resid" in sys.argv
 drop = 0.1 if "drop" in sys.argv else 0.0
 bmn = "bmn" in sys.argv
 dgeglu = "dgeglu" in sys.argv
+geglu = "geglu" in sys.argv and not dgeglu
 A = (torch.randn(M, K, device=dev) * 0.05).half()
 B = (torch.randn(K, N, device=dev) * 0.05).half() if bmn else (torch.randn(N, K, device=dev) * 0.05).half()
 Cc = torch.empty(M, N, dtype=torch.half, device=dev)
@@ -22,8 +23,14 @@ R = torch.randn(M, N, device=dev).half() if resid else None
 if dgeglu:
     Hs = torch.randn(M, 2 * N, device=dev).half()
     Cc = torch.empty(M, 2 * N, dtype=torch.half, device=dev)
+if geglu:  # N = 2F
+    Hs = torch.empty(M, N, dtype=torch.half, device=dev)
+    Cc = torch.empty(M, N // 2, dtype=torch.half, device=dev)
+    bias = torch.randn(N, device=dev).half()
 for _ in range(3):
-    if dgeglu:
+    if geglu:
+        ops.gemm(A, B, Cc, M, N, K, lda=K, ldb=K, ldc=N // 2, epilogue=ops.EPI_GEGLU, bias=bias, H=Hs, ldh=N, F=N // 2)
+    elif dgeglu:
         ops.gemm(A, B, Cc, M, N, K, lda=K, ldb=B.stride(0), ldc=2 * N, b_mn=bmn, epilogue=ops.EPI_DGEGLU, H=Hs, ldh=2 * N, F=N)
     else:
         ops.gemm(A, B, Cc, M, N, K, lda=K, ldb=B.stride(0), ldc=N, b_mn=bmn, resid=R, ldr=N if resid else 0, drop_p=drop, seed=5)
