@@ -703,7 +703,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
         const volatile SkPlan* vp = plan;
         const int role = vp->role[wn];
         if (role != SK_FULL) {
-          mbar_wait(&tfull[as], aph);
+          mbar_wait_backoff(&tfull[as], aph, p.dbg & 16 ? 0u : 100u);
           tc_fence_after();
           if (role == SK_CONTRIB) {
             sk_store_partial<BN>(p, tacc, tile0, vp->peer[wn], prank, ew, half, lane);
@@ -756,7 +756,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
             bulk_wait_group_read<1>();
             for (int k = 0; k < nch && k < NB - 1; ++k) arm(eseq + k, colh + k * 32);
           }
-          mbar_wait(&tfull[as], aph);
+          mbar_wait_backoff(&tfull[as], aph, p.dbg & 16 ? 0u : 100u);
           tc_fence_after();
           if (tl && ew == 0 && lane == 0 && it <= 15) tl[4 + 4 * (it - 1) + 2] = clock64();
           uint32_t r[2][32];
@@ -845,7 +845,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
           }
         };
         fetch(0, va[0], vg[0]);
-        mbar_wait(&tfull[as], aph);
+        mbar_wait_backoff(&tfull[as], aph, p.dbg & 16 ? 0u : 100u);
         tc_fence_after();
         if (tl && ew == 0 && lane == 0 && it <= 15) tl[4 + 4 * (it - 1) + 2] = clock64();
 #pragma unroll
@@ -895,7 +895,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
                              p.N - col0);
           }
         }
-        mbar_wait(&tfull[as], aph);
+        mbar_wait_backoff(&tfull[as], aph, p.dbg & 16 ? 0u : 100u);
         tc_fence_after();
         if (tl && ew == 0 && lane == 0 && it <= 15) tl[4 + 4 * (it - 1) + 2] = clock64();
 #pragma unroll
@@ -983,7 +983,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
           }
         };
         load_p(c_first, pp[0]);
-        mbar_wait(&tfull[as], aph);
+        mbar_wait_backoff(&tfull[as], aph, p.dbg & 16 ? 0u : 100u);
         tc_fence_after();
 #pragma unroll
         for (int ci = 0; ci < CPW; ++ci) {
@@ -1046,7 +1046,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
           }
         }
         issue_h(c_first, la[0], lg[0]);
-        mbar_wait(&tfull[as], aph);
+        mbar_wait_backoff(&tfull[as], aph, p.dbg & 16 ? 0u : 100u);
         tc_fence_after();
 #pragma unroll
         for (int ci = 0; ci < CPW; ++ci) {

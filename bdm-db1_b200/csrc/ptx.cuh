@@ -52,6 +52,12 @@ DEVI void mbar_wait(uint64_t* bar, uint32_t parity) {
   }
 }
 
+// Long waits (an epilogue warp waiting out a whole main loop): poll with a back-off instead of spinning - eight warps
+// spinning on try_wait take issue slots and power from the MMA / TMA threads of a power-capped chip.
+DEVI void mbar_wait_backoff(uint64_t* bar, uint32_t parity, uint32_t ns) {
+  while (!mbar_try_wait(bar, parity)) __nanosleep(ns);
+}
+
 // ---------------------------------------------------------------- fences
 DEVI void fence_proxy_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 DEVI void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }

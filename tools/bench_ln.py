@@ -19,3 +19,7 @@ def t(name, fn, nbytes):
     print("%-10s %.1f us  %.2f TB/s" % (name, min(ts), nbytes / min(ts) / 1e6))
 t("ln_fwd", lambda: ops.layernorm_fwd(y, g, b, out, stats, 1e-5), 2 * R * d * 2)
 t("ln_bwd", lambda: ops.layernorm_bwd(dout, y, g, stats, dy, dz, small[0:d], small[d:2 * d], small[2 * d:], 0.1, 1234), 4 * R * d * 2)
+B, H, L = 4, 16, 1024
+dS = torch.randn(B, H, L, L, device=dev).half().tril_()
+dSr = torch.zeros_like(dS)
+t("rel_unshift", lambda: ops.rel_unshift(dS, dSr, B * H, L), 2.0 * B * H * L * (L + 1))
