@@ -765,15 +765,11 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
 #pragma unroll
           for (int ci = 0; ci < CPW; ++ci) {
             if (ci < nch) {
-              const bool stamp = tl && ew == 0 && lane == 0 && it == 1;
-              if (stamp) tl[32 + ci * 6 + 0] = clock64();
               tmem_ld_wait();
-              if (stamp) tl[32 + ci * 6 + 1] = clock64();
               if (ci + 1 < nch) tmem_ld32(tacc + (c_first + ci + 1) * 32, r[(ci + 1) & 1]);
               const int col0 = colh + ci * 32;
               const unsigned int b = eseq & (NB - 1);
               mbar_wait(&ebh[b], (eseq / NB) & 1u);
-              if (stamp) tl[32 + ci * 6 + 2] = clock64();
               const uint32_t rowp = smem_u32(ebuf + b * 8192 + trow * 64);
               if (e_dot) {
                 epi_chunk<false, 2>(r[ci & 1], rowp, swz, row, col0, e_N, 1.f, nullptr, 0u, 1.f, 0ull, dacc);
@@ -784,11 +780,8 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
                 if (e_in) epi_chunk<false, 1>(r[ci & 1], rowp, swz, row, col0, e_N, 1.f, nullptr, 0u, 1.f, 0ull, dacc);
                 else epi_chunk<false, 0>(r[ci & 1], rowp, swz, row, col0, e_N, 1.f, nullptr, 0u, 1.f, 0ull, dacc);
               }
-              if (stamp) tl[32 + ci * 6 + 3] = clock64();
               fence_proxy_async_smem();
-              if (stamp) tl[32 + ci * 6 + 4] = clock64();
               named_bar_sync(5 + half, 128);
-              if (stamp) tl[32 + ci * 6 + 5] = clock64();
               if (eleader) {
                 if (!(p.dbg & 1)) tma_store_2d(&tmC, ebuf + b * 8192, col0, row0);
                 bulk_commit_group();

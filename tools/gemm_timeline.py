@@ -47,10 +47,5 @@ for c in list(range(0, 8)) + list(range(140, 148)):
             break
         row.append("[%6d %6d | %6d %6d]" % tuple(x - t0 if x else -1 for x in v))
     print(" ".join(row))
-for c in (0, 2):
-    t0 = tl[c, 0].item()
-    print("cta %d first-tile chunk stamps (start, ld_wait, buf_ready, math+sts, fence, barrier):" % c)
-    for ci in range(4):
-        print("   ", [tl[c, 32 + ci * 6 + j].item() - t0 for j in range(6)])
 tot = (tl[:, 1] - tl[:, 0]).float()
 print("kernel span per CTA: mean %.0f max %.0f clk" % (tot.mean().item(), tot.max().item()))
