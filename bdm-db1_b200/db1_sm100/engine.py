@@ -89,7 +89,8 @@ class DB1Engine:
         self._written = set()    # ids of parameters whose bucket view already holds this window's gradient
         self._sink_seen = set()  # ids of parameters that have ever been written through the sink
         self._param_by_id = {id(p): p for b in self.buckets for p in b.params}
-        if self._cuda and direct_grads:
+        self._sink_on = bool(self._cuda and direct_grads)
+        if self._sink_on:
             from . import functions
             functions.set_grad_sink(self)
 
@@ -247,7 +248,15 @@ class DB1Engine:
             b.work = None
             b.post_scale = None
         scaled = loss * (self.loss_scale / self._ga)
-        scaled.backward()
+        if self._sink_on and loss.is_cuda:
+            from . import functions
+            functions.begin_backward(loss.device)  # one zero-filled arena for the blocks' small fp32 accumulators
+            try:
+                scaled.backward()
+            finally:
+                functions.end_backward()
+        else:
+            scaled.backward()
         if self._is_boundary():
             self._zero_unwritten()
         else:

@@ -84,20 +84,98 @@ class _Grad:
         return self.buf
 
 
-def _scatter_small(small, plan):
+# ---------------------------------------------------------------------------------------------------------------------
+# Small fp32 gradient accumulators (du, dv, dgamma, dbeta, biases). Under an engine one zero-filled arena per backward
+# replaces the per-block torch.zeros launches (one memset instead of 48), and the feed-forward block's conversion to
+# fp16 rides along with the attention block's of the same layer (one db1_f32_to_f16_multi launch per layer instead of
+# two): both accumulators are views of the same arena, so one launch can address them through offsets.
+# ---------------------------------------------------------------------------------------------------------------------
+class _Arena:
+    def __init__(self):
+        self.buf = None
+        self.off = 0
+        self.active = False
+        self.want = 0      # floats requested during the last backward (sizes the arena for the next one)
+        self.pending = []  # deferred conversions: (offset of the block's accumulator in the arena, plan, grads)
+
+
+_arena = _Arena()
+
+
+def begin_backward(device):
+    """Called by the engine before autograd runs: (re)arms the arena. The first backward only measures demand."""
+    a = _arena
+    need = a.want + a.want // 4
+    if need > 0 and (a.buf is None or a.buf.numel() < need or a.buf.device != device):
+        a.buf = torch.empty(need, dtype=torch.float32, device=device)
+    a.active = a.buf is not None and a.buf.device == device
+    if a.active:
+        a.buf.zero_()
+    a.off = 0
+    a.want = 0
+    a.pending = []
+
+
+def end_backward():
+    """Called by the engine after autograd returned: converts whatever is still deferred and disarms the arena."""
+    _flush_small()
+    _arena.active = False
+
+
+def _f32zeros(n, dev):
+    a = _arena
+    n4 = (n + 3) // 4 * 4  # 16-byte aligned slices (vector reductions)
+    a.want += n4
+    if a.active and a.off + n4 <= a.buf.numel():
+        v = a.buf[a.off:a.off + n]
+        a.off += n4
+        return v
+    return torch.zeros(n, dtype=torch.float32, device=dev)
+
+
+def _arena_offset(small):
+    a = _arena
+    if not a.active or small.untyped_storage().data_ptr() != a.buf.untyped_storage().data_ptr():
+        return None
+    return small.storage_offset()
+
+
+def _flush_small():
+    a = _arena
+    if not a.pending:
+        return
+    segs, fin = [], []
+    for base, plan, grads in a.pending:
+        for g, (_p, o, n) in zip(grads, plan):
+            segs.append((g.buf, base + o, n, g.acc))
+            fin.append(g)
+    a.pending = []
+    ops.f32_to_f16_multi(a.buf, segs)
+    for g in fin:
+        g.ret()
+
+
+def _scatter_small(small, plan, defer=False):
     """plan: list of (param, offset, n). Converts slices of the fp32 accumulator `small` to fp16 gradients with one
-    launch per 8 parameters; returns the autograd return values in plan order."""
+    launch per 8 parameters; returns the autograd return values in plan order. defer=True (feed-forward block): when
+    every gradient goes straight into an engine bucket and the accumulator lives in the arena, the conversion is left
+    to the next non-deferred call (the attention block of the same layer) and the returns are None."""
     grads = [_Grad(p, (n,)) for p, _o, n in plan]
+    base = _arena_offset(small)
+    direct = base is not None and all(g.direct for g in grads)
+    if direct:
+        _arena.pending.append((base, plan, grads))
+        if not defer:
+            _flush_small()
+        return [None] * len(plan)
+    if _arena.pending:
+        _flush_small()
     ops.f32_to_f16_multi(small, [(g.buf, o, n, g.acc) for g, (_p, o, n) in zip(grads, plan)])
     out = []
     for g, (p, _o, _n) in zip(grads, plan):
         r = g.ret()
         out.append(r.view(p.shape) if r is not None else None)
     return out
-
-
-def _f32zeros(n, dev):
-    return torch.zeros(n, dtype=torch.float32, device=dev)
 
 
 def _to_half(x32, shape):
@@ -292,7 +370,7 @@ class FFBlockFn(torch.autograd.Function):
         ops.gemm(dH, x2, gW1.buf, 2 * F, d, rows, lda=2 * F, ldb=d, ldc=d, a_mn=True, b_mn=True, accumulate=gW1.acc)
         dx = torch.empty(rows, d, dtype=f16, device=dev)
         ops.gemm(dH, W1, dx, rows, d, 2 * F, lda=2 * F, ldb=d, ldc=d, b_mn=True, resid=dy, ldr=d)
-        gg, gb, gb2, gb1 = _scatter_small(small, [(pgamma, 0, d), (pbeta, d, d), (pb2, 2 * d, d), (pb1, 3 * d, 2 * F)])
+        gg, gb, gb2, gb1 = _scatter_small(small, [(pgamma, 0, d), (pbeta, d, d), (pb2, 2 * d, d), (pb1, 3 * d, 2 * F)], defer=True)
         return (dx.view(B, L, d), gW1.ret(), gb1, gW2.ret(), gb2, gg, gb, None, None)
 
 
