@@ -2,14 +2,21 @@
 //
 //   for every batch (z1, z2):  C[M,N] (+)= epilogue( alpha * A[M,K] * B[N,K]^T ),  fp16 operands, fp32 accumulation in TMEM.
 //
-// One CTA per SM walks output tiles (128 x BN) round-robin. Roles:
-//   warp 0     TMA producer : global -> smem ring (STAGES x [A 128x64 | B BNx64], 128B swizzle, 4-D tensor maps
+// One CTA per SM walks output tiles (128 x BN); large un-batched problems run as CTA PAIRS (cta_group::2: a 256 x 256
+// MMA over two vertically adjacent tiles, each CTA staging its 128 rows of A and half of the B tile). Roles:
+//   warp 0     TMA producer : global -> smem ring (STAGES x [A 128x64 | B], 128B swizzle, 4-D tensor maps
 //                             (inner, rows, z1, z2) so batched / strided operands need no gather)
-//   warp 1     MMA issuer   : one elected thread issues tcgen05.mma (M=128, N=BN, K=16), accumulators in TMEM;
+//   warp 1     MMA issuer   : one elected thread issues tcgen05.mma (K = 16 per instruction), accumulators in TMEM;
 //                             the accumulator is double-buffered (2 x BN columns) so tile i+1's main loop
 //                             overlaps tile i's epilogue
-//   warps 2..9 epilogue     : tcgen05.ld -> registers -> fused epilogue -> 16-byte global stores (two warps per
-//                             TMEM lane quadrant, next chunk's global operands prefetched)
+//   warps 2..9 epilogue     : two warps per TMEM lane quadrant, a thread owns one output row. Three styles:
+//                             TMA epilogue (PLAIN on CTA pairs: double-buffered tcgen05.ld -> compile-time specialised
+//                             math -> swizzled smem tile -> cp.async.bulk.tensor store, addend fetched by TMA),
+//                             register-direct (GeGLU backward on pairs: 256-bit row loads / stores, no smem), and
+//                             staged (all others: per-warp smem transpose so every store covers 8 rows x 64 bytes)
+// Tile order: data parallel (pair, pair + G, ...); causal k-ranges: cost order, heaviest first, alternating direction;
+// opt-in: stream-K tail (DB1_GEMM_SK) and 4-CTA clusters with B multicast (DB1_GEMM_CL=4) - see DESIGN.md 3.1 for why
+// both stay off.
 //
 // Either operand may be K-contiguous ("K-major", e.g. activations x weights^T in the forward pass) or
 // MN-contiguous ("MN-major": weights in dgrad, both operands in wgrad) - the UMMA descriptors transpose for free,

@@ -4,21 +4,24 @@
 //   P      = softmax_j(S) on  0 <= i-j < window                    _rel_shift, :98-110, for qlen == klen == L)
 //   O[i]   = sum_j P[i,j] v_j                                      (:209-225)
 //
-// One CTA per (128-query tile, head, sequence). Key tiles are walked from the diagonal outwards; per step three
-// tcgen05 MMAs run on TMEM accumulators:
+// Persistent: one CTA per SM walks a static, balanced list of (128-query tile, head, sequence) items. Key tiles are
+// walked from the diagonal outwards; per step three tcgen05 MMAs run on TMEM accumulators:
 //     S   = Qu . K_j^T                     (128x128, fp32)
 //     BDc = Qv . Rchunk^T                  (128x128: the 128 new relative positions this step needs; the other
 //                                           128 are the previous step's chunk, kept in a 2-slot TMEM ring)
-//     O  += P . V_j                        (128xD)
-// The per-row shift of the position term cannot be expressed by tcgen05.ld (lanes share the column address), so each
-// softmax warp pulls the 64-column window its 32 rows need, stages it in shared memory and reads it back at a
-// lane-dependent offset. Softmax is online (fp32, exp2 with folded scale, lazy rescale of O), no mask tensor exists:
+//     O  += P . V_j                        (128xD)            [mode 0]   /   dP = dO . V_j^T   [mode 2]
+// The per-row shift of the position term cannot be expressed by tcgen05.ld (lanes share the column address): each
+// softmax thread loads the two 32-column blocks its row needs and runs a 5-stage barrel shifter on registers
+// (shift = 31 - lane). Softmax is online (fp32, exp2 with folded scale, lazy rescale of O), no mask tensor exists:
 // the causal / sliding-window predicate is computed from indices.
 //
-// Roles: warp 0 = TMA producer, warp 1 = MMA issuer (one elected thread), warps 2..5 = softmax (one query row per thread).
+// Roles (320 threads): warp 0 = TMA producer, warp 1 = MMA issuer (one elected thread), warps 2..9 = softmax (two per
+// TMEM lane quadrant; a thread owns one query row x half of the 128-key tile).
 //
-// mode 0: writes O [B*L, ldo] fp16 and LSE2 [B,H,L] fp32 (log2 domain).
-// mode 1: reads LSE2 and writes the normalised probabilities P [B,H,L,L] fp16 (recompute for the backward pass).
+// MODE (template parameter):
+//   0: writes O [B*L, ldo] fp16 and LSE2 [B,H,L] fp32 (log2 domain).
+//   1: reads LSE2 and writes the normalised probabilities P [B,H,L,L] fp16 (recompute for the backward pass).
+//   2: as 1, plus dP = dO . V^T on the tensor cores and dS = P * (dP - D) * scale (D given, or formed here from dO and O).
 #include "../../include/db1_sm100.h"
 #include "common.cuh"
 #include "ptx.cuh"
