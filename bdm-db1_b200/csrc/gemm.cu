@@ -748,6 +748,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
           int nch = (e_N - colh + 31) / 32;         // chunks of this half that hold valid columns (ragged N)
           nch = nch < 0 ? 0 : (nch > CPW ? CPW : nch);
           if (p.dbg & 2) nch = 0;
+          const int nch_arm = (p.dbg & 64) ? 0 : nch;
           // leader: make buffer seq % NB ready for chunk `seq` (its previous user, chunk seq - NB, has been stored:
           // callers keep at most ONE store group pending before arming)
           auto arm = [&](unsigned int seq, int col0) {
@@ -759,7 +760,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
               mbar_arrive(&ebh[b]);
             }
           };
-          if (eleader && nch > 0) {  // under the tail of this tile's main loop: the first NB - 1 chunks
+          if (eleader && nch_arm > 0) {  // under the tail of this tile's main loop: the first NB - 1 chunks
             bulk_wait_group_read<1>();
             for (int k = 0; k < nch && k < NB - 1; ++k) arm(eseq + k, colh + k * 32);
           }
@@ -768,12 +769,23 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
           if (tl && ew == 0 && lane == 0 && it <= 15) tl[4 + 4 * (it - 1) + 2] = clock64();
           uint32_t r[2][32];
           float dacc = 0.f;
-          if (nch > 0) tmem_ld32(tacc + c_first * 32, r[0]);
+          if (p.dbg & 32) {
+#pragma unroll
+            for (int k = 0; k < 32; ++k) r[0][k] = r[1][k] = 0u;
+          }
+          if (p.dbg & 64) {  // experiment: TMEM loads only
+            for (int ci = 0; ci < nch; ++ci) {
+              tmem_ld32(tacc + (c_first + ci) * 32, r[0]);
+              tmem_ld_wait();
+            }
+            nch = 0;
+          }
+          if (nch > 0 && !(p.dbg & 32)) tmem_ld32(tacc + c_first * 32, r[0]);
 #pragma unroll
           for (int ci = 0; ci < CPW; ++ci) {
             if (ci < nch) {
               tmem_ld_wait();
-              if (ci + 1 < nch) tmem_ld32(tacc + (c_first + ci + 1) * 32, r[(ci + 1) & 1]);
+              if (ci + 1 < nch && !(p.dbg & 32)) tmem_ld32(tacc + (c_first + ci + 1) * 32, r[(ci + 1) & 1]);
               const int col0 = colh + ci * 32;
               const unsigned int b = eseq & (NB - 1);
               mbar_wait(&ebh[b], (eseq / NB) & 1u);
@@ -1290,10 +1302,12 @@ static int launch_gemm(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUt
   const bool batched = p.Z1 * p.Z2 > 1;
   if (BN == 256 && EPI != DB1_EPI_DS && !batched && p.k_mode == DB1_K_FULL && !p.skip_upper && p.M > BM &&
       ((EPI != DB1_EPI_PLAIN && EPI != DB1_EPI_DGEGLU) || tma_epilogue_ok(p, EPI)) && !getenv("DB1_GEMM_NO_CLUSTER")) {
-    constexpr bool HAS4 = (BN == 256 && EPI == DB1_EPI_PLAIN);
+    constexpr bool HAS4 = (BN == 256 && (EPI == DB1_EPI_PLAIN || EPI == DB1_EPI_DGEGLU));
     if (HAS4 && p.M > 3 * BM) {
       const char* e = getenv("DB1_GEMM_CL");
-      const int want = e ? atoi(e) : 2;  // opt-in: measured equal to CTA pairs (33 clusters = 132 of 148 SMs)
+      // opt-in: measured equal to CTA pairs for both epilogues (33 clusters = 132 of 148 SMs; multicast saves L2 reads,
+      // not the bytes each SM receives - and the SM's inbound port is what the main loop saturates)
+      const int want = e ? atoi(e) : 2;
       const int nc = max_clusters4<BN, HAS4 ? EPI : DB1_EPI_PLAIN>();
       if (want == 4 && nc >= 30)
         return launch_gemm_cl<BN, EPI, HAS4 ? 4 : 2>(tmA, tmB, tmB64, p, stream, nc);
