@@ -1,0 +1,606 @@
+// Attention backward, second half: everything that consumes dS = P * (dP - D) * scale (written once, fp16, by the
+// recompute kernel) on tcgen05 tensor cores, without ever materialising the relative-position re-layout of dS.
+//
+//   dq_i  = sum_j dS[i,j] k_j  +  sum_j dS[i,j] r[j + L-1-i]          (adjoint of transformer_xl.py:161-171 w.r.t. q)
+//   du_h  = sum_{b,i} (dS K)_i ,   dv_h = sum_{b,i} (skew^-1(dS) R)_i   (shared biases r_w_bias / r_r_bias)
+//   dR[c] = sum_{b,(i,j): j+L-1-i = c} dS[i,j] (q_i + v)                (adjoint of _rel_shift :98-110 and of :167)
+//
+// The per-row shift ("un-shift", the adjoint of _rel_shift) is done on registers by the thread that owns the row: it
+// reads its 128 dS values of the tile straight from global memory, shifts them right by 127 - r elements inside a
+// 256-wide zero-padded row (8-element chunks by address arithmetic, words by two select stages, the odd half by a
+// funnel shift) and stores the result as two K-major 128x128 fp16 tiles ("band" tiles: columns = relative positions
+// of the chunk of r this tile pairs with, `new` = positions [cb, cb+128), `prev` = [cb+128, cb+256)) in the 128-byte
+// swizzled layout tcgen05.mma reads. No dSr matrix, no rel_unshift pass, no P / dSr re-reads.
+//
+// Two persistent kernels share the code (template KIND), both with accumulators resident in TMEM:
+//   KIND 0 (query-outer, item = (query tile, head, sequence)): dQu += dS . K_J, dQv += band . R_window per key tile;
+//           epilogue writes dq = dQu + dQv (fp16) and adds the column sums to du / dv.
+//   KIND 1 (diagonal-outer, item = (tile diagonal t, head, pair of sequences)): dR_new += band_new^T . Qv_I,
+//           dR_prev += band_prev^T . Qv_I over all tiles of the diagonal; one fp32 reduction per item. (Reducing dR
+//           per key step costs a 64 KB fp32 reduction per step: measured 6.3k cycles with red.v4, 3.0k with
+//           cp.reduce.async.bulk when all SMs do it - as long as the whole step. tools/ubench_red.cu.)
+// Roles (320 threads): warp 0 TMA producer, warp 1 MMA issuer, warps 2-5 un-shift (thread = tile row), warps 6-9 TMEM
+// drain (epilogue / dR reduction; accumulators are double-buffered so it overlaps the next item).
+#include "../../include/db1_sm100.h"
+#include "common.cuh"
+#include "ptx.cuh"
+
+namespace db1 {
+
+constexpr int BW_THREADS = 320;
+
+struct BandParams {
+  int L, H, B, dh, window;
+  const __half* dS;  // [B,H,L,L] fp16, visited (causal, in-window) tiles valid, masked entries exactly 0
+  __half* dq;        // KIND 0: [B*L, lddq], head h at column h*dh
+  long long lddq;
+  float* du;         // KIND 0: [H*dh] fp32, accumulated
+  float* dv;
+  float* dR;         // KIND 1: [L, lddr] fp32, accumulated (row c <-> r row c)
+  long long lddr;
+};
+
+template <int D, int KIND>
+struct BandSmem {
+  static constexpr int TILE = 128 * D * 2;  // one [128][D] fp16 operand tile (D/64 slabs of [128][64])
+  // KIND 0
+  static constexpr int DS = 0;                   // [128][128] fp16 K-major (2 slabs)
+  static constexpr int BAND = 32768;             // [128][256] fp16 K-major (4 slabs): new = slabs 0,1, prev = 2,3
+  static constexpr int KT = BAND + 65536;        // K_J tile
+  static constexpr int RR = KT + TILE;           // 2-slot ring of 128-row chunks of r
+  // KIND 1
+  static constexpr int BAND2 = 0;                // 2 x 64 KB
+  static constexpr int QV2 = 131072;             // 2 x TILE
+  static constexpr int BARS = (KIND == 0) ? (RR + 2 * TILE) : (QV2 + 2 * TILE);
+  static constexpr int TOTAL = BARS + 256;
+};
+
+// ---- the un-shift of one tile row on registers ------------------------------------------------------------------
+// W[64]: the row's 128 fp16 values (word m = elements 2m, 2m+1). out[c][0..3] (c = 0..16): the 16-byte chunks of the
+// row shifted right by rem = (127 - r) & 7 elements; chunk c belongs at chunk position ((127 - r) >> 3) + c of the
+// 32-chunk (256-element) band row.
+DEVI void unshift_row(const uint32_t (&W)[64], int rem, uint32_t (&out)[17][4]) {
+  const uint32_t sb = (uint32_t)(rem & 1) * 16u;
+  const bool w2 = rem & 4, w1 = rem & 2;
+  // X(m) = elements [2m - (rem&1), +2) of the row, m in [0, 64]; zero outside
+  uint32_t X[65];
+#pragma unroll
+  for (int m = 0; m < 65; ++m) {
+    const uint32_t lo = (m >= 1) ? W[m - 1] : 0u;
+    const uint32_t hi = (m < 64) ? W[m] : 0u;
+    X[m] = __funnelshift_l(lo, hi, sb);
+  }
+  // T(m) = X(m - 2*w2), m in [-1, 67];  Y(m) = T(m - w1), m in [0, 68)
+  uint32_t T[69];  // T[m + 1]
+#pragma unroll
+  for (int m = -1; m < 68; ++m) {
+    const uint32_t x0 = (m >= 0 && m <= 64) ? X[m] : 0u;
+    const uint32_t x2 = (m - 2 >= 0 && m - 2 <= 64) ? X[m - 2] : 0u;
+    T[m + 1] = w2 ? x2 : x0;
+  }
+#pragma unroll
+  for (int c = 0; c < 17; ++c) {
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const int m = 4 * c + j;
+      out[c][j] = w1 ? T[m] : T[m + 1];  // T(m - 1) : T(m)
+    }
+  }
+}
+
+DEVI void sts128(uint32_t saddr, uint32_t a, uint32_t b, uint32_t c, uint32_t d) {
+  asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(saddr), "r"(a), "r"(b), "r"(c), "r"(d) : "memory");
+}
+DEVI void red_add_v4(float* p, float a, float b, float c, float d) {
+  asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(p), "f"(a), "f"(b), "f"(c), "f"(d) : "memory");
+}
+
+// band chunk positions [16*part, 16*part + 16) of row r: data chunks out[c] at position a + c, zeros elsewhere
+DEVI void store_band_half(uint32_t band_base, int r, int a, int part, const uint32_t (&out)[17][4]) {
+  const uint32_t rowb = band_base + (uint32_t)r * 128u;
+  const int rx = r & 7;
+#pragma unroll
+  for (int c = 0; c < 17; ++c) {
+    const int pos = a + c;
+    if ((pos >> 4) == part)
+      sts128(rowb + (uint32_t)(pos >> 3) * 16384u + (uint32_t)(((pos & 7) ^ rx) * 16), out[c][0], out[c][1], out[c][2],
+             out[c][3]);
+  }
+#pragma unroll
+  for (int q = 0; q < 16; ++q) {
+    const int pos = part * 16 + q;
+    if (pos < a || pos > a + 16) sts128(rowb + (uint32_t)(pos >> 3) * 16384u + (uint32_t)(((pos & 7) ^ rx) * 16), 0u, 0u, 0u, 0u);
+  }
+}
+
+// lane l ends with the sum over the warp's 32 lanes of v[l]
+DEVI float warp_colsum32(float (&v)[32], int lane) {
+#pragma unroll
+  for (int off = 16; off >= 1; off >>= 1) {
+    const bool up = lane & off;
+#pragma unroll
+    for (int k = 0; k < off; ++k) {
+      const float send = up ? v[k] : v[k + off];
+      const float keep = up ? v[k + off] : v[k];
+      v[k] = keep + __shfl_xor_sync(0xffffffffu, send, off);
+    }
+  }
+  return v[0];
+}
+
+template <int D, int KIND>
+__global__ void __launch_bounds__(BW_THREADS, 1)
+relattn_bwd_band_kernel(const __grid_constant__ CUtensorMap tmK, const __grid_constant__ CUtensorMap tmR,
+                        const __grid_constant__ CUtensorMap tmQv, const BandParams p) {
+  using SM = BandSmem<D, KIND>;
+  constexpr int NSLAB = D / 64;
+  constexpr int TILE = SM::TILE;
+  extern __shared__ __align__(1024) uint8_t smem[];
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + SM::BARS);
+  // KIND 0: per-step barriers (one phase per global step)      KIND 1: per-buffer barriers (one phase per two steps)
+  uint64_t* bar_k = bars + 0;        //  K_J landed                        bar_qv[2] = bars + 0, 1
+  uint64_t* bar_r = bars + 1;        //  r chunk landed
+  uint64_t* full_ds = bars + 2;      //  un-shift warps -> MMA             full[2] = bars + 2, 3
+  uint64_t* full_prev = bars + 3;
+  uint64_t* full_new = bars + 4;
+  uint64_t* free_ds = bars + 5;      //  MMA commit -> un-shift / TMA      free[2] = bars + 5, 6
+  uint64_t* free_prev = bars + 6;
+  uint64_t* free_new = bars + 7;
+  uint64_t* acc_full = bars + 8;     //  [2] accumulator set complete (commit)
+  uint64_t* acc_free = bars + 10;    //  [2] drained (4 warps)
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 12);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const int nq = (p.L + 127) / 128;
+  const int Wt = (p.window - 1 + 127) / 128;            // largest tile diagonal that holds an unmasked pair
+  const int nT = (nq - 1 < Wt ? nq - 1 : Wt) + 1;       // number of tile diagonals
+  const int HB = p.H * p.B;
+  const int nbp = (p.B + 1) / 2;
+  const int n_items = (KIND == 0) ? nq * HB : nT * p.H * nbp;
+  const int G = gridDim.x;
+  auto item_of = [&](int pass) -> int {
+    const int c = (pass & 1) ? (G - 1 - (int)blockIdx.x) : (int)blockIdx.x;
+    const int k = pass * G + c;
+    return k < n_items ? k : -1;
+  };
+  const int n_pass = (n_items + G - 1) / G;
+  // KIND 0: (I, h, b), steps st = 0..nsteps-1 over key tiles J = I - st.
+  // KIND 1: (t, h, b0, nb), steps over (b, I): tile (I, J = I - t), I = t..nq-1.
+  struct Item {
+    int I, t, h, b, nb, nsteps;
+  };
+  auto decode = [&](int k) -> Item {
+    Item it;
+    if (KIND == 0) {
+      it.I = nq - 1 - k / HB;
+      const int hb = k % HB;
+      it.h = hb % p.H;
+      it.b = hb / p.H;
+      it.t = 0;
+      it.nb = 1;
+      it.nsteps = (it.I < Wt ? it.I : Wt) + 1;
+    } else {
+      it.t = k / (p.H * nbp);
+      const int rest = k % (p.H * nbp);
+      it.h = rest % p.H;
+      it.b = (rest / p.H) * 2;
+      it.nb = (p.B - it.b) < 2 ? (p.B - it.b) : 2;
+      it.I = it.t;
+      it.nsteps = it.nb * (nq - it.t);
+    }
+    return it;
+  };
+
+  if ((smem_u32(smem) & 1023u) != 0) __trap();
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&tmK);
+    tma_prefetch_desc(&tmR);
+    tma_prefetch_desc(&tmQv);
+  }
+  if (warp == 1) {
+    if (lane == 0) {
+      if (KIND == 0) {
+        mbar_init(bar_k, 1);
+        mbar_init(bar_r, 1);
+        mbar_init(full_ds, 4);
+        mbar_init(full_prev, 4);
+        mbar_init(full_new, 4);
+        mbar_init(free_ds, 1);
+        mbar_init(free_prev, 1);
+        mbar_init(free_new, 1);
+      } else {
+        mbar_init(bars + 0, 1);
+        mbar_init(bars + 1, 1);
+        mbar_init(bars + 2, 4);
+        mbar_init(bars + 3, 4);
+        mbar_init(bars + 5, 1);
+        mbar_init(bars + 6, 1);
+      }
+      mbar_init(acc_full + 0, 1);
+      mbar_init(acc_full + 1, 1);
+      mbar_init(acc_free + 0, 4);
+      mbar_init(acc_free + 1, 4);
+      mbar_fence_init();
+    }
+    __syncwarp();
+    tmem_alloc<512>(tmem_slot);
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+  pdl_launch_dependents();
+  pdl_wait();
+
+  if (warp == 0) {
+    // ------------------------------------------------------------------ TMA producer
+    if (lane == 0) {
+      int gs = 0;
+      for (int pass = 0; pass < n_pass; ++pass) {
+        const int k = item_of(pass);
+        if (k < 0) continue;
+        const Item it = decode(k);
+        for (int st = 0; st < it.nsteps; ++st, ++gs) {
+          if (KIND == 0) {
+            const int J0 = (it.I - st) * 128;
+            const int cb = p.L - 128 - 128 * st;  // first r row of this step's new chunk
+            if (gs > 0) mbar_wait(free_ds, (gs - 1) & 1);
+            mbar_expect_tx(bar_k, TILE);
+#pragma unroll
+            for (int s = 0; s < NSLAB; ++s) tma_load_4d(smem + SM::KT + s * 16384, &tmK, bar_k, s * 64, J0, it.h, it.b);
+            if (gs > 0) mbar_wait(free_prev, (gs - 1) & 1);  // the slot's previous chunk was last read by step gs-1
+            mbar_expect_tx(bar_r, TILE);
+#pragma unroll
+            for (int s = 0; s < NSLAB; ++s)
+              tma_load_4d(smem + SM::RR + (gs & 1) * TILE + s * 16384, &tmR, bar_r, s * 64, cb, it.h, 0);
+          } else {
+            const int per = nq - it.t;
+            const int b = it.b + st / per;
+            const int I0 = (it.t + st % per) * 128;
+            const int buf = gs & 1;
+            if (gs >= 2) mbar_wait(bars + 5 + buf, ((gs >> 1) - 1) & 1);
+            mbar_expect_tx(bars + 0 + buf, TILE);
+#pragma unroll
+            for (int s = 0; s < NSLAB; ++s)
+              tma_load_4d(smem + SM::QV2 + buf * TILE + s * 16384, &tmQv, bars + 0 + buf, s * 64, I0, it.h, b);
+          }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ------------------------------------------------------------------ MMA issuer
+    if (lane == 0) {
+      const uint32_t idesc_q = umma_idesc(128, D, 0, 1, 0);  // A K-major (dS / band), B MN-major (K_J / r chunk)
+      const uint32_t idesc_r = umma_idesc(128, D, 1, 1, 0);  // A MN-major (band^T), B MN-major (Qv_I)
+      int gs = 0, ti = 0;
+      for (int pass = 0; pass < n_pass; ++pass) {
+        const int k = item_of(pass);
+        if (k < 0) continue;
+        const Item it = decode(k);
+        const int as = ti & 1;
+        const uint32_t T0 = tmem_base + as * (2 * D);  // dQu | dR_new
+        const uint32_t T1 = T0 + D;                    // dQv | dR_prev
+        for (int st = 0; st < it.nsteps; ++st, ++gs) {
+          if (KIND == 0) {
+            const uint32_t ds = smem_u32(smem + SM::DS), band = smem_u32(smem + SM::BAND), kt = smem_u32(smem + SM::KT);
+            const uint32_t r_new = smem_u32(smem + SM::RR + (gs & 1) * TILE);
+            const uint32_t r_prev = smem_u32(smem + SM::RR + ((gs + 1) & 1) * TILE);
+            // G1: dQu += dS . K_J
+            mbar_wait(bar_k, gs & 1);
+            mbar_wait(full_ds, gs & 1);
+            if (st == 0 && ti >= 2) mbar_wait(acc_free + as, ((ti >> 1) - 1) & 1);
+            tc_fence_after();
+#pragma unroll
+            for (int kk = 0; kk < 8; ++kk)
+              umma_ss(T0, umma_smem_desc(ds + (kk >> 2) * 16384 + (kk & 3) * 32, 16, 1024),
+                      umma_smem_desc(kt + kk * 2048, 16384, 1024), idesc_q, (st | kk) ? 1u : 0u);
+            umma_commit(free_ds);
+            // G2: dQv += band_prev . r[cb+128 .. cb+256)   (nothing on the diagonal tile: its upper triangle is masked)
+            if (st > 0) {
+              mbar_wait(full_prev, gs & 1);
+              tc_fence_after();
+#pragma unroll
+              for (int kk = 0; kk < 8; ++kk)
+                umma_ss(T1, umma_smem_desc(band + (2 + (kk >> 2)) * 16384 + (kk & 3) * 32, 16, 1024),
+                        umma_smem_desc(r_prev + kk * 2048, 16384, 1024), idesc_q, 1u);
+            }
+            umma_commit(free_prev);
+            // G3: dQv += band_new . r[cb .. cb+128)
+            mbar_wait(bar_r, gs & 1);
+            mbar_wait(full_new, gs & 1);
+            tc_fence_after();
+#pragma unroll
+            for (int kk = 0; kk < 8; ++kk)
+              umma_ss(T1, umma_smem_desc(band + (kk >> 2) * 16384 + (kk & 3) * 32, 16, 1024),
+                      umma_smem_desc(r_new + kk * 2048, 16384, 1024), idesc_q, (st | kk) ? 1u : 0u);
+            umma_commit(free_new);
+          } else {
+            const int buf = gs & 1;
+            const uint32_t band = smem_u32(smem + SM::BAND2 + buf * 65536);
+            const uint32_t qv = smem_u32(smem + SM::QV2 + buf * TILE);
+            mbar_wait(bars + 0 + buf, (gs >> 1) & 1);
+            mbar_wait(bars + 2 + buf, (gs >> 1) & 1);
+            if (st == 0 && ti >= 2) mbar_wait(acc_free + as, ((ti >> 1) - 1) & 1);
+            tc_fence_after();
+#pragma unroll
+            for (int kk = 0; kk < 8; ++kk)
+              umma_ss(T0, umma_smem_desc(band + kk * 2048, 16384, 1024), umma_smem_desc(qv + kk * 2048, 16384, 1024),
+                      idesc_r, (st | kk) ? 1u : 0u);
+            if (it.t > 0) {
+#pragma unroll
+              for (int kk = 0; kk < 8; ++kk)
+                umma_ss(T1, umma_smem_desc(band + 2 * 16384 + kk * 2048, 16384, 1024),
+                        umma_smem_desc(qv + kk * 2048, 16384, 1024), idesc_r, (st | kk) ? 1u : 0u);
+            }
+            umma_commit(bars + 5 + buf);
+          }
+        }
+        umma_commit(acc_full + as);
+        ++ti;
+      }
+    }
+  } else if (warp < 6) {
+    // ------------------------------------------------------------------ un-shift warps: thread = tile row
+    const int r = (warp - 2) * 32 + lane;
+    const int sft = 127 - r;
+    const int a = sft >> 3, rem = sft & 7;
+    const int rx = r & 7;
+    uint32_t W[64];
+    auto load_row = [&](const Item& it, int st) {
+      int I0, J0, b;
+      if (KIND == 0) {
+        I0 = it.I * 128;
+        J0 = (it.I - st) * 128;
+        b = it.b;
+      } else {
+        const int per = nq - it.t;
+        b = it.b + st / per;
+        I0 = (it.t + st % per) * 128;
+        J0 = I0 - it.t * 128;
+      }
+      const int i = I0 + r;
+      int nv = p.L - J0;
+      nv = (i < p.L) ? (nv > 128 ? 128 : nv) : 0;
+      const __half* rowp = p.dS + (((long long)b * p.H + it.h) * p.L + i) * (long long)p.L + J0;
+      const bool al32 = ((reinterpret_cast<uintptr_t>(rowp)) & 31) == 0;
+#pragma unroll
+      for (int q = 0; q < 4; ++q) {
+        int n = nv - 32 * q;
+        n = n < 0 ? 0 : (n > 32 ? 32 : n);
+        ldg_row32(rowp + 32 * q, reinterpret_cast<uint32_t(&)[16]>(W[16 * q]), n, al32);
+      }
+    };
+    // flat walk over (item, step) with one step of look-ahead: the next step's row (also across an item boundary) is
+    // fetched right after this step's registers are free, so its latency runs under the stores and the MMAs
+    struct Cursor {
+      int pass, st;
+      Item it;
+      bool valid;
+    };
+    auto advance = [&](Cursor& c) {
+      if (c.valid && c.st + 1 < c.it.nsteps) {
+        ++c.st;
+        return;
+      }
+      for (int ps = c.valid ? c.pass + 1 : 0; ps < n_pass; ++ps) {
+        const int k = item_of(ps);
+        if (k >= 0) {
+          c.pass = ps;
+          c.it = decode(k);
+          c.st = 0;
+          c.valid = true;
+          return;
+        }
+      }
+      c.valid = false;
+    };
+    Cursor cur;
+    cur.valid = false;
+    cur.pass = 0;
+    cur.st = 0;
+    advance(cur);
+    if (cur.valid) load_row(cur.it, cur.st);
+    for (int gs = 0; cur.valid; ++gs) {
+      const Item it = cur.it;
+      const int st = cur.st;
+      uint32_t out[17][4];
+      unshift_row(W, rem, out);
+      const bool with_prev = (KIND == 0) ? (st > 0) : (it.t > 0);
+      if (KIND == 0) {
+        if (gs > 0) mbar_wait(free_ds, (gs - 1) & 1);
+        const uint32_t dsrow = smem_u32(smem + SM::DS) + (uint32_t)r * 128u;
+#pragma unroll
+        for (int c = 0; c < 16; ++c)
+          sts128(dsrow + (uint32_t)(c >> 3) * 16384u + (uint32_t)(((c & 7) ^ rx) * 16), W[4 * c], W[4 * c + 1], W[4 * c + 2],
+                 W[4 * c + 3]);
+        fence_proxy_async_smem();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(full_ds);
+      }
+      advance(cur);
+      if (cur.valid) load_row(cur.it, cur.st);
+      if (KIND == 0) {
+        const uint32_t band = smem_u32(smem + SM::BAND);
+        if (gs > 0) mbar_wait(free_prev, (gs - 1) & 1);
+        if (with_prev) store_band_half(band, r, a, 1, out);
+        fence_proxy_async_smem();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(full_prev);
+        if (gs > 0) mbar_wait(free_new, (gs - 1) & 1);
+        store_band_half(band, r, a, 0, out);
+        fence_proxy_async_smem();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(full_new);
+      } else {
+        const int buf = gs & 1;
+        const uint32_t band = smem_u32(smem + SM::BAND2 + buf * 65536);
+        if (gs >= 2) mbar_wait(bars + 5 + buf, ((gs >> 1) - 1) & 1);
+        if (with_prev) store_band_half(band, r, a, 1, out);
+        store_band_half(band, r, a, 0, out);
+        fence_proxy_async_smem();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(bars + 2 + buf);
+      }
+    }
+  } else {
+    // ------------------------------------------------------------------ TMEM drain warps (one per lane quadrant)
+    const int q = warp & 3;
+    const int row = q * 32 + lane;
+    const uint32_t lane_off = (uint32_t)(q * 32) << 16;
+    int ti = 0;
+    for (int pass = 0; pass < n_pass; ++pass) {
+      const int k = item_of(pass);
+      if (k < 0) continue;
+      const Item it = decode(k);
+      const int as = ti & 1;
+      const uint32_t T0 = tmem_base + as * (2 * D) + lane_off;
+      const uint32_t T1 = T0 + D;
+      mbar_wait_backoff(acc_full + as, (ti >> 1) & 1, 64);
+      tc_fence_after();
+      if (KIND == 0) {
+        const int i = it.I * 128 + row;
+        __half* qrow = p.dq + ((long long)it.b * p.L + i) * p.lddq + (long long)it.h * p.dh;
+        const bool al32 = ((reinterpret_cast<uintptr_t>(qrow)) & 31) == 0;
+#pragma unroll 1
+        for (int c = 0; c < D / 32; ++c) {
+          uint32_t xu[32], xv[32];
+          tmem_ld32(T0 + c * 32, xu);
+          tmem_ld32(T1 + c * 32, xv);
+          tmem_ld_wait();
+          int n = p.dh - c * 32;
+          n = n < 0 ? 0 : (n > 32 ? 32 : n);
+          if (i < p.L && n > 0) {
+            uint32_t pk[16];
+#pragma unroll
+            for (int e = 0; e < 16; ++e)
+              pk[e] = pack_half2(__uint_as_float(xu[2 * e]) + __uint_as_float(xv[2 * e]),
+                                 __uint_as_float(xu[2 * e + 1]) + __uint_as_float(xv[2 * e + 1]));
+            stg_row32(qrow + c * 32, pk, n, al32);
+          }
+          float fu[32], fv[32];
+#pragma unroll
+          for (int e = 0; e < 32; ++e) {
+            fu[e] = __uint_as_float(xu[e]);
+            fv[e] = __uint_as_float(xv[e]);
+          }
+          const float su = warp_colsum32(fu, lane);
+          const float sv = warp_colsum32(fv, lane);
+          if (c * 32 + lane < p.dh) {
+            atomicAdd(p.du + it.h * p.dh + c * 32 + lane, su);
+            atomicAdd(p.dv + it.h * p.dh + c * 32 + lane, sv);
+          }
+        }
+      } else {
+        const int cb = p.L - 128 - 128 * it.t;
+#pragma unroll 1
+        for (int part = 0; part < 2; ++part) {
+          if (part == 1 && it.t == 0) break;
+          const int crow = cb + part * 128 + row;
+          float* drow = p.dR + (long long)crow * p.lddr + (long long)it.h * p.dh;
+#pragma unroll 1
+          for (int c = 0; c < D / 32; ++c) {
+            uint32_t x[32];
+            tmem_ld32((part ? T1 : T0) + c * 32, x);
+            tmem_ld_wait();
+            if (crow >= 0 && crow < p.L) {
+#pragma unroll
+              for (int g = 0; g < 8; ++g)
+                if (c * 32 + g * 4 < p.dh)
+                  red_add_v4(drow + c * 32 + g * 4, __uint_as_float(x[4 * g]), __uint_as_float(x[4 * g + 1]),
+                             __uint_as_float(x[4 * g + 2]), __uint_as_float(x[4 * g + 3]));
+            }
+          }
+        }
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(acc_free + as);
+      ++ti;
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc<512>(tmem_base);
+  }
+}
+
+static int make_head_map_bw(CUtensorMap* tm, const void* base, int dh, int L, int H, int B, long long ld) {
+  uint64_t dims[4] = {(uint64_t)dh, (uint64_t)L, (uint64_t)H, (uint64_t)(B > 0 ? B : 1)};
+  uint64_t str[3] = {(uint64_t)ld * 2, (uint64_t)dh * 2, (uint64_t)L * (uint64_t)ld * 2};
+  uint32_t box[4] = {64, 128, 1, 1};
+  return make_tmap_f16(tm, base, 4, dims, str, box);
+}
+
+template <int D, int KIND>
+static int launch_band(const CUtensorMap* tm, const BandParams& p, cudaStream_t stream) {
+  using SM = BandSmem<D, KIND>;
+  static bool configured = false;
+  if (!configured) {
+    DB1_CUDA(cudaFuncSetAttribute(relattn_bwd_band_kernel<D, KIND>, cudaFuncAttributeMaxDynamicSharedMemorySize, SM::TOTAL));
+    configured = true;
+  }
+  const int nq = (p.L + 127) / 128;
+  const int Wt = (p.window - 1 + 127) / 128;
+  const int nT = (nq - 1 < Wt ? nq - 1 : Wt) + 1;
+  const int n_items = (KIND == 0) ? nq * p.H * p.B : nT * p.H * ((p.B + 1) / 2);
+  const int grid = n_items < sm_count() ? n_items : sm_count();
+  DB1_CUDA(launch_pdl(relattn_bwd_band_kernel<D, KIND>, dim3(grid), dim3(BW_THREADS), SM::TOTAL, stream, 1, tm[0], tm[1],
+                      tm[2], p));
+  return 0;
+}
+
+}  // namespace db1
+
+using namespace db1;
+
+static int band_common_checks(const void* ds, int B, int L, int H, int dh, int window, long long ld_qkv, long long ld_r) {
+  DB1_CHECK_ARG(ds != nullptr, "relattn_bwd: null dS");
+  DB1_CHECK_ARG(B > 0 && L > 0 && H > 0, "relattn_bwd: bad shape B=%d L=%d H=%d", B, L, H);
+  DB1_CHECK_ARG(dh % 8 == 0 && dh >= 8 && dh <= 128, "relattn_bwd: head dim %d unsupported (multiple of 8, <= 128)", dh);
+  DB1_CHECK_ARG(L % 8 == 0, "relattn_bwd: sequence length %d must be a multiple of 8", L);
+  DB1_CHECK_ARG(window > 0, "relattn_bwd: window must be > 0");
+  DB1_CHECK_ARG(ld_qkv % 8 == 0 && ld_r % 8 == 0, "relattn_bwd: row strides must be multiples of 8");
+  DB1_CHECK_ARG((reinterpret_cast<uintptr_t>(ds) & 15) == 0, "relattn_bwd: dS must be 16-byte aligned");
+  return 0;
+}
+
+extern "C" int db1_relattn_bwd_dq(const void* ds, const void* k, long long ld_qkv, const void* r, long long ld_r,
+                                  void* dq, long long ld_dq, float* du, float* dv, int B, int L, int H, int dh,
+                                  int window, void* stream_) {
+  int e = band_common_checks(ds, B, L, H, dh, window, ld_qkv, ld_r);
+  if (e) return e;
+  DB1_CHECK_ARG(k && r && dq && du && dv, "relattn_bwd_dq: null pointer");
+  DB1_CHECK_ARG(ld_dq % 8 == 0 && (reinterpret_cast<uintptr_t>(dq) & 15) == 0, "relattn_bwd_dq: dq rows must be 16-byte aligned");
+  BandParams p;
+  memset(&p, 0, sizeof(p));
+  p.L = L; p.H = H; p.B = B; p.dh = dh; p.window = window;
+  p.dS = (const __half*)ds; p.dq = (__half*)dq; p.lddq = ld_dq; p.du = du; p.dv = dv;
+  CUtensorMap tm[3];
+  if ((e = make_head_map_bw(&tm[0], k, dh, L, H, B, ld_qkv))) return e;
+  if ((e = make_head_map_bw(&tm[1], r, dh, L, H, 1, ld_r))) return e;
+  tm[2] = tm[0];
+  if (dh <= 64) return launch_band<64, 0>(tm, p, (cudaStream_t)stream_);
+  return launch_band<128, 0>(tm, p, (cudaStream_t)stream_);
+}
+
+extern "C" int db1_relattn_bwd_dr(const void* ds, const void* qv, long long ld_qkv, float* dr, long long ld_dr, int B,
+                                  int L, int H, int dh, int window, void* stream_) {
+  int e = band_common_checks(ds, B, L, H, dh, window, ld_qkv, 8);
+  if (e) return e;
+  DB1_CHECK_ARG(qv && dr, "relattn_bwd_dr: null pointer");
+  DB1_CHECK_ARG(ld_dr % 4 == 0 && (reinterpret_cast<uintptr_t>(dr) & 15) == 0, "relattn_bwd_dr: dR rows must be 16-byte aligned");
+  BandParams p;
+  memset(&p, 0, sizeof(p));
+  p.L = L; p.H = H; p.B = B; p.dh = dh; p.window = window;
+  p.dS = (const __half*)ds; p.dR = dr; p.lddr = ld_dr;
+  CUtensorMap tm[3];
+  if ((e = make_head_map_bw(&tm[2], qv, dh, L, H, B, ld_qkv))) return e;
+  tm[0] = tm[2];
+  tm[1] = tm[2];
+  if (dh <= 64) return launch_band<64, 1>(tm, p, (cudaStream_t)stream_);
+  return launch_band<128, 1>(tm, p, (cudaStream_t)stream_);
+}

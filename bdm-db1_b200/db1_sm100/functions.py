@@ -14,15 +14,26 @@ _ws_lock = threading.Lock()
 _ws = {}
 
 
-def _workspace(key, shape, dtype, device, zero=True):
-    """Process-wide cached scratch (attention-backward score buffers, dlogits). Zero-filled once at creation: the kernels
-    rely on never-written regions (above-diagonal tiles) staying zero, and the write pattern depends only on the shape."""
-    k = (key, tuple(shape), dtype, device.index)
+def _workspace(key, shape, dtype, device, zero=True, tag=None):
+    """Process-wide cached scratch (attention-backward score buffers, dlogits). Zero-filled at creation: the causal
+    GEMMs read whole 128-row blocks, so tiles the recompute kernel does not visit (above the diagonal, outside the
+    attention window) must stay zero. The set of visited tiles depends on the shape AND on `tag` (the window): a buffer
+    reused under another tag is zero-filled again. At most one buffer per (key, device) is kept, so a change of shape
+    frees the old one instead of pinning 3*B*H*L*L*2 bytes per distinct (B, L) for the life of the process."""
+    k = (key, device.index)
     with _ws_lock:
-        t = _ws.get(k)
-        if t is None:
+        ent = _ws.get(k)
+        if ent is not None and (ent[0].shape != tuple(shape) or ent[0].dtype != dtype):
+            ent = None
+        if ent is None:
             t = torch.zeros(shape, dtype=dtype, device=device) if zero else torch.empty(shape, dtype=dtype, device=device)
-            _ws[k] = t
+            _ws[k] = (t, tag)
+            return t
+        t, old_tag = ent
+        if old_tag != tag:
+            if zero:
+                t.zero_()
+            _ws[k] = (t, tag)
     return t
 
 
@@ -247,32 +258,26 @@ class AttnBlockFn(torch.autograd.Function):
             ops.gemm(dzz, Wo, do, rows, d, d, lda=d, ldb=d, ldc=d, b_mn=True, dot=(o, Drow, L, H))
         else:
             ops.gemm(dzz, Wo, do, rows, d, d, lda=d, ldb=d, ldc=d, b_mn=True)
-        # attention core: recompute P, then the causal contractions on tensor cores
-        P = _workspace("P", (B, H, L, L), f16, dev)
-        dS = _workspace("dS", (B, H, L, L), f16, dev)
-        dSr = _workspace("dSr", (B, H, L, L), f16, dev)
+        # attention core: the recompute kernel writes P and dS once; dV / dK are causal tensor-core contractions over them;
+        # dq, du, dv and dR come from the two band kernels (csrc/relattn_bwd.cu), which un-shift dS on registers - no
+        # re-laid-out copy of dS, no separate dq / bias-gradient pass
+        P = _workspace("P", (B, H, L, L), f16, dev, tag=window)
+        dS = _workspace("dS", (B, H, L, L), f16, dev, tag=window)
         ops.relattn_bwd_ds(qkv4, rk, do, lse2, Drow, P, dS, B, L, H, dh, window, scale, o=o)
         qu = qkv4[:, 0:d]
         qv = qkv4[:, d:2 * d]
         kk = qkv4[:, 2 * d:3 * d]
         LL = L * L
         sz = (LL, H * LL)
-        ops.rel_unshift(dS, dSr, B * H, L)
         dqkv = torch.empty(rows, 3 * d, dtype=f16, device=dev)
         ops.gemm(P, do, dqkv[:, 2 * d:], L, dh, L, lda=L, ldb=d, ldc=3 * d, a_mn=True, b_mn=True, Z1=H, Z2=B,
                  a_z=sz, b_z=(dh, L * d), c_z=(dh, L * 3 * d), k_mode=ops.K_BEGIN_BY_ROW)
         ops.gemm(dS, qu, dqkv[:, d:2 * d], L, dh, L, lda=L, ldb=4 * d, ldc=3 * d, a_mn=True, b_mn=True, Z1=H, Z2=B,
                  a_z=sz, b_z=(dh, L * 4 * d), c_z=(dh, L * 3 * d), k_mode=ops.K_BEGIN_BY_ROW)
-        dqu = torch.empty(rows, d, dtype=f16, device=dev)
-        dqv = torch.empty(rows, d, dtype=f16, device=dev)
-        ops.gemm(dS, kk, dqu, L, dh, L, lda=L, ldb=4 * d, ldc=d, b_mn=True, Z1=H, Z2=B,
-                 a_z=sz, b_z=(dh, L * 4 * d), c_z=(dh, L * d), k_mode=ops.K_END_BY_ROW)
-        ops.gemm(dSr, rk, dqv, L, dh, L, lda=L, ldb=d, ldc=d, b_mn=True, Z1=H, Z2=B,
-                 a_z=sz, b_z=(dh, 0), c_z=(dh, L * d), k_mode=ops.K_BEGIN_REV)
-        drk = torch.empty(L, d, dtype=f16, device=dev)
-        ops.gemm(dSr, qv, drk, L, dh, L, lda=L, ldb=4 * d, ldc=d, a_mn=True, b_mn=True, Z1=H, Z2=B,
-                 a_z=sz, b_z=(dh, L * 4 * d), c_z=(dh, 0), reduce_z2=True, k_mode=ops.K_BEGIN_REV)
-        ops.dq_finalize(dqu, dqv, dqkv[:, 0:d], du, dv, rows, d)
+        ops.relattn_bwd_dq(dS, kk, rk, dqkv[:, 0:d], du, dv, B, L, H, dh, window)
+        dr32 = _f32zeros(L * d, dev).view(L, d)
+        ops.relattn_bwd_dr(dS, qv, dr32, B, L, H, dh, window)
+        drk = _to_half(dr32, (L, d))
         # r_net / qkv_net
         gWr = _Grad(pWr)
         ops.gemm(drk, r, gWr.buf, d, d, L, lda=d, ldb=d, ldc=d, a_mn=True, b_mn=True, accumulate=gWr.acc)

@@ -215,6 +215,27 @@ def relattn_bwd_ds(qkv4, r, dout, lse2, drow, probs, ds, B, L, H, dh, window, sc
         "db1_relattn_bwd_ds")
 
 
+def relattn_bwd_dq(ds, k_view, r, dq_view, du, dv, B, L, H, dh, window):
+    """dq (fp16 view [B*L, H*dh] with its own row stride), du / dv (fp32 [H*dh], accumulated) from dS, K and r;
+    include/db1_sm100.h:db1_relattn_bwd_dq. k_view: the k columns of the fused QKV buffer."""
+    _need_cuda_half(ds, k_view, r, dq_view)
+    pairs = L * (L + 1) / 2.0 if window >= L else (window * (window + 1) / 2.0 + (L - window) * window)
+    with _Launch("relattn_bwd_dq", 1, B * H * pairs * dh * 4.0, 2.0 * B * H * pairs + 2.0 * B * L * H * dh * 2):
+      check(_lib.lib().db1_relattn_bwd_dq(ptr(ds), ptr(k_view), C.c_longlong(k_view.stride(0)), ptr(r),
+                                          C.c_longlong(r.stride(0)), ptr(dq_view), C.c_longlong(dq_view.stride(0)),
+                                          _f32(du), _f32(dv), B, L, H, dh, int(window), cur_stream()), "db1_relattn_bwd_dq")
+
+
+def relattn_bwd_dr(ds, qv_view, dr32, B, L, H, dh, window):
+    """dr32 (fp32 [L, H*dh], zero-filled by the caller) += the relative-position gradient; db1_relattn_bwd_dr."""
+    _need_cuda_half(ds, qv_view)
+    pairs = L * (L + 1) / 2.0 if window >= L else (window * (window + 1) / 2.0 + (L - window) * window)
+    with _Launch("relattn_bwd_dr", 1, B * H * pairs * dh * 2.0, 2.0 * B * H * pairs + 2.0 * B * L * H * dh):
+      check(_lib.lib().db1_relattn_bwd_dr(ptr(ds), ptr(qv_view), C.c_longlong(qv_view.stride(0)), _f32(dr32),
+                                          C.c_longlong(dr32.stride(0)), B, L, H, dh, int(window), cur_stream()),
+            "db1_relattn_bwd_dr")
+
+
 def _f32(t):
     if t is not None and (not t.is_cuda or t.dtype != torch.float32):
         raise _lib.Db1Error("expected a CUDA fp32 tensor, got %s on %s" % (t.dtype, t.device))

@@ -148,6 +148,20 @@ int db1_relattn_bwd_ds_o(const void* qu, const void* qv, const void* k, const vo
                          const float* lse2, void* probs, void* ds, int B, int L, int H, int dh, int window, float scale,
                          void* stream);
 
+/* Attention backward, second half (csrc/relattn_bwd.cu): everything that consumes dS, on tcgen05 with the accumulators
+ * resident in TMEM; the adjoint of _rel_shift (transformer_xl.py:98-110) is done on registers per tile row, so no
+ * re-laid-out copy of dS (dSr) exists and P / dS are not re-read by generic GEMMs.
+ *   ds : fp16 [B,H,L,L] from db1_relattn_bwd_ds (visited causal / in-window tiles; masked entries exactly 0)
+ * db1_relattn_bwd_dq (query-outer): dq[b*L+i, h*dh..] = sum_j ds[i,j] k_j + sum_j ds[i,j] r[j+L-1-i]   (fp16, written)
+ *   du[h*dh..] += sum_{b,i} (ds . K)_i ;  dv[h*dh..] += sum_{b,i} (unshift(ds) . R)_i     (fp32, accumulated: gradients of
+ *   r_w_bias / r_r_bias, transformer_xl.py:161, :167).   k: fp16 view [B,L,H,dh] with row stride ld_qkv; r: [L, H*dh].
+ * db1_relattn_bwd_dr (diagonal-outer): dr[c, h*dh..] += sum_{b,(i,j): j+L-1-i=c} ds[i,j] * qv[b,i,h,:]   (fp32 [L, ld_dr],
+ *   accumulated: the caller zero-fills it; gradient of r_net's output, adjoint of transformer_xl.py:167-171). */
+int db1_relattn_bwd_dq(const void* ds, const void* k, long long ld_qkv, const void* r, long long ld_r, void* dq,
+                       long long ld_dq, float* du, float* dv, int B, int L, int H, int dh, int window, void* stream);
+int db1_relattn_bwd_dr(const void* ds, const void* qv, long long ld_qkv, float* dr, long long ld_dr, int B, int L, int H,
+                       int dh, int window, void* stream);
+
 /* ------------------------------------------------------------------------------------------------------------------
  * HBM-bound kernels (single pass over the large operand, 16-byte vector accesses, fp32 math).
  * ------------------------------------------------------------------------------------------------------------------ */

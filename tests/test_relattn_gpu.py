@@ -101,3 +101,66 @@ def test_relattn_bwd_ds_matches_autograd(cuda, B, L, H, dh, window):
     assert torch.equal(P2, P)
     assert _rel(dS2.cpu(), ds_ref) < 5e-3
     assert (dS2.float() - dS.float()).abs().max().item() <= 2e-3 * dS.float().abs().max().item()
+
+
+def _unshift_ref(ds):
+    """dsr[..., i, c] = ds[..., i, c - (L-1-i)] (0 where the source column is negative): adjoint of _rel_shift
+    (transformer_xl.py:98-110) for qlen == klen, restated with an index gather."""
+    L = ds.shape[-1]
+    i = torch.arange(L, device=ds.device)[:, None]
+    c = torch.arange(L, device=ds.device)[None, :]
+    j = c - (L - 1 - i)
+    valid = j >= 0
+    g = ds.gather(-1, j.clamp(min=0).expand(ds.shape))
+    return torch.where(valid, g, torch.zeros((), device=ds.device, dtype=ds.dtype))
+
+
+@pytest.mark.parametrize("B,L,H,dh,window", [(1, 128, 1, 128, 1 << 20), (2, 256, 2, 128, 1 << 20), (3, 384, 2, 128, 1 << 20),
+                                             (1, 512, 2, 128, 200), (2, 256, 4, 32, 1 << 20), (1, 200, 2, 64, 77),
+                                             (2, 1024, 2, 128, 1024), (1, 1024, 1, 128, 300)])
+def test_relattn_bwd_dq_dr_match_dense_formulas(cuda, B, L, H, dh, window):
+    """db1_relattn_bwd_dq / db1_relattn_bwd_dr against the dense fp32 formulas:
+    dq = dS K + unshift(dS) R, du = sum dS K, dv = sum unshift(dS) R, dR = sum_b unshift(dS)^T (q+v)."""
+    from db1_sm100 import ops
+    d = H * dh
+    g = torch.Generator().manual_seed(11)
+    i = torch.arange(L)[:, None]
+    j = torch.arange(L)[None, :]
+    ok = (j <= i) & (i - j < window)
+    ds = (torch.randn(B, H, L, L, generator=g) * ok).half().to(cuda)
+    # tiles the recompute kernel never visits hold garbage in production: poison them
+    nq = (L + 127) // 128
+    for I in range(nq):
+        for J in range(nq):
+            jlo = max(0, I * 128 - window + 1)
+            if J > I or J < jlo // 128:
+                ds[:, :, I * 128:(I + 1) * 128, J * 128:(J + 1) * 128] = float("nan")
+    qkv4 = (torch.randn(B * L, 4 * d, generator=g) * 0.7).half().to(cuda)
+    r = (torch.randn(L, d, generator=g) * 0.7).half().to(cuda)
+    qv = qkv4[:, d:2 * d]
+    kk = qkv4[:, 2 * d:3 * d]
+    dqkv = torch.full((B * L, 3 * d), 7.0, dtype=torch.half, device=cuda)
+    du = torch.zeros(d, dtype=torch.float32, device=cuda)
+    dv = torch.zeros(d, dtype=torch.float32, device=cuda)
+    dr = torch.zeros(L, d, dtype=torch.float32, device=cuda)
+    ops.relattn_bwd_dq(ds, kk, r, dqkv[:, 0:d], du, dv, B, L, H, dh, window)
+    ops.relattn_bwd_dr(ds, qv, dr, B, L, H, dh, window)
+    torch.cuda.synchronize()
+    dsf = torch.nan_to_num(ds.float(), nan=0.0) * ok.to(cuda)
+    dsr = _unshift_ref(dsf)
+    K4 = kk.float().reshape(B, L, H, dh)
+    Qv4 = qv.float().reshape(B, L, H, dh)
+    R3 = r.float().reshape(L, H, dh)
+    dqu = torch.einsum("bhij,bjhd->bihd", dsf, K4)
+    dqv = torch.einsum("bhic,chd->bihd", dsr, R3)
+    dq_ref = (dqu + dqv).reshape(B * L, d)
+    assert _rel(dqkv[:, 0:d], dq_ref) < 2e-3
+    assert torch.all(dqkv[:, d:] == 7.0)  # neighbours of the strided output view untouched
+    assert _rel(du, dqu.sum((0, 1)).reshape(d)) < 1e-3
+    assert _rel(dv, dqv.sum((0, 1)).reshape(d)) < 1e-3
+    dr_ref = torch.einsum("bhic,bihd->chd", dsr, Qv4).reshape(L, d)
+    assert _rel(dr, dr_ref) < 1e-3
+    # accumulation contract: a second call adds
+    ops.relattn_bwd_dr(ds, qv, dr, B, L, H, dh, window)
+    torch.cuda.synchronize()
+    assert _rel(dr, 2 * dr_ref) < 1e-3
