@@ -297,8 +297,10 @@ relattn_bwd_band_kernel(const __grid_constant__ CUtensorMap tmK, const __grid_co
                       umma_smem_desc(kt + kk * 2048, 16384, 1024), idesc_q, (st | kk) ? 1u : 0u);
             umma_commit(free_ds);
             // G2: dQv += band_prev . r[cb+128 .. cb+256)   (nothing on the diagonal tile: its upper triangle is masked)
+            // (the barrier is waited for on every step, also when there is nothing to issue: committing free_prev without
+            //  having seen this step's full_prev would let that barrier run two phases ahead of the un-shift warps)
+            mbar_wait(full_prev, gs & 1);
             if (st > 0) {
-              mbar_wait(full_prev, gs & 1);
               tc_fence_after();
 #pragma unroll
               for (int kk = 0; kk < 8; ++kk)

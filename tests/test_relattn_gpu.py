@@ -117,7 +117,8 @@ def _unshift_ref(ds):
 
 @pytest.mark.parametrize("B,L,H,dh,window", [(1, 128, 1, 128, 1 << 20), (2, 256, 2, 128, 1 << 20), (3, 384, 2, 128, 1 << 20),
                                              (1, 512, 2, 128, 200), (2, 256, 4, 32, 1 << 20), (1, 200, 2, 64, 77),
-                                             (2, 1024, 2, 128, 1024), (1, 1024, 1, 128, 300)])
+                                             (2, 1024, 2, 128, 1024), (1, 1024, 1, 128, 300),
+                                             (2, 1024, 16, 128, 1024), (3, 640, 24, 64, 1 << 20)])
 def test_relattn_bwd_dq_dr_match_dense_formulas(cuda, B, L, H, dh, window):
     """db1_relattn_bwd_dq / db1_relattn_bwd_dr against the dense fp32 formulas:
     dq = dS K + unshift(dS) R, du = sum dS K, dv = sum unshift(dS) R, dR = sum_b unshift(dS)^T (q+v)."""
