@@ -43,15 +43,11 @@ struct BandParams {
 template <int D, int KIND>
 struct BandSmem {
   static constexpr int TILE = 128 * D * 2;  // one [128][D] fp16 operand tile (D/64 slabs of [128][64])
-  // KIND 0
-  static constexpr int DS = 0;                   // [128][128] fp16 K-major (2 slabs)
-  static constexpr int BAND = 32768;             // [128][256] fp16 K-major (4 slabs): new = slabs 0,1, prev = 2,3
-  static constexpr int KT = BAND + 65536;        // K_J tile
-  static constexpr int RR = KT + TILE;           // 2-slot ring of 128-row chunks of r
-  // KIND 1
-  static constexpr int BAND2 = 0;                // 2 x 64 KB
-  static constexpr int QV2 = 131072;             // 2 x TILE
-  static constexpr int BARS = (KIND == 0) ? (RR + 2 * TILE) : (QV2 + 2 * TILE);
+  static constexpr int DS = 0;              // 2 x [128][128] fp16 dS tiles, K-major (2 slabs each), written by TMA
+  static constexpr int BAND = 65536;        // [128][256] fp16 K-major (4 slabs): new = slabs 0,1, prev = slabs 2,3
+  static constexpr int KT = BAND + 65536;   // KIND 0: K_J tile                     KIND 1: Qv_I tiles (2 buffers)
+  static constexpr int RR = KT + TILE;      // KIND 0: 2-slot ring of 128-row chunks of r
+  static constexpr int BARS = (KIND == 0) ? (RR + 2 * TILE) : (KT + 2 * TILE);
   static constexpr int TOTAL = BARS + 256;
 };
 
@@ -131,24 +127,27 @@ DEVI float warp_colsum32(float (&v)[32], int lane) {
 template <int D, int KIND>
 __global__ void __launch_bounds__(BW_THREADS, 1)
 relattn_bwd_band_kernel(const __grid_constant__ CUtensorMap tmK, const __grid_constant__ CUtensorMap tmR,
-                        const __grid_constant__ CUtensorMap tmQv, const BandParams p) {
+                        const __grid_constant__ CUtensorMap tmQv, const __grid_constant__ CUtensorMap tmDS,
+                        const BandParams p) {
   using SM = BandSmem<D, KIND>;
   constexpr int NSLAB = D / 64;
   constexpr int TILE = SM::TILE;
   extern __shared__ __align__(1024) uint8_t smem[];
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + SM::BARS);
-  // KIND 0: per-step barriers (one phase per global step)      KIND 1: per-buffer barriers (one phase per two steps)
-  uint64_t* bar_k = bars + 0;        //  K_J landed                        bar_qv[2] = bars + 0, 1
-  uint64_t* bar_r = bars + 1;        //  r chunk landed
-  uint64_t* full_ds = bars + 2;      //  un-shift warps -> MMA             full[2] = bars + 2, 3
-  uint64_t* full_prev = bars + 3;
-  uint64_t* full_new = bars + 4;
-  uint64_t* free_ds = bars + 5;      //  MMA commit -> un-shift / TMA      free[2] = bars + 5, 6
-  uint64_t* free_prev = bars + 6;
-  uint64_t* free_new = bars + 7;
-  uint64_t* acc_full = bars + 8;     //  [2] accumulator set complete (commit)
-  uint64_t* acc_free = bars + 10;    //  [2] drained (4 warps)
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 12);
+  // per-buffer barriers (one phase per two steps)
+  uint64_t* bar_ds = bars + 0;     // [2] dS tile landed (TMA)
+  uint64_t* ds_free = bars + 2;    // [2] un-shift warps have read it (+ KIND 0: the dQu MMAs have)
+  uint64_t* bar_b = bars + 4;      // [2] KIND 1: Qv_I landed              KIND 0: [0] K_J landed, [1] r chunk landed (per step)
+  uint64_t* b_free = bars + 6;     // [2] KIND 1: the step's MMAs are done  KIND 0: [0] dQu MMAs done (K_J free), per step
+  // per-step barriers
+  uint64_t* full_prev = bars + 8;  // un-shift warps -> MMA
+  uint64_t* full_new = bars + 9;
+  uint64_t* free_prev = bars + 10; // MMA commit -> un-shift warps (KIND 0: and the r ring)
+  uint64_t* free_new = bars + 11;
+  // per-item
+  uint64_t* acc_full = bars + 12;  // [2] accumulator set complete (commit)
+  uint64_t* acc_free = bars + 14;  // [2] drained (4 warps)
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 16);
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -191,32 +190,41 @@ relattn_bwd_band_kernel(const __grid_constant__ CUtensorMap tmK, const __grid_co
     }
     return it;
   };
+  // tile of step st of an item: query tile origin, key tile origin, sequence
+  auto tile_of = [&](const Item& it, int st, int& I0, int& J0, int& b) {
+    if (KIND == 0) {
+      I0 = it.I * 128;
+      J0 = (it.I - st) * 128;
+      b = it.b;
+    } else {
+      const int per = nq - it.t;
+      b = it.b + st / per;
+      I0 = (it.t + st % per) * 128;
+      J0 = I0 - it.t * 128;
+    }
+  };
 
   if ((smem_u32(smem) & 1023u) != 0) __trap();
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&tmK);
     tma_prefetch_desc(&tmR);
     tma_prefetch_desc(&tmQv);
+    tma_prefetch_desc(&tmDS);
   }
   if (warp == 1) {
     if (lane == 0) {
-      if (KIND == 0) {
-        mbar_init(bar_k, 1);
-        mbar_init(bar_r, 1);
-        mbar_init(full_ds, 4);
-        mbar_init(full_prev, 4);
-        mbar_init(full_new, 4);
-        mbar_init(free_ds, 1);
-        mbar_init(free_prev, 1);
-        mbar_init(free_new, 1);
-      } else {
-        mbar_init(bars + 0, 1);
-        mbar_init(bars + 1, 1);
-        mbar_init(bars + 2, 4);
-        mbar_init(bars + 3, 4);
-        mbar_init(bars + 5, 1);
-        mbar_init(bars + 6, 1);
-      }
+      mbar_init(bar_ds + 0, 1);
+      mbar_init(bar_ds + 1, 1);
+      mbar_init(ds_free + 0, KIND == 0 ? 5 : 4);
+      mbar_init(ds_free + 1, KIND == 0 ? 5 : 4);
+      mbar_init(bar_b + 0, 1);
+      mbar_init(bar_b + 1, 1);
+      mbar_init(b_free + 0, 1);
+      mbar_init(b_free + 1, 1);
+      mbar_init(full_prev, 4);
+      mbar_init(full_new, 4);
+      mbar_init(free_prev, 1);
+      mbar_init(free_new, 1);
       mbar_init(acc_full + 0, 1);
       mbar_init(acc_full + 1, 1);
       mbar_init(acc_free + 0, 4);
@@ -242,28 +250,30 @@ relattn_bwd_band_kernel(const __grid_constant__ CUtensorMap tmK, const __grid_co
         if (k < 0) continue;
         const Item it = decode(k);
         for (int st = 0; st < it.nsteps; ++st, ++gs) {
+          int I0, J0, b;
+          tile_of(it, st, I0, J0, b);
+          const int buf = gs & 1;
+          if (gs >= 2) mbar_wait(ds_free + buf, ((gs >> 1) - 1) & 1);
+          mbar_expect_tx(bar_ds + buf, 32768);
+          tma_load_3d(smem + SM::DS + buf * 32768, &tmDS, bar_ds + buf, J0, I0, b * p.H + it.h);
+          tma_load_3d(smem + SM::DS + buf * 32768 + 16384, &tmDS, bar_ds + buf, J0 + 64, I0, b * p.H + it.h);
           if (KIND == 0) {
-            const int J0 = (it.I - st) * 128;
             const int cb = p.L - 128 - 128 * st;  // first r row of this step's new chunk
-            if (gs > 0) mbar_wait(free_ds, (gs - 1) & 1);
-            mbar_expect_tx(bar_k, TILE);
+            if (gs > 0) mbar_wait(b_free + 0, (gs - 1) & 1);
+            mbar_expect_tx(bar_b + 0, TILE);
 #pragma unroll
-            for (int s = 0; s < NSLAB; ++s) tma_load_4d(smem + SM::KT + s * 16384, &tmK, bar_k, s * 64, J0, it.h, it.b);
+            for (int s = 0; s < NSLAB; ++s) tma_load_4d(smem + SM::KT + s * 16384, &tmK, bar_b + 0, s * 64, J0, it.h, b);
             if (gs > 0) mbar_wait(free_prev, (gs - 1) & 1);  // the slot's previous chunk was last read by step gs-1
-            mbar_expect_tx(bar_r, TILE);
+            mbar_expect_tx(bar_b + 1, TILE);
 #pragma unroll
             for (int s = 0; s < NSLAB; ++s)
-              tma_load_4d(smem + SM::RR + (gs & 1) * TILE + s * 16384, &tmR, bar_r, s * 64, cb, it.h, 0);
+              tma_load_4d(smem + SM::RR + (gs & 1) * TILE + s * 16384, &tmR, bar_b + 1, s * 64, cb, it.h, 0);
           } else {
-            const int per = nq - it.t;
-            const int b = it.b + st / per;
-            const int I0 = (it.t + st % per) * 128;
-            const int buf = gs & 1;
-            if (gs >= 2) mbar_wait(bars + 5 + buf, ((gs >> 1) - 1) & 1);
-            mbar_expect_tx(bars + 0 + buf, TILE);
+            if (gs >= 2) mbar_wait(b_free + buf, ((gs >> 1) - 1) & 1);
+            mbar_expect_tx(bar_b + buf, TILE);
 #pragma unroll
             for (int s = 0; s < NSLAB; ++s)
-              tma_load_4d(smem + SM::QV2 + buf * TILE + s * 16384, &tmQv, bars + 0 + buf, s * 64, I0, it.h, b);
+              tma_load_4d(smem + SM::KT + buf * TILE + s * 16384, &tmQv, bar_b + buf, s * 64, I0, it.h, b);
           }
         }
       }
@@ -273,6 +283,7 @@ relattn_bwd_band_kernel(const __grid_constant__ CUtensorMap tmK, const __grid_co
     if (lane == 0) {
       const uint32_t idesc_q = umma_idesc(128, D, 0, 1, 0);  // A K-major (dS / band), B MN-major (K_J / r chunk)
       const uint32_t idesc_r = umma_idesc(128, D, 1, 1, 0);  // A MN-major (band^T), B MN-major (Qv_I)
+      const uint32_t band = smem_u32(smem + SM::BAND);
       int gs = 0, ti = 0;
       for (int pass = 0; pass < n_pass; ++pass) {
         const int k = item_of(pass);
@@ -282,23 +293,29 @@ relattn_bwd_band_kernel(const __grid_constant__ CUtensorMap tmK, const __grid_co
         const uint32_t T0 = tmem_base + as * (2 * D);  // dQu | dR_new
         const uint32_t T1 = T0 + D;                    // dQv | dR_prev
         for (int st = 0; st < it.nsteps; ++st, ++gs) {
+          const int buf = gs & 1;
           if (KIND == 0) {
-            const uint32_t ds = smem_u32(smem + SM::DS), band = smem_u32(smem + SM::BAND), kt = smem_u32(smem + SM::KT);
+            const uint32_t ds = smem_u32(smem + SM::DS + buf * 32768), kt = smem_u32(smem + SM::KT);
             const uint32_t r_new = smem_u32(smem + SM::RR + (gs & 1) * TILE);
             const uint32_t r_prev = smem_u32(smem + SM::RR + ((gs + 1) & 1) * TILE);
-            // G1: dQu += dS . K_J
-            mbar_wait(bar_k, gs & 1);
-            mbar_wait(full_ds, gs & 1);
+            // The r chunk is waited for before anything of this step is committed: the producer re-arms its barrier for
+            // step gs+1 as soon as free_prev(gs) fires (immediately on a step without G2), and an arrive.expect_tx on a
+            // barrier whose previous phase still has bytes in flight underflows its pending count (a device fault).
+            mbar_wait(bar_b + 1, gs & 1);
+            // G1: dQu += dS . K_J   (the dS tile is the TMA-written K-major operand itself)
+            mbar_wait(bar_b + 0, gs & 1);
+            mbar_wait(bar_ds + buf, (gs >> 1) & 1);
             if (st == 0 && ti >= 2) mbar_wait(acc_free + as, ((ti >> 1) - 1) & 1);
             tc_fence_after();
 #pragma unroll
             for (int kk = 0; kk < 8; ++kk)
               umma_ss(T0, umma_smem_desc(ds + (kk >> 2) * 16384 + (kk & 3) * 32, 16, 1024),
                       umma_smem_desc(kt + kk * 2048, 16384, 1024), idesc_q, (st | kk) ? 1u : 0u);
-            umma_commit(free_ds);
-            // G2: dQv += band_prev . r[cb+128 .. cb+256)   (nothing on the diagonal tile: its upper triangle is masked)
-            // (the barrier is waited for on every step, also when there is nothing to issue: committing free_prev without
-            //  having seen this step's full_prev would let that barrier run two phases ahead of the un-shift warps)
+            umma_commit(b_free + 0);
+            umma_commit(ds_free + buf);
+            // G2: dQv += band_prev . r[cb+128 .. cb+256)   (nothing on the diagonal tile: its upper triangle is masked).
+            // The barrier is waited for on every step, also when there is nothing to issue: committing free_prev
+            // without having seen this step's full_prev would let it run two phases ahead of the un-shift warps.
             mbar_wait(full_prev, gs & 1);
             if (st > 0) {
               tc_fence_after();
@@ -309,7 +326,6 @@ relattn_bwd_band_kernel(const __grid_constant__ CUtensorMap tmK, const __grid_co
             }
             umma_commit(free_prev);
             // G3: dQv += band_new . r[cb .. cb+128)
-            mbar_wait(bar_r, gs & 1);
             mbar_wait(full_new, gs & 1);
             tc_fence_after();
 #pragma unroll
@@ -318,24 +334,26 @@ relattn_bwd_band_kernel(const __grid_constant__ CUtensorMap tmK, const __grid_co
                       umma_smem_desc(r_new + kk * 2048, 16384, 1024), idesc_q, (st | kk) ? 1u : 0u);
             umma_commit(free_new);
           } else {
-            const int buf = gs & 1;
-            const uint32_t band = smem_u32(smem + SM::BAND2 + buf * 65536);
-            const uint32_t qv = smem_u32(smem + SM::QV2 + buf * TILE);
-            mbar_wait(bars + 0 + buf, (gs >> 1) & 1);
-            mbar_wait(bars + 2 + buf, (gs >> 1) & 1);
+            const uint32_t qv = smem_u32(smem + SM::KT + buf * TILE);
+            mbar_wait(bar_b + buf, (gs >> 1) & 1);
+            mbar_wait(full_new, gs & 1);
             if (st == 0 && ti >= 2) mbar_wait(acc_free + as, ((ti >> 1) - 1) & 1);
             tc_fence_after();
 #pragma unroll
             for (int kk = 0; kk < 8; ++kk)
               umma_ss(T0, umma_smem_desc(band + kk * 2048, 16384, 1024), umma_smem_desc(qv + kk * 2048, 16384, 1024),
                       idesc_r, (st | kk) ? 1u : 0u);
+            umma_commit(free_new);
+            mbar_wait(full_prev, gs & 1);
             if (it.t > 0) {
+              tc_fence_after();
 #pragma unroll
               for (int kk = 0; kk < 8; ++kk)
                 umma_ss(T1, umma_smem_desc(band + 2 * 16384 + kk * 2048, 16384, 1024),
                         umma_smem_desc(qv + kk * 2048, 16384, 1024), idesc_r, (st | kk) ? 1u : 0u);
             }
-            umma_commit(bars + 5 + buf);
+            umma_commit(free_prev);
+            umma_commit(b_free + buf);
           }
         }
         umma_commit(acc_full + as);
@@ -348,101 +366,53 @@ relattn_bwd_band_kernel(const __grid_constant__ CUtensorMap tmK, const __grid_co
     const int sft = 127 - r;
     const int a = sft >> 3, rem = sft & 7;
     const int rx = r & 7;
-    uint32_t W[64];
-    auto load_row = [&](const Item& it, int st) {
-      int I0, J0, b;
-      if (KIND == 0) {
-        I0 = it.I * 128;
-        J0 = (it.I - st) * 128;
-        b = it.b;
-      } else {
-        const int per = nq - it.t;
-        b = it.b + st / per;
-        I0 = (it.t + st % per) * 128;
-        J0 = I0 - it.t * 128;
-      }
-      const int i = I0 + r;
-      int nv = p.L - J0;
-      nv = (i < p.L) ? (nv > 128 ? 128 : nv) : 0;
-      const __half* rowp = p.dS + (((long long)b * p.H + it.h) * p.L + i) * (long long)p.L + J0;
-      const bool al32 = ((reinterpret_cast<uintptr_t>(rowp)) & 31) == 0;
-#pragma unroll
-      for (int q = 0; q < 4; ++q) {
-        int n = nv - 32 * q;
-        n = n < 0 ? 0 : (n > 32 ? 32 : n);
-        ldg_row32(rowp + 32 * q, reinterpret_cast<uint32_t(&)[16]>(W[16 * q]), n, al32);
-      }
-    };
-    // flat walk over (item, step) with one step of look-ahead: the next step's row (also across an item boundary) is
-    // fetched right after this step's registers are free, so its latency runs under the stores and the MMAs
-    struct Cursor {
-      int pass, st;
-      Item it;
-      bool valid;
-    };
-    auto advance = [&](Cursor& c) {
-      if (c.valid && c.st + 1 < c.it.nsteps) {
-        ++c.st;
-        return;
-      }
-      for (int ps = c.valid ? c.pass + 1 : 0; ps < n_pass; ++ps) {
-        const int k = item_of(ps);
-        if (k >= 0) {
-          c.pass = ps;
-          c.it = decode(k);
-          c.st = 0;
-          c.valid = true;
-          return;
-        }
-      }
-      c.valid = false;
-    };
-    Cursor cur;
-    cur.valid = false;
-    cur.pass = 0;
-    cur.st = 0;
-    advance(cur);
-    if (cur.valid) load_row(cur.it, cur.st);
-    for (int gs = 0; cur.valid; ++gs) {
-      const Item it = cur.it;
-      const int st = cur.st;
-      uint32_t out[17][4];
-      unshift_row(W, rem, out);
-      const bool with_prev = (KIND == 0) ? (st > 0) : (it.t > 0);
-      if (KIND == 0) {
-        if (gs > 0) mbar_wait(free_ds, (gs - 1) & 1);
-        const uint32_t dsrow = smem_u32(smem + SM::DS) + (uint32_t)r * 128u;
-#pragma unroll
-        for (int c = 0; c < 16; ++c)
-          sts128(dsrow + (uint32_t)(c >> 3) * 16384u + (uint32_t)(((c & 7) ^ rx) * 16), W[4 * c], W[4 * c + 1], W[4 * c + 2],
-                 W[4 * c + 3]);
-        fence_proxy_async_smem();
-        __syncwarp();
-        if (lane == 0) mbar_arrive(full_ds);
-      }
-      advance(cur);
-      if (cur.valid) load_row(cur.it, cur.st);
-      if (KIND == 0) {
-        const uint32_t band = smem_u32(smem + SM::BAND);
-        if (gs > 0) mbar_wait(free_prev, (gs - 1) & 1);
-        if (with_prev) store_band_half(band, r, a, 1, out);
-        fence_proxy_async_smem();
-        __syncwarp();
-        if (lane == 0) mbar_arrive(full_prev);
-        if (gs > 0) mbar_wait(free_new, (gs - 1) & 1);
-        store_band_half(band, r, a, 0, out);
-        fence_proxy_async_smem();
-        __syncwarp();
-        if (lane == 0) mbar_arrive(full_new);
-      } else {
+    const uint32_t band = smem_u32(smem + SM::BAND);
+    int gs = 0;
+    for (int pass = 0; pass < n_pass; ++pass) {
+      const int k = item_of(pass);
+      if (k < 0) continue;
+      const Item it = decode(k);
+      for (int st = 0; st < it.nsteps; ++st, ++gs) {
         const int buf = gs & 1;
-        const uint32_t band = smem_u32(smem + SM::BAND2 + buf * 65536);
-        if (gs >= 2) mbar_wait(bars + 5 + buf, ((gs >> 1) - 1) & 1);
-        if (with_prev) store_band_half(band, r, a, 1, out);
-        store_band_half(band, r, a, 0, out);
-        fence_proxy_async_smem();
+        const bool with_prev = (KIND == 0) ? (st > 0) : (it.t > 0);
+        // the row from the TMA-written tile: 16 conflict-free 128-bit shared loads (128-byte swizzle)
+        uint32_t W[64];
+        mbar_wait(bar_ds + buf, (gs >> 1) & 1);
+        {
+          const uint32_t dsrow = smem_u32(smem + SM::DS + buf * 32768) + (uint32_t)r * 128u;
+#pragma unroll
+          for (int c = 0; c < 16; ++c) {
+            const Half8 h8 = lds_half8(dsrow + (uint32_t)(c >> 3) * 16384u + (uint32_t)(((c & 7) ^ rx) * 16));
+            W[4 * c] = h8.u.x; W[4 * c + 1] = h8.u.y; W[4 * c + 2] = h8.u.z; W[4 * c + 3] = h8.u.w;
+          }
+        }
+        uint32_t out[17][4];
+        unshift_row(W, rem, out);
         __syncwarp();
-        if (lane == 0) mbar_arrive(bars + 2 + buf);
+        if (lane == 0) mbar_arrive(ds_free + buf);  // the row is in registers
+        if (KIND == 0) {
+          if (gs > 0) mbar_wait(free_prev, (gs - 1) & 1);
+          if (with_prev) store_band_half(band, r, a, 1, out);
+          fence_proxy_async_smem();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(full_prev);
+          if (gs > 0) mbar_wait(free_new, (gs - 1) & 1);
+          store_band_half(band, r, a, 0, out);
+          fence_proxy_async_smem();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(full_new);
+        } else {
+          if (gs > 0) mbar_wait(free_new, (gs - 1) & 1);
+          store_band_half(band, r, a, 0, out);
+          fence_proxy_async_smem();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(full_new);
+          if (gs > 0) mbar_wait(free_prev, (gs - 1) & 1);
+          if (with_prev) store_band_half(band, r, a, 1, out);
+          fence_proxy_async_smem();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(full_prev);
+        }
       }
     }
   } else {
@@ -537,6 +507,15 @@ static int make_head_map_bw(CUtensorMap* tm, const void* base, int dh, int L, in
   return make_tmap_f16(tm, base, 4, dims, str, box);
 }
 
+// dS [B*H, L, L] fp16: box = 128 rows x 64 columns (one K-major slab of the dS tile), 128-byte swizzle; rows / columns
+// beyond L arrive as zeros
+static int make_ds_map(CUtensorMap* tm, const void* ds, int L, int BH) {
+  uint64_t dims[3] = {(uint64_t)L, (uint64_t)L, (uint64_t)BH};
+  uint64_t str[2] = {(uint64_t)L * 2, (uint64_t)L * (uint64_t)L * 2};
+  uint32_t box[3] = {64, 128, 1};
+  return make_tmap_f16(tm, ds, 3, dims, str, box);
+}
+
 template <int D, int KIND>
 static int launch_band(const CUtensorMap* tm, const BandParams& p, cudaStream_t stream) {
   using SM = BandSmem<D, KIND>;
@@ -551,7 +530,7 @@ static int launch_band(const CUtensorMap* tm, const BandParams& p, cudaStream_t 
   const int n_items = (KIND == 0) ? nq * p.H * p.B : nT * p.H * ((p.B + 1) / 2);
   const int grid = n_items < sm_count() ? n_items : sm_count();
   DB1_CUDA(launch_pdl(relattn_bwd_band_kernel<D, KIND>, dim3(grid), dim3(BW_THREADS), SM::TOTAL, stream, 1, tm[0], tm[1],
-                      tm[2], p));
+                      tm[2], tm[3], p));
   return 0;
 }
 
@@ -581,10 +560,11 @@ extern "C" int db1_relattn_bwd_dq(const void* ds, const void* k, long long ld_qk
   memset(&p, 0, sizeof(p));
   p.L = L; p.H = H; p.B = B; p.dh = dh; p.window = window;
   p.dS = (const __half*)ds; p.dq = (__half*)dq; p.lddq = ld_dq; p.du = du; p.dv = dv;
-  CUtensorMap tm[3];
+  CUtensorMap tm[4];
   if ((e = make_head_map_bw(&tm[0], k, dh, L, H, B, ld_qkv))) return e;
   if ((e = make_head_map_bw(&tm[1], r, dh, L, H, 1, ld_r))) return e;
   tm[2] = tm[0];
+  if ((e = make_ds_map(&tm[3], ds, L, B * H))) return e;
   if (dh <= 64) return launch_band<64, 0>(tm, p, (cudaStream_t)stream_);
   return launch_band<128, 0>(tm, p, (cudaStream_t)stream_);
 }
@@ -599,10 +579,11 @@ extern "C" int db1_relattn_bwd_dr(const void* ds, const void* qv, long long ld_q
   memset(&p, 0, sizeof(p));
   p.L = L; p.H = H; p.B = B; p.dh = dh; p.window = window;
   p.dS = (const __half*)ds; p.dR = dr; p.lddr = ld_dr;
-  CUtensorMap tm[3];
+  CUtensorMap tm[4];
   if ((e = make_head_map_bw(&tm[2], qv, dh, L, H, B, ld_qkv))) return e;
   tm[0] = tm[2];
   tm[1] = tm[2];
+  if ((e = make_ds_map(&tm[3], ds, L, B * H))) return e;
   if (dh <= 64) return launch_band<64, 1>(tm, p, (cudaStream_t)stream_);
   return launch_band<128, 1>(tm, p, (cudaStream_t)stream_);
 }
