@@ -500,6 +500,211 @@ relattn_bwd_band_kernel(const __grid_constant__ CUtensorMap tmK, const __grid_co
   }
 }
 
+// ------------------------------------------------------------------------------------------------------------------
+// dV = P^T . dO and dK = dS^T . (q+u), key-outer: item = (key tile J, head, sequence), accumulators [128 keys x dh]
+// resident in TMEM over all query tiles I >= J of the item; P / dS tiles arrive by TMA and are read as MN-major A
+// operands (M = key), dO_I / Qu_I as MN-major B operands - a pure TMA -> tcgen05 pipeline with no CUDA-core work per
+// step (3-stage ring of {score tile, row tile} pairs, accumulators double-buffered for the epilogue). Replaces two
+// batched causal GEMM launches that each re-read a score-sized operand with 128-byte row segments.
+// Roles (192 threads): warp 0 TMA, warp 1 MMA, warps 2-5 epilogue (thread = key row).
+// ------------------------------------------------------------------------------------------------------------------
+constexpr int KV_THREADS = 192;
+constexpr int KV_STAGES = 3;
+
+struct KvParams {
+  int L, H, B, dh, window;
+  __half* dk;  // [B*L, ld], head h at column h*dh
+  __half* dv;
+  long long ld;
+};
+
+template <int D>
+struct KvSmem {
+  static constexpr int TILE = 128 * D * 2;
+  static constexpr int STAGE = 32768 + TILE;  // [128 i][128 j] score tile (2 slabs) + [128 i][D] row tile
+  static constexpr int BARS = KV_STAGES * STAGE;
+  static constexpr int TOTAL = BARS + 256;
+};
+
+template <int D>
+__global__ void __launch_bounds__(KV_THREADS, 1)
+relattn_bwd_dkdv_kernel(const __grid_constant__ CUtensorMap tmP, const __grid_constant__ CUtensorMap tmDS,
+                        const __grid_constant__ CUtensorMap tmDO, const __grid_constant__ CUtensorMap tmQu,
+                        const KvParams p) {
+  using SM = KvSmem<D>;
+  constexpr int NSLAB = D / 64;
+  extern __shared__ __align__(1024) uint8_t smem[];
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + SM::BARS);
+  uint64_t* full = bars;                   // [KV_STAGES] TMA landed
+  uint64_t* empty = bars + KV_STAGES;      // [KV_STAGES] MMAs done reading
+  uint64_t* acc_full = bars + 2 * KV_STAGES;
+  uint64_t* acc_free = acc_full + 2;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_free + 2);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const int nq = (p.L + 127) / 128;
+  const int Wt = (p.window - 1 + 127) / 128;
+  const int HB = p.H * p.B;
+  const int n_items = nq * HB;
+  const int G = gridDim.x;
+  auto item_of = [&](int pass) -> int {
+    const int c = (pass & 1) ? (G - 1 - (int)blockIdx.x) : (int)blockIdx.x;
+    const int k = pass * G + c;
+    return k < n_items ? k : -1;
+  };
+  const int n_pass = (n_items + G - 1) / G;
+  struct Item {
+    int J, h, b, nsteps;
+  };
+  auto decode = [&](int k) -> Item {  // heaviest first: key tile 0 is attended by the most query tiles
+    Item it;
+    it.J = k / HB;
+    const int hb = k % HB;
+    it.h = hb % p.H;
+    it.b = hb / p.H;
+    const int last = (it.J + Wt < nq - 1) ? it.J + Wt : nq - 1;
+    it.nsteps = last - it.J + 1;
+    return it;
+  };
+
+  if ((smem_u32(smem) & 1023u) != 0) __trap();
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&tmP);
+    tma_prefetch_desc(&tmDS);
+    tma_prefetch_desc(&tmDO);
+    tma_prefetch_desc(&tmQu);
+  }
+  if (warp == 1) {
+    if (lane == 0) {
+      for (int i = 0; i < KV_STAGES; ++i) {
+        mbar_init(full + i, 1);
+        mbar_init(empty + i, 1);
+      }
+      mbar_init(acc_full + 0, 1);
+      mbar_init(acc_full + 1, 1);
+      mbar_init(acc_free + 0, 4);
+      mbar_init(acc_free + 1, 4);
+      mbar_fence_init();
+    }
+    __syncwarp();
+    tmem_alloc<512>(tmem_slot);
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+  pdl_launch_dependents();
+  pdl_wait();
+
+  if (warp == 0) {
+    if (lane == 0) {
+      int n = 0;  // sub-step counter: stage = n % KV_STAGES, use = n / KV_STAGES
+      for (int pass = 0; pass < n_pass; ++pass) {
+        const int k = item_of(pass);
+        if (k < 0) continue;
+        const Item it = decode(k);
+        const int J0 = it.J * 128;
+        const int bh = it.b * p.H + it.h;
+        for (int st = 0; st < it.nsteps; ++st) {
+          const int I0 = (it.J + st) * 128;
+#pragma unroll
+          for (int sub = 0; sub < 2; ++sub, ++n) {
+            const int sg = n % KV_STAGES;
+            const int use = n / KV_STAGES;
+            if (use > 0) mbar_wait(empty + sg, (use - 1) & 1);
+            uint8_t* base = smem + sg * SM::STAGE;
+            mbar_expect_tx(full + sg, SM::STAGE);
+            const CUtensorMap* ms = sub ? &tmDS : &tmP;
+            const CUtensorMap* mr = sub ? &tmQu : &tmDO;
+            tma_load_3d(base, ms, full + sg, J0, I0, bh);
+            tma_load_3d(base + 16384, ms, full + sg, J0 + 64, I0, bh);
+#pragma unroll
+            for (int s = 0; s < NSLAB; ++s) tma_load_4d(base + 32768 + s * 16384, mr, full + sg, s * 64, I0, it.h, it.b);
+          }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {
+      const uint32_t idesc = umma_idesc(128, D, 1, 1, 0);  // A MN-major (score tile transposed), B MN-major (row tile)
+      int n = 0, ti = 0;
+      for (int pass = 0; pass < n_pass; ++pass) {
+        const int k = item_of(pass);
+        if (k < 0) continue;
+        const Item it = decode(k);
+        const int as = ti & 1;
+        if (ti >= 2) {
+          mbar_wait(acc_free + as, ((ti >> 1) - 1) & 1);
+          tc_fence_after();
+        }
+        for (int st = 0; st < it.nsteps; ++st) {
+#pragma unroll
+          for (int sub = 0; sub < 2; ++sub, ++n) {
+            const int sg = n % KV_STAGES;
+            const int use = n / KV_STAGES;
+            mbar_wait(full + sg, use & 1);
+            tc_fence_after();
+            const uint32_t a = smem_u32(smem + sg * SM::STAGE), b = a + 32768;
+            const uint32_t acc = tmem_base + as * (2 * D) + sub * D;  // sub 0: dV, sub 1: dK
+#pragma unroll
+            for (int kk = 0; kk < 8; ++kk)
+              umma_ss(acc, umma_smem_desc(a + kk * 2048, 16384, 1024), umma_smem_desc(b + kk * 2048, 16384, 1024), idesc,
+                      (st | kk) ? 1u : 0u);
+            umma_commit(empty + sg);
+          }
+        }
+        umma_commit(acc_full + as);
+        ++ti;
+      }
+    }
+  } else {
+    const int q = warp & 3;
+    const int row = q * 32 + lane;
+    const uint32_t lane_off = (uint32_t)(q * 32) << 16;
+    int ti = 0;
+    for (int pass = 0; pass < n_pass; ++pass) {
+      const int k = item_of(pass);
+      if (k < 0) continue;
+      const Item it = decode(k);
+      const int as = ti & 1;
+      const int j = it.J * 128 + row;
+      mbar_wait_backoff(acc_full + as, (ti >> 1) & 1, 64);
+      tc_fence_after();
+#pragma unroll 1
+      for (int sub = 0; sub < 2; ++sub) {
+        __half* orow = (sub ? p.dk : p.dv) + ((long long)it.b * p.L + j) * p.ld + (long long)it.h * p.dh;
+        const bool al32 = ((reinterpret_cast<uintptr_t>(orow)) & 31) == 0;
+#pragma unroll 1
+        for (int c = 0; c < D / 32; ++c) {
+          uint32_t x[32];
+          tmem_ld32(tmem_base + as * (2 * D) + sub * D + lane_off + c * 32, x);
+          tmem_ld_wait();
+          int nv = p.dh - c * 32;
+          nv = nv < 0 ? 0 : (nv > 32 ? 32 : nv);
+          if (j < p.L && nv > 0) {
+            uint32_t pk[16];
+#pragma unroll
+            for (int e = 0; e < 16; ++e) pk[e] = pack_half2(__uint_as_float(x[2 * e]), __uint_as_float(x[2 * e + 1]));
+            stg_row32(orow + c * 32, pk, nv, al32);
+          }
+        }
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(acc_free + as);
+      ++ti;
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc<512>(tmem_base);
+  }
+}
+
 static int make_head_map_bw(CUtensorMap* tm, const void* base, int dh, int L, int H, int B, long long ld) {
   uint64_t dims[4] = {(uint64_t)dh, (uint64_t)L, (uint64_t)H, (uint64_t)(B > 0 ? B : 1)};
   uint64_t str[3] = {(uint64_t)ld * 2, (uint64_t)dh * 2, (uint64_t)L * (uint64_t)ld * 2};
@@ -531,6 +736,21 @@ static int launch_band(const CUtensorMap* tm, const BandParams& p, cudaStream_t 
   const int grid = n_items < sm_count() ? n_items : sm_count();
   DB1_CUDA(launch_pdl(relattn_bwd_band_kernel<D, KIND>, dim3(grid), dim3(BW_THREADS), SM::TOTAL, stream, 1, tm[0], tm[1],
                       tm[2], tm[3], p));
+  return 0;
+}
+
+template <int D>
+static int launch_dkdv(const CUtensorMap* tm, const KvParams& p, cudaStream_t stream) {
+  using SM = KvSmem<D>;
+  static bool configured = false;
+  if (!configured) {
+    DB1_CUDA(cudaFuncSetAttribute(relattn_bwd_dkdv_kernel<D>, cudaFuncAttributeMaxDynamicSharedMemorySize, SM::TOTAL));
+    configured = true;
+  }
+  const int n_items = ((p.L + 127) / 128) * p.H * p.B;
+  const int grid = n_items < sm_count() ? n_items : sm_count();
+  DB1_CUDA(launch_pdl(relattn_bwd_dkdv_kernel<D>, dim3(grid), dim3(KV_THREADS), SM::TOTAL, stream, 1, tm[0], tm[1], tm[2],
+                      tm[3], p));
   return 0;
 }
 
@@ -586,4 +806,27 @@ extern "C" int db1_relattn_bwd_dr(const void* ds, const void* qv, long long ld_q
   if ((e = make_ds_map(&tm[3], ds, L, B * H))) return e;
   if (dh <= 64) return launch_band<64, 1>(tm, p, (cudaStream_t)stream_);
   return launch_band<128, 1>(tm, p, (cudaStream_t)stream_);
+}
+
+extern "C" int db1_relattn_bwd_dkdv(const void* probs, const void* ds, const void* dout, long long ld_do, const void* qu,
+                                    long long ld_qkv, void* dk, void* dv, long long ld_dkv, int B, int L, int H, int dh,
+                                    int window, void* stream_) {
+  int e = band_common_checks(ds, B, L, H, dh, window, ld_qkv, 8);
+  if (e) return e;
+  DB1_CHECK_ARG(probs && dout && qu && dk && dv, "relattn_bwd_dkdv: null pointer");
+  DB1_CHECK_ARG((reinterpret_cast<uintptr_t>(probs) & 15) == 0, "relattn_bwd_dkdv: probs must be 16-byte aligned");
+  DB1_CHECK_ARG(ld_do % 8 == 0 && ld_dkv % 8 == 0 &&
+                    ((reinterpret_cast<uintptr_t>(dk) | reinterpret_cast<uintptr_t>(dv)) & 15) == 0,
+                "relattn_bwd_dkdv: dk / dv rows must be 16-byte aligned");
+  KvParams p;
+  memset(&p, 0, sizeof(p));
+  p.L = L; p.H = H; p.B = B; p.dh = dh; p.window = window;
+  p.dk = (__half*)dk; p.dv = (__half*)dv; p.ld = ld_dkv;
+  CUtensorMap tm[4];
+  if ((e = make_ds_map(&tm[0], probs, L, B * H))) return e;
+  if ((e = make_ds_map(&tm[1], ds, L, B * H))) return e;
+  if ((e = make_head_map_bw(&tm[2], dout, dh, L, H, B, ld_do))) return e;
+  if ((e = make_head_map_bw(&tm[3], qu, dh, L, H, B, ld_qkv))) return e;
+  if (dh <= 64) return launch_dkdv<64>(tm, p, (cudaStream_t)stream_);
+  return launch_dkdv<128>(tm, p, (cudaStream_t)stream_);
 }

@@ -258,22 +258,17 @@ class AttnBlockFn(torch.autograd.Function):
             ops.gemm(dzz, Wo, do, rows, d, d, lda=d, ldb=d, ldc=d, b_mn=True, dot=(o, Drow, L, H))
         else:
             ops.gemm(dzz, Wo, do, rows, d, d, lda=d, ldb=d, ldc=d, b_mn=True)
-        # attention core: the recompute kernel writes P and dS once; dV / dK are causal tensor-core contractions over them;
-        # dq, du, dv and dR come from the two band kernels (csrc/relattn_bwd.cu), which un-shift dS on registers - no
-        # re-laid-out copy of dS, no separate dq / bias-gradient pass
-        P = _workspace("P", (B, H, L, L), f16, dev, tag=window)
-        dS = _workspace("dS", (B, H, L, L), f16, dev, tag=window)
+        # attention core: the recompute kernel writes P and dS once; three kernels with TMEM-resident accumulators consume them
+        # (csrc/relattn_bwd.cu): key-outer dV / dK, query-outer dq (+ du, dv), diagonal-outer dR; the adjoint of _rel_shift
+        # is done on registers - no re-laid-out copy of dS, no generic batched GEMMs, no separate dq / bias-gradient pass
+        P = _workspace("P", (B, H, L, L), f16, dev, zero=False)    # only tiles the recompute kernel wrote are ever read
+        dS = _workspace("dS", (B, H, L, L), f16, dev, zero=False)
         ops.relattn_bwd_ds(qkv4, rk, do, lse2, Drow, P, dS, B, L, H, dh, window, scale, o=o)
         qu = qkv4[:, 0:d]
         qv = qkv4[:, d:2 * d]
         kk = qkv4[:, 2 * d:3 * d]
-        LL = L * L
-        sz = (LL, H * LL)
         dqkv = torch.empty(rows, 3 * d, dtype=f16, device=dev)
-        ops.gemm(P, do, dqkv[:, 2 * d:], L, dh, L, lda=L, ldb=d, ldc=3 * d, a_mn=True, b_mn=True, Z1=H, Z2=B,
-                 a_z=sz, b_z=(dh, L * d), c_z=(dh, L * 3 * d), k_mode=ops.K_BEGIN_BY_ROW)
-        ops.gemm(dS, qu, dqkv[:, d:2 * d], L, dh, L, lda=L, ldb=4 * d, ldc=3 * d, a_mn=True, b_mn=True, Z1=H, Z2=B,
-                 a_z=sz, b_z=(dh, L * 4 * d), c_z=(dh, L * 3 * d), k_mode=ops.K_BEGIN_BY_ROW)
+        ops.relattn_bwd_dkdv(P, dS, do, qu, dqkv[:, d:2 * d], dqkv[:, 2 * d:], B, L, H, dh, window)
         ops.relattn_bwd_dq(dS, kk, rk, dqkv[:, 0:d], du, dv, B, L, H, dh, window)
         dr32 = _f32zeros(L * d, dev).view(L, d)
         ops.relattn_bwd_dr(dS, qv, dr32, B, L, H, dh, window)

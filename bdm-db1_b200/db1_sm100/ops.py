@@ -215,6 +215,20 @@ def relattn_bwd_ds(qkv4, r, dout, lse2, drow, probs, ds, B, L, H, dh, window, sc
         "db1_relattn_bwd_ds")
 
 
+def relattn_bwd_dkdv(probs, ds, dout, qu_view, dk_view, dv_view, B, L, H, dh, window):
+    """dv = P^T dO, dk = dS^T (q+u) per (sequence, head), key-outer with TMEM-resident accumulators;
+    include/db1_sm100.h:db1_relattn_bwd_dkdv. dk_view / dv_view: fp16 views [B*L, H*dh] with a common row stride."""
+    _need_cuda_half(probs, ds, dout, qu_view, dk_view, dv_view)
+    if dk_view.stride(0) != dv_view.stride(0):
+        raise _lib.Db1Error("relattn_bwd_dkdv: dk and dv views need the same row stride")
+    pairs = L * (L + 1) / 2.0 if window >= L else (window * (window + 1) / 2.0 + (L - window) * window)
+    with _Launch("relattn_bwd_dkdv", 1, B * H * pairs * dh * 4.0, 4.0 * B * H * pairs + 4.0 * B * L * H * dh * 2):
+      check(_lib.lib().db1_relattn_bwd_dkdv(ptr(probs), ptr(ds), ptr(dout), C.c_longlong(dout.stride(0)), ptr(qu_view),
+                                            C.c_longlong(qu_view.stride(0)), ptr(dk_view), ptr(dv_view),
+                                            C.c_longlong(dk_view.stride(0)), B, L, H, dh, int(window), cur_stream()),
+            "db1_relattn_bwd_dkdv")
+
+
 def relattn_bwd_dq(ds, k_view, r, dq_view, du, dv, B, L, H, dh, window):
     """dq (fp16 view [B*L, H*dh] with its own row stride), du / dv (fp32 [H*dh], accumulated) from dS, K and r;
     include/db1_sm100.h:db1_relattn_bwd_dq. k_view: the k columns of the fused QKV buffer."""

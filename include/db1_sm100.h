@@ -157,6 +157,12 @@ int db1_relattn_bwd_ds_o(const void* qu, const void* qv, const void* k, const vo
  *   r_w_bias / r_r_bias, transformer_xl.py:161, :167).   k: fp16 view [B,L,H,dh] with row stride ld_qkv; r: [L, H*dh].
  * db1_relattn_bwd_dr (diagonal-outer): dr[c, h*dh..] += sum_{b,(i,j): j+L-1-i=c} ds[i,j] * qv[b,i,h,:]   (fp32 [L, ld_dr],
  *   accumulated: the caller zero-fills it; gradient of r_net's output, adjoint of transformer_xl.py:167-171). */
+/* db1_relattn_bwd_dkdv (key-outer): dv[b*L+j, h*dh..] = sum_i probs[i,j] dout[b*L+i, h*dh..]  (adjoint of transformer_xl.py:220),
+ *   dk[b*L+j, h*dh..] = sum_i ds[i,j] qu[b,i,h,:]  (adjoint of :161-165); fp16, written; dk / dv share the row stride ld_dkv.
+ *   probs : fp16 [B,H,L,L] from db1_relattn_bwd_ds (same tiles valid as ds). */
+int db1_relattn_bwd_dkdv(const void* probs, const void* ds, const void* dout, long long ld_do, const void* qu,
+                         long long ld_qkv, void* dk, void* dv, long long ld_dkv, int B, int L, int H, int dh, int window,
+                         void* stream);
 int db1_relattn_bwd_dq(const void* ds, const void* k, long long ld_qkv, const void* r, long long ld_r, void* dq,
                        long long ld_dq, float* du, float* dv, int B, int L, int H, int dh, int window, void* stream);
 int db1_relattn_bwd_dr(const void* ds, const void* qv, long long ld_qkv, float* dr, long long ld_dr, int B, int L, int H,

@@ -165,3 +165,17 @@ def test_relattn_bwd_dq_dr_match_dense_formulas(cuda, B, L, H, dh, window):
     ops.relattn_bwd_dr(ds, qv, dr, B, L, H, dh, window)
     torch.cuda.synchronize()
     assert _rel(dr, 2 * dr_ref) < 1e-3
+    # key-outer kernel: dv = P^T dO, dk = dS^T (q+u)
+    probs = (torch.rand(B, H, L, L, generator=g) * ok).half().to(cuda)
+    probs = torch.where(torch.isnan(ds), ds, probs)  # same unvisited tiles poisoned
+    do = (torch.randn(B * L, d, generator=g) * 0.7).half().to(cuda)
+    qu = qkv4[:, 0:d]
+    dqkv.fill_(7.0)
+    ops.relattn_bwd_dkdv(probs, ds, do, qu, dqkv[:, d:2 * d], dqkv[:, 2 * d:], B, L, H, dh, window)
+    torch.cuda.synchronize()
+    pf = torch.nan_to_num(probs.float(), nan=0.0) * ok.to(cuda)
+    dv_ref = torch.einsum("bhij,bihd->bjhd", pf, do.float().reshape(B, L, H, dh)).reshape(B * L, d)
+    dk_ref = torch.einsum("bhij,bihd->bjhd", dsf, qu.float().reshape(B, L, H, dh)).reshape(B * L, d)
+    assert _rel(dqkv[:, 2 * d:], dv_ref) < 2e-3
+    assert _rel(dqkv[:, d:2 * d], dk_ref) < 2e-3
+    assert torch.all(dqkv[:, 0:d] == 7.0)

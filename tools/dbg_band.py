@@ -27,7 +27,10 @@ du = torch.zeros(d, dtype=torch.float32, device=dev)
 dv = torch.zeros(d, dtype=torch.float32, device=dev)
 dr = torch.zeros(L, d, dtype=torch.float32, device=dev)
 torch.cuda.synchronize()
-for name, fn in (("dq", lambda: ops.relattn_bwd_dq(ds, kk, r, dqkv[:, 0:d], du, dv, B, L, H, dh, window)),
+P = (torch.rand(B, H, L, L, generator=g, device=dev) * ok).half()
+do = (torch.randn(B * L, d, generator=g, device=dev) * 0.7).half()
+for name, fn in (("dkdv", lambda: ops.relattn_bwd_dkdv(P, ds, do, qkv4[:, 0:d], dqkv[:, d:2 * d], dqkv[:, 2 * d:], B, L, H, dh, window)),
+                 ("dq", lambda: ops.relattn_bwd_dq(ds, kk, r, dqkv[:, 0:d], du, dv, B, L, H, dh, window)),
                  ("dr", lambda: ops.relattn_bwd_dr(ds, qv, dr, B, L, H, dh, window))):
     print("launch", name, flush=True)
     t0 = time.time()
