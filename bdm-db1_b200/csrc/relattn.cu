@@ -48,6 +48,7 @@ struct AttnParams {
   long long lddo, ldop;
   float scale;         // mode 2: softmax scale (natural domain) applied to dS
   int q_start;         // first query row that is computed (memory-augmented inference: rows < q_start are memory)
+  int tiled;           // modes 1 / 2: P / dS are written as contiguous 128 x 128 tiles (see db1_relattn_bwd_ds_tiled)
 };
 
 template <int D>
@@ -462,9 +463,18 @@ relattn_fwd_kernel(const __grid_constant__ CUtensorMap tmQu, const __grid_consta
             }
             __syncwarp();
           };
-          const bool direct = (p.L & 15) == 0;  // rows 32-byte aligned: 256-bit stores straight from the row's owner
-          const long long zme = zrow0 + (long long)lane * p.L + J0 + cc * 32;
-          const int nvalid = (lane < rows_valid) ? (cols_valid > 32 ? 32 : (cols_valid < 0 ? 0 : cols_valid)) : 0;
+          // Tiled layout (what the backward's consumer kernels read by TMA): tile (b, h, I, J) = 32 KB contiguous, two
+          // slabs of [128 rows][64 columns]; every element of a visited tile is written (rows beyond the sequence as
+          // zeros), so a consumer's 16 KB box is one contiguous read and needs no bounds.
+          const long long tme = ((((long long)b * p.H + h) * nq + I) * nq + (I - st)) * 16384 + (cc >> 1) * 8192 +
+                                (long long)r * 64 + (cc & 1) * 32;
+          const bool direct = p.tiled || (p.L & 15) == 0;  // rows 32-byte aligned: 256-bit stores from the row's owner
+          const long long zme = p.tiled ? tme : zrow0 + (long long)lane * p.L + J0 + cc * 32;
+          const int nvalid = p.tiled ? 32 : ((lane < rows_valid) ? (cols_valid > 32 ? 32 : (cols_valid < 0 ? 0 : cols_valid)) : 0);
+          if (p.tiled && i >= p.L) {
+#pragma unroll
+            for (int t = 0; t < 16; ++t) pk[t] = 0u;
+          }
           if (direct) stg_row32(p.P + zme, pk, nvalid, true);
           else store_tile(pk, p.P + zrow0 + J0 + cc * 32);
           if (MODE == 2) {
@@ -477,6 +487,10 @@ relattn_fwd_kernel(const __grid_constant__ CUtensorMap tmQu, const __grid_consta
               const float2 pp = unpack_half2(pk[t]);
               dk[t] = pack_half2(pp.x * (__uint_as_float(dp[2 * t]) - d_row) * p.scale,
                                  pp.y * (__uint_as_float(dp[2 * t + 1]) - d_row) * p.scale);
+            }
+            if (p.tiled && i >= p.L) {
+#pragma unroll
+              for (int t = 0; t < 16; ++t) dk[t] = 0u;
             }
             if (direct) stg_row32(p.dS + zme, dk, nvalid, true);
             else store_tile(dk, p.dS + zrow0 + J0 + cc * 32);
@@ -577,12 +591,12 @@ static int relattn_launch(const void* qu, const void* qv, const void* k, const v
                           const void* r, long long ld_r, void* out, long long ld_out, float* lse2, void* probs,
                           const void* dout, long long ld_do, const float* drow, void* ds, int B, int L, int H, int dh,
                           int window, float scale, int mode, int q_start, cudaStream_t stream,
-                          const void* o_for_d = nullptr, long long ld_o_for_d = 0) {
+                          const void* o_for_d = nullptr, long long ld_o_for_d = 0, int tiled = 0) {
   DB1_CHECK_ARG(qu && qv && k && r && lse2, "relattn: null pointer");
   DB1_CHECK_ARG(q_start >= 0 && q_start < L && (q_start == 0 || mode == 0), "relattn: bad q_start %d", q_start);
   DB1_CHECK_ARG(B > 0 && L > 0 && H > 0, "relattn: bad shape B=%d L=%d H=%d", B, L, H);
   DB1_CHECK_ARG(dh % 8 == 0 && dh >= 8 && dh <= 128, "relattn: head dim %d unsupported (multiple of 8, <= 128)", dh);
-  DB1_CHECK_ARG(mode == 0 || L % 8 == 0, "relattn: sequence length %d must be a multiple of 8 for the P / dS outputs", L);
+  DB1_CHECK_ARG(mode == 0 || tiled || L % 8 == 0, "relattn: sequence length %d must be a multiple of 8 for the P / dS outputs", L);
   DB1_CHECK_ARG(ld_qkv % 8 == 0 && ld_r % 8 == 0 && ld_out % 8 == 0 && ld_do % 8 == 0,
                 "relattn: row strides must be multiples of 8");
   DB1_CHECK_ARG(window > 0, "relattn: window (mem_len) must be > 0; mem_len == 0 masks every key");
@@ -590,7 +604,7 @@ static int relattn_launch(const void* qu, const void* qv, const void* k, const v
   p.L = L; p.H = H; p.B = B; p.dh = dh; p.window = window;
   p.scale_log2 = scale * 1.4426950408889634f;
   p.O = (__half*)out; p.ldo = ld_out; p.lse2 = lse2; p.P = (__half*)probs; p.mode = mode;
-  p.dS = (__half*)ds; p.Drow = drow; p.scale = scale; p.q_start = q_start;
+  p.dS = (__half*)ds; p.Drow = drow; p.scale = scale; p.q_start = q_start; p.tiled = tiled;
   p.dOp = (const __half*)dout; p.lddo = ld_do; p.Op = (const __half*)o_for_d; p.ldop = ld_o_for_d;
   CUtensorMap tm[6];
   int e;
@@ -644,4 +658,20 @@ extern "C" int db1_relattn_bwd_ds_o(const void* qu, const void* qv, const void* 
   DB1_CHECK_ARG(ld_o % 8 == 0 && (((uintptr_t)o | (uintptr_t)dout) & 15) == 0, "relattn_bwd_ds_o: o / dout must be 16-byte aligned rows");
   return relattn_launch(qu, qv, k, v, ld_qkv, r, ld_r, nullptr, 0, const_cast<float*>(lse2), probs, dout, ld_do, nullptr,
                         ds, B, L, H, dh, window, scale, 2, 0, (cudaStream_t)stream_, o, ld_o);
+}
+
+/* Same as db1_relattn_bwd_ds / _o (drow may be NULL when o is given, and vice versa), writing P and dS in the TILED
+ * layout the consumer kernels of csrc/relattn_bwd.cu read: [B][H][nq][nq][2][128][64] fp16 with nq = ceil(L / 128) -
+ * tile (I, J) of a head = two contiguous slabs of 128 rows x 64 columns. Only visited (causal, in-window) tiles are
+ * written, completely (masked entries and rows beyond L as zeros). No restriction on L. */
+extern "C" int db1_relattn_bwd_ds_tiled(const void* qu, const void* qv, const void* k, const void* v, long long ld_qkv,
+                                        const void* r, long long ld_r, const void* dout, long long ld_do, const void* o,
+                                        long long ld_o, const float* lse2, const float* drow, void* probs, void* ds,
+                                        int B, int L, int H, int dh, int window, float scale, void* stream_) {
+  DB1_CHECK_ARG(v && dout && (o || drow) && probs && ds, "relattn_bwd_ds_tiled: null pointer");
+  DB1_CHECK_ARG(!o || (ld_o % 8 == 0 && (((uintptr_t)o | (uintptr_t)dout) & 15) == 0),
+                "relattn_bwd_ds_tiled: o / dout must be 16-byte aligned rows");
+  DB1_CHECK_ARG((((uintptr_t)probs | (uintptr_t)ds) & 31) == 0, "relattn_bwd_ds_tiled: probs / ds must be 32-byte aligned");
+  return relattn_launch(qu, qv, k, v, ld_qkv, r, ld_r, nullptr, 0, const_cast<float*>(lse2), probs, dout, ld_do, drow, ds,
+                        B, L, H, dh, window, scale, 2, 0, (cudaStream_t)stream_, drow ? nullptr : o, ld_o, 1);
 }

@@ -31,7 +31,7 @@ constexpr int BW_THREADS = 320;
 
 struct BandParams {
   int L, H, B, dh, window;
-  const __half* dS;  // [B,H,L,L] fp16, visited (causal, in-window) tiles valid, masked entries exactly 0
+  const __half* dS;  // tiled [B,H,nq,nq,2,128,64] fp16 (db1_relattn_bwd_ds_tiled): visited tiles valid, masked entries exactly 0
   __half* dq;        // KIND 0: [B*L, lddq], head h at column h*dh
   long long lddq;
   float* du;         // KIND 0: [H*dh] fp32, accumulated
@@ -255,8 +255,9 @@ relattn_bwd_band_kernel(const __grid_constant__ CUtensorMap tmK, const __grid_co
           const int buf = gs & 1;
           if (gs >= 2) mbar_wait(ds_free + buf, ((gs >> 1) - 1) & 1);
           mbar_expect_tx(bar_ds + buf, 32768);
-          tma_load_3d(smem + SM::DS + buf * 32768, &tmDS, bar_ds + buf, J0, I0, b * p.H + it.h);
-          tma_load_3d(smem + SM::DS + buf * 32768 + 16384, &tmDS, bar_ds + buf, J0 + 64, I0, b * p.H + it.h);
+          const int tile2 = (((b * p.H + it.h) * nq + (I0 >> 7)) * nq + (J0 >> 7)) * 2;  // slab index in the tiled dS
+          tma_load_3d(smem + SM::DS + buf * 32768, &tmDS, bar_ds + buf, 0, 0, tile2);
+          tma_load_3d(smem + SM::DS + buf * 32768 + 16384, &tmDS, bar_ds + buf, 0, 0, tile2 + 1);
           if (KIND == 0) {
             const int cb = p.L - 128 - 128 * st;  // first r row of this step's new chunk
             if (gs > 0) mbar_wait(b_free + 0, (gs - 1) & 1);
@@ -604,7 +605,6 @@ relattn_bwd_dkdv_kernel(const __grid_constant__ CUtensorMap tmP, const __grid_co
         const int k = item_of(pass);
         if (k < 0) continue;
         const Item it = decode(k);
-        const int J0 = it.J * 128;
         const int bh = it.b * p.H + it.h;
         for (int st = 0; st < it.nsteps; ++st) {
           const int I0 = (it.J + st) * 128;
@@ -617,8 +617,9 @@ relattn_bwd_dkdv_kernel(const __grid_constant__ CUtensorMap tmP, const __grid_co
             mbar_expect_tx(full + sg, SM::STAGE);
             const CUtensorMap* ms = sub ? &tmDS : &tmP;
             const CUtensorMap* mr = sub ? &tmQu : &tmDO;
-            tma_load_3d(base, ms, full + sg, J0, I0, bh);
-            tma_load_3d(base + 16384, ms, full + sg, J0 + 64, I0, bh);
+            const int tile2 = ((bh * nq + (I0 >> 7)) * nq + it.J) * 2;  // slab index in the tiled P / dS
+            tma_load_3d(base, ms, full + sg, 0, 0, tile2);
+            tma_load_3d(base + 16384, ms, full + sg, 0, 0, tile2 + 1);
 #pragma unroll
             for (int s = 0; s < NSLAB; ++s) tma_load_4d(base + 32768 + s * 16384, mr, full + sg, s * 64, I0, it.h, it.b);
           }
@@ -712,11 +713,12 @@ static int make_head_map_bw(CUtensorMap* tm, const void* base, int dh, int L, in
   return make_tmap_f16(tm, base, 4, dims, str, box);
 }
 
-// dS [B*H, L, L] fp16: box = 128 rows x 64 columns (one K-major slab of the dS tile), 128-byte swizzle; rows / columns
-// beyond L arrive as zeros
+// P / dS in the tiled layout written by db1_relattn_bwd_ds_tiled: [B*H][nq][nq][2 slabs][128 rows][64 columns] fp16.
+// One box = one slab = 16 KB contiguous (128-byte swizzle on the way into shared memory): index = tile * 2 + slab.
 static int make_ds_map(CUtensorMap* tm, const void* ds, int L, int BH) {
-  uint64_t dims[3] = {(uint64_t)L, (uint64_t)L, (uint64_t)BH};
-  uint64_t str[2] = {(uint64_t)L * 2, (uint64_t)L * (uint64_t)L * 2};
+  const int nq = (L + 127) / 128;
+  uint64_t dims[3] = {64, 128, (uint64_t)BH * nq * nq * 2};
+  uint64_t str[2] = {128, 16384};
   uint32_t box[3] = {64, 128, 1};
   return make_tmap_f16(tm, ds, 3, dims, str, box);
 }
@@ -762,7 +764,6 @@ static int band_common_checks(const void* ds, int B, int L, int H, int dh, int w
   DB1_CHECK_ARG(ds != nullptr, "relattn_bwd: null dS");
   DB1_CHECK_ARG(B > 0 && L > 0 && H > 0, "relattn_bwd: bad shape B=%d L=%d H=%d", B, L, H);
   DB1_CHECK_ARG(dh % 8 == 0 && dh >= 8 && dh <= 128, "relattn_bwd: head dim %d unsupported (multiple of 8, <= 128)", dh);
-  DB1_CHECK_ARG(L % 8 == 0, "relattn_bwd: sequence length %d must be a multiple of 8", L);
   DB1_CHECK_ARG(window > 0, "relattn_bwd: window must be > 0");
   DB1_CHECK_ARG(ld_qkv % 8 == 0 && ld_r % 8 == 0, "relattn_bwd: row strides must be multiples of 8");
   DB1_CHECK_ARG((reinterpret_cast<uintptr_t>(ds) & 15) == 0, "relattn_bwd: dS must be 16-byte aligned");

@@ -195,6 +195,12 @@ def _to_half(x32, shape):
     return out
 
 
+def _attn_bwd_chunk(B):
+    import os
+    v = int(os.environ.get("DB1_ATTN_BWD_CHUNK", "0"))
+    return B if v <= 0 else min(B, v)
+
+
 class AttnBlockFn(torch.autograd.Function):
     """RelPartialLearnableMultiHeadAttn.forward, post-LN branch (transformer_xl.py:112-243):
     out = LayerNorm(w + dropout(o_net(rel_attention(qkv_net(w), r_net(r)))))."""
@@ -261,17 +267,23 @@ class AttnBlockFn(torch.autograd.Function):
         # attention core: the recompute kernel writes P and dS once; three kernels with TMEM-resident accumulators consume them
         # (csrc/relattn_bwd.cu): key-outer dV / dK, query-outer dq (+ du, dv), diagonal-outer dR; the adjoint of _rel_shift
         # is done on registers - no re-laid-out copy of dS, no generic batched GEMMs, no separate dq / bias-gradient pass
-        P = _workspace("P", (B, H, L, L), f16, dev, zero=False)    # only tiles the recompute kernel wrote are ever read
-        dS = _workspace("dS", (B, H, L, L), f16, dev, zero=False)
-        ops.relattn_bwd_ds(qkv4, rk, do, lse2, Drow, P, dS, B, L, H, dh, window, scale, o=o)
-        qu = qkv4[:, 0:d]
-        qv = qkv4[:, d:2 * d]
-        kk = qkv4[:, 2 * d:3 * d]
+        # The four kernels run per chunk of `bc` sequences so that the chunk's P + dS scratch (2 * bc * H * nq^2 * 32 KB) can
+        # stay in the 126 MB L2 between its producer and its three consumers (DB1_ATTN_BWD_CHUNK, default: whole batch).
+        bc = _attn_bwd_chunk(B)
+        tshape = ops.score_tiles_shape(bc, L, H)  # tiled scratch: only tiles the recompute kernel wrote are ever read
+        P = _workspace("P", tshape, f16, dev, zero=False)
+        dS = _workspace("dS", tshape, f16, dev, zero=False)
         dqkv = torch.empty(rows, 3 * d, dtype=f16, device=dev)
-        ops.relattn_bwd_dkdv(P, dS, do, qu, dqkv[:, d:2 * d], dqkv[:, 2 * d:], B, L, H, dh, window)
-        ops.relattn_bwd_dq(dS, kk, rk, dqkv[:, 0:d], du, dv, B, L, H, dh, window)
         dr32 = _f32zeros(L * d, dev).view(L, d)
-        ops.relattn_bwd_dr(dS, qv, dr32, B, L, H, dh, window)
+        for b0 in range(0, B, bc):
+            nb = min(bc, B - b0)
+            rs = slice(b0 * L, (b0 + nb) * L)
+            q4, do_c, o_c, dq_c = qkv4[rs], do[rs], o[rs], dqkv[rs]
+            ops.relattn_bwd_ds_tiled(q4, rk, do_c, lse2[b0:b0 + nb], Drow[b0:b0 + nb] if Drow is not None else None, P, dS,
+                                     nb, L, H, dh, window, scale, o=o_c)
+            ops.relattn_bwd_dkdv(P, dS, do_c, q4[:, 0:d], dq_c[:, d:2 * d], dq_c[:, 2 * d:], nb, L, H, dh, window)
+            ops.relattn_bwd_dq(dS, q4[:, 2 * d:3 * d], rk, dq_c[:, 0:d], du, dv, nb, L, H, dh, window)
+            ops.relattn_bwd_dr(dS, q4[:, d:2 * d], dr32, nb, L, H, dh, window)
         drk = _to_half(dr32, (L, d))
         # r_net / qkv_net
         gWr = _Grad(pWr)

@@ -250,6 +250,27 @@ def relattn_bwd_dr(ds, qv_view, dr32, B, L, H, dh, window):
             "db1_relattn_bwd_dr")
 
 
+def score_tiles_shape(B, L, H):
+    """Shape of the tiled P / dS scratch (include/db1_sm100.h:db1_relattn_bwd_ds_tiled)."""
+    nq = (L + 127) // 128
+    return (B, H, nq, nq, 2, 128, 64)
+
+
+def relattn_bwd_ds_tiled(qkv4, r, dout, lse2, drow, probs, ds, B, L, H, dh, window, scale, o=None):
+    """P and dS = P * (dO V^T - D) * scale in the tiled layout read by relattn_bwd_dkdv / _dq / _dr."""
+    _need_cuda_half(qkv4, r, dout, probs, ds, o)
+    d = H * dh
+    es = qkv4.element_size()
+    base = qkv4.data_ptr()
+    pairs = L * (L + 1) / 2.0 if window >= L else (window * (window + 1) / 2.0 + (L - window) * window)
+    with _Launch("relattn_bwd_ds", 1, B * H * pairs * dh * 6.0):
+      check(_lib.lib().db1_relattn_bwd_ds_tiled(
+        C.c_void_p(base), C.c_void_p(base + d * es), C.c_void_p(base + 2 * d * es), C.c_void_p(base + 3 * d * es),
+        C.c_longlong(qkv4.stride(0)), ptr(r), C.c_longlong(r.stride(0)), ptr(dout), C.c_longlong(dout.stride(0)),
+        ptr(o), C.c_longlong(o.stride(0) if o is not None else 0), _f32(lse2), _f32(drow) if drow is not None else None,
+        ptr(probs), ptr(ds), B, L, H, dh, int(window), C.c_float(scale), cur_stream()), "db1_relattn_bwd_ds_tiled")
+
+
 def _f32(t):
     if t is not None and (not t.is_cuda or t.dtype != torch.float32):
         raise _lib.Db1Error("expected a CUDA fp32 tensor, got %s on %s" % (t.dtype, t.device))

@@ -148,10 +148,20 @@ int db1_relattn_bwd_ds_o(const void* qu, const void* qv, const void* k, const vo
                          const float* lse2, void* probs, void* ds, int B, int L, int H, int dh, int window, float scale,
                          void* stream);
 
+/* As db1_relattn_bwd_ds (drow given) / db1_relattn_bwd_ds_o (o given, drow NULL), but P and dS are written in the TILED
+ * layout [B][H][nq][nq][2][128][64] fp16, nq = ceil(L/128): tile (I, J) of a head = two contiguous slabs of 128 rows x 64
+ * columns. Visited tiles are written completely (masked entries, rows / columns beyond L: zeros); any L. This is the
+ * producer for db1_relattn_bwd_dkdv / _dq / _dr, whose TMA boxes are then single contiguous 16 KB reads. */
+int db1_relattn_bwd_ds_tiled(const void* qu, const void* qv, const void* k, const void* v, long long ld_qkv, const void* r,
+                             long long ld_r, const void* dout, long long ld_do, const void* o, long long ld_o,
+                             const float* lse2, const float* drow, void* probs, void* ds, int B, int L, int H, int dh,
+                             int window, float scale, void* stream);
+
 /* Attention backward, second half (csrc/relattn_bwd.cu): everything that consumes dS, on tcgen05 with the accumulators
  * resident in TMEM; the adjoint of _rel_shift (transformer_xl.py:98-110) is done on registers per tile row, so no
  * re-laid-out copy of dS (dSr) exists and P / dS are not re-read by generic GEMMs.
- *   ds : fp16 [B,H,L,L] from db1_relattn_bwd_ds (visited causal / in-window tiles; masked entries exactly 0)
+ *   ds : fp16, TILED layout [B,H,nq,nq,2,128,64] from db1_relattn_bwd_ds_tiled (nq = ceil(L/128); visited causal /
+ *        in-window tiles complete, masked entries exactly 0; tile (I,J) = two contiguous 16 KB slabs = one TMA box each)
  * db1_relattn_bwd_dq (query-outer): dq[b*L+i, h*dh..] = sum_j ds[i,j] k_j + sum_j ds[i,j] r[j+L-1-i]   (fp16, written)
  *   du[h*dh..] += sum_{b,i} (ds . K)_i ;  dv[h*dh..] += sum_{b,i} (unshift(ds) . R)_i     (fp32, accumulated: gradients of
  *   r_w_bias / r_r_bias, transformer_xl.py:161, :167).   k: fp16 view [B,L,H,dh] with row stride ld_qkv; r: [L, H*dh].
@@ -159,7 +169,7 @@ int db1_relattn_bwd_ds_o(const void* qu, const void* qv, const void* k, const vo
  *   accumulated: the caller zero-fills it; gradient of r_net's output, adjoint of transformer_xl.py:167-171). */
 /* db1_relattn_bwd_dkdv (key-outer): dv[b*L+j, h*dh..] = sum_i probs[i,j] dout[b*L+i, h*dh..]  (adjoint of transformer_xl.py:220),
  *   dk[b*L+j, h*dh..] = sum_i ds[i,j] qu[b,i,h,:]  (adjoint of :161-165); fp16, written; dk / dv share the row stride ld_dkv.
- *   probs : fp16 [B,H,L,L] from db1_relattn_bwd_ds (same tiles valid as ds). */
+ *   probs : fp16, tiled like ds (db1_relattn_bwd_ds_tiled). */
 int db1_relattn_bwd_dkdv(const void* probs, const void* ds, const void* dout, long long ld_do, const void* qu,
                          long long ld_qkv, void* dk, void* dv, long long ld_dkv, int B, int L, int H, int dh, int window,
                          void* stream);

@@ -101,6 +101,41 @@ def test_relattn_bwd_ds_matches_autograd(cuda, B, L, H, dh, window):
     assert torch.equal(P2, P)
     assert _rel(dS2.cpu(), ds_ref) < 5e-3
     assert (dS2.float() - dS.float()).abs().max().item() <= 2e-3 * dS.float().abs().max().item()
+    # tiled producer (what the model's backward uses): same values on every visited tile, zeros where masked
+    shp = ops.score_tiles_shape(B, L, H)
+    Pt = torch.full(shp, float("nan"), dtype=torch.half, device=cuda)
+    dSt = torch.full(shp, float("nan"), dtype=torch.half, device=cuda)
+    ops.relattn_bwd_ds_tiled(qkv4, r, do_d, lse2, None, Pt, dSt, B, L, H, dh, window, scale, o=out)
+    torch.cuda.synchronize()
+    nq = (L + 127) // 128
+    for I in range(nq):
+        jlo = max(0, I * 128 - window + 1) // 128
+        for J in range(nq):
+            rows = slice(I * 128, min(L, (I + 1) * 128))
+            cols = slice(J * 128, min(L, (J + 1) * 128))
+            if jlo <= J <= I:
+                assert not torch.isnan(Pt[:, :, I, J]).any() and not torch.isnan(dSt[:, :, I, J]).any()
+                assert torch.equal(_from_tiles(Pt, L)[:, :, rows, cols], P2[:, :, rows, cols])
+                assert torch.equal(_from_tiles(dSt, L)[:, :, rows, cols], dS2[:, :, rows, cols])
+            else:
+                assert torch.isnan(Pt[:, :, I, J]).all()  # never touched
+    # rows / columns beyond the sequence inside visited tiles are zeros
+    full = _from_tiles(torch.nan_to_num(Pt, nan=0.0), nq * 128)
+    assert full[:, :, L:, :].abs().max().item() == 0 if nq * 128 > L else True
+
+
+def _to_tiles(x):
+    """[B,H,L,L] -> the tiled scratch layout [B,H,nq,nq,2,128,64] (zero padded to whole tiles)."""
+    B, H, L, _ = x.shape
+    nq = (L + 127) // 128
+    xp = torch.zeros(B, H, nq * 128, nq * 128, dtype=x.dtype, device=x.device)
+    xp[:, :, :L, :L] = x
+    return xp.view(B, H, nq, 128, nq, 2, 64).permute(0, 1, 2, 4, 5, 3, 6).contiguous()
+
+
+def _from_tiles(t, L):
+    B, H, nq = t.shape[:3]
+    return t.permute(0, 1, 2, 5, 3, 4, 6).reshape(B, H, nq * 128, nq * 128)[:, :, :L, :L]
 
 
 def _unshift_ref(ds):
@@ -118,7 +153,7 @@ def _unshift_ref(ds):
 @pytest.mark.parametrize("B,L,H,dh,window", [(1, 128, 1, 128, 1 << 20), (2, 256, 2, 128, 1 << 20), (3, 384, 2, 128, 1 << 20),
                                              (1, 512, 2, 128, 200), (2, 256, 4, 32, 1 << 20), (1, 200, 2, 64, 77),
                                              (2, 1024, 2, 128, 1024), (1, 1024, 1, 128, 300),
-                                             (2, 1024, 16, 128, 1024), (3, 640, 24, 64, 1 << 20)])
+                                             (2, 1024, 16, 128, 1024), (3, 640, 24, 64, 1 << 20), (2, 331, 3, 64, 1 << 20)])
 def test_relattn_bwd_dq_dr_match_dense_formulas(cuda, B, L, H, dh, window):
     """db1_relattn_bwd_dq / db1_relattn_bwd_dr against the dense fp32 formulas:
     dq = dS K + unshift(dS) R, du = sum dS K, dv = sum unshift(dS) R, dR = sum_b unshift(dS)^T (q+v)."""
@@ -129,13 +164,12 @@ def test_relattn_bwd_dq_dr_match_dense_formulas(cuda, B, L, H, dh, window):
     j = torch.arange(L)[None, :]
     ok = (j <= i) & (i - j < window)
     ds = (torch.randn(B, H, L, L, generator=g) * ok).half().to(cuda)
+    ds_t = _to_tiles(ds)
     # tiles the recompute kernel never visits hold garbage in production: poison them
     nq = (L + 127) // 128
-    for I in range(nq):
-        for J in range(nq):
-            jlo = max(0, I * 128 - window + 1)
-            if J > I or J < jlo // 128:
-                ds[:, :, I * 128:(I + 1) * 128, J * 128:(J + 1) * 128] = float("nan")
+    unvisited = [(I, J) for I in range(nq) for J in range(nq) if J > I or J < max(0, I * 128 - window + 1) // 128]
+    for I, J in unvisited:
+        ds_t[:, :, I, J] = float("nan")
     qkv4 = (torch.randn(B * L, 4 * d, generator=g) * 0.7).half().to(cuda)
     r = (torch.randn(L, d, generator=g) * 0.7).half().to(cuda)
     qv = qkv4[:, d:2 * d]
@@ -144,10 +178,10 @@ def test_relattn_bwd_dq_dr_match_dense_formulas(cuda, B, L, H, dh, window):
     du = torch.zeros(d, dtype=torch.float32, device=cuda)
     dv = torch.zeros(d, dtype=torch.float32, device=cuda)
     dr = torch.zeros(L, d, dtype=torch.float32, device=cuda)
-    ops.relattn_bwd_dq(ds, kk, r, dqkv[:, 0:d], du, dv, B, L, H, dh, window)
-    ops.relattn_bwd_dr(ds, qv, dr, B, L, H, dh, window)
+    ops.relattn_bwd_dq(ds_t, kk, r, dqkv[:, 0:d], du, dv, B, L, H, dh, window)
+    ops.relattn_bwd_dr(ds_t, qv, dr, B, L, H, dh, window)
     torch.cuda.synchronize()
-    dsf = torch.nan_to_num(ds.float(), nan=0.0) * ok.to(cuda)
+    dsf = ds.float() * ok.to(cuda)
     dsr = _unshift_ref(dsf)
     K4 = kk.float().reshape(B, L, H, dh)
     Qv4 = qv.float().reshape(B, L, H, dh)
@@ -162,18 +196,20 @@ def test_relattn_bwd_dq_dr_match_dense_formulas(cuda, B, L, H, dh, window):
     dr_ref = torch.einsum("bhic,bihd->chd", dsr, Qv4).reshape(L, d)
     assert _rel(dr, dr_ref) < 1e-3
     # accumulation contract: a second call adds
-    ops.relattn_bwd_dr(ds, qv, dr, B, L, H, dh, window)
+    ops.relattn_bwd_dr(ds_t, qv, dr, B, L, H, dh, window)
     torch.cuda.synchronize()
     assert _rel(dr, 2 * dr_ref) < 1e-3
     # key-outer kernel: dv = P^T dO, dk = dS^T (q+u)
     probs = (torch.rand(B, H, L, L, generator=g) * ok).half().to(cuda)
-    probs = torch.where(torch.isnan(ds), ds, probs)  # same unvisited tiles poisoned
+    probs_t = _to_tiles(probs)
+    for I, J in unvisited:
+        probs_t[:, :, I, J] = float("nan")
     do = (torch.randn(B * L, d, generator=g) * 0.7).half().to(cuda)
     qu = qkv4[:, 0:d]
     dqkv.fill_(7.0)
-    ops.relattn_bwd_dkdv(probs, ds, do, qu, dqkv[:, d:2 * d], dqkv[:, 2 * d:], B, L, H, dh, window)
+    ops.relattn_bwd_dkdv(probs_t, ds_t, do, qu, dqkv[:, d:2 * d], dqkv[:, 2 * d:], B, L, H, dh, window)
     torch.cuda.synchronize()
-    pf = torch.nan_to_num(probs.float(), nan=0.0) * ok.to(cuda)
+    pf = probs.float() * ok.to(cuda)
     dv_ref = torch.einsum("bhij,bihd->bjhd", pf, do.float().reshape(B, L, H, dh)).reshape(B * L, d)
     dk_ref = torch.einsum("bhij,bihd->bjhd", dsf, qu.float().reshape(B, L, H, dh)).reshape(B * L, d)
     assert _rel(dqkv[:, 2 * d:], dv_ref) < 2e-3

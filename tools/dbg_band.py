@@ -18,7 +18,7 @@ g = torch.Generator(device="cuda").manual_seed(1)
 i = torch.arange(L, device=dev)[:, None]
 j = torch.arange(L, device=dev)[None, :]
 ok = (j <= i) & (i - j < window)
-ds = (torch.randn(B, H, L, L, generator=g, device=dev) * ok).half()
+ds = (torch.randn(ops.score_tiles_shape(B, L, H), generator=g, device=dev)).half()
 qkv4 = (torch.randn(B * L, 4 * d, generator=g, device=dev) * 0.7).half()
 r = (torch.randn(L, d, generator=g, device=dev) * 0.7).half()
 qv, kk = qkv4[:, d:2 * d], qkv4[:, 2 * d:3 * d]
@@ -27,7 +27,7 @@ du = torch.zeros(d, dtype=torch.float32, device=dev)
 dv = torch.zeros(d, dtype=torch.float32, device=dev)
 dr = torch.zeros(L, d, dtype=torch.float32, device=dev)
 torch.cuda.synchronize()
-P = (torch.rand(B, H, L, L, generator=g, device=dev) * ok).half()
+P = (torch.rand(ops.score_tiles_shape(B, L, H), generator=g, device=dev)).half()
 do = (torch.randn(B * L, d, generator=g, device=dev) * 0.7).half()
 for name, fn in (("dkdv", lambda: ops.relattn_bwd_dkdv(P, ds, do, qkv4[:, 0:d], dqkv[:, d:2 * d], dqkv[:, 2 * d:], B, L, H, dh, window)),
                  ("dq", lambda: ops.relattn_bwd_dq(ds, kk, r, dqkv[:, 0:d], du, dv, B, L, H, dh, window)),
