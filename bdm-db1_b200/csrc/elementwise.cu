@@ -458,10 +458,14 @@ ce_fwd_kernel(const __half* __restrict__ logits, long long ld, const long long* 
   const float tot = block_sum2(sm, 0.f, scratch).x;
   if (threadIdx.x == 0) {
     const float lse = bm + logf(tot);
+    // A label outside [0, V) is never dereferenced: the row contributes zero loss (and zero gradient in ce_bwd), which is
+    // what nn.CrossEntropyLoss does for its ignore_index (-100); sum(mask) in the denominator is unchanged, as in
+    // transformer_xl.py:606-609. (Other out-of-range labels make the reference raise a device assert.)
     const long long lab = labels[row];
-    const float zl = __half2float(z[lab]);
+    const bool ok = lab >= 0 && lab < (long long)V;
+    const float zl = ok ? __half2float(z[lab]) : 0.f;
     row_lse[row] = lse;
-    row_loss[row] = (lse - zl) * mask[row];
+    row_loss[row] = ok ? (lse - zl) * mask[row] : 0.f;
   }
 }
 
@@ -489,9 +493,11 @@ ce_bwd_kernel(const __half* __restrict__ logits, long long ld, const long long* 
   const int row = blockIdx.x;
   const __half* z = logits + (size_t)row * ld;
   __half* dzp = dlogits + (size_t)row * ldd;
-  const float w = mask[row] / loss2[1] * gscale[0];
+  const long long lab_ll = labels[row];
+  const bool lab_ok = lab_ll >= 0 && lab_ll < (long long)V;
+  const float w = lab_ok ? mask[row] / loss2[1] * gscale[0] : 0.f;  // ignored row: no gradient (see ce_fwd_kernel)
   const float lse = row_lse[row];
-  const int lab = (int)labels[row];
+  const int lab = lab_ok ? (int)lab_ll : -1;
   const int nch = (V + 7) / 8;
   for (int ch = threadIdx.x; ch < nch; ch += CE_THREADS) {
     float f[8], o[8];
@@ -793,7 +799,7 @@ rowdot_rows_kernel(const __half* __restrict__ a, const __half* __restrict__ b, l
 
 // sinusoid rows in the reference order: row c <-> distance min(klen-1-c, clamp); [sin | cos]; fp32 math -> fp16, dropout
 __global__ void posemb_kernel(__half* __restrict__ out, const float* __restrict__ inv_freq, int klen, int d,
-                              int clamp_len, uint32_t drop_thr16, float drop_scale, uint64_t seed) {
+                              int clamp_len, uint32_t drop_thr16, float drop_scale, uint64_t seed, int half_phase) {
   const int idx = blockIdx.x * blockDim.x + threadIdx.x;
   const int half_d = d / 2;
   if (idx >= klen * half_d) return;
@@ -801,7 +807,12 @@ __global__ void posemb_kernel(__half* __restrict__ out, const float* __restrict_
   float pos = (float)(klen - 1 - c);
   if (clamp_len > 0 && pos > (float)clamp_len) pos = (float)clamp_len;
   // inv_freq is the module's registered buffer (transformer_xl.py:40-41), so both sides use identical frequencies
-  const float ang = pos * inv_freq[k];
+  float ang = pos * inv_freq[k];
+  if (half_phase) {
+    // what the reference computes after module.half() (transformer_xl.py:569-571 with fp16 hidden states, :44 with the
+    // fp16-cast inv_freq buffer): position, frequency and their product are each rounded to fp16 before sin / cos
+    ang = __half2float(__float2half_rn(__half2float(__float2half_rn(pos)) * __half2float(__float2half_rn(inv_freq[k]))));
+  }
   float sv = sinf(ang), cv = cosf(ang);
   if (drop_thr16) {
     const uint64_t e1 = (uint64_t)c * d + k, e2 = (uint64_t)c * d + half_d + k;
@@ -1005,15 +1016,25 @@ extern "C" int db1_rowdot(const void* a, const void* b, long long ld, float* out
   return 0;
 }
 
-extern "C" int db1_posemb(void* out, const float* inv_freq, int klen, int d, int clamp_len, float drop_p, uint64_t seed,
-                          void* stream) {
+static int posemb_launch(void* out, const float* inv_freq, int klen, int d, int clamp_len, float drop_p, uint64_t seed,
+                         int half_phase, void* stream) {
   DB1_CHECK_ARG(out && inv_freq && klen > 0 && d > 0 && d % 2 == 0, "posemb: bad arguments");
   const uint32_t t = thr16(drop_p);
   const int n = klen * (d / 2);
   posemb_kernel<<<(n + 255) / 256, 256, 0, (cudaStream_t)stream>>>((__half*)out, inv_freq, klen, d, clamp_len, t, dscale(t),
-                                                                 seed);
+                                                                 seed, half_phase);
   DB1_CUDA(cudaGetLastError());
   return 0;
+}
+
+extern "C" int db1_posemb(void* out, const float* inv_freq, int klen, int d, int clamp_len, float drop_p, uint64_t seed,
+                          void* stream) {
+  return posemb_launch(out, inv_freq, klen, d, clamp_len, drop_p, seed, 0, stream);
+}
+
+extern "C" int db1_posemb_half_phase(void* out, const float* inv_freq, int klen, int d, int clamp_len, float drop_p,
+                                     uint64_t seed, void* stream) {
+  return posemb_launch(out, inv_freq, klen, d, clamp_len, drop_p, seed, 1, stream);
 }
 
 extern "C" int db1_rel_unshift(const void* ds, void* dsr, int Z, int L, void* stream) {

@@ -50,9 +50,14 @@ transpose_kernel(const __half* __restrict__ in, __half* __restrict__ out, int ro
 // ------------------------------------------------------------------------------------------------ standardise + conv1
 // One CTA (256 threads = pixels) per patch. xs [P, C, 256] keeps the standardised pixels (fp16) for the weight
 // gradient; y1 [P, 256, 64] = conv3x3(xs) + bias.
-template <int C>
+DEVI float px_to_float(__half v) { return __half2float(v); }
+DEVI float px_to_float(float v) { return v; }
+
+// PT = pixel storage type: fp16, or fp32 (the reference standardises in the INPUT dtype, :73-77, and only then casts to
+// the module dtype, :79 - with fp32 frames the mean / std must see the unrounded pixels)
+template <int C, typename PT>
 __global__ void __launch_bounds__(256)
-patch_conv1_fwd_kernel(const __half* __restrict__ pixels, const __half* __restrict__ W1, const __half* __restrict__ b1,
+patch_conv1_fwd_kernel(const PT* __restrict__ pixels, const __half* __restrict__ W1, const __half* __restrict__ b1,
                        __half* __restrict__ xs, __half* __restrict__ y1, int Himg, int Wimg, int h0, int w0) {
   __shared__ float xpad[C][PADW * PADW];
   __shared__ float wsm[C * 9][CH];  // [ci*9 + tap][co]
@@ -69,7 +74,7 @@ patch_conv1_fwd_kernel(const __half* __restrict__ pixels, const __half* __restri
   float v[C];
 #pragma unroll
   for (int c = 0; c < C; ++c)
-    v[c] = __half2float(pixels[(((size_t)n * C + c) * Himg + (pr * 16 + y)) * Wimg + pc * 16 + x]);
+    v[c] = px_to_float(pixels[(((size_t)n * C + c) * Himg + (pr * 16 + y)) * Wimg + pc * 16 + x]);
   // mean, then centred unbiased variance (torch.std default), per channel over the 256 pixels
   float part[2 * C];
 #pragma unroll
@@ -375,8 +380,9 @@ extern "C" int db1_transpose_f16(const void* in, void* out, int batch, int rows,
   return 0;
 }
 
-extern "C" int db1_patch_conv1_fwd(const void* pixels, const void* W1, const void* b1, void* xs, void* y1, int N, int C,
-                                   int Himg, int Wimg, void* stream) {
+template <typename PT>
+static int patch_conv1_fwd_launch(const void* pixels, const void* W1, const void* b1, void* xs, void* y1, int N, int C,
+                                  int Himg, int Wimg, void* stream) {
   DB1_CHECK_ARG(pixels && W1 && b1 && xs && y1, "patch_conv1_fwd: null pointer");
   DB1_CHECK_ARG(N > 0 && Himg > 0 && Wimg > 0 && Himg % 16 == 0 && Wimg % 16 == 0,
                 "patch_conv1_fwd: image %dx%d must be a multiple of the 16x16 patch (as the reference's rearrange requires)",
@@ -385,15 +391,25 @@ extern "C" int db1_patch_conv1_fwd(const void* pixels, const void* W1, const voi
   const int h0 = Himg / 16, w0 = Wimg / 16;
   const int P = N * h0 * w0;
   if (C == 3)
-    patch_conv1_fwd_kernel<3><<<P, 256, 0, (cudaStream_t)stream>>>((const __half*)pixels, (const __half*)W1,
-                                                                  (const __half*)b1, (__half*)xs, (__half*)y1, Himg,
-                                                                  Wimg, h0, w0);
+    patch_conv1_fwd_kernel<3, PT><<<P, 256, 0, (cudaStream_t)stream>>>((const PT*)pixels, (const __half*)W1,
+                                                                      (const __half*)b1, (__half*)xs, (__half*)y1, Himg,
+                                                                      Wimg, h0, w0);
   else
-    patch_conv1_fwd_kernel<1><<<P, 256, 0, (cudaStream_t)stream>>>((const __half*)pixels, (const __half*)W1,
-                                                                  (const __half*)b1, (__half*)xs, (__half*)y1, Himg,
-                                                                  Wimg, h0, w0);
+    patch_conv1_fwd_kernel<1, PT><<<P, 256, 0, (cudaStream_t)stream>>>((const PT*)pixels, (const __half*)W1,
+                                                                      (const __half*)b1, (__half*)xs, (__half*)y1, Himg,
+                                                                      Wimg, h0, w0);
   DB1_CUDA(cudaGetLastError());
   return 0;
+}
+
+extern "C" int db1_patch_conv1_fwd(const void* pixels, const void* W1, const void* b1, void* xs, void* y1, int N, int C,
+                                   int Himg, int Wimg, void* stream) {
+  return patch_conv1_fwd_launch<__half>(pixels, W1, b1, xs, y1, N, C, Himg, Wimg, stream);
+}
+
+extern "C" int db1_patch_conv1_fwd_f32(const float* pixels, const void* W1, const void* b1, void* xs, void* y1, int N,
+                                       int C, int Himg, int Wimg, void* stream) {
+  return patch_conv1_fwd_launch<float>(pixels, W1, b1, xs, y1, N, C, Himg, Wimg, stream);
 }
 
 extern "C" int db1_patch_conv1_bwd(const void* xs, const void* dy1, float* dW1, int P, int C, void* stream) {

@@ -295,7 +295,9 @@ class DB1Engine:
             total += f.float().pow(2).sum()
         norm = total.sqrt() * inv
         if not torch.isfinite(norm):
-            self.loss_scale = max(self.loss_scale / 2, 1.0)
+            self.loss_scale = max(self.loss_scale / 2, self._min_scale)
+            self._good_steps = 0
+            self.skipped_steps = getattr(self, "skipped_steps", 0) + 1
             return
         coef = inv
         if self.clip_grad > 0:
@@ -305,6 +307,9 @@ class DB1Engine:
         self.optimizer.step()
         if self.lr_scheduler is not None:
             self.lr_scheduler.step()
+        self._good_steps += 1  # same growth window as the fused path (DeepSpeed's dynamic loss scaler)
+        if self._scale_window > 0 and self._good_steps % self._scale_window == 0:
+            self.loss_scale *= 2.0
 
     def _fused_step(self):
         """Unscale, global-norm clip, overflow check and Adam(W) on fp32 masters: two passes over the flat buckets
@@ -344,14 +349,21 @@ class DB1Engine:
         rank = dist.get_rank() if dist.is_available() and dist.is_initialized() else 0
         if rank == 0:
             os.makedirs(path, exist_ok=True)
-            state = {"module": self.module.state_dict(), "global_steps": self.global_steps,
+            # key set of DeepSpeed 0.6.7's mp_rank_00_model_states.pt (engine.py:_save_checkpoint) + this engine's extras
+            state = {"module": self.module.state_dict(), "buffer_names": [n for n, _ in self.module.named_buffers()],
+                     "optimizer": None, "lr_scheduler": None, "sparse_tensor_module_names": [],
+                     "skipped_steps": getattr(self, "skipped_steps", 0), "global_steps": self.global_steps,
+                     "global_samples": self.global_steps * self._ga * self._world, "dp_world_size": self._world,
+                     "mp_world_size": 1, "ds_config": None, "ds_version": "db1_sm100",
                      "micro_steps": self.micro_steps, "loss_scale": self.loss_scale}
+            if self.lr_scheduler is not None and hasattr(self.lr_scheduler, "state_dict"):
+                state["lr_scheduler"] = self.lr_scheduler.state_dict()
             if self._fused is not None:
-                state["optimizer"] = {"fused_adam": self._fused.state_dict(),
+                state["optimizer"] = {"db1_engine": True, "fused_adam": self._fused.state_dict(),
                                       "buckets": [{"key": b.key, "master": b.master.cpu(), "m": b.m.cpu(), "v": b.v.cpu()}
                                                   for b in self.buckets]}
             elif self.optimizer is not None:
-                state["optimizer"] = self.optimizer.state_dict()
+                state["optimizer"] = {"db1_engine": True, "torch_optimizer": self.optimizer.state_dict()}
             state.update(client_state or {})
             torch.save(state, os.path.join(path, "mp_rank_00_model_states.pt"))
             with open(os.path.join(save_dir, "latest"), "w") as f:
@@ -361,27 +373,55 @@ class DB1Engine:
         return True
 
     def load_checkpoint(self, load_dir, tag=None, load_optimizer_states=True):
+        """Reads `<dir>/<tag>/mp_rank_00_model_states.pt` (tag from `<dir>/latest` when omitted) - the file DeepSpeed 0.6.7
+        writes (src/checkpointing.py:17-22, evaluate_rl.py:509-511) as well as this engine's own. Module weights always
+        load; optimizer state is restored only when it was written by this engine (marker `db1_engine`): DeepSpeed stores
+        None or an FP16_Optimizer dict there, in which case the fp32 masters are rebuilt from the loaded weights and the
+        moments start from zero (with a warning). Everything that is not engine bookkeeping comes back as client state."""
+        import warnings
         if tag is None:
             with open(os.path.join(load_dir, "latest")) as f:
                 tag = f.read().strip()
         path = os.path.join(load_dir, str(tag), "mp_rank_00_model_states.pt")
         state = torch.load(path, map_location="cpu", weights_only=False)
         self.module.load_state_dict(state["module"], strict=True)
-        self.global_steps = state.get("global_steps", 0)
-        self.micro_steps = state.get("micro_steps", 0)
-        self.loss_scale = state.get("loss_scale", self.loss_scale)
+        self.global_steps = int(state.get("global_steps", 0) or 0)
+        self.micro_steps = int(state.get("micro_steps", self.global_steps * self._ga) or 0)
+        opt = state.get("optimizer")
+        ours = isinstance(opt, dict) and opt.get("db1_engine") is True
+        if "loss_scale" in state:
+            self.loss_scale = float(state["loss_scale"])
+        elif isinstance(opt, dict) and "cur_scale" in opt:  # DeepSpeed FP16_Optimizer
+            self.loss_scale = float(opt["cur_scale"])
         if self._fused is not None:
             # parameters are views of the flat buffers: load_state_dict above copied into them in place
-            if load_optimizer_states and "optimizer" in state and "buckets" in state["optimizer"]:
-                self._fused.load_state_dict(state["optimizer"]["fused_adam"])
-                for b, sb in zip(self.buckets, state["optimizer"]["buckets"]):
+            restored = False
+            if load_optimizer_states and ours and "buckets" in opt and len(opt["buckets"]) == len(self.buckets):
+                self._fused.load_state_dict(opt["fused_adam"])
+                for b, sb in zip(self.buckets, opt["buckets"]):
                     b.master.copy_(sb["master"]); b.m.copy_(sb["m"]); b.v.copy_(sb["v"])
-            else:
+                restored = True
+            if not restored:
+                if load_optimizer_states and opt is not None:
+                    warnings.warn("checkpoint optimizer state was not written by DB1Engine (DeepSpeed layout?): fp32 master "
+                                  "weights rebuilt from the loaded fp16 weights, Adam moments reset")
                 for b in self.buckets:
                     b.master.copy_(b.pflat.float())
-        elif load_optimizer_states and self.optimizer is not None and "optimizer" in state:
-            self.optimizer.load_state_dict(state["optimizer"])
-        known = {"module", "global_steps", "micro_steps", "loss_scale", "optimizer"}
+                    b.m.zero_(); b.v.zero_()
+        elif load_optimizer_states and self.optimizer is not None and opt is not None:
+            if ours and "torch_optimizer" in opt:
+                self.optimizer.load_state_dict(opt["torch_optimizer"])
+            elif isinstance(opt, dict) and "state" in opt and "param_groups" in opt:
+                self.optimizer.load_state_dict(opt)
+            else:
+                warnings.warn("checkpoint optimizer state is not a torch optimizer state_dict (DeepSpeed FP16_Optimizer "
+                              "layout?): optimizer state not restored")
+        known = {"module", "global_steps", "micro_steps", "loss_scale", "optimizer", "lr_scheduler", "buffer_names",
+                 "sparse_tensor_module_names", "skipped_steps", "global_samples", "dp_world_size", "mp_world_size",
+                 "ds_config", "ds_version", "csr_tensor_module_names", "param_shapes"}
+        if self.lr_scheduler is not None and state.get("lr_scheduler") is not None and hasattr(self.lr_scheduler, "load_state_dict"):
+            self.lr_scheduler.load_state_dict(state["lr_scheduler"])
+        self.skipped_steps = int(state.get("skipped_steps", getattr(self, "skipped_steps", 0)) or 0)
         return path, {k: v for k, v in state.items() if k not in known}
 
 

@@ -491,11 +491,12 @@ class EmbedFn(torch.autograd.Function):
         return None, None, gW.ret(), gT.ret() if gT is not None else None, dvis, None
 
 
-def positional_rows(inv_freq, klen, d, clamp_len, drop_p):
-    """PositionalEmbedding + its dropout (transformer_xl.py:569-575) -> [klen, d] fp16, reference row order."""
+def positional_rows(inv_freq, klen, d, clamp_len, drop_p, half_phase=False):
+    """PositionalEmbedding + its dropout (transformer_xl.py:569-575) -> [klen, d] fp16, reference row order.
+    half_phase: phase arithmetic in fp16 as the reference does after module.half()."""
     out = torch.empty(klen, d, dtype=torch.float16, device=inv_freq.device)
     seed = seeds.next() if drop_p > 0 else 0
-    ops.posemb(out, inv_freq, klen, d, clamp_len, drop_p, seed)
+    ops.posemb(out, inv_freq, klen, d, clamp_len, drop_p, seed, half_phase=half_phase)
     return out
 
 

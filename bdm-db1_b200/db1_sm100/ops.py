@@ -358,11 +358,12 @@ def rowdot(a, b, out, B, L, H, dh):
           "db1_rowdot")
 
 
-def posemb(out, inv_freq, klen, d, clamp_len, drop_p=0.0, seed=0):
+def posemb(out, inv_freq, klen, d, clamp_len, drop_p=0.0, seed=0, half_phase=False):
     _need_cuda_half(out)
+    fn = _lib.lib().db1_posemb_half_phase if half_phase else _lib.lib().db1_posemb
     with _Launch("posemb", 1):
-      check(_lib.lib().db1_posemb(ptr(out), _f32(inv_freq), klen, d, clamp_len, C.c_float(drop_p), C.c_uint64(seed),
-                                cur_stream()), "db1_posemb")
+      check(fn(ptr(out), _f32(inv_freq), klen, d, clamp_len, C.c_float(drop_p), C.c_uint64(seed), cur_stream()),
+            "db1_posemb")
 
 
 def f32_to_f16(src, dst, accumulate=False):
@@ -388,8 +389,15 @@ def transpose(x, out, batch, rows, cols):
 
 
 def patch_conv1_fwd(pixels, W1, b1, xs, y1):
-    _need_cuda_half(pixels, W1, b1, xs, y1)
+    """pixels: CUDA fp16 or fp32 [N,C,H,W] (fp32 frames are standardised from their unrounded values)."""
+    _need_cuda_half(W1, b1, xs, y1)
     N, Cc, Hh, Ww = pixels.shape
+    if pixels.dtype == torch.float32 and pixels.is_cuda:
+        with _Launch("patch_conv1_fwd", 1):
+          check(_lib.lib().db1_patch_conv1_fwd_f32(_f32(pixels), ptr(W1), ptr(b1), ptr(xs), ptr(y1), N, Cc, Hh, Ww,
+                                                   cur_stream()), "db1_patch_conv1_fwd_f32")
+        return
+    _need_cuda_half(pixels)
     with _Launch("patch_conv1_fwd", 1):
       check(_lib.lib().db1_patch_conv1_fwd(ptr(pixels), ptr(W1), ptr(b1), ptr(xs), ptr(y1), N, Cc, Hh, Ww, cur_stream()),
           "db1_patch_conv1_fwd")

@@ -121,8 +121,8 @@ def patch_embed(module, pixel_values, pos_sum):
     from ._lib import Db1Error
     if not pixel_values.is_cuda:
         raise Db1Error("PatchEmbeddings runs on CUDA fp16 tensors only (no CPU / PyTorch fallback)")
-    if pixel_values.dtype != torch.float16:
-        pixel_values = pixel_values.to(torch.float16)  # the reference casts to the module dtype as well (:79)
+    if pixel_values.dtype not in (torch.float16, torch.float32):
+        pixel_values = pixel_values.to(torch.float32)  # uint8 / fp64 frames: standardise from fp32, cast afterwards (:73-79)
     if module.patch_size != 16:
         raise NotImplementedError("sm_100a patch embedder is built for 16x16 patches (the released configuration)")
     rp = module.residual_path

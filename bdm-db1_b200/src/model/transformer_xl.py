@@ -33,21 +33,30 @@ def _require_kernel_tensor(t, what):
 
 
 class PositionalEmbedding(nn.Module):
-    """Sinusoid table of relative distances (reference :34-50). `inv_freq` stays an fp32 buffer on the kernel path."""
+    """Sinusoid table of relative distances (reference :34-50), evaluated by db1_posemb.
+
+    Phase precision follows the reference: after module.half() the reference builds pos_seq in fp16 (:569-571) and
+    multiplies by the fp16-cast `inv_freq` buffer (:44), i.e. position, frequency and product are rounded to fp16
+    before sin / cos - a property of everything trained / released under DeepSpeed fp16. That mode is the default here
+    whenever the buffer has been cast to fp16; `phase_dtype = torch.float32` opts into exact fp32 phases (what the
+    fp32 oracle and the fp32 reference compute)."""
 
     def __init__(self, demb):
         super().__init__()
         self.demb = demb
         inv_freq = 1 / (10000 ** (torch.arange(0.0, demb, 2.0) / demb))
         self.register_buffer("inv_freq", inv_freq)
+        self.phase_dtype = None  # None: follow the buffer's dtype (reference behaviour); torch.float32: exact phases
 
     def rows(self, klen, clamp_len, drop_p):
         """[klen, demb] fp16: row c holds distance min(klen-1-c, clamp_len) (reference :569-575 incl. the dropout)."""
         inv = self.inv_freq
+        half_phase = (inv.dtype == torch.float16) if self.phase_dtype is None else (self.phase_dtype == torch.float16)
         if inv.dtype != torch.float32:
-            # module.half() casts buffers too; rebuild the fp32 frequencies exactly as the constructor does
+            # module.half() casts buffers too; the kernel takes the constructor's fp32 frequencies and does the fp16
+            # rounding itself (fp16(fp32 value) == the cast buffer)
             inv = (1 / (10000 ** (torch.arange(0.0, self.demb, 2.0) / self.demb))).to(inv.device)
-        return F_.positional_rows(inv.contiguous(), klen, self.demb, clamp_len, drop_p)
+        return F_.positional_rows(inv.contiguous(), klen, self.demb, clamp_len, drop_p, half_phase=half_phase)
 
     def forward(self, pos_seq, bsz=None):
         raise RuntimeError("PositionalEmbedding is evaluated by db1_posemb; use .rows(klen, clamp_len, drop_p)")

@@ -10,8 +10,11 @@ discretiser and RL token layout), dropout on (the reference's training defaults)
 loss scale 4096; for N > 1 each rank runs its own micro-batch and the step includes the bucketed gradient all-reduce
 overlapped with backward (weak scaling). Prints ONE JSON line (rank 0).
 
-`--impl reference` times the reference's algorithm on the host CPU cores (the oracle port — the Python reference cannot
-travel to the GPU box) on the same metric; bounded sample, rank 0 only.
+`--impl reference` times the reference's own CPU path on the host cores: the UNMODIFIED reference module
+(src.model.TransformerXL, installed under oracle/_ref/reference by `make -C oracle`, run by oracle/ref_runner.py in its
+own process, which maps no product binary); if that install is absent it falls back to the oracle port. Bounded sample
+(B=1 x L=1024 per step), rank 0 only. The N=1 line of our arm also carries `gpu_eager_baseline`: the same reference
+module `.half().cuda()` at the headline shape on the same B200.
 """
 import argparse
 import json
@@ -22,8 +25,8 @@ import threading
 import time
 
 ROOT = os.path.dirname(os.path.abspath(__file__))
-sys.path.insert(0, os.path.join(ROOT, "bdm-db1_b200"))
 sys.path.insert(0, ROOT)
+PKG = os.path.join(ROOT, "bdm-db1_b200")  # added to sys.path by run_ours() only: the reference arm maps no product code
 
 METRIC = "tokens/sec DB1-1.3B seq1024 fwd+bwd"
 B_MICRO, SEQ = 4, 1024
@@ -99,19 +102,20 @@ def make_config(fp16=True, **kw):
 
 # ------------------------------------------------------------------------------------------------------------------
 def cpu_port_tokens_per_s(budget_s=25.0, max_iters=1, layers=24):
-    """Reference algorithm on the host cores: oracle port, fp32, B=1, L=1024, full model fwd+bwd."""
+    """Fallback when oracle/_ref/reference is absent: the oracle port on the host cores (fp32, B=1, L=1024, fwd+bwd).
+    The batch comes from the oracle's own discretiser / layout (no product code in the reference arm)."""
     import torch
     from oracle import db1_oracle as orc
-    from db1_sm100 import synth
+    from oracle import ref_runner
     torch.set_num_threads(os.cpu_count() or 1)
     cfg = orc.default_config(n_layer=layers)
     sd = orc.synth_state_dict(cfg, seed=0)
     for k, v in sd.items():
         if v.is_floating_point() and k != "pos_emb.inv_freq":
             v.requires_grad_(True)
-    t = synth.rl_continuous_batch(cfg, 1, SEQ, seed=1234)
-    task = dict(type="rl", tensor_seq=t.tensor_seq.numpy(), label=t.label.numpy(), loss_mask=t.loss_mask.numpy(),
-                position_id=t.position_id.numpy(), vision_seq=None)
+    t = ref_runner.rl_batch(orc, cfg, 1, SEQ, seed=1234)
+    task = dict(type="rl", tensor_seq=t["tensor_seq"].numpy(), label=t["label"].numpy(),
+                loss_mask=t["loss_mask"].numpy(), position_id=t["position_id"].numpy(), vision_seq=None)
     times = []
     t_all = time.perf_counter()
     while len(times) < max_iters and (not times or time.perf_counter() - t_all < budget_s):
@@ -125,20 +129,52 @@ def cpu_port_tokens_per_s(budget_s=25.0, max_iters=1, layers=24):
     return SEQ / dt, dt, len(times), torch.get_num_threads()
 
 
+def run_ref_runner(extra, timeout_s):
+    """oracle/ref_runner.py in its own process (the reference and the product share the package name `src`)."""
+    env = dict(os.environ)
+    env.pop("PYTHONPATH", None)
+    for k in ("RANK", "LOCAL_RANK", "WORLD_SIZE", "MASTER_ADDR", "MASTER_PORT"):
+        env.pop(k, None)
+    try:
+        r = subprocess.run([sys.executable, os.path.join(ROOT, "oracle", "ref_runner.py")] + extra, cwd=ROOT, env=env,
+                           capture_output=True, text=True, timeout=timeout_s)
+    except subprocess.TimeoutExpired:
+        return {"error": "timeout after %d s" % timeout_s}
+    for line in reversed(r.stdout.splitlines()):
+        if line.startswith("REF_RUNNER "):
+            return json.loads(line[len("REF_RUNNER "):])
+    return {"error": "no result (rc=%d): %s" % (r.returncode, (r.stderr or r.stdout)[-300:])}
+
+
+def reference_cpu(iters, warmup, budget_s):
+    """(tokens/s, seconds per step, timed iterations, threads, kind, sample description)."""
+    have = os.path.isfile(os.path.join(ROOT, "oracle", "_ref", "reference", "src", "model", "transformer_xl.py"))
+    if have:
+        out = run_ref_runner(["--device", "cpu", "--batch", "1", "--seq", str(SEQ), "--iters", str(iters),
+                              "--warmup", str(warmup), "--budget-s", str(budget_s)], timeout_s=budget_s * 3 + 240)
+        if "error" not in out:
+            return (out["tokens_per_s"], out["ms_per_step"] / 1e3, out["iters"], out["threads"], "reference",
+                    "unmodified reference src.model.TransformerXL (oracle/_ref/reference), fp32 torch CPU, train mode, "
+                    "B=1 x L=1024, full 24-layer model fwd+bwd, %d timed iteration(s) after %d warm-up" % (out["iters"], warmup))
+        sys.stderr.write("reference install failed to run (%s); falling back to the oracle port\n" % out["error"])
+    tps, dt, n, threads = cpu_port_tokens_per_s(budget_s=budget_s, max_iters=iters)
+    return (tps, dt, n, threads, "port",
+            "oracle port (fp32 torch CPU restatement of the reference), B=1 x L=1024, full 24-layer model fwd+bwd, "
+            "%d timed iteration(s), no warm-up" % n)
+
+
 def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
     # bounded sample: 1 sequence x 1024 tokens through the full model per step; steps are capped by a time budget
-    tps, dt, n, threads = cpu_port_tokens_per_s(budget_s=150.0, max_iters=max(1, min(args.steps, 6)))
+    tps, dt, n, threads, kind, sample = reference_cpu(max(1, min(args.steps, 6)), min(args.warmup, 1), budget_s=120.0)
     line = {"impl": "reference", "metric": METRIC, "value": tps, "unit": "tokens/s", "n_gpus": args.gpus,
-            "steps": n, "warmup": 0, "ms_per_step": dt * 1e3, "higher_is_better": True, "scaling": "weak",
+            "steps": n, "warmup": min(args.warmup, 1), "ms_per_step": dt * 1e3, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "f32", "data": "synthetic",
             "config": {"workload": "DB1-1.3B fwd+bwd, RL continuous-control batch (obs17/act6), seq_len 1024",
                        "micro_batch": 1, "seq_len": SEQ},
-            "cpu_baseline": {"value": tps, "unit": "tokens/s", "cores": threads, "kind": "port",
-                             "sample": "oracle port (fp32 torch CPU restatement of the reference), B=1 x L=1024, "
-                                       "full 24-layer model fwd+bwd, %d timed iteration(s), no warm-up" % n},
+            "cpu_baseline": {"value": tps, "unit": "tokens/s", "cores": threads, "kind": kind, "sample": sample},
             "e2e": {"value": tps, "unit": "tokens/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
     print(json.dumps(line), flush=True)
 
@@ -147,6 +183,7 @@ def run_reference(args):
 def run_ours(args):
     global B_MICRO, SEQ
     B_MICRO, SEQ = args.micro_batch, args.seq_len  # defaults = BASELINE config 2 (4 x 1024); others are sweep points
+    sys.path.insert(0, PKG)
     import torch
     import torch.distributed as dist
     from db1_sm100 import engine as eng_mod, ops, synth
@@ -259,26 +296,106 @@ def run_ours(args):
     e2e_value = tokens_per_step * args.steps / (ms2.item() / 1e3)
     clocks = sampler.stop(t_host0, time.time())  # samples under load: the resident, per-kernel and end-to-end regions
 
+    def timed(inputs, n, warm=2):
+        """tokens/s of `n` steps over resident inputs (max over ranks)."""
+        for _ in range(warm):
+            step(inputs)
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        barrier()
+        a.record()
+        for _ in range(n):
+            step(inputs)
+        b.record()
+        barrier()
+        t = torch.tensor([a.elapsed_time(b)], device=dev)
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return t.item() / n
+
+    # ---- exposed communication: the same steps with the gradient all-reduce switched off (N > 1)
+    exposed_ms = None
+    if world > 1:
+        engine.enable_backward_allreduce = False
+        ms_nocomm = timed(resident, min(args.steps, 5), warm=1)
+        engine.enable_backward_allreduce = True
+        exposed_ms = ms_total / args.steps - ms_nocomm
+
+    # ---- dp_check (N > 1): the overlapped bucketed all-reduce against a plain mean of the per-rank gradients, and
+    # bit-identity of the reduced buckets across ranks. Deterministic pass (eval mode: no dropout), same inputs.
+    dp_check = None
+    if world > 1:
+        engine.eval()
+        step(resident)
+        torch.cuda.synchronize()
+        avg = [b.flat.clone() for b in engine.buckets]
+        engine.enable_backward_allreduce = False
+        step(resident)
+        torch.cuda.synchronize()
+        engine.enable_backward_allreduce = True
+        worst_rel, worst_rank_diff = 0.0, 0.0
+        for b, a in zip(engine.buckets, avg):
+            ref = b.flat.float()
+            dist.all_reduce(ref, op=dist.ReduceOp.SUM)
+            ref /= world
+            den = ref.abs().max().clamp_min(1e-20)
+            worst_rel = max(worst_rel, ((a.float() - ref).abs().max() / den).item())
+            r0 = a.clone()
+            dist.broadcast(r0, src=0)
+            worst_rank_diff = max(worst_rank_diff, (a.float() - r0.float()).abs().max().item())
+        t = torch.tensor([worst_rel, worst_rank_diff], device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        dp_check = {"allreduced_vs_mean_of_rank_grads_max_rel": t[0].item(), "max_abs_diff_vs_rank0": t[1].item(),
+                    "buckets": len(engine.buckets), "tolerance_rel": 2e-3,
+                    "ok": bool(t[0].item() <= 2e-3 and t[1].item() == 0.0),
+                    "how": "eval-mode fwd+bwd on each rank's own batch: engine buckets after the overlapped NCCL AVG vs "
+                           "all_reduce(SUM)/N of the same step's local gradients; reduced buckets compared bit-wise with rank 0"}
+        engine.train()
+
+    # ---- the other BASELINE configurations, short runs (C3 Atari frames through the patch embedder, C4 mixed batch)
+    extra = {}
+    if args.workload == "rl" and not args.no_extra and B_MICRO == 4 and SEQ == 1024:
+        wls = {"atari_C3": [synth.rl_atari_batch(cfg, B_MICRO, SEQ, seed=1234 + rank)],
+               "mixed_C4": [synth.rl_continuous_batch(cfg, 2, SEQ, seed=1234 + rank), synth.nlp_batch(cfg, 1, SEQ, seed=2234 + rank),
+                            synth.ic_batch(cfg, 1, SEQ, seed=3234 + rank)]}
+        for name, hostb in wls.items():
+            ms_w = timed([synth.to_device(t, dev) for t in hostb], 5, warm=2)
+            extra[name] = {"value": tokens_per_step / (ms_w / 1e3), "unit": "tokens/s", "ms_per_step": ms_w, "steps": 5,
+                           "warmup": 2}
+
     if rank == 0:
         pk = peaks()
         summ = prof.summary()
-        gemm = [v for k, v in summ.items() if k.startswith("gemm_")]
-        g_flops = sum(v["flops"] for v in gemm)
-        g_ms = sum(v["ms"] for v in gemm)
-        achieved = g_flops / (g_ms / 1e3) / 1e12 if g_ms > 0 else 0.0
+
+        def tf(keys):
+            sel = [v for k, v in summ.items() if any(k.startswith(x) for x in keys)]
+            fl, ms_ = sum(v["flops"] for v in sel), sum(v["ms"] for v in sel)
+            return (fl / (ms_ / 1e3) / 1e12 if ms_ > 0 else 0.0), ms_ / n_prof, sum(v["n"] for v in sel) / n_prof
+
         traffic = None
         tpath = os.path.join(ROOT, "profiles", "traffic.json")
         if os.path.exists(tpath):
             with open(tpath) as f:
                 traffic = json.load(f).get("gemm_dram_bytes_per_launch")
         step_flops = algorithmic_flops(B_MICRO, SEQ, window=cfg.mem_len)
+        step_tf = step_flops * world / (ms_total / args.steps / 1e3) / 1e12 / world
+        dom_tf, dom_ms, dom_n = tf(["gemm_plain"]) if "gemm_plain" in summ else (0.0, 0.0, 0)
+        if "gemm_plain_batched" in summ:  # the un-batched PLAIN instantiation alone
+            v = summ["gemm_plain"]
+            dom_tf, dom_ms, dom_n = v["flops"] / (v["ms"] / 1e3) / 1e12, v["ms"] / n_prof, v["n"] / n_prof
+        all_tf, all_ms, all_n = tf(["gemm_"])
+        af_tf, af_ms, af_n = tf(["relattn_fwd"])
+        ab_tf, ab_ms, ab_n = tf(["relattn_bwd"])
+        peak = pk["tflops"]
+        frac = lambda x: (x / peak) if peak else None  # noqa: E731
         line = {
             "metric": METRIC.replace("seq1024", "seq%d" % SEQ), "value": value, "unit": "tokens/s", "n_gpus": world,
             "steps": args.steps,
             "warmup": max(args.warmup, 3), "ms_per_step": ms_total / args.steps, "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "f16", "data": "synthetic",
             "config": {"workload": "DB1-1.3B (24 layers, d 2048, 16 heads, GeGLU 8192, vocab 33025) fwd+bwd, "
-                                   + wl + ", dropout 0.1, loss scale 4096" + (" + fused AdamW step" if args.optimizer else ""),
+                                   + wl + ", dropout 0.1 (train mode: masks are reproducible, not oracle-comparable; parity "
+                                   "is pinned in eval mode by tests/), loss scale 4096"
+                                   + (" + fused AdamW step" if args.optimizer else ""),
                        "micro_batch_per_gpu": B_MICRO, "seq_len": SEQ, "global_batch": B_MICRO * world,
                        "parallelism": "dp%d" % world,
                        "cache": "no L2 flush needed: 2.4 GB of weights + 6 GB of saved activations stream per step (>> 126 MB L2)"},
@@ -288,15 +405,32 @@ def run_ours(args):
                            "host synchronisation at the end of the timed region"},
             "gpu_launches": count.launches,
             "clocks": clocks,
-            "roofline": {"bound": "tensor", "achieved": achieved, "peak": pk["tflops"], "unit": "TFLOP/s",
-                         "frac": achieved / pk["tflops"] if pk["tflops"] else None, "traffic": traffic,
-                         "kernel": "gemm_kernel<BN,EPI> (all tcgen05 GEMM launches of the step)",
-                         "peak_source": pk["src"] + " sustained bf16",
-                         "launches_per_step": sum(v["n"] for v in gemm) / n_prof,
-                         "timing": "CUDA events around every launch, %d extra steps right after the timed region" % n_prof,
-                         "step_model_tflops": step_flops * world / (ms_total / args.steps / 1e3) / 1e12},
+            "roofline": {"bound": "tensor", "achieved": dom_tf, "peak": peak, "unit": "TFLOP/s", "frac": frac(dom_tf),
+                         "traffic": traffic,
+                         "kernel": "gemm_kernel<256, PLAIN, CTA pair> (the dominant kernel: %d launches, %.2f of %.2f ms "
+                                   "per step)" % (dom_n, dom_ms, ms_total / args.steps),
+                         "peak_source": pk["src"] + " sustained bf16 (cuBLAS 8192^3 back to back)",
+                         "launches_per_step": dom_n,
+                         "timing": "CUDA events around every launch on the launching stream, %d extra steps right after "
+                                   "the timed region" % n_prof},
+            "roofline_more": [
+                {"what": "all tcgen05 GEMM launches (incl. fused QKV / GeGLU / GeGLU-backward epilogues)", "bound": "tensor",
+                 "achieved": all_tf, "peak": peak, "unit": "TFLOP/s", "frac": frac(all_tf), "ms_per_step": all_ms,
+                 "launches_per_step": all_n},
+                {"what": "relattn_fwd_kernel (fused rel-pos attention forward)", "bound": "tensor", "achieved": af_tf,
+                 "peak": peak, "unit": "TFLOP/s", "frac": frac(af_tf), "ms_per_step": af_ms, "launches_per_step": af_n},
+                {"what": "attention backward (recompute + dK/dV + dq + dR kernels)", "bound": "tensor", "achieved": ab_tf,
+                 "peak": peak, "unit": "TFLOP/s", "frac": frac(ab_tf), "ms_per_step": ab_ms, "launches_per_step": ab_n},
+                {"what": "whole step (SURVEY 8d algorithmic FLOP / ms_per_step), per GPU", "bound": "tensor",
+                 "achieved": step_tf, "peak": peak, "unit": "TFLOP/s", "frac": frac(step_tf)}],
             "loss": last,
         }
+        if extra:
+            line["extra_workloads"] = extra
+        if dp_check is not None:
+            line["dp_check"] = dp_check
+        if exposed_ms is not None:
+            line["exposed_comm_ms"] = exposed_ms
         breakdown = {k: {"n_per_step": v["n"] / n_prof, "ms_per_step": v["ms"] / n_prof,
                          "tflops": (v["flops"] / (v["ms"] / 1e3) / 1e12) if v["ms"] > 0 and v["flops"] else None,
                          "gbs": (v["bytes"] / (v["ms"] / 1e3) / 1e9) if v["ms"] > 0 and v["bytes"] else None}
@@ -306,15 +440,28 @@ def run_ours(args):
             with open(os.path.join(out_dir, "bench_breakdown_n%d.json" % world), "w") as f:
                 json.dump(breakdown, f, indent=1)
         sys.stderr.write("per-kernel breakdown (ms/step): " + json.dumps(breakdown) + "\n")
-        if world == 1 and not args.no_cpu_baseline:
-            tps, dt, n, threads = cpu_port_tokens_per_s(budget_s=25.0, max_iters=1)
-            line["cpu_baseline"] = {"value": tps, "unit": "tokens/s", "cores": threads, "kind": "port",
-                                    "sample": "oracle port (fp32 torch CPU), B=1 x L=1024, full 24-layer model "
-                                              "fwd+bwd, 1 iteration (%.1f s), no warm-up" % dt}
-        print(json.dumps(line), flush=True)
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()
+    if rank == 0:
+        if world == 1 and not args.no_cpu_baseline:
+            # the reference module itself on this GPU (eager PyTorch, fp16, same shape), then on the host cores
+            del engine, model
+            torch.cuda.empty_cache()
+            g = run_ref_runner(["--device", "cuda", "--half", "--batch", str(B_MICRO), "--seq", str(SEQ), "--iters", "3",
+                                "--warmup", "2"], timeout_s=300)
+            if "error" in g:
+                line["gpu_eager_baseline"] = {"unavailable": g["error"]}
+            else:
+                line["gpu_eager_baseline"] = {
+                    "value": g["tokens_per_s"], "unit": "tokens/s", "ms_per_step": g["ms_per_step"], "dtype": "f16",
+                    "what": "the unmodified reference src.model.TransformerXL (oracle/_ref/reference) .half().cuda(), eager "
+                            "PyTorch (cuBLAS / ATen kernels), train mode, same RL batch shape B=%d x L=%d, fwd+bwd, CUDA "
+                            "events, 3 steps after 2 warm-up, run right after our timed region on the same GPU"
+                            % (B_MICRO, SEQ)}
+            tps, dt, n, threads, kind, sample = reference_cpu(2, 0, budget_s=30.0)
+            line["cpu_baseline"] = {"value": tps, "unit": "tokens/s", "cores": threads, "kind": kind, "sample": sample}
+        print(json.dumps(line), flush=True)
 
 
 def main():
@@ -323,7 +470,8 @@ def main():
     ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-cpu-baseline", action="store_true", help="skip the reference legs (gpu_eager_baseline, cpu_baseline)")
+    ap.add_argument("--no-extra", action="store_true", help="skip the short C3 / C4 runs (extra_workloads)")
     ap.add_argument("--workload", default="rl", choices=["rl", "atari", "mixed"],
                     help="rl = BASELINE config 2 (headline, default); atari = config 3; mixed = config 4's per-rank batch")
     ap.add_argument("--profile-only", action="store_true", help="warm-up + steps only (for runs under ncu)")

@@ -221,6 +221,11 @@ int db1_rowdot(const void* a, const void* b, long long ld, float* out, int B, in
 /* Sinusoid rows of PositionalEmbedding (transformer_xl.py:43-50, 569-575): row c = [sin|cos](min(klen-1-c, clamp)*inv_freq) */
 int db1_posemb(void* out, const float* inv_freq, int klen, int d, int clamp_len, float drop_p, uint64_t seed,
                void* stream);
+/* Same rows with the phase arithmetic of the reference under module.half() (what DeepSpeed fp16 training and the released
+ * checkpoint use): position, inv_freq and their product each rounded to fp16 before sin / cos (:44 with the fp16-cast
+ * buffer, :569-571 with fp16 hidden states). inv_freq is still passed as fp32 (the constructor's values). */
+int db1_posemb_half_phase(void* out, const float* inv_freq, int klen, int d, int clamp_len, float drop_p, uint64_t seed,
+                          void* stream);
 /* dsr[z][i][c] = ds[z][i][c-(L-1-i)] for c >= L-1-i, else 0: adjoint of _rel_shift (transformer_xl.py:98-110) */
 int db1_rel_unshift(const void* ds, void* dsr, int Z, int L, void* stream);
 int db1_f32_to_f16(const float* src, void* dst, long long n, int accumulate, void* stream);
@@ -240,6 +245,10 @@ int db1_transpose_f16(const void* in, void* out, int batch, int rows, int cols, 
  * (:80). pixels [N,C,H,W] fp16; xs [P,C,256] (standardised pixels, kept for the weight gradient); y1 [P,256,64]. */
 int db1_patch_conv1_fwd(const void* pixels, const void* W1, const void* b1, void* xs, void* y1, int N, int C, int Himg,
                         int Wimg, void* stream);
+/* Same with fp32 pixels: mean / std are formed from the unrounded values, as the reference does (it standardises in the
+ * input dtype, :73-77, and casts to the module dtype afterwards, :79). */
+int db1_patch_conv1_fwd_f32(const float* pixels, const void* W1, const void* b1, void* xs, void* y1, int N, int C,
+                            int Himg, int Wimg, void* stream);
 /* dW1 [64, C*9] fp32 += sum over patches and pixels of dy1 (x) shifted xs (weight gradient of conv1). */
 int db1_patch_conv1_bwd(const void* xs, const void* dy1, float* dW1, int P, int C, void* stream);
 /* GroupNorm(32 groups of 2 channels, eps) -> exact GELU -> im2col: col [P*256, 576], col[q][tap*64+ci] = a[q+tap][ci]

@@ -134,12 +134,18 @@ def total_vocab(cfg):
     return v + 1
 
 
-def positional_rows(klen, d_model, clamp_len):
-    """transformer_xl.py:34-50, 569-574: row c holds the sinusoid of distance min(klen-1-c, clamp_len)."""
+def positional_rows(klen, d_model, clamp_len, half_phase=False):
+    """transformer_xl.py:34-50, 569-574: row c holds the sinusoid of distance min(klen-1-c, clamp_len).
+    half_phase=True restates what those lines compute after module.half() (DeepSpeed fp16): pos_seq is built in fp16,
+    inv_freq is the fp16-cast buffer, their outer product and the sin / cos results are fp16 (pinned by
+    tests/golden/posemb_half.npz, generated from the reference module after .half())."""
     inv_freq = 1 / (10000 ** (torch.arange(0.0, d_model, 2.0) / d_model))
     pos = torch.arange(klen - 1, -1, -1.0)
     if clamp_len > 0:
         pos = pos.clamp(max=clamp_len)
+    if half_phase:
+        s = torch.outer(pos.half().float(), inv_freq.half().float()).half().float()
+        return torch.cat([s.sin().half().float(), s.cos().half().float()], dim=-1)
     s = torch.outer(pos, inv_freq)
     return torch.cat([s.sin(), s.cos()], dim=-1)
 
@@ -295,7 +301,7 @@ def forward(tasks, sd, cfg, compute_loss=True, mems=None, return_hidden=False):
         ok = attention_mask_ok(Q, K, mem_len, True)
     else:
         ok = attention_mask_ok(Q, K, mem_len, False)
-    pe = positional_rows(K, cfg.n_embed, cfg.n_position)
+    pe = positional_rows(K, cfg.n_embed, cfg.n_position, half_phase=bool(getattr(cfg, "pos_phase_half", False)))
     hids = []
     for li in range(cfg.n_layer):
         hids.append(x)

@@ -37,6 +37,7 @@ def _worker(rank, world, port, out):
         model = TransformerXL(cfg)
         model.load_state_dict(sd, strict=True)
         model = model.half().to(dev).eval()
+        model.pos_emb.phase_dtype = torch.float32
         SCALE = 1024.0
         batches = [[synth.rl_continuous_batch(cfg, 2, 256, obs_len=5, act_len=2, seed=40 + r),
                     synth.nlp_batch(cfg, 1, 256, seed=50 + r)] for r in range(world)]

@@ -113,6 +113,42 @@ def test_masked_cross_entropy_fwd_bwd(cuda, rows, V):
     assert dl[:, V:(V + 7) // 8 * 8].abs().max().item() == 0 if V % 8 else True
 
 
+def test_cross_entropy_out_of_range_labels_are_ignored_rows(cuda):
+    """Labels outside [0, V) (ignore_index -100, image-slot -1, garbage padding) are never dereferenced: the row gives
+    zero loss and zero gradient like nn.CrossEntropyLoss's ignore_index, the denominator stays sum(mask)
+    (transformer_xl.py:602-609); the loss stays finite even when such a row is masked in."""
+    from db1_sm100 import ops
+    rows, V = 64, 1000
+    Vp = (V + 127) // 128 * 128
+    g = torch.Generator().manual_seed(21)
+    logits = torch.zeros(rows, Vp, dtype=torch.half, device=cuda)
+    logits[:, :V] = (torch.randn(rows, V, generator=g) * 3).half().to(cuda)
+    labels = torch.randint(0, V, (rows,), generator=g)
+    labels[3], labels[10], labels[11], labels[40] = -100, -1, V, 1 << 40
+    labels = labels.to(cuda)
+    mask = torch.ones(rows, dtype=torch.float32, device=cuda)
+    mask[10] = 0.0
+    row_loss = torch.empty(rows, dtype=torch.float32, device=cuda)
+    row_lse = torch.empty_like(row_loss)
+    loss2 = torch.empty(2, dtype=torch.float32, device=cuda)
+    ops.ce_fwd(logits, labels, mask, row_loss, row_lse, loss2, V)
+    bad = torch.tensor([3, 10, 11, 40], device=cuda)
+    safe = labels.clone()
+    safe[bad] = -100
+    lr = logits[:, :V].float().requires_grad_(True)
+    ce = torch.nn.functional.cross_entropy(lr, safe, reduction="none", ignore_index=-100)
+    ref = (ce * mask).sum() / mask.sum()
+    assert torch.isfinite(loss2).all()
+    assert abs(loss2[0].item() - ref.item()) <= 1e-5 * abs(ref.item())
+    assert row_loss[bad].abs().max().item() == 0.0
+    ref.backward()
+    dl = torch.empty(rows, Vp, dtype=torch.half, device=cuda)
+    gs = torch.ones(1, dtype=torch.float32, device=cuda)
+    ops.ce_bwd(logits, labels, mask, row_lse, loss2, gs, dl, V)
+    assert dl[bad].abs().max().item() == 0.0
+    assert _rel(dl[:, :V], lr.grad) < 1e-3
+
+
 def test_embedding_assembly_fwd_bwd(cuda):
     from db1_sm100 import ops
     B, L, d, V, nT, nvis = 3, 40, 256, 500, 33, 6

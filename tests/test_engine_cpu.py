@@ -92,3 +92,48 @@ def test_engine_gloo_world2(ga):
     port = _free_port()
     with tempfile.TemporaryDirectory() as tmp:
         mp.spawn(_worker, args=(2, port, tmp, ga), nprocs=2, join=True)
+
+
+def test_load_deepspeed_layout_checkpoint_cpu(tmp_path):
+    """A mp_rank_00_model_states.pt in DeepSpeed 0.6.7's key layout (FP16_Optimizer dict under `optimizer`, or None)
+    loads into the engine: weights restored, DeepSpeed bookkeeping consumed, client state returned, no crash on the
+    foreign optimizer state; the engine's own checkpoints still round-trip their optimizer state."""
+    import warnings
+    import torch
+    from db1_sm100.engine import DB1Engine
+    from tests.ds_ckpt import write_deepspeed_style_checkpoint
+    torch.manual_seed(0)
+    net = torch.nn.Sequential(torch.nn.Linear(8, 16), torch.nn.Linear(16, 4))
+    src = {k: torch.randn_like(v) for k, v in net.state_dict().items()}
+    for fp16_opt in (True, False):
+        d = tmp_path / ("ds_%d" % fp16_opt)
+        write_deepspeed_style_checkpoint(str(d), src, fp16_optimizer=fp16_opt)
+        opt = torch.optim.SGD(net.parameters(), lr=0.1, momentum=0.9)
+        eng = DB1Engine(net, optimizer=opt, loss_scale=128.0)
+        with warnings.catch_warnings(record=True) as w:
+            warnings.simplefilter("always")
+            path, client = eng.load_checkpoint(str(d))
+        assert path.endswith("global_step1234/mp_rank_00_model_states.pt")
+        assert client == {"iteration": 1234, "args": {"n_layer": 24}}
+        assert eng.global_steps == 1234 and eng.skipped_steps == 3
+        assert eng.loss_scale == (32768.0 if fp16_opt else 128.0)
+        assert bool(w) == fp16_opt  # foreign optimizer state: warned about, not loaded
+        for k, v in net.state_dict().items():
+            assert torch.equal(v, src[k])
+    # own format: optimizer state round trip
+    opt = torch.optim.SGD(net.parameters(), lr=0.1, momentum=0.9)
+    eng = DB1Engine(net, optimizer=opt, loss_scale=64.0)
+    loss = net(torch.randn(3, 8)).pow(2).mean()
+    eng.backward(loss)
+    eng.step()
+    d = tmp_path / "own"
+    eng.save_checkpoint(str(d), tag="t1", client_state={"iteration": 7})
+    st = torch.load(str(d / "t1" / "mp_rank_00_model_states.pt"), weights_only=False)
+    for key in ("module", "buffer_names", "optimizer", "lr_scheduler", "sparse_tensor_module_names", "skipped_steps",
+                "global_steps", "global_samples", "dp_world_size", "mp_world_size", "ds_config", "ds_version"):
+        assert key in st, key
+    opt2 = torch.optim.SGD(net.parameters(), lr=0.1, momentum=0.9)
+    eng2 = DB1Engine(net, optimizer=opt2, loss_scale=1.0)
+    _path, client = eng2.load_checkpoint(str(d))
+    assert client == {"iteration": 7} and eng2.loss_scale == 64.0 and eng2.global_steps == 1
+    assert len(opt2.state_dict()["state"]) == len(opt.state_dict()["state"]) > 0

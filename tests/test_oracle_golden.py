@@ -230,3 +230,21 @@ def test_host_index_builders_match_live_reference_when_built():
         with contextlib.redirect_stdout(io.StringIO()):
             ref = np.asarray(helpers.build_sample_idx(sizes, doc_idx, seq, ep, int(sizes.sum())))
         assert np.array_equal(_gpt_idx(sizes, doc_idx, seq, ep, int(sizes.sum())), ref)
+
+
+def test_positional_rows_half_phase_match_reference_after_half():
+    """oracle.positional_rows(half_phase=True) == the reference's PositionalEmbedding after module.half() (bit-exact:
+    fp16 positions, fp16-cast inv_freq, fp16 product, fp16 sin / cos); the fp32 phases differ from it by percents on
+    far rows, which is why the B200 module defaults to the half-phase mode when its buffers are fp16."""
+    g = _load("posemb_half")
+    n = 0
+    worst = 0.0
+    while "case%d" % n in g:
+        klen, demb, clamp, rs, cs = [int(x) for x in g["case%d" % n]]
+        got = orc.positional_rows(klen, demb, clamp, half_phase=True)[::rs, ::cs]
+        ref = torch.from_numpy(g["rows%d" % n].astype(np.float32))
+        assert torch.equal(got, ref), "case %d" % n
+        f32 = orc.positional_rows(klen, demb, clamp)[::rs, ::cs]
+        worst = max(worst, ((f32 - ref).norm() / ref.norm()).item())
+        n += 1
+    assert n == 3 and worst > 1e-2  # the two modes really are different tables

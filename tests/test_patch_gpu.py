@@ -59,6 +59,31 @@ def test_patch_embed_fwd_bwd_matches_oracle(cuda, N, H, W, d):
     assert max(worst.values()) <= 2e-2, worst
 
 
+def test_patch_embed_fp32_low_contrast_pixels(cuda):
+    """fp32 frames are standardised from their unrounded values, as the reference does (vision_embedding.py:73-79:
+    standardise in the input dtype, cast afterwards). On low-contrast patches (Atari backgrounds) a prior fp16 cast of
+    the pixels is amplified by 1/(1e-6 + std) to percent-level errors; the fp32 path stays at kernel rounding."""
+    from db1_sm100 import vision
+    from oracle import db1_oracle as orc
+    N, C, H, W, d = 2, 3, 32, 32, 128
+    sd = {k: v.half().float() for k, v in _params(d, C, 3).items()}
+    g = torch.Generator().manual_seed(9)
+    pixels = 0.62 + 2e-3 * torch.rand(N, C, H, W, generator=g)  # contrast of a few fp16 ulps around 0.62
+    cfg = SimpleNamespace(vision_patch_size=16)
+    with torch.no_grad():
+        ref = orc.patch_embeddings(pixels, sd, "pe.", cfg)
+        ref16 = orc.patch_embeddings(pixels.half().float(), sd, "pe.", cfg)
+    dev = {k: v.half().to(cuda) for k, v in sd.items()}
+    names = ["conv1.weight", "conv1.bias", "residual_path.0.weight", "residual_path.0.bias", "residual_path.2.weight",
+             "residual_path.2.bias", "residual_path.3.weight", "residual_path.3.bias", "residual_path.5.weight",
+             "residual_path.5.bias", "projection.weight", "projection.bias"]
+    with torch.no_grad():
+        out = vision.PatchEmbedFn.apply(pixels.to(cuda), None, *[dev["pe." + n] for n in names], 1e-5, 1e-5)
+    err32 = util.rel_err(out, ref)
+    assert err32 <= 3e-3, err32
+    assert util.rel_err(ref16, ref) > 10 * err32  # what casting the pixels first would have cost
+
+
 def test_transpose_and_dropout_kernels(cuda):
     from db1_sm100 import ops
     x = torch.randn(7, 64, 9).half().to(cuda)

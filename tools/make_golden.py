@@ -248,8 +248,29 @@ def gen_attn_layer():
     np.savez_compressed(os.path.join(OUT, "layer.npz"), **out)
 
 
+def gen_posemb_half():
+    """PositionalEmbedding as the reference evaluates it after module.half() (DeepSpeed fp16): fp16 pos_seq (:569-571),
+    fp16-cast inv_freq buffer (:44). Full table for demb 128; a strided sample of rows / columns for demb 2048."""
+    from src.model.transformer_xl import PositionalEmbedding
+    out = {}
+    for n, (klen, demb, clamp, rs, cs) in enumerate([(300, 128, 256, 1, 1), (1024, 2048, 1024, 37, 29),
+                                                      (2048, 2048, 1024, 61, 31)]):
+        pe = PositionalEmbedding(demb).half()
+        pos = torch.arange(klen - 1, -1, -1.0, dtype=torch.float16)
+        pos.clamp_(max=clamp)
+        t = pe(pos)[0]
+        assert t.dtype == torch.float16
+        out["case%d" % n] = np.array([klen, demb, clamp, rs, cs])
+        out["rows%d" % n] = t[::rs, ::cs].numpy()
+    np.savez_compressed(os.path.join(OUT, "posemb_half.npz"), **out)
+
+
 if __name__ == "__main__":
     os.makedirs(OUT, exist_ok=True)
+    if "--only-posemb-half" in sys.argv:
+        gen_posemb_half()
+        raise SystemExit(0)
+    gen_posemb_half()
     gen_tokenizer()
     gen_rl_layout()
     gen_patch_positions()

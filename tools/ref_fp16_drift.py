@@ -18,8 +18,9 @@ for m in ("gym", "d4rl", "tree"):
 from src.model import TransformerXL  # noqa: E402  (the reference's)
 from src.data.input_specs import NLPTaskInput  # noqa: E402
 
-nl = int(sys.argv[1]) if len(sys.argv) > 1 else 24
-L = int(sys.argv[2]) if len(sys.argv) > 2 else 128
+_pos = [a for a in sys.argv[1:] if not a.startswith("--")]
+nl = int(_pos[0]) if len(_pos) > 0 else 24
+L = int(_pos[1]) if len(_pos) > 1 else 128
 cfg = orc.default_config(n_layer=nl)
 ns = types.SimpleNamespace(**vars(cfg))
 torch.manual_seed(0)
@@ -39,5 +40,14 @@ with torch.no_grad():
     l16, _ = model([mk()])
     print("fp16 forward %.1f s" % (time.time() - t0), flush=True)
 d = (l16.float() - l32)
-print("reference fp16 vs reference fp32, %d layers, L=%d: max-norm rel %.3e, rms rel %.3e" %
-      (nl, L, (d.abs().max() / l32.abs().max()).item(), (d.pow(2).mean().sqrt() / l32.pow(2).mean().sqrt()).item()))
+mx, rms = (d.abs().max() / l32.abs().max()).item(), (d.pow(2).mean().sqrt() / l32.pow(2).mean().sqrt()).item()
+print("reference fp16 vs reference fp32, %d layers, L=%d: max-norm rel %.3e, rms rel %.3e" % (nl, L, mx, rms))
+if "--write" in sys.argv:
+    import json
+    out = os.path.join(ROOT, "tests", "golden", "ref_fp16_drift.json")
+    with open(out, "w") as f:
+        json.dump({"what": "logits of the UNMODIFIED reference after module.half() vs the same module in fp32 (CPU), random-init "
+                           "weights from oracle.synth_state_dict(seed=21) rounded to fp16, one NLP sequence",
+                   "n_layer": nl, "seq_len": L, "max_norm_rel": mx, "rms_rel": rms,
+                   "generated_by": "python tools/ref_fp16_drift.py %d %d --write" % (nl, L)}, f, indent=1)
+    print("written", out)
