@@ -70,7 +70,9 @@ bool pdl_enabled() {
   return v != 0;
 }
 
-int sm_count() {
+static int g_sm_budget = 0;  // 0 = every SM; else the number of SMs persistent grids may cover (db1_set_sm_budget)
+
+int sm_count_physical() {
   static int n = 0;
   if (!n) {
     int dev = 0;
@@ -81,7 +83,25 @@ int sm_count() {
   return n;
 }
 
+int sm_count() {
+  const int n = sm_count_physical();
+  return (g_sm_budget > 0 && g_sm_budget < n) ? g_sm_budget : n;
+}
+
+void set_sm_budget(int n) { g_sm_budget = n; }
+
 }  // namespace db1
 
 extern "C" const char* db1_last_error() { return db1::err_buf(); }
 extern "C" int db1_abi_version() { return 2; }
+
+/* Persistent kernels of this library size their grids to one CTA (or CTA pair) per SM. While a communication kernel
+ * (NCCL all-reduce) is co-resident it occupies some SMs for its whole duration; a 148-CTA grid then needs a second wave
+ * for the CTAs that found no SM, i.e. up to twice the kernel time. The caller that knows a collective is in flight
+ * (DB1Engine during backward) lowers the budget to physical SMs minus the collective's CTAs, and resets it with 0. */
+extern "C" int db1_set_sm_budget(int n_sms) {
+  DB1_CHECK_ARG(n_sms >= 0, "db1_set_sm_budget: negative budget");
+  db1::set_sm_budget(n_sms >= 8 || n_sms == 0 ? n_sms : 8);
+  return 0;
+}
+extern "C" int db1_sm_count(void) { return db1::sm_count_physical(); }

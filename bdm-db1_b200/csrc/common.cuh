@@ -30,7 +30,8 @@ int set_err(int code, const char* fmt, ...);
 int make_tmap_f16(CUtensorMap* out, const void* base, int rank, const uint64_t* dims, const uint64_t* strides_bytes,
                   const uint32_t* box, int swizzle_bytes = 128);
 
-int sm_count();
+int sm_count();           // SMs persistent grids may cover (physical count unless db1_set_sm_budget lowered it)
+int sm_count_physical();
 bool pdl_enabled();  // programmatic dependent launch on (default) unless DB1_NO_PDL is set
 
 // cudaLaunchKernelEx with (optionally) a cluster dimension and programmatic stream serialization.

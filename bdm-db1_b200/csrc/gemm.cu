@@ -1371,7 +1371,7 @@ extern "C" int db1_gemm_sk_plan(int pair, long long tiles, int KB, int sk_tiles,
 }
 
 extern "C" long long db1_gemm_workspace_bytes(void) {
-  return SK_CNT_BYTES + (long long)(sm_count() / 2) * 2 * BM * 256 * 4;
+  return SK_CNT_BYTES + (long long)(sm_count_physical() / 2) * 2 * BM * 256 * 4;
 }
 
 extern "C" int db1_gemm_f16(const db1_gemm_desc* d, void* stream_) {

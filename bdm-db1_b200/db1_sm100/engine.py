@@ -71,6 +71,10 @@ class DB1Engine:
         self._cuda = p0.is_cuda
         self._overlap = bool(overlap_comm) and self._cuda and self._world > 1
         self._comm_stream = torch.cuda.Stream(device=self.device, priority=-1) if self._overlap else None
+        # SMs left to the collective while it overlaps backward: the persistent kernels' grids are sized to the rest
+        # (include/db1_sm100.h:db1_set_sm_budget). NCCL_MAX_CTAS (set before the communicator is created) bounds how many
+        # CTAs NCCL takes; DB1_COMM_SMS overrides the reservation (0 disables it).
+        self._comm_sms = int(os.environ.get("DB1_COMM_SMS", os.environ.get("NCCL_MAX_CTAS", "0") or 0)) if self._overlap else 0
         self._build_buckets(bucket_of)
         self._hooks = []
         if self._world > 1:
@@ -248,6 +252,10 @@ class DB1Engine:
             b.work = None
             b.post_scale = None
         scaled = loss * (self.loss_scale / self._ga)
+        reserve = self._comm_sms if (self._overlap and self._is_boundary() and self.enable_backward_allreduce) else 0
+        if reserve > 0:
+            from . import _lib
+            _lib.lib().db1_set_sm_budget(max(8, _lib.lib().db1_sm_count() - reserve))
         if self._sink_on and loss.is_cuda:
             from . import functions
             functions.begin_backward(loss.device)  # one zero-filled arena for the blocks' small fp32 accumulators
@@ -257,6 +265,8 @@ class DB1Engine:
                 functions.end_backward()
         else:
             scaled.backward()
+        if reserve > 0:
+            _lib.lib().db1_set_sm_budget(0)
         if self._is_boundary():
             self._zero_unwritten()
         else:

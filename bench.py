@@ -198,6 +198,9 @@ def run_ours(args):
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
     if world > 1:
+        # NCCL's CTAs stay resident for a whole all-reduce and take SMs from the persistent compute kernels: bound them
+        # (the engine sizes its grids to the remaining SMs during backward). Must be set before the communicator exists.
+        os.environ.setdefault("NCCL_MAX_CTAS", "8")
         dist.init_process_group("nccl", device_id=dev)
         mpu.initialize_model_parallel()
     torch.manual_seed(0)

@@ -25,6 +25,11 @@ extern "C" {
 const char* db1_last_error(void);
 /* ABI version of this header; bumped whenever a struct layout changes. */
 int db1_abi_version(void);
+/* Number of SMs the persistent kernels may cover (0 = all). Lower it while a long-running communication kernel occupies
+ * SMs (DB1Engine does during backward at world size > 1: physical SMs minus NCCL's CTAs), so that a grid never needs a
+ * second wave for CTAs that found no free SM. Process-wide; takes effect at the next launch. */
+int db1_set_sm_budget(int n_sms);
+int db1_sm_count(void);
 
 /* ------------------------------------------------------------------------------------------------------------------
  * Tensor-core GEMM (tcgen05.mma, TMEM accumulators, TMA-fed smem ring; persistent, one CTA per SM).
