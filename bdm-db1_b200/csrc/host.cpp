@@ -11,6 +11,8 @@
 #include <math.h>
 #include <stdint.h>
 #include <string.h>
+#include <vector>
+#include <string.h>
 
 extern "C" {
 
@@ -139,6 +141,103 @@ long long db1_build_sample_idx(const int32_t* sizes, const int32_t* doc_idx, lon
     out[2 * k + 1] = (int32_t)(start - slot_begin);
   }
   return rows;
+}
+
+
+// One RL sample from raw arrays: RLFullDataset.get (src/data/rl_dataset.py:614-752) with postprocess_obs_and_act
+// (:393-473) for the observation kinds {image frames, float vector} and float / discrete actions.
+//   per transition: [n_img_slots x -1 | n_float continuous-bin tokens | SEP | act_len action tokens]     (:651-697)
+//   float -> token: discretize + text_vocab (+ n_disc unless overlap_with_text)                           (:429-435, :459-464)
+//   discrete action -> token: value (+ text_vocab unless overlap_with_text)                               (:465-471)
+//   SEP = n_cont + text_vocab (+ n_disc unless overlap_with_text)                                          (:683-685)
+//   pad / truncate to seq_len + 1 (:711-716), then the observation slots of the padded frames T..n_frames-1 are set to -1
+//   (:718-726: the reference overwrites the WHOLE observation span of those transitions), then the shift (:738-746).
+int db1_rl_assemble(const float* obs_float, int n_float, int n_img_slots, const float* act_float,
+                    const long long* act_disc, int act_len, int T, int n_frames, int text_vocab, int n_disc, int n_cont,
+                    int overlap_with_text, int seq_len, int prepend_trans_num, long long* tensor_seq, long long* label,
+                    float* loss_mask, long long* position_id) {
+  if (!tensor_seq || !label || !loss_mask || !position_id) return -1;
+  if (T <= 0 || n_float < 0 || n_img_slots < 0 || act_len <= 0 || seq_len <= 0) return -1;
+  if ((n_float > 0 && !obs_float) || ((act_float == nullptr) == (act_disc == nullptr))) return -1;
+  const int obs_len = n_img_slots + n_float;
+  const long long cont0 = (long long)text_vocab + (overlap_with_text ? 0 : n_disc);
+  const long long disc0 = overlap_with_text ? 0 : text_vocab;
+  const long long sep = (long long)n_cont + cont0;
+  std::vector<long long> obs((size_t)T * (obs_len > 0 ? obs_len : 1)), act((size_t)T * act_len);
+  std::vector<int32_t> tmp((size_t)T * (n_float > act_len ? n_float : act_len));
+  if (n_float > 0 && db1_discretize(obs_float, tmp.data(), (long long)T * n_float, 0, n_cont, 100.0f, 256.0f)) return -1;
+  for (int t = 0; t < T; ++t) {
+    for (int o = 0; o < n_img_slots; ++o) obs[(size_t)t * obs_len + o] = -1;
+    for (int o = 0; o < n_float; ++o) obs[(size_t)t * obs_len + n_img_slots + o] = tmp[(size_t)t * n_float + o] + cont0;
+  }
+  if (act_float) {
+    if (db1_discretize(act_float, tmp.data(), (long long)T * act_len, 1, n_cont, 100.0f, 256.0f)) return -1;
+    for (size_t i = 0; i < (size_t)T * act_len; ++i) act[i] = tmp[i] + cont0;
+  } else {
+    for (size_t i = 0; i < (size_t)T * act_len; ++i) {
+      if (act_disc[i] < 0 || act_disc[i] >= n_disc) return -3;  // the reference asserts the range (:466)
+      act[i] = act_disc[i] + disc0;
+    }
+  }
+  // layout into a (seq_len + 1)-token window first: the -1 fill of padded frames applies to the un-shifted sequence
+  const int n = seq_len + 1;
+  std::vector<long long> ts(n + 1), lb(n + 1), ps(n + 1);
+  std::vector<float> lm(n + 1);
+  // db1_rl_layout on n tokens gives tensor_seq = joined[0..n), label = joined[1..n+1): run it with seq_len = n and keep
+  // tensor_seq / position_id (the un-shifted window) and the flags through its label-aligned loss_mask
+  if (db1_rl_layout(obs.data(), act.data(), T, obs_len, act_len, sep, n, 0, prepend_trans_num, ts.data(), lb.data(), lm.data(),
+                    ps.data()))
+    return -1;
+  const int step = obs_len + act_len + 1;
+  for (int i = T; i < n_frames; ++i) {
+    const long long b = (long long)i * step;
+    long long e = b + obs_len;
+    if (e > n) e = n;
+    for (long long q = b; q < e; ++q) ts[q] = -1;
+  }
+  for (int q = 0; q < seq_len; ++q) {
+    tensor_seq[q] = ts[q];
+    position_id[q] = ps[q];
+    label[q] = ts[q + 1];
+    loss_mask[q] = lm[q];  // flag of token q+1 (db1_rl_layout already shifts the flags by one)
+  }
+  return 0;
+}
+
+// my_collate_fn (src/data/data_samplers.py:28-42), the grouping: samples are grouped by task type in order of first
+// appearance (the reference's defaultdict insertion order), inside a group in list order. perm[n]: sample indices
+// group by group; group_type / group_count [<= n]: one entry per group. Returns the number of groups.
+int db1_collate_plan(const int* type_ids, int n, int* perm, int* group_type, int* group_count) {
+  if (!type_ids || !perm || !group_type || !group_count || n <= 0) return -1;
+  int ng = 0;
+  for (int i = 0; i < n; ++i) {
+    int g = 0;
+    while (g < ng && group_type[g] != type_ids[i]) ++g;
+    if (g == ng) {
+      group_type[ng] = type_ids[i];
+      group_count[ng] = 0;
+      ++ng;
+    }
+    ++group_count[g];
+  }
+  int w = 0;
+  for (int g = 0; g < ng; ++g)
+    for (int i = 0; i < n; ++i)
+      if (type_ids[i] == group_type[g]) perm[w++] = i;
+  return ng;
+}
+
+// ... and the concatenation on dim 0 (`x.apply(torch.cat, dim=0)`): n contiguous blocks copied back to back into dst
+// (typically a pinned staging buffer, so the batch is ready for one asynchronous host-to-device copy).
+int db1_concat_rows(void* dst, const void* const* srcs, const long long* nbytes, int n) {
+  if (!dst || !srcs || !nbytes || n <= 0) return -1;
+  char* w = static_cast<char*>(dst);
+  for (int i = 0; i < n; ++i) {
+    if (nbytes[i] < 0 || (nbytes[i] > 0 && !srcs[i])) return -1;
+    memcpy(w, srcs[i], (size_t)nbytes[i]);
+    w += nbytes[i];
+  }
+  return 0;
 }
 
 }  // extern "C"

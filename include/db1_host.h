@@ -35,6 +35,21 @@ long long db1_build_rl_sample_idx(const int32_t* path_lengths, long long n_paths
 long long db1_build_sample_idx(const int32_t* sizes, const int32_t* doc_idx, long long n_doc_idx, int seq_length,
                                int num_epochs, long long tokens_per_epoch, int32_t* out, long long out_rows);
 
+/* One RL sample from RAW arrays - RLFullDataset.get (src/data/rl_dataset.py:614-752) with postprocess_obs_and_act
+ * (:393-473): per transition [n_img_slots x -1 | n_float mu-law tokens | SEP | act_len action tokens]; exactly one of
+ * act_float (continuous, no mu-law) / act_disc (values in [0, n_disc)) is non-NULL; n_frames >= T is the length of the
+ * zero-padded frame sequence (the observation slots of transitions T..n_frames-1 become -1, :718-726), 0 without images.
+ * Outputs as db1_rl_layout. Returns -3 if a discrete action is out of range (the reference asserts). */
+int db1_rl_assemble(const float* obs_float, int n_float, int n_img_slots, const float* act_float,
+                    const long long* act_disc, int act_len, int T, int n_frames, int text_vocab, int n_disc, int n_cont,
+                    int overlap_with_text, int seq_len, int prepend_trans_num, long long* tensor_seq, long long* label,
+                    float* loss_mask, long long* position_id);
+/* my_collate_fn (src/data/data_samplers.py:28-42): samples grouped by task type in order of first appearance; perm[n] =
+ * sample indices group by group, group_type / group_count one entry per group. Returns the number of groups. */
+int db1_collate_plan(const int* type_ids, int n, int* perm, int* group_type, int* group_count);
+/* The concatenation on dim 0 of one field of one group: n contiguous blocks copied back to back into dst. */
+int db1_concat_rows(void* dst, const void* const* srcs, const long long* nbytes, int n);
+
 #ifdef __cplusplus
 }
 #endif

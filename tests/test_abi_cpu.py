@@ -27,7 +27,8 @@ def test_host_library_exports_every_declared_symbol():
     from db1_sm100 import _lib
     lib = _lib.hostlib()
     names = _declared("db1_host.h")
-    assert names == ["db1_build_rl_sample_idx", "db1_build_sample_idx", "db1_decode", "db1_discretize", "db1_rl_layout"]
+    assert names == ["db1_build_rl_sample_idx", "db1_build_sample_idx", "db1_collate_plan", "db1_concat_rows", "db1_decode",
+                     "db1_discretize", "db1_rl_assemble", "db1_rl_layout"]
     for n in names:
         assert hasattr(lib, n), "libdb1_host.so does not export %s" % n
 

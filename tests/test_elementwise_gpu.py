@@ -145,7 +145,7 @@ def test_cross_entropy_out_of_range_labels_are_ignored_rows(cuda):
     dl = torch.empty(rows, Vp, dtype=torch.half, device=cuda)
     gs = torch.ones(1, dtype=torch.float32, device=cuda)
     ops.ce_bwd(logits, labels, mask, row_lse, loss2, gs, dl, V)
-    assert dl[bad].abs().max().item() == 0.0
+    assert dl[bad][:, :V].abs().max().item() == 0.0  # (columns >= V are padding, never written)
     assert _rel(dl[:, :V], lr.grad) < 1e-3
 
 

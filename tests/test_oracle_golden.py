@@ -248,3 +248,59 @@ def test_positional_rows_half_phase_match_reference_after_half():
         worst = max(worst, ((f32 - ref).norm() / ref.norm()).item())
         n += 1
     assert n == 3 and worst > 1e-2  # the two modes really are different tables
+
+
+def test_host_rl_assemble_matches_reference_get_bit_exact():
+    """libdb1_host.so:db1_rl_assemble vs RLFullDataset.get of the unmodified reference (tests/golden/rl_assemble.npz, made by
+    tools/make_golden.py:gen_rl_assemble): continuous control, a window past the episode end, frames + discrete actions
+    with frame padding (-1 fill), dict observation {image, float}; both vocabulary-overlap settings."""
+    from db1_sm100 import host
+    g = _load("rl_assemble")
+
+    def check(n, res):
+        for k in ("tensor_seq", "label", "position_id"):
+            assert np.array_equal(getattr(res, k)[0].numpy(), g["%s%d" % (k, n)]), (n, k)
+        assert np.array_equal(res.loss_mask[0].numpy(), g["loss_mask%d" % n]), n
+    for n in (0, 1):
+        pl, start, end, L, tn, ov, od, ad = [int(x) for x in g["meta%d" % n]]
+        e = min(end, pl)
+        check(n, host.rl_assemble(g["obs%d" % n][start:e], g["act%d" % n][start:e], L, overlap_with_text=bool(ov)))
+    pl, start, end, L, tn, ov, od, ad = [int(x) for x in g["meta2"]]
+    e = min(end, pl)
+    frames = np.zeros(tuple(g["img_shape2"]), np.float32)
+    res = host.rl_assemble(None, g["act2"][start:e], L, frames=frames[start:e], transition_num=tn, overlap_with_text=bool(ov))
+    check(2, res)
+    assert tuple(res.vision_seq.shape) == tuple(g["vision_shape2"])
+    pl, start, end, L, tn, ov, od, ad = [int(x) for x in g["meta3"]]
+    e = min(end, pl)
+    frames = np.zeros(tuple(g["img_shape3"]), np.float32)
+    res = host.rl_assemble(g["state3"][start:e], g["act3"][start:e], L, frames=frames[start:e], transition_num=tn,
+                           overlap_with_text=bool(ov))
+    check(3, res)
+    assert tuple(res.vision_seq.shape) == tuple(g["vision_shape3"])
+
+
+def test_host_collate_matches_reference_my_collate_fn():
+    """db1_collate_plan + db1_concat_rows vs my_collate_fn of the unmodified reference (tests/golden/collate.npz): grouping by
+    task type in order of first appearance, fields concatenated on dim 0, None fields stay None."""
+    from db1_sm100 import host
+    from src.data.input_specs import ICTaskInput, NLPTaskInput, RLTaskInput
+    g = _load("collate")
+    cls = {"nlp": NLPTaskInput, "rl": RLTaskInput, "ic": ICTaskInput}
+    from dataclasses import fields
+    samples = []
+    for i, t in enumerate(g["order"]):
+        kw = {f.name: (torch.from_numpy(g["in%d:%s" % (i, f.name)]) if "in%d:%s" % (i, f.name) in g else None)
+              for f in fields(cls[str(t)])}
+        samples.append(cls[str(t)](**kw))
+    merged = host.collate(samples)
+    assert [type(m).__name__ for m in merged] == [str(x) for x in g["out_types"]]
+    for gi, m in enumerate(merged):
+        for f in fields(m):
+            v = getattr(m, f.name)
+            key = "out%d:%s" % (gi, f.name)
+            if key in g:
+                assert isinstance(v, torch.Tensor) and v.dtype == torch.from_numpy(g[key]).dtype
+                assert np.array_equal(v.numpy(), g[key]), key
+            else:
+                assert v is None, key

@@ -248,6 +248,114 @@ def gen_attn_layer():
     np.savez_compressed(os.path.join(OUT, "layer.npz"), **out)
 
 
+def gen_rl_assemble():
+    """RLFullDataset.get (rl_dataset.py:614-752) + postprocess_obs_and_act (:393-473) on raw arrays, run UNBOUND on a
+    stand-in `self` that carries exactly the attributes those two methods read (the real constructor needs d4rl / gym
+    environments that do not exist here). Cases: continuous control inside an episode; a window that runs past the
+    episode end (action flags zeroed, padding); image frames + discrete actions with fewer transitions than
+    transition_num (frame padding, -1 fill of the padded transitions' observation slots); dict observation."""
+    import types as _t
+    from src.data import rl_dataset as rd
+    from src.tokenizer.scalar_tokenizer import ContinuousScalarTokenizer
+
+    def map_structure(f, *xs):  # dm-tree is absent: the two shapes the reference uses (array or flat dict of arrays)
+        if isinstance(xs[0], dict):
+            return {k: f(*[x[k] for x in xs]) for k in xs[0]}
+        return f(*xs)
+    rd.tree.map_structure = map_structure
+    rng = np.random.default_rng(5)
+    out = {}
+
+    def run(n, obs, act, obs_types, obs_dims, path_length, start, end, L, transition_num, overlap, obs_dim, act_dim):
+        fake = _t.SimpleNamespace()
+        fake.indices = np.array([[0, start, end]])
+        fake.path_lengths = [path_length]
+        fake.discretizer = ContinuousScalarTokenizer(1024)
+        fake.num_discrete_values = 1024
+        fake.use_prompt = False
+        fake.vision_patch_size = 16
+        fake.transition_num = transition_num
+        fake.text_tokenizer = _t.SimpleNamespace(vocab_size=32000)
+        fake.overlap_with_text = overlap
+        fake.observation_dim = obs_dim
+        fake.action_dim = act_dim
+        fake.output_sequence_length = L
+        fake.env = object()
+        fake.obs_type_spec = obs_types
+        fake.observation_dims_for_spec = obs_dims
+        sl = lambda x: x[start:min(end, path_length)]  # noqa: E731
+        fake.get_obs_action_by_path_idx = lambda p, s_, e_: (map_structure(sl, obs), act[start:min(end, path_length)])
+        fake.postprocess_obs_and_act = _t.MethodType(rd.RLFullDataset.postprocess_obs_and_act, fake)
+        res = rd.RLFullDataset.get(fake, 0)
+        out["meta%d" % n] = np.array([path_length, start, end, L, transition_num, int(overlap), obs_dim, act_dim])
+        for k in ("tensor_seq", "label", "loss_mask", "position_id"):
+            out["%s%d" % (k, n)] = getattr(res, k)[0].numpy()
+        if res.vision_seq is not None:
+            out["vision_shape%d" % n] = np.array(res.vision_seq.shape)
+        return res
+
+    # 0: continuous control, window inside the episode (obs 17 floats, act 6 floats), truncated to L
+    o = rng.standard_normal((60, 17)).astype(np.float32) * 3
+    a = rng.uniform(-1, 1, (60, 6)).astype(np.float32)
+    out["obs0"], out["act0"] = o, a
+    run(0, o, a, "float", 17, 60, 5, 5 + 43, 1024, 43, True, 17, 6)
+    # 1: window past the episode end (end_ind > path_length): flags zeroed from the episode end on, zero padding
+    out["obs1"], out["act1"] = o, a
+    run(1, o, a, "float", 17, 60, 40, 40 + 43, 1024, 43, False, 17, 6)
+    # 2: frames + discrete actions, fewer transitions than transition_num -> frame padding and -1 fill
+    img = rng.random((30, 3, 32, 48)).astype(np.float32)
+    ad = rng.integers(0, 18, size=(30,)).astype(np.int64)
+    out["img_shape2"], out["act2"] = np.array(img.shape), ad
+    run(2, img, ad, "image", 6, 30, 22, 22 + 12, 128, 12, True, 6, 1)
+    # 3: dict observation {image, float state}
+    st = rng.standard_normal((30, 4)).astype(np.float32)
+    out["img_shape3"], out["state3"], out["act3"] = np.array(img.shape), st, ad
+    run(3, {"a_img": img, "b_state": st}, ad, {"a_img": "image", "b_state": "float"}, {"a_img": 6, "b_state": 4}, 30, 3, 3 + 9,
+        128, 9, False, 10, 1)
+    np.savez_compressed(os.path.join(OUT, "rl_assemble.npz"), **out)
+
+
+def gen_collate():
+    """my_collate_fn (data_samplers.py:28-42) on a shuffled list of single-sample task objects of three types."""
+    from src.data.data_samplers import my_collate_fn
+    from src.data.input_specs import ICTaskInput, NLPTaskInput, RLTaskInput
+    g = torch.Generator().manual_seed(8)
+    L = 16
+
+    def rl(i, with_img):
+        return RLTaskInput(position_id=torch.randint(0, 5, (1, L), generator=g), attention_mask=None,
+                           loss_mask=torch.randint(0, 2, (1, L), generator=g).float(), label=torch.randint(0, 99, (1, L), generator=g),
+                           text_seq=None, vision_seq=torch.rand(1, 2, 3, 16, 16, generator=g) if with_img else None,
+                           tensor_seq=torch.randint(0, 99, (1, L), generator=g))
+
+    def nlp(i):
+        return NLPTaskInput(position_id=None, attention_mask=None, loss_mask=torch.ones(1, L), label=torch.randint(0, 99, (1, L), generator=g),
+                            text_seq=torch.randint(0, 99, (1, L), generator=g), text_len=None)
+
+    def ic(i):
+        return ICTaskInput(position_id=None, attention_mask=None, loss_mask=torch.ones(1, L), label=torch.randint(0, 99, (1, L), generator=g),
+                           prompt_seq=torch.randint(0, 99, (1, 3), generator=g), img_seq=torch.rand(1, 3, 16, 16, generator=g),
+                           text_seq=torch.randint(0, 99, (1, L - 4), generator=g), img_id_seq=None)
+    order = ["nlp", "rl", "ic", "rl", "nlp", "nlp", "ic", "rl"]
+    samples = [dict(nlp=nlp, rl=lambda i: rl(i, True), ic=ic)[t](i) for i, t in enumerate(order)]
+    out = {"order": np.array(order)}
+    from dataclasses import fields
+    for i, smp in enumerate(samples):
+        for f in fields(smp):
+            v = getattr(smp, f.name)
+            if isinstance(v, torch.Tensor):
+                out["in%d:%s" % (i, f.name)] = v.numpy()
+    import copy
+    merged = my_collate_fn([copy.deepcopy(x) for x in samples])
+    out["out_types"] = np.array([type(m).__name__ for m in merged])
+    for gi, m in enumerate(merged):
+        for f in fields(m):
+            v = getattr(m, f.name)
+            if isinstance(v, torch.Tensor):
+                out["out%d:%s" % (gi, f.name)] = v.numpy()
+    np.savez_compressed(os.path.join(OUT, "collate.npz"), **out)
+
+
 def gen_posemb_half():
     """PositionalEmbedding as the reference evaluates it after module.half() (DeepSpeed fp16): fp16 pos_seq (:569-571),
     fp16-cast inv_freq buffer (:44). Full table for demb 128; a strided sample of rows / columns for demb 2048."""
@@ -267,10 +375,14 @@ def gen_posemb_half():
 
 if __name__ == "__main__":
     os.makedirs(OUT, exist_ok=True)
-    if "--only-posemb-half" in sys.argv:
+    if "--only-new" in sys.argv:  # fixtures added in round 2 (the others are unchanged)
         gen_posemb_half()
+        gen_rl_assemble()
+        gen_collate()
         raise SystemExit(0)
     gen_posemb_half()
+    gen_rl_assemble()
+    gen_collate()
     gen_tokenizer()
     gen_rl_layout()
     gen_patch_positions()
