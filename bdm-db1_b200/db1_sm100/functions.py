@@ -327,6 +327,65 @@ def attn_block_with_memory(w, mem, r, Wqkv, Wr, Wo, u, v, gamma, beta, H, eps, w
     return out.view(B, qlen, d)
 
 
+class KVMemory:
+    """Transformer-XL memory for the decode loop with cached projections. Per layer: ring buffers of the
+    layer-input hidden states (what the reference's `mems` hold), their keys and their values, [B, mem_len, d] fp16 each,
+    starting from zeros exactly like init_mem (transformer_xl.py:470-485: zero hidden rows ARE attended, their k = v = 0).
+    `head` = slot of the oldest row. to_mems() returns the reference-format list (logical order)."""
+
+    def __init__(self, n_layer, batch_size, mem_len, d, device):
+        z = lambda: torch.zeros(batch_size, mem_len, d, dtype=torch.float16, device=device)  # noqa: E731
+        self.hid = [z() for _ in range(n_layer)]
+        self.k = [z() for _ in range(n_layer)]
+        self.v = [z() for _ in range(n_layer)]
+        self.cap = mem_len
+        self.head = 0
+        self.batch_size = batch_size
+        self.rk = {}   # (layer, klen) -> r_net(pos_emb(klen)) [klen, d]
+        self.ws = None
+
+    def to_mems(self):
+        return [torch.roll(h, -self.head, dims=1) for h in self.hid]
+
+    def __len__(self):
+        return len(self.hid)
+
+
+def attn_block_cached(w, li, mem, r, Wqkv, Wr, Wo, u, v, gamma, beta, H, eps, window):
+    """One attention block of a decode step on a KVMemory: only the B*Q new rows go through qkv_net; the attention runs
+    over [cached k / v | new k / v] (db1_relattn_decode); afterwards the new rows replace the oldest ring slots."""
+    B, Q, d = w.shape
+    dh = d // H
+    dev = w.device
+    f16 = torch.float16
+    K = mem.cap + Q
+    x2 = w.reshape(B * Q, d)
+    if not x2.is_contiguous():
+        x2 = x2.contiguous()
+    qkv4 = torch.empty(B * Q, 4 * d, dtype=f16, device=dev)
+    ops.gemm(x2, Wqkv, qkv4, B * Q, 3 * d, d, lda=d, ldb=d, ldc=4 * d, epilogue=ops.EPI_QKV, u=u.reshape(d), v=v.reshape(d),
+             d_model=d)
+    rk = mem.rk.get((li, K))
+    if rk is None:  # depends on the layer's r_net and on klen only
+        rk = torch.empty(K, d, dtype=f16, device=dev)
+        ops.gemm(r, Wr, rk, K, d, d, lda=d, ldb=d, ldc=d)
+        mem.rk[(li, K)] = rk
+    need = B * Q * H * ops.decode_splits(B, Q, H) * (dh + 2)
+    if mem.ws is None or mem.ws.numel() < need:
+        mem.ws = torch.empty(need, dtype=torch.float32, device=dev)
+    o = torch.empty(B * Q, d, dtype=f16, device=dev)
+    ops.relattn_decode(qkv4, mem.k[li], mem.v[li], mem.head, rk, o, mem.ws, B, Q, H, dh, window, 1.0 / math.sqrt(dh))
+    ops.ring_append(x2, mem.hid[li], mem.head, B, Q)
+    ops.ring_append(qkv4[:, 2 * d:3 * d], mem.k[li], mem.head, B, Q)
+    ops.ring_append(qkv4[:, 3 * d:], mem.v[li], mem.head, B, Q)
+    y = torch.empty(B * Q, d, dtype=f16, device=dev)
+    ops.gemm(o, Wo, y, B * Q, d, d, lda=d, ldb=d, ldc=d, resid=x2, ldr=d)
+    out = torch.empty(B * Q, d, dtype=f16, device=dev)
+    stats = torch.empty(B * Q, 2, dtype=torch.float32, device=dev)
+    ops.layernorm_fwd(y, gamma, beta, out, stats, eps)
+    return out.view(B, Q, d)
+
+
 class FFBlockFn(torch.autograd.Function):
     """PositionwiseFF.forward, post-LN branch with GeGLU (transformer_xl.py:276-292, activations.py:19-32):
     out = LayerNorm(x + dropout(W2 (a * gelu(g)) + b2)), [a|g] = W1 x + b1."""

@@ -463,3 +463,43 @@ def adam_step(g16, p16, master, m, v, gcoef, lr, beta1, beta2, eps, weight_decay
       check(_lib.lib().db1_adam_step(ptr(g16), ptr(p16), _f32(master), _f32(m), _f32(v), C.c_longlong(g16.numel()),
                                    _f32(gcoef), C.c_float(lr), C.c_float(beta1), C.c_float(beta2), C.c_float(eps),
                                    C.c_float(weight_decay), int(step), int(adamw), cur_stream()), "db1_adam_step")
+
+
+def decode_splits(B, Q, H):
+    return int(_lib.lib().db1_decode_splits(B, Q, H))
+
+
+def relattn_decode(qkv4, kcache, vcache, head, r, out, ws, B, Q, H, dh, window, scale):
+    """Few-query attention over [ring cache | new rows]; include/db1_sm100.h:db1_relattn_decode. qkv4: the new rows' fused
+    [q+u | q+v | k | v] buffer [B*Q, 4*H*dh]; kcache / vcache [B, cap, H*dh]."""
+    _need_cuda_half(qkv4, kcache, vcache, r, out)
+    d = H * dh
+    es = qkv4.element_size()
+    base = qkv4.data_ptr()
+    cap = kcache.shape[1]
+    nbytes = 2.0 * B * (cap + Q) * d * 2 + (cap + Q) * d * 2.0
+    with _Launch("relattn_decode", 2, 0.0, nbytes):
+      check(_lib.lib().db1_relattn_decode(
+        C.c_void_p(base), C.c_void_p(base + d * es), C.c_void_p(base + 2 * d * es), C.c_void_p(base + 3 * d * es),
+        C.c_longlong(qkv4.stride(0)), ptr(kcache), ptr(vcache), cap, int(head), ptr(r), C.c_longlong(r.stride(0)), ptr(out),
+        C.c_longlong(out.stride(0)), _f32(ws), C.c_longlong(ws.numel()), B, Q, H, dh, int(window), C.c_float(scale),
+        cur_stream()), "db1_relattn_decode")
+
+
+def ring_append(src, ring, head, B, Q):
+    """ring [B, cap, n] <- the Q new rows per sequence of src [B*Q, >= n] (row stride src.stride(0))."""
+    _need_cuda_half(src, ring)
+    with _Launch("ring_append", 1):
+      check(_lib.lib().db1_ring_append(ptr(src), C.c_longlong(src.stride(0)), ptr(ring), ring.shape[1], int(head), B, Q,
+                                       ring.shape[2], cur_stream()), "db1_ring_append")
+
+
+def masked_argmax(logits2d, lo, hi, add_mask=None):
+    """argmax over token columns [lo, hi) of every row of logits2d (fp16 [rows, ld]); returns int64 [rows]."""
+    _need_cuda_half(logits2d)
+    out = torch.empty(logits2d.shape[0], dtype=torch.int64, device=logits2d.device)
+    with _Launch("masked_argmax", 1):
+      check(_lib.lib().db1_masked_argmax(ptr(logits2d), C.c_longlong(logits2d.stride(0)), logits2d.shape[0], int(lo), int(hi),
+                                         _f32(add_mask) if add_mask is not None else None, ptr(out), cur_stream()),
+            "db1_masked_argmax")
+    return out

@@ -103,6 +103,13 @@ class RelPartialLearnableMultiHeadAttn(nn.Module):
             # reference semantics (:177): a mask that is all zeros is an error
             pass
         win = int(window) if window is not None else (1 << 30)
+        if isinstance(mem, tuple) and isinstance(mem[1], F_.KVMemory):
+            # decode step on cached keys / values (F_.attn_block_cached): mem = (layer index, KVMemory)
+            with torch.no_grad():
+                out = F_.attn_block_cached(w, mem[0], mem[1], r2, self.qkv_net.weight, self.r_net.weight, self.o_net.weight,
+                                           self.r_w_bias, self.r_r_bias, self.layer_norm.weight, self.layer_norm.bias,
+                                           self.n_head, self.layer_norm.eps, min(win, 1 << 30))
+            return (out,)
         if mem is not None and mem.size(1) > 0:
             # memory-augmented inference (reference :124-133): no autograd, no dropout (callers run under eval())
             if torch.is_grad_enabled() and (w.requires_grad or self.qkv_net.weight.requires_grad) and self.training:
@@ -234,7 +241,13 @@ class TransformerXL(nn.Module):
             if hasattr(module, "r_w_bias"):
                 module.r_w_bias.data.normal_(mean=0.0, std=0.02)
 
-    def init_mem(self, batch_size):
+    def init_mem(self, batch_size, kv_cache=False):
+        """Reference :470-485. kv_cache=True returns a db1_sm100.functions.KVMemory instead of the list of hidden-state
+        tensors: forward(..., mems=<KVMemory>) then runs the decode step on cached keys / values (same logits, no
+        re-projection of the memory) and returns the same object, updated in place, as `new_mems`."""
+        if self.mem_len > 0 and kv_cache:
+            param = next(self.parameters())
+            return F_.KVMemory(self.n_layer, batch_size, self.mem_len, self.n_embed, param.device)
         if self.mem_len > 0:
             param = next(self.parameters())
             return [torch.zeros(batch_size, self.mem_len, self.n_embed, dtype=param.dtype, device=param.device)
@@ -275,7 +288,10 @@ class TransformerXL(nn.Module):
         hidden = embs[0] if len(embs) == 1 else torch.cat(embs, dim=0)
 
         qlen = hidden.size(1)
-        mlen = mems[0].size(1) if mems is not None else 0
+        cached = isinstance(mems, F_.KVMemory)
+        if cached and (self.training or not self.same_length or mems.batch_size != hidden.size(0) or qlen > mems.cap):
+            raise ValueError("KVMemory decode needs eval mode, same_length, qlen <= mem_len and the memory's batch size")
+        mlen = (mems.cap if cached else mems[0].size(1)) if mems is not None else 0
         klen = mlen + qlen
         # same_length: every query sees exactly mem_len keys once klen exceeds mem_len (reference :551-562);
         # otherwise plain causal. mem_len == 0 with same_length masks everything -> the reference raises ValueError.
@@ -289,11 +305,16 @@ class TransformerXL(nn.Module):
 
         hids = []
         for li, block in enumerate(self.h):
-            if mems is not None:
+            if mems is not None and not cached:
                 hids.append(hidden)
-            hidden = block(hidden, pos_rows, attention_mask=None, mems=None if mems is None else mems[li],
+            layer_mem = None if mems is None else ((li, mems) if cached else mems[li])
+            hidden = block(hidden, pos_rows, attention_mask=None, mems=layer_mem,
                            head_mask=None, output_attentions=False, deepnorm_alpha=self.deepnorm_alpha, window=window)[0]
-        new_mems = self._update_mem(hids, mems, mlen, qlen) if mems is not None else None
+        if cached:
+            mems.head = (mems.head + qlen) % mems.cap  # every layer appended its qlen new rows over the oldest slots
+            new_mems = mems
+        else:
+            new_mems = self._update_mem(hids, mems, mlen, qlen) if mems is not None else None
 
         W = self.word_embedding.weight if self.share_input_output_embedding else self.lm_head.weight
         if compute_loss:

@@ -184,6 +184,31 @@ int db1_relattn_bwd_dr(const void* ds, const void* qv, long long ld_qkv, float* 
                        int dh, int window, void* stream);
 
 /* ------------------------------------------------------------------------------------------------------------------
+ * Memory-augmented decode step with cached keys / values (csrc/decode.cu). The reference recomputes qkv_net over
+ * cat(mem, w) for every call of forward(..., mems=...) (transformer_xl.py:124-141); here the k / v rows of the memory
+ * are kept per layer in ring buffers [B, cap, H*dh] (cap = mem_len, always full: init_mem starts from zeros, :470-485)
+ * and only the new rows go through the projection GEMMs. Logical memory row j lives in slot (head + j) % cap.
+ * ------------------------------------------------------------------------------------------------------------------ */
+/* number of key splits db1_relattn_decode uses for this problem (sizes its workspace) */
+int db1_decode_splits(int B, int Q, int H);
+/* out[b*Q+i, h*dh..] = softmax_j( scale * ((q_i+u).k_j + (q_i+v).r[Q-1-i+j]) ) v_j over the keys query i may see
+ * (j <= i + cap and cap + i - j < window; j < cap: cache rows in logical order, j >= cap: the new rows), fp32 softmax.
+ * qu / qv / knew / vnew: columns of the NEW rows' fused qkv buffer [B*Q, ld_qkv]; r: [cap + Q, ld_r] = r_net(pos_emb) in the
+ * reference's row order; ws: fp32 workspace of B*Q*H * db1_decode_splits(B,Q,H) * (dh + 2) floats. */
+int db1_relattn_decode(const void* qu, const void* qv, const void* knew, const void* vnew, long long ld_qkv,
+                       const void* kcache, const void* vcache, int cap, int head, const void* r, long long ld_r, void* out,
+                       long long ld_out, float* ws, long long ws_floats, int B, int Q, int H, int dh, int window,
+                       float scale, void* stream);
+/* ring[b][(head + t) % cap][0..n) = src[b*Q + t][0..n): appends the Q new rows of every sequence over the oldest slots - the
+ * in-place form of _update_mem's cat(mem, h)[:, -mem_len:] (transformer_xl.py:487-504); the caller advances head by Q. */
+int db1_ring_append(const void* src, long long ld_src, void* ring, int cap, int head, int B, int Q, int n, void* stream);
+/* out[row] = argmax over columns [lo, hi) of logits[row] (- add_mask[c - lo] if given); first maximum wins.
+ * = masked_logits_for_action (evaluate_rl.py:96-124: everything outside the action-token range gets -1e10, optional
+ * environment action mask) followed by argmax (:196-199). */
+int db1_masked_argmax(const void* logits, long long ld, int rows, int lo, int hi, const float* add_mask, long long* out,
+                      void* stream);
+
+/* ------------------------------------------------------------------------------------------------------------------
  * HBM-bound kernels (single pass over the large operand, 16-byte vector accesses, fp32 math).
  * ------------------------------------------------------------------------------------------------------------------ */
 

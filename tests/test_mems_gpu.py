@@ -62,3 +62,59 @@ def test_init_mem_and_stepwise_decode_equals_one_shot(cuda):
     step_logits = torch.cat(outs, 1)
     assert util.rel_err(step_logits, ref_logits) <= 3e-3
     assert mems[0].shape == (1, L, cfg.n_embed)
+
+
+@pytest.mark.parametrize("B", [1, 2])
+def test_kv_cached_decode_matches_recompute_path_and_oracle(cuda, B):
+    """init_mem(kv_cache=True) + forward(..., mems=<KVMemory>) - the decode loop of evaluate_rl.py:157-266
+    (a transition's observation tokens, then one action token at a time) on cached keys / values - gives, step by step,
+    the logits of the reference-format memory path (full re-projection of cat(mem, w)) and of the oracle, and ends with
+    the same memories. Starts from init_mem's zero memories (which ARE attended), runs long enough for the ring buffer to
+    wrap; the masked arg-max (evaluate_rl.py:96-138, :196-199) is checked on the same logits."""
+    from oracle import db1_oracle as orc
+    from db1_sm100 import ops
+    cfg = orc.tiny_config(text_vocab_size=480, mem_len=64, n_position=64)
+    model, sd = _build(cfg, 13, cuda)
+    model.eval()
+    sdo = {k: v.clone() for k, v in sd.items()}
+    for k in list(sdo):
+        if k.startswith("h.") and k.endswith(("r_r_bias", "r_w_bias")):
+            sdo[k] = sdo[k.split(".")[-1]]
+    g = torch.Generator().manual_seed(7)
+    V = orc.total_vocab(cfg)
+    kv = model.init_mem(B, kv_cache=True)
+    mems = model.init_mem(B)
+    omems = [m.float().cpu() for m in mems]
+    qlens = [9, 1, 1, 1, 12, 1, 1, 30, 1, 17, 1, 1]  # 76 rows > mem_len = 64: the ring wraps
+    for step, q in enumerate(qlens):
+        tok = torch.randint(0, 480, (B, q), generator=g)
+        task = dict(type="nlp", text_seq=tok.numpy(), label=np.zeros((B, q), np.int64), loss_mask=np.ones((B, q), np.float32))
+        with torch.no_grad():
+            lg_kv, none, kv2 = model(util.to_model_inputs([task], cuda), compute_loss=False, mems=kv)
+            lg_re, _, mems = model(util.to_model_inputs([task], cuda), compute_loss=False, mems=mems)
+            ol, _, omems = orc.forward([task], sdo, cfg, compute_loss=False, mems=omems)
+        assert kv2 is kv and none is None
+        assert util.rel_err(lg_kv, lg_re) <= 2e-3, step
+        assert util.rel_err(lg_kv, ol) <= 3e-3, step
+        # continuous-action head: arg-max over [text_vocab, V - 1) (everything else -1e10, :107-112), last position
+        last = lg_kv[:, -1, :]
+        buf = last.contiguous()
+        pred = ops.masked_argmax(buf, cfg.text_vocab_size, V - 1)
+        ref = last.float().clone()
+        ref[:, :cfg.text_vocab_size] -= 1e10
+        ref[:, -1] -= 1e10
+        assert torch.equal(pred, ref.argmax(-1))
+        # discrete head with an environment action mask (:113-123)
+        n_act = 18
+        amask = (torch.rand(n_act, generator=g) < 0.5).float()
+        amask[3] = 1.0
+        pen = ((amask - 1).abs() * 1e10).to(cuda)
+        pred_d = ops.masked_argmax(buf, 0, n_act, add_mask=pen)
+        ref_d = last.float().clone()
+        ref_d[:, n_act:] -= 1e10
+        ref_d[:, :n_act] -= pen
+        assert torch.equal(pred_d, ref_d.argmax(-1))
+    for a, b_, c in zip(kv.to_mems(), mems, omems):
+        assert a.shape == b_.shape
+        assert util.rel_err(a, b_) <= 2e-3
+        assert util.rel_err(a, c) <= 3e-3
