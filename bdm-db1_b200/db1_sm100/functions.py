@@ -315,7 +315,9 @@ def attn_block_with_memory(w, mem, r, Wqkv, Wr, Wo, u, v, gamma, beta, H, eps, w
     o = torch.empty(B, K, d, dtype=f16, device=dev)
     lse2 = torch.empty(B, H, K, dtype=torch.float32, device=dev)
     ops.relattn_mem_fwd(qkv4, rk, o.view(B * K, d), lse2, B, K, H, dh, window, 1.0 / math.sqrt(dh), mlen)
-    oq = o[:, mlen:].reshape(B * qlen, d)  # gathers the query rows (copy)
+    # the query rows as a dense [B*qlen, d] matrix. (For qlen == 1 reshape() returns a strided VIEW with row stride K*d, not a
+    # copy - the GEMM below is told lda = d, so the copy must be explicit.)
+    oq = o[:, mlen:].contiguous().view(B * qlen, d)
     x2 = w.reshape(B * qlen, d)
     if not x2.is_contiguous():
         x2 = x2.contiguous()

@@ -151,4 +151,4 @@ def test_1p3b_width_image_and_mixed_batches_vs_oracle(cuda, workload):
     print("%s worst gradient rel-L2:" % workload, sorted(worst.items(), key=lambda kv: -kv[1])[:6])
     assert max(worst.values()) <= 2e-2, {k: v for k, v in worst.items() if v > 2e-2}
     if workload == "atari_C3":
-        assert any(k.startswith("vision_encoder.patch_embedding.projection") for k in worst)
+        assert any("patch_embeddings.projection" in k or "patch_embedding.projection" in k for k in worst), sorted(worst)[:40]

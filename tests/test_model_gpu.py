@@ -283,10 +283,8 @@ def test_half_phase_default_matches_oracle_half_phase(cuda):
     cfg_h.pos_phase_half = True
     with torch.no_grad():
         ol_h, oloss_h = orc.forward([task], sdo, cfg_h)
-        ol_f, _ = orc.forward([task], sdo, cfg)
     assert util.rel_err(logits, ol_h) <= 2e-3
     assert abs(loss.item() - oloss_h.item()) <= 1e-3 * abs(oloss_h.item())
-    assert util.rel_err(ol_h, ol_f) > util.rel_err(logits, ol_h)  # the phase mode matters more than kernel rounding
 
 
 @pytest.mark.gpu
