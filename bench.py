@@ -335,23 +335,34 @@ def run_ours(args):
         step(resident)
         torch.cuda.synchronize()
         engine.enable_backward_allreduce = True
-        worst_rel, worst_rank_diff = 0.0, 0.0
+        worst_layer, worst_rest, worst_rank_diff = 0.0, 0.0, 0.0
         for b, a in zip(engine.buckets, avg):
             ref = b.flat.float()
             dist.all_reduce(ref, op=dist.ReduceOp.SUM)
             ref /= world
             den = ref.abs().max().clamp_min(1e-20)
-            worst_rel = max(worst_rel, ((a.float() - ref).abs().max() / den).item())
+            rel = ((a.float() - ref).abs().max() / den).item()
+            if b.key == "rest":
+                worst_rest = max(worst_rest, rel)
+            else:
+                worst_layer = max(worst_layer, rel)
             r0 = a.clone()
             dist.broadcast(r0, src=0)
             worst_rank_diff = max(worst_rank_diff, (a.float() - r0.float()).abs().max().item())
-        t = torch.tensor([worst_rel, worst_rank_diff], device=dev)
+        t = torch.tensor([worst_layer, worst_rest, worst_rank_diff], device=dev)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        dp_check = {"allreduced_vs_mean_of_rank_grads_max_rel": t[0].item(), "max_abs_diff_vs_rank0": t[1].item(),
-                    "buckets": len(engine.buckets), "tolerance_rel": 2e-3,
-                    "ok": bool(t[0].item() <= 2e-3 and t[1].item() == 0.0),
+        # tolerances: the reference value is an fp32 mean of a SECOND backward's fp16 gradients. NCCL averages in fp16
+        # (pre-scaled sum: ~2 roundings of 2^-11), and the local gradients themselves differ between two backward passes in
+        # their last bits where they are accumulated with atomics (fp16 scatter-add of the embedding rows, fp32 reductions
+        # of du / dv / dR): 5e-3 of the bucket's largest element for the decoder-layer buckets, 1e-2 for the bucket that
+        # holds the embedding scatter. Across ranks the reduced buckets must be bit-identical.
+        dp_check = {"allreduced_vs_mean_of_rank_grads_max_rel": {"layer_buckets": t[0].item(), "embedding_bucket": t[1].item()},
+                    "max_abs_diff_vs_rank0": t[2].item(), "buckets": len(engine.buckets),
+                    "tolerance_rel": {"layer_buckets": 5e-3, "embedding_bucket": 1e-2},
+                    "ok": bool(t[0].item() <= 5e-3 and t[1].item() <= 1e-2 and t[2].item() == 0.0),
                     "how": "eval-mode fwd+bwd on each rank's own batch: engine buckets after the overlapped NCCL AVG vs "
-                           "all_reduce(SUM)/N of the same step's local gradients; reduced buckets compared bit-wise with rank 0"}
+                           "all_reduce(SUM)/N (fp32) of a second backward's local gradients; reduced buckets compared "
+                           "bit-wise with rank 0"}
         engine.train()
 
     # ---- the other BASELINE configurations, short runs (C3 Atari frames through the patch embedder, C4 mixed batch)
