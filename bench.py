@@ -200,7 +200,9 @@ def run_ours(args):
     if world > 1:
         # NCCL's CTAs stay resident for a whole all-reduce and take SMs from the persistent compute kernels: bound them
         # (the engine sizes its grids to the remaining SMs during backward). Must be set before the communicator exists.
-        os.environ.setdefault("NCCL_MAX_CTAS", "8")
+        # Measured at 8 GPUs (profiles/scale_sweep_r2.md): no cap / no reservation 38.16 ms, 16 / 16 37.43 ms (best), 8 / 8
+        # 43.6 ms (the collective starves and becomes exposed), 32 / 32 41.2 ms.
+        os.environ.setdefault("NCCL_MAX_CTAS", "16")
         dist.init_process_group("nccl", device_id=dev)
         mpu.initialize_model_parallel()
     torch.manual_seed(0)
