@@ -26,6 +26,7 @@ struct DecParams {
   const __half* kc;
   const __half* vc;   // ring caches [B, cap, H*dh]
   int cap, head;      // logical memory row j lives in slot (head + j) % cap
+  const int* head_dev;  // if not NULL the head is read from device memory (a captured CUDA graph replays with a moving head)
   const __half* r;    // [cap + Q, H*dh], row c <-> distance cap + Q - 1 - c
   long long ld_r;
   float* ws;          // [B*H*Q, S, dh + 2] partial (max, sum, acc)
@@ -54,6 +55,7 @@ __global__ void __launch_bounds__(DEC_THREADS) relattn_decode_kernel(const DecPa
   const int d0 = lane * 4;
   const bool act = d0 < p.dh;
   const int M = p.cap, K = p.cap + p.Q;
+  const int head = p.head_dev ? *p.head_dev : p.head;
   const long long hoff = (long long)h * p.dh + d0;
   float qu[4] = {0, 0, 0, 0}, qv[4] = {0, 0, 0, 0};
   if (act) {
@@ -72,7 +74,7 @@ __global__ void __launch_bounds__(DEC_THREADS) relattn_decode_kernel(const DecPa
   for (int j = j0 + warp; j < j1; j += 4) {
     const __half *kp, *vp;
     if (j < M) {
-      int slot = p.head + j;
+      int slot = head + j;
       if (slot >= p.cap) slot -= p.cap;
       const long long ro = ((long long)b * p.cap + slot) * ((long long)p.H * p.dh) + hoff;
       kp = p.kc + ro;
@@ -147,15 +149,21 @@ __global__ void relattn_decode_merge_kernel(const float* __restrict__ ws, __half
   out[(long long)(b * Q + i) * ld_out + (long long)h * dh + d] = __float2half_rn(o / ll);
 }
 
-// dst[b][(head + t) % cap][:] = src[b*Q + t][:]  (n % 8 == 0 halves per row)
-__global__ void ring_append_kernel(const __half* __restrict__ src, long long ld_src, __half* __restrict__ dst, int cap,
-                                   int head, int Q, int n) {
+// ring_z[b][(head + t) % cap][:] = src_z[b*Q + t][:] for up to three (source, ring) pairs in one launch (blockIdx.y):
+// the layer input rows and the new k / v rows (n % 8 == 0 halves per row)
+struct RingArgs {
+  const __half* src[3];
+  long long ld[3];
+  __half* dst[3];
+};
+__global__ void ring_append_kernel(const RingArgs a, int cap, int head_val, const int* __restrict__ head_dev, int Q, int n) {
   const int row = blockIdx.x;  // b * Q + t
+  const int z = blockIdx.y;
   const int b = row / Q, t = row % Q;
-  int slot = head + t;
+  int slot = (head_dev ? *head_dev : head_val) + t;
   if (slot >= cap) slot -= cap;
-  const __half* s = src + (long long)row * ld_src;
-  __half* d = dst + ((long long)b * cap + slot) * n;
+  const __half* s = a.src[z] + (long long)row * a.ld[z];
+  __half* d = a.dst[z] + ((long long)b * cap + slot) * n;
   for (int c = threadIdx.x * 8; c < n; c += blockDim.x * 8) st_half8(d + c, ld_half8(s + c));
 }
 
@@ -218,9 +226,9 @@ extern "C" int db1_decode_splits(int B, int Q, int H) {
 }
 
 extern "C" int db1_relattn_decode(const void* qu, const void* qv, const void* knew, const void* vnew, long long ld_qkv,
-                                  const void* kcache, const void* vcache, int cap, int head, const void* r, long long ld_r,
-                                  void* out, long long ld_out, float* ws, long long ws_floats, int B, int Q, int H, int dh,
-                                  int window, float scale, void* stream_) {
+                                  const void* kcache, const void* vcache, int cap, int head, const int* head_dev,
+                                  const void* r, long long ld_r, void* out, long long ld_out, float* ws, long long ws_floats,
+                                  int B, int Q, int H, int dh, int window, float scale, void* stream_) {
   DB1_CHECK_ARG(qu && qv && knew && vnew && kcache && vcache && r && out && ws, "relattn_decode: null pointer");
   DB1_CHECK_ARG(B > 0 && Q > 0 && H > 0 && cap > 0 && head >= 0 && head < cap, "relattn_decode: bad shape");
   DB1_CHECK_ARG(dh % 4 == 0 && dh >= 4 && dh <= 128, "relattn_decode: head dim %d unsupported (multiple of 4, <= 128)", dh);
@@ -229,7 +237,7 @@ extern "C" int db1_relattn_decode(const void* qu, const void* qv, const void* kn
   DB1_CHECK_ARG(ws_floats >= (long long)B * Q * H * S * (dh + 2), "relattn_decode: workspace too small");
   DecParams p;
   p.qu = (const __half*)qu; p.qv = (const __half*)qv; p.knew = (const __half*)knew; p.vnew = (const __half*)vnew;
-  p.ld_qkv = ld_qkv; p.kc = (const __half*)kcache; p.vc = (const __half*)vcache; p.cap = cap; p.head = head;
+  p.ld_qkv = ld_qkv; p.kc = (const __half*)kcache; p.vc = (const __half*)vcache; p.cap = cap; p.head = head; p.head_dev = head_dev;
   p.r = (const __half*)r; p.ld_r = ld_r; p.ws = ws; p.B = B; p.Q = Q; p.H = H; p.dh = dh; p.S = S; p.window = window;
   p.scale_log2 = scale * 1.4426950408889634f;
   cudaStream_t st = (cudaStream_t)stream_;
@@ -239,12 +247,20 @@ extern "C" int db1_relattn_decode(const void* qu, const void* qv, const void* kn
   return 0;
 }
 
-extern "C" int db1_ring_append(const void* src, long long ld_src, void* ring, int cap, int head, int B, int Q, int n,
-                               void* stream_) {
-  DB1_CHECK_ARG(src && ring && cap > 0 && head >= 0 && head < cap && B > 0 && Q > 0 && Q <= cap && n > 0 && n % 8 == 0 &&
-                    ld_src % 8 == 0,
+extern "C" int db1_ring_append(const void* const* srcs, const long long* ld_srcs, void* const* rings, int nring, int cap,
+                               int head, const int* head_dev, int B, int Q, int n, void* stream_) {
+  DB1_CHECK_ARG(srcs && ld_srcs && rings && nring >= 1 && nring <= 3 && cap > 0 && head >= 0 && head < cap && B > 0 && Q > 0 &&
+                    Q <= cap && n > 0 && n % 8 == 0,
                 "ring_append: bad arguments");
-  ring_append_kernel<<<B * Q, 128, 0, (cudaStream_t)stream_>>>((const __half*)src, ld_src, (__half*)ring, cap, head, Q, n);
+  RingArgs a;
+  for (int z = 0; z < 3; ++z) {
+    const int y = z < nring ? z : 0;
+    DB1_CHECK_ARG(srcs[y] && rings[y] && ld_srcs[y] % 8 == 0, "ring_append: bad source / ring %d", y);
+    a.src[z] = (const __half*)srcs[y];
+    a.ld[z] = ld_srcs[y];
+    a.dst[z] = (__half*)rings[y];
+  }
+  ring_append_kernel<<<dim3(B * Q, nring), 128, 0, (cudaStream_t)stream_>>>(a, cap, head, head_dev, Q, n);
   DB1_CUDA(cudaGetLastError());
   return 0;
 }

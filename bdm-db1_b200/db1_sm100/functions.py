@@ -341,7 +341,8 @@ class KVMemory:
         self.k = [z() for _ in range(n_layer)]
         self.v = [z() for _ in range(n_layer)]
         self.cap = mem_len
-        self.head = 0
+        self.head = 0                                                        # host copy (to_mems)
+        self.head_dev = torch.zeros(1, dtype=torch.int32, device=device)    # what the kernels read (CUDA-graph safe)
         self.batch_size = batch_size
         self.rk = {}   # (layer, klen) -> r_net(pos_emb(klen)) [klen, d]
         self.ws = None
@@ -349,8 +350,52 @@ class KVMemory:
     def to_mems(self):
         return [torch.roll(h, -self.head, dims=1) for h in self.hid]
 
+    def advance(self, q):
+        """The q rows every layer appended become the newest memory rows. (In-place device update: captured by graphs.)"""
+        self.head_dev.add_(q).remainder_(self.cap)
+        self.head = (self.head + q) % self.cap
+
     def __len__(self):
         return len(self.hid)
+
+
+class DecodeGraph:
+    """One decode step of fixed shape (B sequences x q new tokens) captured in a CUDA graph: the ~350 kernel launches of a
+    24-layer step replay as one submission (the step is launch-bound from Python otherwise). The ring-buffer head lives
+    in device memory, so every replay appends at the right slots.
+        g = DecodeGraph(model, mem, q);  logits = g.step(tokens [B, q], position_id [B, q])   # logits: static buffer"""
+
+    def __init__(self, model, mem, q, task_cls=None):
+        from src.data.input_specs import RLTaskInput
+        dev = mem.head_dev.device
+        B = mem.batch_size
+        self.mem, self.q = mem, q
+        self.tok = torch.zeros(B, q, dtype=torch.int64, device=dev)
+        self.pos = torch.zeros(B, q, dtype=torch.int64, device=dev)
+        self.inputs = [RLTaskInput(position_id=self.pos, attention_mask=None, loss_mask=None, label=None, text_seq=None,
+                                   vision_seq=None, tensor_seq=self.tok)]
+        keep = [(t, t.clone()) for lst in (mem.hid, mem.k, mem.v) for t in lst] + [(mem.head_dev, mem.head_dev.clone())]
+        head0 = mem.head
+        side = torch.cuda.Stream(device=dev)
+        side.wait_stream(torch.cuda.current_stream(dev))
+        with torch.cuda.stream(side), torch.no_grad():  # warm-up: workspaces, r-table cache, allocator pools
+            for _ in range(2):
+                model(self.inputs, compute_loss=False, mems=mem)
+        torch.cuda.current_stream(dev).wait_stream(side)
+        self.graph = torch.cuda.CUDAGraph()
+        with torch.no_grad(), torch.cuda.graph(self.graph):
+            self.logits, _none, _m = model(self.inputs, compute_loss=False, mems=mem)
+        for t, c in keep:  # warm-up and capture bookkeeping must not leave traces in the memory
+            t.copy_(c)
+        mem.head = head0
+
+    def step(self, tok, pos=None):
+        self.tok.copy_(tok, non_blocking=True)
+        if pos is not None:
+            self.pos.copy_(pos, non_blocking=True)
+        self.graph.replay()
+        self.mem.head = (self.mem.head + self.q) % self.mem.cap
+        return self.logits
 
 
 def attn_block_cached(w, li, mem, r, Wqkv, Wr, Wo, u, v, gamma, beta, H, eps, window):
@@ -376,10 +421,10 @@ def attn_block_cached(w, li, mem, r, Wqkv, Wr, Wo, u, v, gamma, beta, H, eps, wi
     if mem.ws is None or mem.ws.numel() < need:
         mem.ws = torch.empty(need, dtype=torch.float32, device=dev)
     o = torch.empty(B * Q, d, dtype=f16, device=dev)
-    ops.relattn_decode(qkv4, mem.k[li], mem.v[li], mem.head, rk, o, mem.ws, B, Q, H, dh, window, 1.0 / math.sqrt(dh))
-    ops.ring_append(x2, mem.hid[li], mem.head, B, Q)
-    ops.ring_append(qkv4[:, 2 * d:3 * d], mem.k[li], mem.head, B, Q)
-    ops.ring_append(qkv4[:, 3 * d:], mem.v[li], mem.head, B, Q)
+    ops.relattn_decode(qkv4, mem.k[li], mem.v[li], mem.head, rk, o, mem.ws, B, Q, H, dh, window, 1.0 / math.sqrt(dh),
+                       head_dev=mem.head_dev)
+    ops.ring_append([(x2, mem.hid[li]), (qkv4[:, 2 * d:3 * d], mem.k[li]), (qkv4[:, 3 * d:], mem.v[li])], mem.head, B, Q,
+                    head_dev=mem.head_dev)
     y = torch.empty(B * Q, d, dtype=f16, device=dev)
     ops.gemm(o, Wo, y, B * Q, d, d, lda=d, ldb=d, ldc=d, resid=x2, ldr=d)
     out = torch.empty(B * Q, d, dtype=f16, device=dev)

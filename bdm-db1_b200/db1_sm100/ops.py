@@ -469,9 +469,9 @@ def decode_splits(B, Q, H):
     return int(_lib.lib().db1_decode_splits(B, Q, H))
 
 
-def relattn_decode(qkv4, kcache, vcache, head, r, out, ws, B, Q, H, dh, window, scale):
+def relattn_decode(qkv4, kcache, vcache, head, r, out, ws, B, Q, H, dh, window, scale, head_dev=None):
     """Few-query attention over [ring cache | new rows]; include/db1_sm100.h:db1_relattn_decode. qkv4: the new rows' fused
-    [q+u | q+v | k | v] buffer [B*Q, 4*H*dh]; kcache / vcache [B, cap, H*dh]."""
+    [q+u | q+v | k | v] buffer [B*Q, 4*H*dh]; kcache / vcache [B, cap, H*dh]; head_dev: int32 device scalar or None."""
     _need_cuda_half(qkv4, kcache, vcache, r, out)
     d = H * dh
     es = qkv4.element_size()
@@ -481,17 +481,22 @@ def relattn_decode(qkv4, kcache, vcache, head, r, out, ws, B, Q, H, dh, window, 
     with _Launch("relattn_decode", 2, 0.0, nbytes):
       check(_lib.lib().db1_relattn_decode(
         C.c_void_p(base), C.c_void_p(base + d * es), C.c_void_p(base + 2 * d * es), C.c_void_p(base + 3 * d * es),
-        C.c_longlong(qkv4.stride(0)), ptr(kcache), ptr(vcache), cap, int(head), ptr(r), C.c_longlong(r.stride(0)), ptr(out),
-        C.c_longlong(out.stride(0)), _f32(ws), C.c_longlong(ws.numel()), B, Q, H, dh, int(window), C.c_float(scale),
-        cur_stream()), "db1_relattn_decode")
+        C.c_longlong(qkv4.stride(0)), ptr(kcache), ptr(vcache), cap, int(head), ptr(head_dev), ptr(r),
+        C.c_longlong(r.stride(0)), ptr(out), C.c_longlong(out.stride(0)), _f32(ws), C.c_longlong(ws.numel()), B, Q, H, dh,
+        int(window), C.c_float(scale), cur_stream()), "db1_relattn_decode")
 
 
-def ring_append(src, ring, head, B, Q):
-    """ring [B, cap, n] <- the Q new rows per sequence of src [B*Q, >= n] (row stride src.stride(0))."""
-    _need_cuda_half(src, ring)
+def ring_append(pairs, head, B, Q, head_dev=None):
+    """pairs: up to three (src [B*Q, >= n] with its own row stride, ring [B, cap, n]); one launch."""
+    k = len(pairs)
+    _need_cuda_half(*[t for pr in pairs for t in pr])
+    srcs = (C.c_void_p * k)(*[s_.data_ptr() for s_, _r in pairs])
+    lds = (C.c_longlong * k)(*[s_.stride(0) for s_, _r in pairs])
+    rings = (C.c_void_p * k)(*[r_.data_ptr() for _s, r_ in pairs])
+    ring0 = pairs[0][1]
     with _Launch("ring_append", 1):
-      check(_lib.lib().db1_ring_append(ptr(src), C.c_longlong(src.stride(0)), ptr(ring), ring.shape[1], int(head), B, Q,
-                                       ring.shape[2], cur_stream()), "db1_ring_append")
+      check(_lib.lib().db1_ring_append(srcs, lds, rings, k, ring0.shape[1], int(head), ptr(head_dev), B, Q, ring0.shape[2],
+                                       cur_stream()), "db1_ring_append")
 
 
 def masked_argmax(logits2d, lo, hi, add_mask=None):

@@ -311,7 +311,7 @@ class TransformerXL(nn.Module):
             hidden = block(hidden, pos_rows, attention_mask=None, mems=layer_mem,
                            head_mask=None, output_attentions=False, deepnorm_alpha=self.deepnorm_alpha, window=window)[0]
         if cached:
-            mems.head = (mems.head + qlen) % mems.cap  # every layer appended its qlen new rows over the oldest slots
+            mems.advance(qlen)  # every layer appended its qlen new rows over the oldest slots
             new_mems = mems
         else:
             new_mems = self._update_mem(hids, mems, mlen, qlen) if mems is not None else None

@@ -196,12 +196,17 @@ int db1_decode_splits(int B, int Q, int H);
  * qu / qv / knew / vnew: columns of the NEW rows' fused qkv buffer [B*Q, ld_qkv]; r: [cap + Q, ld_r] = r_net(pos_emb) in the
  * reference's row order; ws: fp32 workspace of B*Q*H * db1_decode_splits(B,Q,H) * (dh + 2) floats. */
 int db1_relattn_decode(const void* qu, const void* qv, const void* knew, const void* vnew, long long ld_qkv,
-                       const void* kcache, const void* vcache, int cap, int head, const void* r, long long ld_r, void* out,
-                       long long ld_out, float* ws, long long ws_floats, int B, int Q, int H, int dh, int window,
-                       float scale, void* stream);
-/* ring[b][(head + t) % cap][0..n) = src[b*Q + t][0..n): appends the Q new rows of every sequence over the oldest slots - the
- * in-place form of _update_mem's cat(mem, h)[:, -mem_len:] (transformer_xl.py:487-504); the caller advances head by Q. */
-int db1_ring_append(const void* src, long long ld_src, void* ring, int cap, int head, int B, int Q, int n, void* stream);
+                       const void* kcache, const void* vcache, int cap, int head, const int* head_dev, const void* r,
+                       long long ld_r, void* out, long long ld_out, float* ws, long long ws_floats, int B, int Q, int H,
+                       int dh, int window, float scale, void* stream);
+/* rings[z][b][(head + t) % cap][0..n) = srcs[z][b*Q + t][0..n) for nring <= 3 (source, ring) pairs in ONE launch (layer
+ * input rows, new k rows, new v rows): appends the Q new rows of every sequence over the oldest slots - the in-place form
+ * of _update_mem's cat(mem, h)[:, -mem_len:] (transformer_xl.py:487-504); the caller advances the head by Q afterwards.
+ * srcs / ld_srcs / rings are HOST arrays of device pointers / row strides.
+ * head_dev (both calls): if not NULL the head is read from this device int instead of `head`, so that a decode step
+ * captured in a CUDA graph replays correctly while the head moves. */
+int db1_ring_append(const void* const* srcs, const long long* ld_srcs, void* const* rings, int nring, int cap, int head,
+                    const int* head_dev, int B, int Q, int n, void* stream);
 /* out[row] = argmax over columns [lo, hi) of logits[row] (- add_mask[c - lo] if given); first maximum wins.
  * = masked_logits_for_action (evaluate_rl.py:96-124: everything outside the action-token range gets -1e10, optional
  * environment action mask) followed by argmax (:196-199). */

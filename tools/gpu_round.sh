@@ -24,3 +24,25 @@ if has ncufull; then
       python bench.py --steps 1 --warmup 1 --profile-only > gpurun_out/ncu_lnbwd_$TAG.log 2>&1
   ls -la gpurun_out/*_$TAG.ncu-rep
 fi
+
+# ---- round 2 additions
+KM="gpu__time_duration.sum,sm__pipe_tensor_cycles_active.avg.pct_of_peak_sustained_active,smsp__issue_active.avg.pct_of_peak_sustained_active,dram__bytes_read.sum,dram__bytes_write.sum,gpu__dram_throughput.avg.pct_of_peak_sustained_elapsed,lts__throughput.avg.pct_of_peak_sustained_elapsed,l1tex__data_bank_conflicts_pipe_lsu_mem_shared.sum,launch__registers_per_thread,launch__grid_size"
+if has kmetrics; then
+  # one metrics pass over every launch of one step of each workload (+ the fused optimizer step, + the decode loop)
+  timeout 900 ncu --metrics $KM --clock-control none --profile-from-start off -c 1500 --csv --log-file gpurun_out/kmetrics_rl_$TAG.csv \
+      python bench.py --steps 1 --warmup 2 --profile-only --optimizer > gpurun_out/kmetrics_rl_$TAG.log 2>&1
+  timeout 900 ncu --metrics $KM --clock-control none --profile-from-start off -c 1500 --csv --log-file gpurun_out/kmetrics_atari_$TAG.csv \
+      python bench.py --steps 1 --warmup 2 --profile-only --workload atari > gpurun_out/kmetrics_atari_$TAG.log 2>&1
+  timeout 600 ncu --metrics $KM --clock-control none -k regex:"decode|ring_append|masked_argmax" -s 200 -c 200 --csv --log-file gpurun_out/kmetrics_decode_$TAG.csv \
+      python tools/bench_decode.py 1 8 > gpurun_out/kmetrics_decode_$TAG.log 2>&1
+  ls -la gpurun_out/kmetrics_*_$TAG.csv
+fi
+if has decode; then timeout 600 python tools/bench_decode.py 1 32 2>&1 | tee gpurun_out/bench_decode_$TAG.json; fi
+if has ncufull2; then
+  for k in "gemm_kernel" "relattn_fwd_kernel<128, 0>" "relattn_fwd_kernel<128, 2>" "relattn_bwd_dkdv" "relattn_bwd_band_kernel<128, 0>" "relattn_bwd_band_kernel<128, 1>" "ln_bwd" "ln_fwd"; do
+    f=$(echo "$k" | tr -c 'a-zA-Z0-9' '_')
+    timeout 400 ncu --set full --clock-control none --import-source on --profile-from-start off -k regex:"$k" -s 30 -c 1 -o gpurun_out/full_${f}_$TAG -f \
+        python bench.py --steps 1 --warmup 2 --profile-only > gpurun_out/full_${f}_$TAG.log 2>&1
+  done
+  ls -la gpurun_out/full_*_$TAG.ncu-rep
+fi
