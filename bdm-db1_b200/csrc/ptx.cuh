@@ -412,6 +412,12 @@ DEVI Half8 half8_zero() {
   v.u = make_uint4(0u, 0u, 0u, 0u);
   return v;
 }
+// 2^x on the MUFU alone (no denormal rescue around it: results below 2^-126 flush to zero, which is what a softmax wants)
+DEVI float ex2_approx(float x) {
+  float y;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
 DEVI void named_bar_sync(int id, int nthreads) {
   asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
 }

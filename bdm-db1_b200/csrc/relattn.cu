@@ -428,8 +428,8 @@ relattn_fwd_kernel(const __grid_constant__ CUtensorMap tmQu, const __grid_consta
         uint32_t pk[16];
 #pragma unroll
         for (int t = 0; t < 16; ++t) {
-          const float p0 = exp2f(fmaf(sc[c2][2 * t], p.scale_log2, -m_use));
-          const float p1 = exp2f(fmaf(sc[c2][2 * t + 1], p.scale_log2, -m_use));
+          const float p0 = ex2_approx(fmaf(sc[c2][2 * t], p.scale_log2, -m_use));
+          const float p1 = ex2_approx(fmaf(sc[c2][2 * t + 1], p.scale_log2, -m_use));
           sum += p0 + p1;
           pk[t] = pack_half2(p0, p1);
         }

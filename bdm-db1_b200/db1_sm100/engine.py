@@ -25,11 +25,24 @@ import torch.distributed as dist
 
 
 def _default_bucket_of(name):
-    """Bucket key for a parameter name: decoder layer index, or 'rest' (embeddings, vision, shared u/v, head)."""
+    """Bucket key for a parameter name. Decoder layer l: 'h.l.ff' (the two feed-forward weight matrices: their gradients
+    are complete half a layer earlier in backward) and 'h.l.attn' (the attention block + the layer's small vectors, whose
+    fp32 accumulators are converted together at the end of the layer); 'emb' = the (tied) word embedding; 'vision' = the image patch embedder; 'rest' = everything
+    else (shared u / v, timestep embedding, an untied head)."""
     parts = name.split(".")
     if len(parts) > 2 and parts[0] == "h" and parts[1].isdigit():
-        return "h.%s" % parts[1]
+        ff = parts[2] == "pos_ff" and "CoreNet" in parts and parts[-1] == "weight"
+        return "h.%s.%s" % (parts[1], "ff" if ff else "attn")
+    if name == "word_embedding.weight":
+        return "emb"
+    if parts[0] == "vision_encoder":
+        return "vision"
     return "rest"
+
+
+# buckets whose parameters are used more than once per forward (or whose use is data dependent): they are never launched
+# from inside backward by the completion count
+_LATE = ("rest", "emb", "vision")
 
 
 class _Bucket:
@@ -93,10 +106,11 @@ class DB1Engine:
         self._written = set()    # ids of parameters whose bucket view already holds this window's gradient
         self._sink_seen = set()  # ids of parameters that have ever been written through the sink
         self._param_by_id = {id(p): p for b in self.buckets for p in b.params}
-        self._sink_on = bool(self._cuda and direct_grads)
+        self._sink_on = bool((self._cuda and direct_grads) or direct_grads == "force")
         if self._sink_on:
             from . import functions
             functions.set_grad_sink(self)
+        self._setup_emb_split()
 
     # ------------------------------------------------------------------------------------------ buckets
     def _build_buckets(self, bucket_of):
@@ -121,6 +135,104 @@ class DB1Engine:
                 off += (p.numel() + 7) // 8 * 8
                 self._bucket_of_param[id(p)] = b
             self.buckets.append(b)
+
+    # ------------------------------------------------------------------------------------------ tied-embedding split
+    # The tied embedding's gradient has a dense part (the head's weight gradient, complete right after backward starts)
+    # and a sparse part (the embedding scatter, the very last kernel of backward). All-reduce is linear, so the dense part
+    # is reduced at once - hidden under the whole backward - and the scatter goes to a zero-kept side buffer of which only
+    # the row range [lo, hi) that any rank's tokens touched this window is reduced afterwards and added. The range is
+    # agreed by a 3-element MAX all-reduce enqueued before the first bucket of the step (so every rank slices the same
+    # rows); its third element says whether any rank fed the image patch embedder, else the (all-zero) 'vision' bucket is
+    # not communicated at all. What is left exposed after backward is then the first layer's attention bucket plus a few MB.
+    def _setup_emb_split(self):
+        self._emb = None
+        self._vision = None
+        for b in self.buckets:
+            if b.key == "emb" and len(b.params) == 1 and b.params[0].dim() == 2:
+                self._emb = b
+            if b.key == "vision":
+                self._vision = b
+        on = os.environ.get("DB1_EMB_SPLIT", "1") != "0"
+        if not (self._sink_on and self._world > 1 and on):
+            self._emb = None
+        self._emb_phase = 0
+        self._split_active = False
+        self._rng = None
+        if self._world > 1 and self._sink_on and on and (self._emb is not None or self._vision is not None):
+            dev = self.device
+            self._rng_init = torch.tensor([-(1 << 40), -1, 0], dtype=torch.int64, device=dev)  # [-min token, max token, vision]
+            self._rng = self._rng_init.clone()
+            self._rng_host = torch.zeros(3, dtype=torch.int64, pin_memory=self._cuda)
+            self._rng_ev = torch.cuda.Event() if self._cuda else None
+        if self._emb is not None:
+            p = self._emb.params[0]
+            self._scatter = torch.zeros_like(p)  # kept all-zero between uses
+
+    def note_tokens(self, tok):
+        """Called by the embedding forward with the token ids it looks up (device tensor; -1 = image slot)."""
+        if self._rng is None or self._emb is None:
+            return
+        mn, mx = torch.aminmax(tok)
+        torch.maximum(self._rng[:2], torch.stack([-mn, mx]).to(torch.int64), out=self._rng[:2])
+
+    def note_vision(self):
+        """Called by the image patch embedder's forward: its parameters receive gradients this window."""
+        if self._rng is not None:
+            self._rng[2:3].fill_(1)
+
+    def _agree_begin(self):
+        """Enqueue the MAX all-reduce of (token range, vision flag) ahead of this step's bucket collectives."""
+        if self._overlap:
+            ev = torch.cuda.Event()
+            ev.record(torch.cuda.current_stream(self.device))
+            with torch.cuda.stream(self._comm_stream):
+                self._comm_stream.wait_event(ev)
+                dist.all_reduce(self._rng, op=dist.ReduceOp.MAX, group=self._group)
+                self._rng_host.copy_(self._rng, non_blocking=True)
+                self._rng_ev.record(self._comm_stream)
+        else:
+            dist.all_reduce(self._rng, op=dist.ReduceOp.MAX, group=self._group)
+
+    def _agree_end(self):
+        """(lo, hi, vision_used) as host integers, identical on every rank; re-arms the device vector."""
+        if self._overlap:
+            self._rng_ev.synchronize()  # enqueued before backward's first kernel: long complete, no pipeline bubble
+            nlo, hi, vis = [int(x) for x in self._rng_host.tolist()]
+            with torch.cuda.stream(self._comm_stream):
+                self._rng.copy_(self._rng_init)
+        else:
+            nlo, hi, vis = [int(x) for x in self._rng.tolist()]
+            self._rng.copy_(self._rng_init)
+        return max(0, -nlo), hi + 1, vis != 0
+
+    def _finish_emb_split(self, lo, hi):
+        """Reduce rows [lo, hi) of the scatter buffer, add them to the (already reduced) dense part, re-zero them."""
+        p = self._emb.params[0]
+        hi = min(hi, p.shape[0])
+        if hi <= lo:
+            return
+        rows = self._scatter[lo:hi]
+        if self._overlap:
+            ev = torch.cuda.Event()
+            ev.record(torch.cuda.current_stream(self.device))
+            with torch.cuda.stream(self._comm_stream):
+                self._comm_stream.wait_event(ev)
+                dist.all_reduce(rows, op=dist.ReduceOp.AVG, group=self._group)
+                self._emb.work.wait()  # the dense part (enqueued long before)
+                p.grad[lo:hi].add_(rows)
+                rows.zero_()
+        else:
+            if dist.get_backend(self._group) == "gloo":
+                dist.all_reduce(rows, op=dist.ReduceOp.SUM, group=self._group)
+                rows.mul_(1.0 / self._world)
+            else:
+                dist.all_reduce(rows, op=dist.ReduceOp.AVG, group=self._group)
+            self._emb.work.wait()
+            if getattr(self._emb, "post_scale", None):
+                self._emb.flat.mul_(self._emb.post_scale)
+                self._emb.post_scale = None
+            p.grad[lo:hi].add_(rows)
+            rows.zero_()
 
     def _setup_fused_adam(self, cfg):
         betas = cfg.get("betas", (0.9, 0.999))
@@ -159,6 +271,10 @@ class DB1Engine:
                 # autograd runs AccumulateGrad (and this hook) even when the Function returned None because its kernel
                 # already wrote the bucket view; those parameters are accounted for by done()
                 return
+            if bucket.key in _LATE:
+                # launched after backward in bucket order: whether these complete inside backward depends on the rank's
+                # data (an unused patch embedder never does), and every rank must issue its collectives in one order
+                return
             bucket.pending -= 1
             if bucket.pending == 0:
                 self._launch_allreduce(bucket)
@@ -171,6 +287,8 @@ class DB1Engine:
         pid = id(param)
         if pid not in self._param_by_id:
             return None
+        if self._split_active and self._emb_phase == 1 and param is self._emb.params[0]:
+            return self._scatter, True  # the dense part is already on the wire: scatter-adds go to the side buffer
         acc = pid in self._written
         self._written.add(pid)
         return param.grad, acc
@@ -180,9 +298,16 @@ class DB1Engine:
         once per forward, so this completes them; the shared 'rest' bucket (embeddings, u/v, vision) is launched after
         backward returns."""
         b = self._bucket_of_param.get(id(param))
-        if b is None or b.key == "rest" or self._world == 1:
+        if b is None or self._world == 1:
             return
         if not self._is_boundary() or not self.enable_backward_allreduce:
+            return
+        if b is self._emb and self._split_active:
+            if self._emb_phase == 0:  # first complete contribution (the head's dense gradient): reduce it now
+                self._emb_phase = 1
+                self._launch_allreduce(b)
+            return
+        if b.key in _LATE:
             return
         b.pending -= 1
         if b.pending == 0:
@@ -252,6 +377,12 @@ class DB1Engine:
             b.work = None
             b.post_scale = None
         scaled = loss * (self.loss_scale / self._ga)
+        comm_step = self._world > 1 and self._is_boundary() and self.enable_backward_allreduce
+        self._split_active = bool(comm_step and self._emb is not None)
+        self._emb_phase = 0
+        agree = comm_step and self._rng is not None
+        if agree:
+            self._agree_begin()
         reserve = self._comm_sms if (self._overlap and self._is_boundary() and self.enable_backward_allreduce) else 0
         if reserve > 0:
             from . import _lib
@@ -272,11 +403,16 @@ class DB1Engine:
         else:
             self._sink_seen |= self._written
         if self._world > 1 and self._is_boundary() and self.enable_backward_allreduce:
-            # buckets whose parameters got no gradient at all this step still take part (zero contribution)
+            lo, hi, vision_used = self._agree_end() if agree else (0, 0, True)
+            if self._split_active and self._emb_phase == 1:
+                self._finish_emb_split(lo, hi)
+            # buckets whose parameters got no gradient at all this step still take part (zero contribution) - except
+            # the patch embedder's when no rank used it in this window (all zeros everywhere)
             for b in self.buckets:
-                if b.work is None:
+                if b.work is None and not (b is self._vision and agree and not vision_used):
                     self._launch_allreduce(b)
             self._finish_allreduce()
+            self._split_active = False
         self.micro_steps += 1
         return loss
 

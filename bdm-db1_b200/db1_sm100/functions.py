@@ -568,6 +568,9 @@ class EmbedFn(torch.autograd.Function):
         out = torch.empty(B, L, d, dtype=torch.float16, device=dev)
         slot = torch.empty(B, L, dtype=torch.int32, device=dev)
         seed = seeds.next() if drop_p > 0 else 0
+        note = getattr(_sink, "note_tokens", None)
+        if note is not None and W.requires_grad:
+            note(tok)  # the engine agrees on the embedding rows this window touches (range-limited all-reduce)
         ops.embed_fwd(tok, pos, slot, W, T if pos is not None else None, vis, out, L * d, B, L, d, V, drop_p, seed, 0)
         ctx.save_for_backward(tok, pos, slot)
         ctx.cfg = (B, L, d, V, drop_p, seed, T.shape[0] if T is not None else 0,
@@ -609,6 +612,9 @@ def positional_rows(inv_freq, klen, d, clamp_len, drop_p, half_phase=False):
 def patch_embed(module, pixel_values, pos_sum):
     """PatchEmbeddings.forward (vision_embedding.py:65-86) on the sm_100a kernels."""
     from . import vision
+    note = getattr(_sink, "note_vision", None)
+    if note is not None and torch.is_grad_enabled():
+        note()
     return vision.patch_embed(module, pixel_values, pos_sum)
 
 

@@ -55,7 +55,13 @@ class PositionalEmbedding(nn.Module):
         if inv.dtype != torch.float32:
             # module.half() casts buffers too; the kernel takes the constructor's fp32 frequencies and does the fp16
             # rounding itself (fp16(fp32 value) == the cast buffer)
-            inv = (1 / (10000 ** (torch.arange(0.0, self.demb, 2.0) / self.demb))).to(inv.device)
+            # (built once per device: a pageable host-to-device copy in every forward would synchronise the stream and
+            # cannot be captured in a CUDA graph)
+            cached = getattr(self, "_inv32", None)
+            if cached is None or cached.device != inv.device:
+                cached = (1 / (10000 ** (torch.arange(0.0, self.demb, 2.0) / self.demb))).to(inv.device)
+                self._inv32 = cached
+            inv = cached
         return F_.positional_rows(inv.contiguous(), klen, self.demb, clamp_len, drop_p, half_phase=half_phase)
 
     def forward(self, pos_seq, bsz=None):

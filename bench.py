@@ -344,7 +344,7 @@ def run_ours(args):
             ref /= world
             den = ref.abs().max().clamp_min(1e-20)
             rel = ((a.float() - ref).abs().max() / den).item()
-            if b.key == "rest":
+            if b.key in ("rest", "emb", "vision"):
                 worst_rest = max(worst_rest, rel)
             else:
                 worst_layer = max(worst_layer, rel)

@@ -50,7 +50,7 @@ def _worker(rank, world, port, tmp, ga):
         ref = _Toy()
         ref.load_state_dict(model.state_dict())
         eng = DB1Engine(model, mpu=mpu, gradient_accumulation_steps=ga, loss_scale=8.0)
-        assert [b.key for b in eng.buckets] == ["rest", "h.0", "h.1", "h.2"]
+        assert [b.key for b in eng.buckets] == ["emb", "h.0.attn", "h.1.attn", "h.2.attn", "rest"]
         assert eng.gradient_accumulation_steps() == ga
         # per-rank batches; rank 1 also exercises the otherwise unused branch
         batches = [[torch.randint(0, 11, (4, 5), generator=torch.Generator().manual_seed(100 * r + i))
@@ -85,6 +85,132 @@ def _worker(rank, world, port, tmp, ga):
         dist.barrier()
     finally:
         dist.destroy_process_group()
+
+
+class _TiedHead(torch.autograd.Function):
+    """logits = x @ W^T with the weight gradient written through the gradient sink (as HeadLossFn does on the GPU)."""
+
+    @staticmethod
+    def forward(ctx, x, W):
+        ctx.save_for_backward(x, W)
+        ctx.param = W
+        return x @ W.t()
+
+    @staticmethod
+    def backward(ctx, dy):
+        from db1_sm100 import functions as F_
+        x, W = ctx.saved_tensors
+        g = F_._Grad(ctx.param)
+        val = dy.reshape(-1, dy.shape[-1]).t() @ x.reshape(-1, x.shape[-1])
+        if g.acc:
+            g.buf.add_(val)
+        else:
+            g.buf.copy_(val)
+        return dy @ W, g.ret()
+
+
+class _Lookup(torch.autograd.Function):
+    """e = W[tok] with the scatter-add of the gradient done through the sink (as EmbedFn does on the GPU)."""
+
+    @staticmethod
+    def forward(ctx, tok, W):
+        from db1_sm100 import functions as F_
+        F_._sink.note_tokens(tok)
+        ctx.save_for_backward(tok)
+        ctx.param = W
+        return W[tok]
+
+    @staticmethod
+    def backward(ctx, de):
+        from db1_sm100 import functions as F_
+        (tok,) = ctx.saved_tensors
+        g = F_._Grad(ctx.param, zero=True)
+        if g.direct and not g.acc:
+            g.buf.zero_()
+        g.buf.index_add_(0, tok.reshape(-1), de.reshape(-1, de.shape[-1]).to(g.buf.dtype))
+        return None, g.ret()
+
+
+class _TiedToy(nn.Module):
+    def __init__(self):
+        super().__init__()
+        self.word_embedding = nn.Embedding(23, 8)
+        self.h = nn.ModuleList([nn.Linear(8, 8) for _ in range(2)])
+        self.vision_encoder = nn.Linear(8, 8)
+
+    def forward(self, toks, use_vision=False):
+        """toks: list of token tensors (task segments), each embedded by its own lookup."""
+        W = self.word_embedding.weight
+        x = torch.cat([_Lookup.apply(t, W) for t in toks], dim=0)
+        if use_vision:
+            from db1_sm100 import functions as F_
+            F_._sink.note_vision()
+            x = x + self.vision_encoder(x)
+        for l in self.h:
+            x = torch.tanh(l(x))
+        return None, _TiedHead.apply(x, W).pow(2).mean()
+
+    def plain(self, toks, use_vision=False):
+        W = self.word_embedding.weight
+        x = torch.cat([W[t] for t in toks], dim=0)
+        if use_vision:
+            x = x + self.vision_encoder(x)
+        for l in self.h:
+            x = torch.tanh(l(x))
+        return (x @ W.t()).pow(2).mean()
+
+
+def _worker_tied(rank, world, port, ga, vision):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        from db1_sm100 import functions as F_
+        from db1_sm100.engine import DB1Engine
+        torch.manual_seed(0)
+        model = _TiedToy()
+        ref = _TiedToy()
+        ref.load_state_dict(model.state_dict())
+        eng = DB1Engine(model, gradient_accumulation_steps=ga, loss_scale=4.0, direct_grads="force")
+        assert [b.key for b in eng.buckets] == ["emb", "h.0.attn", "h.1.attn", "vision"]
+        assert eng._emb is not None and eng._vision is not None
+        sent = []
+        orig = eng._launch_allreduce
+        eng._launch_allreduce = lambda b: (sent.append(b.key), orig(b))[1]
+        for window in range(2):  # second window: the side buffer must have been left all-zero
+            los = [3 + window, 9 + window]  # rank r's tokens lie in [los[r], los[r] + 7): agreed range = union
+            batches = [[[torch.randint(los[r], los[r] + 4, (3, 5), generator=torch.Generator().manual_seed(100 * r + 10 * window + i)),
+                         torch.randint(los[r] + 2, los[r] + 7, (2, 5), generator=torch.Generator().manual_seed(7 + 100 * r + i))]
+                        for i in range(ga)] for r in range(world)]
+            del sent[:]
+            for i in range(ga):
+                _, loss = eng(batches[rank][i], use_vision=(vision and rank == 1))
+                eng.backward(loss)
+            assert sent[0] == "emb", sent  # the dense (head) part leaves first, from inside backward
+            assert ("vision" in sent) == vision, sent
+            assert eng._scatter.abs().max().item() == 0.0
+            exp = {n: torch.zeros_like(p) for n, p in ref.named_parameters()}
+            for r in range(world):
+                ref.zero_grad()
+                for i in range(ga):
+                    (ref.plain(batches[r][i], use_vision=(vision and r == 1)) * (4.0 / ga)).backward()
+                for n, p in ref.named_parameters():
+                    if p.grad is not None:
+                        exp[n] += p.grad / world
+            for n, p in model.named_parameters():
+                assert torch.allclose(p.grad, exp[n], rtol=1e-5, atol=1e-6), (n, window)
+            eng.step()
+        F_.set_grad_sink(None)
+        dist.barrier()
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("ga,vision", [(1, False), (2, True)])
+def test_engine_tied_embedding_split_gloo_world2(ga, vision):
+    """The tied embedding's gradient: dense head part all-reduced from inside backward, scatter part through the side
+    buffer over the agreed row range only; the patch embedder's bucket is skipped when no rank used it."""
+    port = _free_port()
+    mp.spawn(_worker_tied, args=(2, port, ga, vision), nprocs=2, join=True)
 
 
 @pytest.mark.parametrize("ga", [1, 2])

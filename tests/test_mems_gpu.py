@@ -120,3 +120,43 @@ def test_kv_cached_decode_matches_recompute_path_and_oracle(cuda, B):
         assert a.shape == b_.shape
         assert util.rel_err(a, b_) <= 2e-3
         assert util.rel_err(a, c) <= 3e-3
+
+
+def test_decode_graph_replays_the_cached_step(cuda):
+    """DecodeGraph (one cached decode step captured in a CUDA graph; the ring head lives in device memory) gives, replay
+    after replay, what the same steps give when launched one kernel at a time, including across the ring wrap, and leaves
+    the same memories behind."""
+    from oracle import db1_oracle as orc
+    from db1_sm100.functions import DecodeGraph
+    from src.data.input_specs import RLTaskInput
+    cfg = orc.tiny_config(text_vocab_size=480, mem_len=64, n_position=64)
+    model, _sd = _build(cfg, 21, cuda)
+    model.eval()
+    B = 2
+    g = torch.Generator().manual_seed(3)
+    kv_a = model.init_mem(B, kv_cache=True)
+    kv_b = model.init_mem(B, kv_cache=True)
+    # a few eager steps first, so that the graph is captured on a memory whose head is not at slot 0
+    for _ in range(5):
+        tok = torch.randint(0, 480, (B, 1), generator=g).to(cuda)
+        for kv in (kv_a, kv_b):
+            inp = [RLTaskInput(position_id=torch.zeros(B, 1, dtype=torch.int64, device=cuda), attention_mask=None,
+                               loss_mask=None, label=None, text_seq=None, vision_seq=None, tensor_seq=tok)]
+            with torch.no_grad():
+                model(inp, compute_loss=False, mems=kv)
+    graph = DecodeGraph(model, kv_a, 1)
+    assert kv_a.head == kv_b.head == 5
+    for a, b_ in zip(kv_a.to_mems(), kv_b.to_mems()):
+        assert torch.equal(a, b_)  # capture and warm-up left no trace
+    for step in range(70):  # 5 + 70 > mem_len: the ring wraps under the graph
+        tok = torch.randint(0, 480, (B, 1), generator=g).to(cuda)
+        pos = torch.full((B, 1), step % 7, dtype=torch.int64, device=cuda)
+        lg_g = graph.step(tok, pos).clone()
+        inp = [RLTaskInput(position_id=pos, attention_mask=None, loss_mask=None, label=None, text_seq=None,
+                           vision_seq=None, tensor_seq=tok)]
+        with torch.no_grad():
+            lg_e, _, _ = model(inp, compute_loss=False, mems=kv_b)
+        assert util.rel_err(lg_g, lg_e) <= 1e-6, step
+    assert kv_a.head == kv_b.head and int(kv_a.head_dev.item()) == kv_a.head
+    for a, b_ in zip(kv_a.to_mems(), kv_b.to_mems()):
+        assert torch.equal(a, b_)
