@@ -7,6 +7,8 @@
 #include <stdio.h>
 #include <string.h>
 
+#include "../../include/db1_sm100.h"
+
 namespace db1 {
 
 // thread-local last-error string returned by db1_last_error()
@@ -64,5 +66,9 @@ static inline cudaError_t launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 b
 }
 
 static inline int cdiv(int a, int b) { return (a + b - 1) / b; }
+
+// csrc/skinny.cu: the few-row (M <= 8) GEMM of the decode step; db1_gemm_f16 routes to it when it applies
+bool skinny_gemm_applies(const db1_gemm_desc* d);
+int skinny_gemm(const db1_gemm_desc* d, cudaStream_t stream);
 
 }  // namespace db1

@@ -4,11 +4,14 @@
 //
 //   db1_ring_append      new rows -> ring buffer slots (the `cat(mem, h)[:, -mem_len:]` of _update_mem, in place)
 //   db1_relattn_decode   few-query relative-position attention over [ring cache | new rows]; HBM-bound on the cache:
-//                        grid = (sequence, head, query) x key splits, fp32 online softmax per split, then a merge
+//                        grid = (sequence, head) x key splits, K / V / r tiles staged in shared memory and shared by all
+//                        the queries, fp32 online softmax per split, then a merge
 //   db1_masked_argmax    masked_logits_for_action + argmax (evaluate_rl.py:96-138): argmax over a token range
 //
 // The decode attention is a CUDA-core kernel on purpose: with <= a few query rows per (sequence, head) there is no tile
 // for a tensor core to fill; the work is one pass over K, V and r (2 * K * dh * 2 B + K * dh * 2 B per head).
+#include <stdlib.h>
+
 #include "../../include/db1_sm100.h"
 #include "common.cuh"
 #include "ptx.cuh"
@@ -130,6 +133,248 @@ __global__ void __launch_bounds__(DEC_THREADS) relattn_decode_kernel(const DecPa
   }
 }
 
+// ------------------------------------------------------------------------------------------------------------------
+// Tiled variant (head dim % 8 == 0): CTA = (sequence, head, key split). The split's keys are walked in tiles of 64; per
+// tile the K, V and r rows are staged in shared memory with every thread's 16-byte loads issued back to back (the
+// per-key kernel above exposes one memory round trip per key), then for blocks of up to 8 queries: scores (thread =
+// key x query subset, 128-bit conflict-free shared loads: row pitch dh + 8 halves), online softmax per query (one warp
+// per query), P . V (thread = 8 head dims x key slice, the slices reduced through shared memory at the end). All
+// queries of a (sequence, head) share the staged rows, so K / V / r cross HBM once per split whatever Q is.
+// ------------------------------------------------------------------------------------------------------------------
+constexpr int DT_KEYS = 64;  // keys per tile
+constexpr int DT_QB = 8;     // queries per block
+
+template <int DH>
+struct DecSmem {
+  static constexpr int PITCH = DH + 8;                      // halves per staged row
+  static constexpr int K_OFF = 0;                           // [64][PITCH] halves
+  static constexpr int V_OFF = K_OFF + DT_KEYS * PITCH * 2;
+  static constexpr int R_OFF = V_OFF + DT_KEYS * PITCH * 2; // [64 + 7][PITCH]
+  static constexpr int Q_OFF = R_OFF + (DT_KEYS + DT_QB - 1) * PITCH * 2;  // qu[8][DH], qv[8][DH] halves
+  static constexpr int S_OFF = Q_OFF + 2 * DT_QB * DH * 2;  // scores / probabilities [8][64] floats
+  static constexpr int ST_OFF = S_OFF + DT_QB * DT_KEYS * 4;  // m[8], l[8], f[8] floats
+  static constexpr int PART_OFF = ST_OFF + 3 * DT_QB * 4;   // [8 groups][DH] floats
+  static constexpr int TOTAL = PART_OFF + 8 * DH * 4;
+};
+
+DEVI float dot8h(const uint4& a, const uint4& b, float acc) {
+  const float2 a0 = unpack_half2(a.x), a1 = unpack_half2(a.y), a2 = unpack_half2(a.z), a3 = unpack_half2(a.w);
+  const float2 b0 = unpack_half2(b.x), b1 = unpack_half2(b.y), b2 = unpack_half2(b.z), b3 = unpack_half2(b.w);
+  acc = fmaf(a0.x, b0.x, acc); acc = fmaf(a0.y, b0.y, acc);
+  acc = fmaf(a1.x, b1.x, acc); acc = fmaf(a1.y, b1.y, acc);
+  acc = fmaf(a2.x, b2.x, acc); acc = fmaf(a2.y, b2.y, acc);
+  acc = fmaf(a3.x, b3.x, acc); acc = fmaf(a3.y, b3.y, acc);
+  return acc;
+}
+
+template <int DH>
+__global__ void __launch_bounds__(DEC_THREADS) relattn_decode_tiled_kernel(const DecParams p) {
+  using SM = DecSmem<DH>;
+  constexpr int PITCH = SM::PITCH;
+  constexpr int NC = DH / 8;  // 16-byte chunks per row
+  extern __shared__ __align__(16) uint8_t dsm[];
+  __half* sK = reinterpret_cast<__half*>(dsm + SM::K_OFF);
+  __half* sV = reinterpret_cast<__half*>(dsm + SM::V_OFF);
+  __half* sR = reinterpret_cast<__half*>(dsm + SM::R_OFF);
+  __half* sQu = reinterpret_cast<__half*>(dsm + SM::Q_OFF);
+  __half* sQv = sQu + DT_QB * DH;
+  float* sS = reinterpret_cast<float*>(dsm + SM::S_OFF);
+  float* sM = reinterpret_cast<float*>(dsm + SM::ST_OFF);
+  float* sL = sM + DT_QB;
+  float* sF = sL + DT_QB;
+  float* sPart = reinterpret_cast<float*>(dsm + SM::PART_OFF);
+
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int h = blockIdx.x % p.H, b = blockIdx.x / p.H, s = blockIdx.y;
+  const int M = p.cap, Q = p.Q, K = p.cap + p.Q;
+  const int head = p.head_dev ? *p.head_dev : p.head;
+  const long long hoff = (long long)h * p.dh;
+  const long long crow = (long long)p.H * p.dh;  // cache row stride
+  const int chunk = (K + p.S - 1) / p.S;
+  const int c0 = s * chunk;
+  const int c1 = (c0 + chunk < K) ? c0 + chunk : K;
+
+  for (int qb = 0; qb < Q; qb += DT_QB) {
+    const int nq = (Q - qb < DT_QB) ? Q - qb : DT_QB;
+    // key range any query of the block may see, cut to this split
+    int jlo = M + qb - p.window + 1;
+    if (jlo < 0) jlo = 0;
+    const int jhi = M + qb + nq - 1;  // inclusive
+    const int j0 = c0 > jlo ? c0 : jlo;
+    const int j1 = (c1 < jhi + 1) ? c1 : jhi + 1;
+    // P.V mapping: 8 groups of 16 threads; query qi gets KS groups, each a key slice jj = ks (mod KS)
+    const int nq2 = nq <= 1 ? 1 : (nq <= 2 ? 2 : (nq <= 4 ? 4 : 8));
+    const int KS = 8 / nq2;
+    const int grp = tid >> 4, dc = tid & 15;
+    const int pv_q = grp / KS, pv_ks = grp % KS;
+    float acc[8];
+#pragma unroll
+    for (int e = 0; e < 8; ++e) acc[e] = 0.f;
+    __syncthreads();  // the previous block's readers of sQu / sM / sPart are done
+    for (int idx = tid; idx < nq * NC; idx += DEC_THREADS) {
+      const int qi = idx / NC, c = idx % NC;
+      const long long ro = (long long)(b * Q + qb + qi) * p.ld_qkv + hoff + c * 8;
+      const bool act = c * 8 < p.dh;
+      *reinterpret_cast<uint4*>(sQu + qi * DH + c * 8) = act ? *reinterpret_cast<const uint4*>(p.qu + ro) : make_uint4(0, 0, 0, 0);
+      *reinterpret_cast<uint4*>(sQv + qi * DH + c * 8) = act ? *reinterpret_cast<const uint4*>(p.qv + ro) : make_uint4(0, 0, 0, 0);
+    }
+    if (tid < DT_QB) {
+      sM[tid] = -INFINITY;
+      sL[tid] = 0.f;
+    }
+    for (int t0 = j0; t0 < j1; t0 += DT_KEYS) {
+      const int len = (j1 - t0 < DT_KEYS) ? j1 - t0 : DT_KEYS;
+      __syncthreads();  // previous tile fully consumed (and the block prologue visible)
+      // ---- stage K, V rows [t0, t0 + len) and r rows [rbase, rbase + len + nq - 1): fixed trip counts, every load of
+      // a thread issued before its first shared store (one memory round trip per tile instead of one per row)
+      const int rbase = t0 + Q - 1 - (qb + nq - 1);  // r row of (last query of the block, first key of the tile)
+      {
+        constexpr int KIT = DT_KEYS * NC / DEC_THREADS;
+        constexpr int RIT = ((DT_KEYS + DT_QB - 1) * NC + DEC_THREADS - 1) / DEC_THREADS;
+        uint4 kreg[KIT], vreg[KIT], rreg[RIT];
+#pragma unroll
+        for (int it = 0; it < KIT; ++it) {
+          const int idx = tid + it * DEC_THREADS;
+          const int jj = idx / NC, c = idx % NC;
+          const int j = t0 + jj;
+          kreg[it] = vreg[it] = make_uint4(0u, 0u, 0u, 0u);
+          if (jj < len && c * 8 < p.dh) {
+            if (j < M) {
+              int slot = head + j;
+              if (slot >= p.cap) slot -= p.cap;
+              const long long ro = ((long long)b * p.cap + slot) * crow + hoff + c * 8;
+              kreg[it] = *reinterpret_cast<const uint4*>(p.kc + ro);
+              vreg[it] = *reinterpret_cast<const uint4*>(p.vc + ro);
+            } else {
+              const long long ro = (long long)(b * Q + (j - M)) * p.ld_qkv + hoff + c * 8;
+              kreg[it] = *reinterpret_cast<const uint4*>(p.knew + ro);
+              vreg[it] = *reinterpret_cast<const uint4*>(p.vnew + ro);
+            }
+          }
+        }
+#pragma unroll
+        for (int it = 0; it < RIT; ++it) {
+          const int idx = tid + it * DEC_THREADS;
+          const int rr = idx / NC, c = idx % NC;
+          const int ri = rbase + rr;
+          rreg[it] = make_uint4(0u, 0u, 0u, 0u);
+          if (rr < len + nq - 1 && c * 8 < p.dh && ri >= 0 && ri < K)
+            rreg[it] = *reinterpret_cast<const uint4*>(p.r + (long long)ri * p.ld_r + hoff + c * 8);
+        }
+#pragma unroll
+        for (int it = 0; it < KIT; ++it) {
+          const int idx = tid + it * DEC_THREADS;
+          const int jj = idx / NC, c = idx % NC;
+          *reinterpret_cast<uint4*>(sK + jj * PITCH + c * 8) = kreg[it];
+          *reinterpret_cast<uint4*>(sV + jj * PITCH + c * 8) = vreg[it];
+        }
+#pragma unroll
+        for (int it = 0; it < RIT; ++it) {
+          const int idx = tid + it * DEC_THREADS;
+          const int rr = idx / NC, c = idx % NC;
+          if (rr < DT_KEYS + DT_QB - 1) *reinterpret_cast<uint4*>(sR + rr * PITCH + c * 8) = rreg[it];
+        }
+      }
+      __syncthreads();
+      // ---- scores: thread = key jj x queries qs, qs + 2, ...
+      {
+        const int jj = tid & 63, qs = tid >> 6;
+        float sc[4] = {0.f, 0.f, 0.f, 0.f};
+        if (jj < len) {
+#pragma unroll 4
+          for (int c = 0; c < NC; ++c) {
+            const uint4 kc = *reinterpret_cast<const uint4*>(sK + jj * PITCH + c * 8);
+#pragma unroll
+            for (int z = 0; z < 4; ++z) {
+              const int qi = qs + 2 * z;
+              if (qi < nq) {
+                const uint4 qu = *reinterpret_cast<const uint4*>(sQu + qi * DH + c * 8);
+                const uint4 qv = *reinterpret_cast<const uint4*>(sQv + qi * DH + c * 8);
+                const uint4 rc = *reinterpret_cast<const uint4*>(sR + (jj + nq - 1 - qi) * PITCH + c * 8);
+                sc[z] = dot8h(qv, rc, dot8h(qu, kc, sc[z]));
+              }
+            }
+          }
+        }
+#pragma unroll
+        for (int z = 0; z < 4; ++z) {
+          const int qi = qs + 2 * z;
+          if (qi < nq) {
+            const int i = qb + qi, j = t0 + jj;
+            const bool ok = jj < len && j <= M + i && M + i - j < p.window;
+            sS[qi * DT_KEYS + jj] = ok ? sc[z] * p.scale_log2 : -INFINITY;
+          }
+        }
+      }
+      __syncthreads();
+      // ---- online softmax: warp w takes queries w, w + 4
+      for (int qi = warp; qi < nq; qi += 4) {
+        const float s0 = sS[qi * DT_KEYS + lane], s1 = sS[qi * DT_KEYS + 32 + lane];
+        float mx = fmaxf(s0, s1);
+#pragma unroll
+        for (int o = 16; o; o >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+        const float m_old = sM[qi];
+        const float m_new = fmaxf(m_old, mx);
+        float p0 = 0.f, p1 = 0.f, f = 1.f;
+        if (m_new != -INFINITY) {
+          p0 = exp2f(s0 - m_new);
+          p1 = exp2f(s1 - m_new);
+          f = (m_old == -INFINITY) ? 0.f : exp2f(m_old - m_new);
+        }
+        float sum = p0 + p1;
+#pragma unroll
+        for (int o = 16; o; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
+        sS[qi * DT_KEYS + lane] = p0;
+        sS[qi * DT_KEYS + 32 + lane] = p1;
+        if (lane == 0) {
+          sM[qi] = m_new;
+          sL[qi] = sL[qi] * f + sum;
+          sF[qi] = f;
+        }
+      }
+      __syncthreads();
+      // ---- P . V: thread = 8 head dims (dc) of query pv_q over the keys jj = pv_ks (mod KS)
+      if (pv_q < nq) {
+        const float f = sF[pv_q];
+#pragma unroll
+        for (int e = 0; e < 8; ++e) acc[e] *= f;
+        if (dc < NC) {
+          for (int jj = pv_ks; jj < len; jj += KS) {
+            const float pr = sS[pv_q * DT_KEYS + jj];
+            const uint4 vv = *reinterpret_cast<const uint4*>(sV + jj * PITCH + dc * 8);
+            const float2 v0 = unpack_half2(vv.x), v1 = unpack_half2(vv.y), v2 = unpack_half2(vv.z), v3 = unpack_half2(vv.w);
+            acc[0] = fmaf(pr, v0.x, acc[0]); acc[1] = fmaf(pr, v0.y, acc[1]);
+            acc[2] = fmaf(pr, v1.x, acc[2]); acc[3] = fmaf(pr, v1.y, acc[3]);
+            acc[4] = fmaf(pr, v2.x, acc[4]); acc[5] = fmaf(pr, v2.y, acc[5]);
+            acc[6] = fmaf(pr, v3.x, acc[6]); acc[7] = fmaf(pr, v3.y, acc[7]);
+          }
+        }
+      }
+    }
+    // ---- reduce the key slices of every query and write the split's partial (max, sum, acc)
+    __syncthreads();
+    if (dc < NC) {
+#pragma unroll
+      for (int e = 0; e < 8; ++e) sPart[grp * DH + dc * 8 + e] = acc[e];
+    }
+    __syncthreads();
+    for (int idx = tid; idx < nq * DH; idx += DEC_THREADS) {
+      const int qi = idx / DH, d = idx % DH;
+      if (d < p.dh) {
+        float o = 0.f;
+        for (int ks = 0; ks < KS; ++ks) o += sPart[(qi * KS + ks) * DH + d];
+        const long long bhq = ((long long)b * p.H + h) * Q + qb + qi;
+        float* wp = p.ws + (bhq * p.S + s) * (p.dh + 2);
+        wp[2 + d] = o;
+        if (d == 0) {
+          wp[0] = sM[qi];
+          wp[1] = sL[qi];
+        }
+      }
+    }
+  }
+}
+
 __global__ void relattn_decode_merge_kernel(const float* __restrict__ ws, __half* __restrict__ out, long long ld_out, int B,
                                             int Q, int H, int dh, int S) {
   const int bhq = blockIdx.x;
@@ -219,7 +464,8 @@ __global__ void masked_argmax_kernel(const __half* __restrict__ logits, long lon
 using namespace db1;
 
 extern "C" int db1_decode_splits(int B, int Q, int H) {
-  int s = (2 * sm_count_physical()) / (B * Q * H > 0 ? B * Q * H : 1);
+  (void)Q;  // the queries of a (sequence, head) share a CTA: the split count follows B * H alone
+  int s = (2 * sm_count_physical()) / (B * H > 0 ? B * H : 1);
   if (s < 1) s = 1;
   if (s > 32) s = 32;
   return s;
@@ -241,7 +487,29 @@ extern "C" int db1_relattn_decode(const void* qu, const void* qv, const void* kn
   p.r = (const __half*)r; p.ld_r = ld_r; p.ws = ws; p.B = B; p.Q = Q; p.H = H; p.dh = dh; p.S = S; p.window = window;
   p.scale_log2 = scale * 1.4426950408889634f;
   cudaStream_t st = (cudaStream_t)stream_;
-  relattn_decode_kernel<<<dim3(B * Q * H, S), DEC_THREADS, 0, st>>>(p);
+  const bool al16 = ((((uintptr_t)qu | (uintptr_t)qv | (uintptr_t)knew | (uintptr_t)vnew | (uintptr_t)kcache |
+                       (uintptr_t)vcache | (uintptr_t)r) & 15) == 0) && ld_qkv % 8 == 0 && ld_r % 8 == 0 && dh % 8 == 0;
+  static int force_old = -1;
+  if (force_old < 0) force_old = getenv("DB1_DECODE_PER_KEY") ? 1 : 0;
+  if (al16 && !force_old) {
+    if (dh <= 64) {
+      static bool cfg64 = false;
+      if (!cfg64) {
+        DB1_CUDA(cudaFuncSetAttribute(relattn_decode_tiled_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, DecSmem<64>::TOTAL));
+        cfg64 = true;
+      }
+      relattn_decode_tiled_kernel<64><<<dim3(B * H, S), DEC_THREADS, DecSmem<64>::TOTAL, st>>>(p);
+    } else {
+      static bool cfg128 = false;
+      if (!cfg128) {
+        DB1_CUDA(cudaFuncSetAttribute(relattn_decode_tiled_kernel<128>, cudaFuncAttributeMaxDynamicSharedMemorySize, DecSmem<128>::TOTAL));
+        cfg128 = true;
+      }
+      relattn_decode_tiled_kernel<128><<<dim3(B * H, S), DEC_THREADS, DecSmem<128>::TOTAL, st>>>(p);
+    }
+  } else {
+    relattn_decode_kernel<<<dim3(B * Q * H, S), DEC_THREADS, 0, st>>>(p);
+  }
   relattn_decode_merge_kernel<<<B * Q * H, 128, 0, st>>>(ws, (__half*)out, ld_out, B, Q, H, dh, S);
   DB1_CUDA(cudaGetLastError());
   return 0;

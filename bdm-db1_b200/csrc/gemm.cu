@@ -96,30 +96,6 @@ struct GemmCfg {
   static constexpr int TMEM_COLS = 2 * BN;  // 512 or 256
 };
 
-// Exact-erf GELU (F.gelu default, activations.py:29) and its derivative from ONE exp and ONE reciprocal:
-// erf(t) = 1 - (a1 s + ... + a5 s^5) exp(-t^2), s = 1 / (1 + p t), t >= 0   (Abramowitz & Stegun 7.1.26, |err| <= 1.5e-7,
-// far below the fp16 resolution of the stored activations); exp(-t^2) with t = |x| / sqrt(2) is also the Gaussian
-// factor of gelu'(x) = Phi(x) + x * phi(x). erff() + expf() cost ~4x more issue slots and made the GeGLU-backward
-// epilogue, not the MMA, the pacing stage.
-DEVI void gelu_erf_both(float x, float& gl, float& dgl) {
-  const float t = fabsf(x) * 0.70710678118654752f;
-  const float e = __expf(-t * t);
-  const float s = __fdividef(1.0f, fmaf(0.3275911f, t, 1.0f));
-  float poly = fmaf(s, 1.061405429f, -1.453152027f);
-  poly = fmaf(poly, s, 1.421413741f);
-  poly = fmaf(poly, s, -0.284496736f);
-  poly = fmaf(poly, s, 0.254829592f);
-  const float erf_abs = fmaf(-poly * s, e, 1.0f);
-  const float cdf = 0.5f + 0.5f * copysignf(erf_abs, x);
-  gl = x * cdf;
-  dgl = fmaf(x * 0.3989422804014327f, e, cdf);
-}
-DEVI float gelu_erf(float x) {
-  float a, b;
-  gelu_erf_both(x, a, b);
-  return a;
-}
-
 // Store a warp's 32 x 32 fp16 tile (thread = row, hv = its 32 columns) with full-sector writes: the tile is transposed
 // through a per-warp staging buffer so that every store instruction covers 8 rows x 64 contiguous bytes. (16-byte
 // row-strided stores straight from the accumulator layout write half sectors, which the L2 turns into
@@ -1388,6 +1364,8 @@ extern "C" int db1_gemm_f16(const db1_gemm_desc* d, void* stream_) {
   DB1_CHECK_ARG(d->k_mode >= 0 && d->k_mode <= 3, "gemm: unknown k_mode %d", d->k_mode);
   const int Z1 = d->Z1 > 0 ? d->Z1 : 1, Z2 = d->Z2 > 0 ? d->Z2 : 1;
   const bool batched = Z1 * Z2 > 1;
+  // one to eight activation rows (the decode step): a stream over B on the CUDA cores, HBM-bound (csrc/skinny.cu)
+  if (skinny_gemm_applies(d)) return skinny_gemm(d, stream);
   DB1_CHECK_ARG((d->a_z1 % 8 == 0) && (d->a_z2 % 8 == 0) && (d->b_z1 % 8 == 0) && (d->b_z2 % 8 == 0) &&
                     (d->c_z1 % 8 == 0) && (d->c_z2 % 8 == 0),
                 "gemm: batch strides must be multiples of 8 elements");

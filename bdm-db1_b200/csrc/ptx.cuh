@@ -422,6 +422,30 @@ DEVI void named_bar_sync(int id, int nthreads) {
   asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
 }
 
+// Exact-erf GELU (F.gelu default, activations.py:29) and its derivative from ONE exp and ONE reciprocal:
+// erf(t) = 1 - (a1 s + ... + a5 s^5) exp(-t^2), s = 1 / (1 + p t), t >= 0   (Abramowitz & Stegun 7.1.26, |err| <= 1.5e-7,
+// far below the fp16 resolution of the stored activations); exp(-t^2) with t = |x| / sqrt(2) is also the Gaussian
+// factor of gelu'(x) = Phi(x) + x * phi(x). erff() + expf() cost ~4x more issue slots and made the GeGLU-backward
+// epilogue, not the MMA, the pacing stage.
+DEVI void gelu_erf_both(float x, float& gl, float& dgl) {
+  const float t = fabsf(x) * 0.70710678118654752f;
+  const float e = __expf(-t * t);
+  const float s = __fdividef(1.0f, fmaf(0.3275911f, t, 1.0f));
+  float poly = fmaf(s, 1.061405429f, -1.453152027f);
+  poly = fmaf(poly, s, 1.421413741f);
+  poly = fmaf(poly, s, -0.284496736f);
+  poly = fmaf(poly, s, 0.254829592f);
+  const float erf_abs = fmaf(-poly * s, e, 1.0f);
+  const float cdf = 0.5f + 0.5f * copysignf(erf_abs, x);
+  gl = x * cdf;
+  dgl = fmaf(x * 0.3989422804014327f, e, cdf);
+}
+DEVI float gelu_erf(float x) {
+  float a, b;
+  gelu_erf_both(x, a, b);
+  return a;
+}
+
 // Stateless counter-based RNG for dropout (splitmix64 of seed + group index). One 64-bit draw covers four
 // consecutive elements (16 bits each), so the mask is a pure function of (seed, flat element index) and
 // forward and backward regenerate it without storing it. keep iff draw16 >= thr16 (thr16 = p * 65536).

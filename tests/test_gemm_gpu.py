@@ -326,3 +326,50 @@ def test_gemm_rowdot_side_output(cuda):
     assert _rel(Cc, ref) < 2e-3
     refD = (ref * O.float()).view(Bq, L, Hh, dh).sum(-1).permute(0, 2, 1)
     assert _rel(D, refD) < 2e-3
+
+
+@pytest.mark.parametrize("M", [1, 3, 8])
+def test_few_row_gemm_matches_fp32_and_the_tensor_core_path(cuda, M):
+    """db1_gemm_f16 with M <= 8 (the decode step) runs the weight-streaming kernel of csrc/skinny.cu: plain (+bias,
+    +residual, alpha, ragged N as the tied head has), the QKV split (+u / +v) and GeGLU (H and a * gelu(g)) against fp32
+    torch on the same fp16 inputs; M = 9 of the same problem goes through the tcgen05 kernel and must agree."""
+    import torch.nn.functional as Fn
+    from db1_sm100 import ops
+    d, K, F = 256, 512, 384
+    A9 = _mk((9, K), cuda, 1.0, 21)
+    A = A9[:M].contiguous()
+    # plain, ragged N, strided C
+    N = 1001
+    B = _mk((N, K), cuda, 0.2, 22)
+    bias = _mk((N + 7,), cuda, 1.0, 23)[:N]
+    resid = _mk((9, 1008), cuda, 1.0, 24)
+    C1 = torch.zeros(M, 1008, dtype=torch.half, device=cuda)
+    ops.gemm(A, B, C1, M, N, K, lda=K, ldb=K, ldc=1008, alpha=0.5)
+    assert _rel(C1[:, :N], 0.5 * (A.float() @ B.float().t())) < 2e-3
+    assert C1[:, N:].abs().max().item() == 0
+    Nb = 1000
+    C2 = torch.zeros(M, 1008, dtype=torch.half, device=cuda)
+    ops.gemm(A, B, C2, M, Nb, K, lda=K, ldb=K, ldc=1008, bias=bias[:Nb], resid=resid[:M], ldr=1008)
+    ref2 = A.float() @ B[:Nb].float().t() + bias[:Nb].float() + resid[:M, :Nb].float()
+    assert _rel(C2[:, :Nb], ref2) < 2e-3
+    C2t = torch.zeros(9, 1008, dtype=torch.half, device=cuda)
+    ops.gemm(A9, B, C2t, 9, Nb, K, lda=K, ldb=K, ldc=1008, bias=bias[:Nb], resid=resid, ldr=1008)
+    assert _rel(C2[:, :Nb], C2t[:M, :Nb]) < 2e-3
+    # QKV split
+    Wqkv = _mk((3 * d, K), cuda, 0.2, 25)
+    u, v = _mk((d,), cuda, 1.0, 26), _mk((d,), cuda, 1.0, 27)
+    Q4 = torch.empty(M, 4 * d, dtype=torch.half, device=cuda)
+    ops.gemm(A, Wqkv, Q4, M, 3 * d, K, lda=K, ldb=K, ldc=4 * d, epilogue=ops.EPI_QKV, u=u, v=v, d_model=d)
+    qkv = A.float() @ Wqkv.float().t()
+    refq = torch.cat([qkv[:, :d] + u.float(), qkv[:, :d] + v.float(), qkv[:, d:]], 1)
+    assert _rel(Q4, refq) < 2e-3
+    # GeGLU
+    W1 = _mk((2 * F, K), cuda, 0.1, 28)
+    b1 = _mk((2 * F,), cuda, 0.5, 29)
+    Hb = torch.empty(M, 2 * F, dtype=torch.half, device=cuda)
+    G = torch.empty(M, F, dtype=torch.half, device=cuda)
+    ops.gemm(A, W1, G, M, 2 * F, K, lda=K, ldb=K, ldc=F, epilogue=ops.EPI_GEGLU, bias=b1, H=Hb, ldh=2 * F, F=F)
+    h = A.float() @ W1.float().t() + b1.float()
+    assert _rel(Hb, h) < 2e-3
+    hh = Hb.float()
+    assert _rel(G, hh[:, :F] * Fn.gelu(hh[:, F:])) < 2e-3
