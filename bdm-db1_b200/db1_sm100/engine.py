@@ -107,6 +107,9 @@ class DB1Engine:
         self._sink_seen = set()  # ids of parameters that have ever been written through the sink
         self._param_by_id = {id(p): p for b in self.buckets for p in b.params}
         self._sink_on = bool((self._cuda and direct_grads) or direct_grads == "force")
+        # weight-gradient GEMMs may run on a side stream (functions.wgrad_stream): only meaningful with the sink, where
+        # nothing but this engine reads the gradients before the end of backward
+        self.wgrad_side_stream = bool(self._cuda and self._sink_on)
         if self._sink_on:
             from . import functions
             functions.set_grad_sink(self)
@@ -313,16 +316,32 @@ class DB1Engine:
         if b.pending == 0:
             self._launch_allreduce(b)
 
+    def _side_stream(self):
+        if not (self._sink_on and self._cuda):
+            return None
+        from . import functions
+        return functions.wgrad_stream(self.device)
+
     def _launch_allreduce(self, bucket):
         if bucket.work is not None or self._world == 1:
             return
         if self._overlap:
             ev = torch.cuda.Event()
             ev.record(torch.cuda.current_stream(self.device))
+            side = self._side_stream()
+            ev2 = None
+            if side is not None:  # the bucket's weight gradients were written there
+                ev2 = torch.cuda.Event()
+                ev2.record(side)
             with torch.cuda.stream(self._comm_stream):
                 self._comm_stream.wait_event(ev)
+                if ev2 is not None:
+                    self._comm_stream.wait_event(ev2)
                 bucket.work = dist.all_reduce(bucket.flat, op=dist.ReduceOp.AVG, group=self._group, async_op=True)
         else:
+            side = self._side_stream()
+            if side is not None:
+                torch.cuda.current_stream(self.device).wait_stream(side)
             if dist.get_backend(self._group) == "gloo":
                 bucket.work = dist.all_reduce(bucket.flat, op=dist.ReduceOp.SUM, group=self._group, async_op=True)
                 bucket.post_scale = 1.0 / self._world
@@ -398,6 +417,9 @@ class DB1Engine:
             scaled.backward()
         if reserve > 0:
             _lib.lib().db1_set_sm_budget(0)
+        side = self._side_stream()
+        if side is not None:  # weight gradients written on the side stream are part of this backward
+            torch.cuda.current_stream(self.device).wait_stream(side)
         if self._is_boundary():
             self._zero_unwritten()
         else:

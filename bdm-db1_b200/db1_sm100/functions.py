@@ -96,6 +96,60 @@ class _Grad:
 
 
 # ---------------------------------------------------------------------------------------------------------------------
+# Weight-gradient GEMMs on a second stream - OPT-IN (DB1_WGRAD_STREAM=1), measured and rejected as a default.
+# Every large GEMM of the step covers the 74 CTA pairs with 64 / 128 / 192 / 256 / 384 pair-tiles - a last wave that is
+# 86 % full at best, and a persistent launch cannot start before the previous one has drained. The weight gradients are
+# off the critical chain of backward (nothing but the all-reduce consumes them), so they can be enqueued on a side
+# stream where their CTAs take the SMs the data-gradient GEMM's last wave leaves idle, and vice versa. Inputs are
+# fenced by an event of the main stream, lifetimes by record_stream; the engine fences the bucket all-reduces and the
+# end of backward on both streams. Measured on a B200 (profiles/README.md, round 2): 42.2 ms per step against 34.6 ms
+# on one stream - two persistent tcgen05 GEMMs sharing the SMs lose the lock-step in which the CTAs of one launch
+# re-use each other's operand tiles in L2 (the same effect that made the stream-K tail lose), which costs far more
+# than the idle tail waves.
+# ---------------------------------------------------------------------------------------------------------------------
+_side_streams = {}
+
+
+def wgrad_stream(device):
+    """The side stream of `device` when weight-gradient GEMMs run concurrently (engine sink registered), else None."""
+    import os
+    if _sink is None or not getattr(_sink, "wgrad_side_stream", False) or os.environ.get("DB1_WGRAD_STREAM", "0") != "1":
+        return None
+    st = _side_streams.get(device.index)
+    if st is None:
+        st = torch.cuda.Stream(device=device)
+        _side_streams[device.index] = st
+    return st
+
+
+class _Side:
+    """with _Side(dev, inputs...): <weight-gradient GEMM launches>"""
+    __slots__ = ("st", "ctx")
+
+    def __init__(self, device, *tensors):
+        self.st = wgrad_stream(device)
+        self.ctx = None
+        if self.st is not None:
+            ev = torch.cuda.Event()
+            ev.record(torch.cuda.current_stream(device))
+            self.st.wait_event(ev)
+            for t in tensors:
+                if t is not None:
+                    t.record_stream(self.st)
+
+    def __enter__(self):
+        if self.st is not None:
+            self.ctx = torch.cuda.stream(self.st)
+            self.ctx.__enter__()
+        return self
+
+    def __exit__(self, *exc):
+        if self.ctx is not None:
+            self.ctx.__exit__(*exc)
+        return False
+
+
+# ---------------------------------------------------------------------------------------------------------------------
 # Small fp32 gradient accumulators (du, dv, dgamma, dbeta, biases). Under an engine one zero-filled arena per backward
 # replaces the per-block torch.zeros launches (one memset instead of 48), and the feed-forward block's conversion to
 # fp16 rides along with the attention block's of the same layer (one db1_f32_to_f16_multi launch per layer instead of
@@ -254,7 +308,8 @@ class AttnBlockFn(torch.autograd.Function):
         pWqkv, pWr, pWo, pu, pv, pgamma, pbeta = ctx.params
         # o_net
         gWo = _Grad(pWo)
-        ops.gemm(dzz, o, gWo.buf, d, d, rows, lda=d, ldb=d, ldc=d, a_mn=True, b_mn=True, accumulate=gWo.acc)
+        with _Side(dev, dzz, o):
+            ops.gemm(dzz, o, gWo.buf, d, d, rows, lda=d, ldb=d, ldc=d, a_mn=True, b_mn=True, accumulate=gWo.acc)
         do = torch.empty(rows, d, dtype=f16, device=dev)
         # D = rowsum(dO * O), the softmax-backward row term: from the dO GEMM's own epilogue at model size (head dim 128),
         # else inside the recompute kernel; no separate db1_rowdot pass over dO / O either way
@@ -287,10 +342,11 @@ class AttnBlockFn(torch.autograd.Function):
         drk = _to_half(dr32, (L, d))
         # r_net / qkv_net
         gWr = _Grad(pWr)
-        ops.gemm(drk, r, gWr.buf, d, d, L, lda=d, ldb=d, ldc=d, a_mn=True, b_mn=True, accumulate=gWr.acc)
         gWqkv = _Grad(pWqkv)
-        ops.gemm(dqkv, x2, gWqkv.buf, 3 * d, d, rows, lda=3 * d, ldb=d, ldc=d, a_mn=True, b_mn=True,
-                 accumulate=gWqkv.acc)
+        with _Side(dev, drk, r, dqkv, x2):
+            ops.gemm(drk, r, gWr.buf, d, d, L, lda=d, ldb=d, ldc=d, a_mn=True, b_mn=True, accumulate=gWr.acc)
+            ops.gemm(dqkv, x2, gWqkv.buf, 3 * d, d, rows, lda=3 * d, ldb=d, ldc=d, a_mn=True, b_mn=True,
+                     accumulate=gWqkv.acc)
         dx = torch.empty(rows, d, dtype=f16, device=dev)
         ops.gemm(dqkv, Wqkv, dx, rows, d, 3 * d, lda=3 * d, ldb=d, ldc=d, b_mn=True, resid=dy, ldr=d)
         gu, gv, gg, gb = _scatter_small(small, [(pu, 0, d), (pv, d, d), (pgamma, 2 * d, d), (pbeta, 3 * d, d)])
@@ -479,13 +535,15 @@ class FFBlockFn(torch.autograd.Function):
         dzz = dz if dz is not None else dy
         pW1, pb1, pW2, pb2, pgamma, pbeta = ctx.params
         gW2 = _Grad(pW2)
-        ops.gemm(dzz, g, gW2.buf, d, F, rows, lda=d, ldb=F, ldc=F, a_mn=True, b_mn=True, accumulate=gW2.acc)
+        with _Side(dev, dzz, g):
+            ops.gemm(dzz, g, gW2.buf, d, F, rows, lda=d, ldb=F, ldc=F, a_mn=True, b_mn=True, accumulate=gW2.acc)
         dH = torch.empty(rows, 2 * F, dtype=f16, device=dev)
         ops.gemm(dzz, W2, dH, rows, F, d, lda=d, ldb=F, ldc=2 * F, b_mn=True, epilogue=ops.EPI_DGEGLU, H=Hb,
                  ldh=2 * F, F=F)
         ops.colsum(dH, db1, rows, 2 * F)
         gW1 = _Grad(pW1)
-        ops.gemm(dH, x2, gW1.buf, 2 * F, d, rows, lda=2 * F, ldb=d, ldc=d, a_mn=True, b_mn=True, accumulate=gW1.acc)
+        with _Side(dev, dH, x2):
+            ops.gemm(dH, x2, gW1.buf, 2 * F, d, rows, lda=2 * F, ldb=d, ldc=d, a_mn=True, b_mn=True, accumulate=gW1.acc)
         dx = torch.empty(rows, d, dtype=f16, device=dev)
         ops.gemm(dH, W1, dx, rows, d, 2 * F, lda=2 * F, ldb=d, ldc=d, b_mn=True, resid=dy, ldr=d)
         gg, gb, gb2, gb1 = _scatter_small(small, [(pgamma, 0, d), (pbeta, d, d), (pb2, 2 * d, d), (pb1, 3 * d, 2 * F)], defer=True)
@@ -534,7 +592,8 @@ class HeadLossFn(torch.autograd.Function):
         dl = _workspace("dlogits", (rows, Vp), torch.float16, dev)
         ops.ce_bwd(buf, lab, msk, row_lse, loss2, gs, dl, V)
         gW = _Grad(ctx.params[0])
-        ops.gemm(dl, h2, gW.buf, V, d, rows, lda=Vp, ldb=d, ldc=d, a_mn=True, b_mn=True, accumulate=gW.acc)
+        with _Side(dev, dl, h2):
+            ops.gemm(dl, h2, gW.buf, V, d, rows, lda=Vp, ldb=d, ldc=d, a_mn=True, b_mn=True, accumulate=gW.acc)
         dh = torch.empty(rows, d, dtype=torch.float16, device=dev)
         ops.gemm(dl, W, dh, rows, d, V, lda=Vp, ldb=d, ldc=d, b_mn=True)
         return dh.view(B, L, d), gW.ret(), None, None
@@ -587,6 +646,10 @@ class EmbedFn(torch.autograd.Function):
         # scatter-adds: straight into the gradient bucket when it already holds this window's gradient, else into zeros
         pW, pT = ctx.params
         gW = _Grad(pW, zero=True)
+        side = wgrad_stream(dev)
+        if side is not None and gW.direct:
+            # a tied head's weight gradient went into the same buffer on the side stream at the start of backward
+            torch.cuda.current_stream(dev).wait_stream(side)
         if gW.direct and not gW.acc:
             gW.buf.zero_()
         gT = None
