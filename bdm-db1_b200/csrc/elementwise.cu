@@ -260,11 +260,16 @@ ln_bwd_fused_kernel(const __half* __restrict__ dout, const __half* __restrict__ 
   __shared__ float red[2][NW][2 * ROWS];
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int off = tid * 8;
-  float g[8];
-  h8_to_f(*reinterpret_cast<const H8*>(gamma + off), g);
-  float ag[8], ab[8], az[8];
+  float2 g2[4], ag2[4], ab2[4], az2[4];
+  {
+    const H8 hg = *reinterpret_cast<const H8*>(gamma + off);
+    const uint32_t* w = reinterpret_cast<const uint32_t*>(&hg);
 #pragma unroll
-  for (int i = 0; i < 8; ++i) ag[i] = ab[i] = az[i] = 0.f;
+    for (int i = 0; i < 4; ++i) {
+      g2[i] = unpack_half2(w[i]);
+      ag2[i] = ab2[i] = az2[i] = make_float2(0.f, 0.f);
+    }
+  }
   const int ngroups = (rows + ROWS - 1) / ROWS;
   H8 ngo[ROWS], ny[ROWS];
   auto fetch = [&](int grp) {
@@ -290,28 +295,34 @@ ln_bwd_fused_kernel(const __half* __restrict__ dout, const __half* __restrict__ 
       hy[r] = ny[r];
     }
     fetch(grp + gridDim.x);  // next group's loads fly under this group's reduction and stores
-    // the packed fp16 inputs stay in registers (4 regs per row each); xhat / dxhat are recomputed in the second phase
+    // the packed fp16 inputs stay in registers (4 regs per row each); xhat / dxhat are recomputed in the second phase.
+    // All per-element arithmetic runs on Blackwell's packed fp32 pairs (FFMA2 / FADD2 / FMUL2: one issue slot per two
+    // elements): xhat = fma(y, rstd, -mean * rstd), and dy = fma(-c1, xhat, fma(dout * gamma, rstd, -c0)) with
+    // c0 = rstd * mean(dxhat), c1 = rstd * mean(dxhat * xhat).
     float mean[ROWS], rstd[ROWS], part[2 * ROWS];
 #pragma unroll
     for (int r = 0; r < ROWS; ++r) {
       const int rr = (r0 + r < rows) ? r0 + r : rows - 1;
       mean[r] = stats[2 * rr];
       rstd[r] = stats[2 * rr + 1];
-      float go[8], yv[8];
-      h8_to_f(hgo[r], go);
-      h8_to_f(hy[r], yv);
-      float s1 = 0.f, s2 = 0.f;
+      const float2 rs2 = make_float2(rstd[r], rstd[r]);
+      const float nm = -mean[r] * rstd[r];
+      const float2 nm2 = make_float2(nm, nm);
+      float2 s1 = make_float2(0.f, 0.f), s2 = make_float2(0.f, 0.f);
+      const uint32_t* wg = reinterpret_cast<const uint32_t*>(&hgo[r]);
+      const uint32_t* wy = reinterpret_cast<const uint32_t*>(&hy[r]);
 #pragma unroll
-      for (int i = 0; i < 8; ++i) {
-        const float xh = (yv[i] - mean[r]) * rstd[r];
-        const float dx = go[i] * g[i];
-        s1 += dx;
-        s2 += dx * xh;
-        ag[i] += go[i] * xh;  // out-of-range rows contribute go == 0
-        ab[i] += go[i];
+      for (int i = 0; i < 4; ++i) {
+        const float2 go = unpack_half2(wg[i]);
+        const float2 xh = __ffma2_rn(unpack_half2(wy[i]), rs2, nm2);
+        const float2 dx = __fmul2_rn(go, g2[i]);
+        s1 = __fadd2_rn(s1, dx);
+        s2 = __ffma2_rn(dx, xh, s2);
+        ag2[i] = __ffma2_rn(go, xh, ag2[i]);  // out-of-range rows contribute go == 0
+        ab2[i] = __fadd2_rn(ab2[i], go);
       }
-      part[2 * r] = s1;
-      part[2 * r + 1] = s2;
+      part[2 * r] = s1.x + s1.y;
+      part[2 * r + 1] = s2.x + s2.y;
     }
 #pragma unroll
     for (int k = 0; k < 2 * ROWS; ++k) part[k] = warp_sum(part[k]);
@@ -331,13 +342,22 @@ ln_bwd_fused_kernel(const __half* __restrict__ dout, const __half* __restrict__ 
 #pragma unroll
     for (int r = 0; r < ROWS; ++r) {
       if (r0 + r >= rows) break;
-      float o[8], go[8], yv[8];
-      h8_to_f(hgo[r], go);
-      h8_to_f(hy[r], yv);
+      const float2 rs2 = make_float2(rstd[r], rstd[r]);
+      const float nm = -mean[r] * rstd[r];
+      const float2 nm2 = make_float2(nm, nm);
+      const float c0 = -rstd[r] * part[2 * r], c1 = -rstd[r] * part[2 * r + 1];
+      const float2 c02 = make_float2(c0, c0), c12 = make_float2(c1, c1);
+      const uint32_t* wg = reinterpret_cast<const uint32_t*>(&hgo[r]);
+      const uint32_t* wy = reinterpret_cast<const uint32_t*>(&hy[r]);
+      H8 hv;
+      uint32_t* wv = reinterpret_cast<uint32_t*>(&hv);
 #pragma unroll
-      for (int i = 0; i < 8; ++i)
-        o[i] = rstd[r] * (go[i] * g[i] - part[2 * r] - (yv[i] - mean[r]) * rstd[r] * part[2 * r + 1]);
-      const H8 hv = f_to_h8(o);
+      for (int i = 0; i < 4; ++i) {
+        const float2 xh = __ffma2_rn(unpack_half2(wy[i]), rs2, nm2);
+        const float2 dx = __fmul2_rn(unpack_half2(wg[i]), g2[i]);
+        const float2 o = __ffma2_rn(c12, xh, __ffma2_rn(dx, rs2, c02));
+        wv[i] = pack_half2(o.x, o.y);
+      }
       *reinterpret_cast<H8*>(dy + (size_t)(r0 + r) * d + off) = hv;
       if (dz != nullptr || dbias != nullptr) {
         float z[8];
@@ -356,10 +376,17 @@ ln_bwd_fused_kernel(const __half* __restrict__ dout, const __half* __restrict__ 
         }
         if (dbias != nullptr) {
 #pragma unroll
-          for (int i = 0; i < 8; ++i) az[i] += z[i];
+          for (int i = 0; i < 4; ++i) az2[i] = __fadd2_rn(az2[i], make_float2(z[2 * i], z[2 * i + 1]));
         }
       }
     }
+  }
+  float ag[8], ab[8], az[8];
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    ag[2 * i] = ag2[i].x; ag[2 * i + 1] = ag2[i].y;
+    ab[2 * i] = ab2[i].x; ab[2 * i + 1] = ab2[i].y;
+    az[2 * i] = az2[i].x; az[2 * i + 1] = az2[i].y;
   }
   red_add_f32x4(dgamma + off, ag[0], ag[1], ag[2], ag[3]);
   red_add_f32x4(dgamma + off + 4, ag[4], ag[5], ag[6], ag[7]);

@@ -333,7 +333,9 @@ relattn_fwd_kernel(const __grid_constant__ CUtensorMap tmQu, const __grid_consta
       mbar_wait(bar_s, gs & 1);
       tc_fence_after();
       // ---- pass 1: content + shifted position scores -> registers (raw, unscaled), row max over this half
-      float sc[2][32];
+      // scores are kept as packed fp32 pairs: the add of the position term, the scale-and-shift before the exponential
+      // and the row sum issue as FADD2 / FFMA2 (one slot per two elements)
+      float2 sc[2][16];
       float mx = NEG_BIG;
 #pragma unroll
       for (int c2 = 0; c2 < 2; ++c2) {
@@ -361,21 +363,22 @@ relattn_fwd_kernel(const __grid_constant__ CUtensorMap tmQu, const __grid_consta
         for (int t = 0; t < 33; ++t) x[t] = b2 ? x[t + 2] : x[t];
 #pragma unroll
         for (int t = 0; t < 32; ++t) x[t] = b1 ? x[t + 1] : x[t];
+#pragma unroll
+        for (int t = 0; t < 16; ++t)
+          sc[c2][t] = __fadd2_rn(make_float2(__uint_as_float(s[2 * t]), __uint_as_float(s[2 * t + 1])),
+                                 make_float2(x[2 * t], x[2 * t + 1]));
         if (need_mask) {
 #pragma unroll
-          for (int t = 0; t < 32; ++t) {
-            const int j = J0 + cc * 32 + t;
-            const bool ok = (j <= i) && (i - j < p.window) && (j < p.L);
-            sc[c2][t] = ok ? (__uint_as_float(s[t]) + x[t]) : NEG_BIG;
-            mx = fmaxf(mx, sc[c2][t]);
-          }
-        } else {
-#pragma unroll
-          for (int t = 0; t < 32; ++t) {
-            sc[c2][t] = __uint_as_float(s[t]) + x[t];
-            mx = fmaxf(mx, sc[c2][t]);
+          for (int t = 0; t < 16; ++t) {
+            const int j = J0 + cc * 32 + 2 * t;
+            const bool ok0 = (j <= i) && (i - j < p.window) && (j < p.L);
+            const bool ok1 = (j + 1 <= i) && (i - j - 1 < p.window) && (j + 1 < p.L);
+            sc[c2][t].x = ok0 ? sc[c2][t].x : NEG_BIG;
+            sc[c2][t].y = ok1 ? sc[c2][t].y : NEG_BIG;
           }
         }
+#pragma unroll
+        for (int t = 0; t < 16; ++t) mx = fmaxf(mx, fmaxf(sc[c2][t].x, sc[c2][t].y));
       }
       // S and the previous band chunk are consumed: the MMA warp may overwrite them with step st+1's scores
       tc_fence_before();
@@ -421,17 +424,18 @@ relattn_fwd_kernel(const __grid_constant__ CUtensorMap tmQu, const __grid_consta
       }
       const float m_use = (MODE == 0) ? m_run : lse_row;
       // ---- pass 2: probabilities from the registers, p = exp2(raw * scale_log2 - m)
-      float sum = 0.f;
+      float2 sum2 = make_float2(0.f, 0.f);
+      const float2 sl2 = make_float2(p.scale_log2, p.scale_log2), nm2 = make_float2(-m_use, -m_use);
 #pragma unroll
       for (int c2 = 0; c2 < 2; ++c2) {
         const int cc = half * 2 + c2;
         uint32_t pk[16];
 #pragma unroll
         for (int t = 0; t < 16; ++t) {
-          const float p0 = ex2_approx(fmaf(sc[c2][2 * t], p.scale_log2, -m_use));
-          const float p1 = ex2_approx(fmaf(sc[c2][2 * t + 1], p.scale_log2, -m_use));
-          sum += p0 + p1;
-          pk[t] = pack_half2(p0, p1);
+          const float2 a = __ffma2_rn(sc[c2][t], sl2, nm2);
+          const float2 pr = make_float2(ex2_approx(a.x), ex2_approx(a.y));
+          sum2 = __fadd2_rn(sum2, pr);
+          pk[t] = pack_half2(pr.x, pr.y);
         }
         if (MODE == 0) {
           // K-major SW128 tile: slab = cc/2 (64 keys each), 16-byte chunk index within the row = (cc&1)*4 + g
@@ -482,11 +486,13 @@ relattn_fwd_kernel(const __grid_constant__ CUtensorMap tmQu, const __grid_consta
             uint32_t dp[32], dk[16];
             tmem_ld32(T_O + lane_off + cc * 32, dp);
             tmem_ld_wait();
+            const float2 nd2 = make_float2(-d_row, -d_row), s2 = make_float2(p.scale, p.scale);
 #pragma unroll
             for (int t = 0; t < 16; ++t) {
               const float2 pp = unpack_half2(pk[t]);
-              dk[t] = pack_half2(pp.x * (__uint_as_float(dp[2 * t]) - d_row) * p.scale,
-                                 pp.y * (__uint_as_float(dp[2 * t + 1]) - d_row) * p.scale);
+              const float2 dd = __fadd2_rn(make_float2(__uint_as_float(dp[2 * t]), __uint_as_float(dp[2 * t + 1])), nd2);
+              const float2 ds2 = __fmul2_rn(__fmul2_rn(pp, dd), s2);
+              dk[t] = pack_half2(ds2.x, ds2.y);
             }
             if (p.tiled && i >= p.L) {
 #pragma unroll
@@ -497,7 +503,7 @@ relattn_fwd_kernel(const __grid_constant__ CUtensorMap tmQu, const __grid_consta
           }
         }
       }
-      l_run += sum;
+      l_run += sum2.x + sum2.y;
       // publish: P is in smem (generic proxy -> async proxy) / dP has been read
       fence_proxy_async_smem();
       tc_fence_before();
