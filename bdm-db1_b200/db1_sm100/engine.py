@@ -32,6 +32,8 @@ def _default_bucket_of(name):
     parts = name.split(".")
     if len(parts) > 2 and parts[0] == "h" and parts[1].isdigit():
         ff = parts[2] == "pos_ff" and "CoreNet" in parts and parts[-1] == "weight"
+        if os.environ.get("DB1_BUCKET_SPLIT_FF", "1") == "0":
+            ff = False  # one bucket per decoder layer
         return "h.%s.%s" % (parts[1], "ff" if ff else "attn")
     if name == "word_embedding.weight":
         return "emb"
