@@ -25,16 +25,17 @@ import torch.distributed as dist
 
 
 def _default_bucket_of(name):
-    """Bucket key for a parameter name. Decoder layer l: 'h.l.ff' (the two feed-forward weight matrices: their gradients
-    are complete half a layer earlier in backward) and 'h.l.attn' (the attention block + the layer's small vectors, whose
-    fp32 accumulators are converted together at the end of the layer); 'emb' = the (tied) word embedding; 'vision' = the image patch embedder; 'rest' = everything
-    else (shared u / v, timestep embedding, an untied head)."""
+    """Bucket key for a parameter name: 'h.l' = decoder layer l; 'emb' = the (tied) word embedding; 'vision' = the image
+    patch embedder; 'rest' = everything else (shared u / v, timestep embedding, an untied head).
+    DB1_BUCKET_SPLIT_FF=1 splits a layer into 'h.l.ff' (the two feed-forward matrices, complete half a layer earlier in
+    backward) and 'h.l.attn': measured on 8 GPUs (profiles/README.md) the 24 extra collectives cost more than the finer
+    overlap gains (38.6 against 36.6 ms per step), so one bucket per layer is the default."""
     parts = name.split(".")
     if len(parts) > 2 and parts[0] == "h" and parts[1].isdigit():
-        ff = parts[2] == "pos_ff" and "CoreNet" in parts and parts[-1] == "weight"
-        if os.environ.get("DB1_BUCKET_SPLIT_FF", "1") == "0":
-            ff = False  # one bucket per decoder layer
-        return "h.%s.%s" % (parts[1], "ff" if ff else "attn")
+        if os.environ.get("DB1_BUCKET_SPLIT_FF", "0") == "1":
+            ff = parts[2] == "pos_ff" and "CoreNet" in parts and parts[-1] == "weight"
+            return "h.%s.%s" % (parts[1], "ff" if ff else "attn")
+        return "h.%s" % parts[1]
     if name == "word_embedding.weight":
         return "emb"
     if parts[0] == "vision_encoder":
