@@ -93,7 +93,7 @@ void set_sm_budget(int n) { g_sm_budget = n; }
 }  // namespace db1
 
 extern "C" const char* db1_last_error() { return db1::err_buf(); }
-extern "C" int db1_abi_version() { return 2; }
+extern "C" int db1_abi_version() { return 3; }
 
 /* Persistent kernels of this library size their grids to one CTA (or CTA pair) per SM. While a communication kernel
  * (NCCL all-reduce) is co-resident it occupies some SMs for its whole duration; a 148-CTA grid then needs a second wave

@@ -16,7 +16,8 @@
 namespace db1 {
 
 constexpr int SK_THREADS = 128;  // 4 warps: small N (2048 columns = 512 groups) still spreads over 128 CTAs
-constexpr int SK_ROWS = 4;  // output columns (weight rows) per warp pass
+// Output columns (weight rows) per warp pass: R in {1, 2, 4}, chosen per launch so that the 16 loads a lane keeps in
+// flight cover as much of K as possible in ONE round trip (K = 2048: 8 chunks per lane and row -> R = 2; K >= 4096: R = 1).
 
 struct SkinnyParams {
   const __half* A;
@@ -56,7 +57,7 @@ DEVI float dot8(const uint4& a, const uint4& b, float acc) {
 
 // MT: compile-time bound on the activation rows (1, 2, 4, 8). NR weight rows per pass: SK_ROWS, twice that for GeGLU
 // (column n of the a half and column n of the g half are finished by the same warp).
-template <int MT, int EPI>
+template <int MT, int EPI, int SK_ROWS>
 __global__ void __launch_bounds__(SK_THREADS) skinny_gemm_kernel(const SkinnyParams p) {
   constexpr int NR = (EPI == DB1_EPI_GEGLU) ? 2 * SK_ROWS : SK_ROWS;
   extern __shared__ uint4 sA[];  // [MT][K / 8]
@@ -167,21 +168,32 @@ __global__ void __launch_bounds__(SK_THREADS) skinny_gemm_kernel(const SkinnyPar
   }
 }
 
-template <int MT, int EPI>
-static int launch_skinny_me(const SkinnyParams& p, cudaStream_t stream) {
+template <int MT, int EPI, int R>
+static int launch_skinny_mer(const SkinnyParams& p, cudaStream_t stream) {
   const size_t smem = (size_t)MT * p.K * 2;
   static size_t configured = 0;
   if (smem > 48 * 1024 && smem > configured) {
-    DB1_CUDA(cudaFuncSetAttribute(skinny_gemm_kernel<MT, EPI>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    DB1_CUDA(cudaFuncSetAttribute(skinny_gemm_kernel<MT, EPI, R>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     configured = smem;
   }
   const int NO = (EPI == DB1_EPI_GEGLU) ? p.F : p.N;
-  const int ngroups = cdiv(NO, SK_ROWS);
+  const int ngroups = cdiv(NO, R);
   int grid = cdiv(ngroups, SK_THREADS / 32);
   const int cap = 4 * sm_count();  // persistent: every warp walks several column groups (amortises the A fill)
   if (grid > cap) grid = cap;
-  DB1_CUDA(launch_pdl(skinny_gemm_kernel<MT, EPI>, dim3(grid), dim3(SK_THREADS), smem, stream, 1, p));
+  DB1_CUDA(launch_pdl(skinny_gemm_kernel<MT, EPI, R>, dim3(grid), dim3(SK_THREADS), smem, stream, 1, p));
   return 0;
+}
+
+template <int MT, int EPI>
+static int launch_skinny_me(const SkinnyParams& p, cudaStream_t stream) {
+  // chunks per lane and weight row: K / 256. With 16 loads in flight per lane, R * (GeGLU ? 2 : 1) * chunks <= 16 keeps a
+  // column group to one memory round trip.
+  const int per_lane = cdiv(p.K, 256);
+  const int rows16 = 16 / ((EPI == DB1_EPI_GEGLU ? 2 : 1) * (per_lane < 1 ? 1 : per_lane));
+  if (rows16 >= 4) return launch_skinny_mer<MT, EPI, 4>(p, stream);
+  if (rows16 >= 2) return launch_skinny_mer<MT, EPI, 2>(p, stream);
+  return launch_skinny_mer<MT, EPI, 1>(p, stream);
 }
 
 template <int EPI>

@@ -15,12 +15,7 @@ cap gemm_dgeglu     "gemm_kernel<.int.256, .int.3, .int.2>"            5  $B
 cap gemm_qkv        "gemm_kernel<.int.256, .int.1, .int.2>"            5  $B
 cap attn_fwd        "relattn_fwd_kernel<.int.128, .int.0>"        5  $B
 cap attn_bwd_ds     "relattn_fwd_kernel<.int.128, .int.2>"        5  $B
-cap attn_bwd_dkdv   "relattn_bwd_dkdv_kernel"           5  $B
 cap attn_bwd_dq     "relattn_bwd_band_kernel<.int.128, .int.0>"   5  $B
 cap attn_bwd_dr     "relattn_bwd_band_kernel<.int.128, .int.1>"   5  $B
-cap ln_bwd          "ln_bwd_fused_kernel"               5  $B
-cap ln_fwd          "ln_fwd_warp_kernel"                5  $B
-cap ce_fwd          "ce_fwd_kernel"                     0  $B
-cap decode_attn     "relattn_decode_tiled_kernel"       5  python tools/decode_kernel_times.py
 cap skinny_geglu    "skinny_gemm_kernel<.int.1, .int.2>"          5  python tools/decode_kernel_times.py
 ls -la gpurun_out/full_*_r2.ncu-rep | awk '{print $5, $9}'
