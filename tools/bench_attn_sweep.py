@@ -1,8 +1,8 @@
 """Attention sweep with the backward included (BASELINE.json config 5): B=4, H=16, dh=128, L in {512, 1024, 2048, 4096}.
 Per L: the fused forward (db1_relattn_fwd) and the four backward kernels (recompute P/dS, key-outer dK/dV, query-outer dq,
 diagonal-outer dR), CUDA-event timed one kernel at a time, as TFLOP/s over the unmasked pairs and as algorithmic GB/s.
-    python tools/bench_attn_sweep.py [L ...]            (DB1_ATTN_SPLIT=2 selects the 8-softmax-warp build)
-Writes gpurun_out/attn_sweep_<split>.json when that directory exists."""
+    python tools/bench_attn_sweep.py [L ...]
+Writes gpurun_out/attn_sweep.json when that directory exists."""
 import json
 import math
 import os
@@ -17,7 +17,6 @@ from db1_sm100 import ops  # noqa: E402
 dev = torch.device("cuda")
 B, H, dh = 4, 16, 128
 d = H * dh
-split = os.environ.get("DB1_ATTN_SPLIT", "4")
 
 
 def timeit(fn, iters=10):
@@ -46,7 +45,7 @@ for L in Ls:
     pairs = L * (L + 1) / 2
     unit = B * H * 2.0 * dh * pairs  # one [L x L] x dh causal contraction
     io = B * L * d * 2.0             # one [B*L, d] fp16 operand
-    res = dict(L=L, split=int(split))
+    res = dict(L=L)
 
     def rec(name, us, n_contractions, nbytes):
         res[name] = dict(us=us, tflops=n_contractions * unit / us / 1e6, gbs=nbytes / us / 1e3)
@@ -75,5 +74,5 @@ for L in Ls:
     del P, dS
 out = os.path.join(ROOT, "gpurun_out")
 if os.path.isdir(out):
-    with open(os.path.join(out, "attn_sweep_split%s.json" % split), "w") as f:
+    with open(os.path.join(out, "attn_sweep.json"), "w") as f:
         json.dump(rows, f, indent=1)
