@@ -6,6 +6,13 @@
 // (10-20 us whatever M is); here every warp of a persistent grid owns groups of four output columns, streams their
 // weight rows with 16-byte non-allocating loads (sixteen of them in flight per lane), multiplies against the activation
 // rows held in shared memory, reduces with shuffles and applies the same fused epilogues db1_gemm_f16 offers on this path (bias, residual, the QKV split with +u / +v, GeGLU).
+// With db1_gemm_desc.b_static (weights nobody is writing: inference) the first batch of every warp's loads is issued
+// BEFORE griddepcontrol.wait, so the weight stream of a launch starts under the previous kernel's tail.
+// A second kernel stages the weight rows in shared memory with 1-D bulk copies (cp.async.bulk, a 3- to 6-stage ring of
+// 32 KB filled by one producer thread). Measured on the decode step (profiles/README.md): 1.38 - 1.41 ms per step against
+// 1.27 ms for the register-streaming kernel - a launch is a 10 - 35 MB stream, so its fixed cost (launch, fill, first
+// round trip, drain) decides, and 128-thread CTAs with 4 KB of shared memory overlap consecutive launches better than
+// one 100 - 200 KB CTA per SM. Kept as an opt-in: DB1_SKINNY_BULK=1.
 // db1_gemm_f16 routes here by itself (include/db1_sm100.h); DB1_NO_SKINNY=1 keeps the tensor-core kernel.
 #include <stdlib.h>
 
@@ -35,6 +42,7 @@ struct SkinnyParams {
   long long ldh;
   int M, N, K, F, d_model;
   float alpha;
+  int b_static;  // weights: may be requested before griddepcontrol.wait
 };
 
 DEVI uint4 ldg_stream(const __half* p) {
@@ -63,17 +71,34 @@ __global__ void __launch_bounds__(SK_THREADS) skinny_gemm_kernel(const SkinnyPar
   extern __shared__ uint4 sA[];  // [MT][K / 8]
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int kc = p.K >> 3;
+  constexpr int U = 16 / NR;  // chunks per row and batch: U * NR = 16 independent 16-byte loads per lane in flight
+  const int NO = (EPI == DB1_EPI_GEGLU) ? p.F : p.N;  // output column groups run over [0, NO)
+  const int ngroups = (NO + SK_ROWS - 1) / SK_ROWS;
+  const int nwarps = gridDim.x * (SK_THREADS / 32);
+  const int g_first = blockIdx.x * (SK_THREADS / 32) + warp;
   pdl_launch_dependents();
+  // b_static (weights nobody is writing): the first batch of the warp's first column group - for K <= 4096 all of it - is
+  // requested BEFORE waiting for the previous kernel, so the weight stream runs under that kernel's tail
+  uint4 pre[U][NR];
+  const bool preloaded = p.b_static && g_first < ngroups && lane + 32 * (U - 1) < kc;
+  if (preloaded) {
+#pragma unroll
+    for (int r = 0; r < NR; ++r) {
+      int n = g_first * SK_ROWS + (r % SK_ROWS);
+      if (n >= NO) n = NO - 1;
+      if (EPI == DB1_EPI_GEGLU && r >= SK_ROWS) n += p.F;
+      const __half* row = p.B + (long long)n * p.ldb;
+#pragma unroll
+      for (int x = 0; x < U; ++x) pre[x][r] = ldg_stream(row + (lane + 32 * x) * 8);
+    }
+  }
   pdl_wait();
   for (int idx = tid; idx < MT * kc; idx += SK_THREADS) {
     const int m = idx / kc, c = idx - m * kc;
     sA[idx] = (m < p.M) ? *reinterpret_cast<const uint4*>(p.A + (long long)m * p.lda + c * 8) : make_uint4(0u, 0u, 0u, 0u);
   }
   __syncthreads();
-  const int NO = (EPI == DB1_EPI_GEGLU) ? p.F : p.N;  // output column groups run over [0, NO)
-  const int ngroups = (NO + SK_ROWS - 1) / SK_ROWS;
-  const int nwarps = gridDim.x * (SK_THREADS / 32);
-  for (int g = blockIdx.x * (SK_THREADS / 32) + warp; g < ngroups; g += nwarps) {
+  for (int g = g_first; g < ngroups; g += nwarps) {
     const int n0 = g * SK_ROWS;
     const __half* brow[NR];
 #pragma unroll
@@ -88,15 +113,20 @@ __global__ void __launch_bounds__(SK_THREADS) skinny_gemm_kernel(const SkinnyPar
     for (int r = 0; r < NR; ++r)
 #pragma unroll
       for (int m = 0; m < MT; ++m) acc[r][m] = 0.f;
-    // U chunks per row and iteration: U * NR = 16 independent 16-byte loads per lane in flight
-    constexpr int U = 16 / NR;
     int c = lane;
     for (; c + 32 * (U - 1) < kc; c += 32 * U) {
       uint4 bb[U][NR];
+      if (preloaded && g == g_first && c == lane) {
 #pragma unroll
-      for (int x = 0; x < U; ++x)
+        for (int x = 0; x < U; ++x)
 #pragma unroll
-        for (int r = 0; r < NR; ++r) bb[x][r] = ldg_stream(brow[r] + (c + 32 * x) * 8);
+          for (int r = 0; r < NR; ++r) bb[x][r] = pre[x][r];
+      } else {
+#pragma unroll
+        for (int x = 0; x < U; ++x)
+#pragma unroll
+          for (int r = 0; r < NR; ++r) bb[x][r] = ldg_stream(brow[r] + (c + 32 * x) * 8);
+      }
 #pragma unroll
       for (int x = 0; x < U; ++x)
 #pragma unroll
@@ -168,6 +198,204 @@ __global__ void __launch_bounds__(SK_THREADS) skinny_gemm_kernel(const SkinnyPar
   }
 }
 
+// ------------------------------------------------------------------------------------------------------------------
+// Bulk-copy staged variant. A stage holds RB weight rows of K halves (GeGLU: RB/2 rows of the a half followed by the
+// matching RB/2 rows of the g half). Warp 4 = producer (one thread), warps 0-3 = consumers: warp w finishes the output
+// columns w, w + 4, ... of the stage (lanes stride over the 16-byte chunks of K, activations from shared memory).
+// ------------------------------------------------------------------------------------------------------------------
+constexpr int SKB_CONSUMERS = 128;
+constexpr int SKB_THREADS = SKB_CONSUMERS + 32;
+constexpr int SKB_MAX_STAGES = 6;
+
+DEVI void bulk_load_1d(void* smem_dst, const void* gsrc, uint32_t bytes, uint64_t* bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_u32(smem_dst)),
+               "l"(gsrc), "r"(bytes), "r"(smem_u32(bar))
+               : "memory");
+}
+
+struct SkinnyBulkCfg {
+  int rb;       // weight rows per stage (GeGLU: a rows + g rows)
+  int stages;
+  int a_bytes;  // MT * K * 2, rounded up to 128
+  int stage_bytes;
+};
+
+template <int MT, int EPI>
+__global__ void __launch_bounds__(SKB_THREADS) skinny_bulk_kernel(const SkinnyParams p, const SkinnyBulkCfg cfg) {
+  extern __shared__ __align__(128) uint8_t sk_smem[];
+  uint4* sA = reinterpret_cast<uint4*>(sk_smem);
+  uint8_t* stage0 = sk_smem + cfg.a_bytes;
+  uint64_t* full = reinterpret_cast<uint64_t*>(stage0 + (size_t)cfg.stages * cfg.stage_bytes);
+  uint64_t* empty = full + SKB_MAX_STAGES;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int kc = p.K >> 3;
+  const uint32_t row_bytes = (uint32_t)p.K * 2u;
+  const int NO = (EPI == DB1_EPI_GEGLU) ? p.F : p.N;            // output columns
+  const int cols = (EPI == DB1_EPI_GEGLU) ? cfg.rb / 2 : cfg.rb;  // output columns per stage
+  const int nblocks = (NO + cols - 1) / cols;
+  if (tid == 0) {
+    for (int i = 0; i < cfg.stages; ++i) {
+      mbar_init(&full[i], 1);
+      mbar_init(&empty[i], SKB_CONSUMERS / 32);
+    }
+    mbar_fence_init();
+  }
+  __syncthreads();
+  pdl_launch_dependents();
+  if (warp == SKB_CONSUMERS / 32) {
+    // ---- producer: with b_static the weights are parameters, not outputs of the previous kernel, and are requested
+    // without waiting for it (their stream overlaps its tail)
+    if (lane == 0) {
+      if (!p.b_static) pdl_wait();
+      int s = 0;
+      uint32_t ph = 0;
+      for (int blk = blockIdx.x; blk < nblocks; blk += gridDim.x) {
+        mbar_wait(&empty[s], ph ^ 1);
+        const int n0 = blk * cols;
+        const int nv = (NO - n0 < cols) ? NO - n0 : cols;
+        mbar_expect_tx(&full[s], (uint32_t)nv * row_bytes * (EPI == DB1_EPI_GEGLU ? 2u : 1u));
+        uint8_t* dst = stage0 + (size_t)s * cfg.stage_bytes;
+        for (int r = 0; r < nv; ++r) {
+          bulk_load_1d(dst + (size_t)r * row_bytes, p.B + (long long)(n0 + r) * p.ldb, row_bytes, &full[s]);
+          if (EPI == DB1_EPI_GEGLU)
+            bulk_load_1d(dst + (size_t)(cols + r) * row_bytes, p.B + (long long)(p.F + n0 + r) * p.ldb, row_bytes, &full[s]);
+        }
+        if (++s == cfg.stages) {
+          s = 0;
+          ph ^= 1;
+        }
+      }
+    }
+    return;
+  }
+  // ---- consumers
+  pdl_wait();  // the activations come from the previous kernel
+  for (int idx = tid; idx < MT * kc; idx += SKB_CONSUMERS) {
+    const int m = idx / kc, c = idx - m * kc;
+    sA[idx] = (m < p.M) ? *reinterpret_cast<const uint4*>(p.A + (long long)m * p.lda + c * 8) : make_uint4(0u, 0u, 0u, 0u);
+  }
+  named_bar_sync(1, SKB_CONSUMERS);
+  int s = 0;
+  uint32_t ph = 0;
+  for (int blk = blockIdx.x; blk < nblocks; blk += gridDim.x) {
+    mbar_wait(&full[s], ph);
+    const uint8_t* st = stage0 + (size_t)s * cfg.stage_bytes;
+    const int n0 = blk * cols;
+    for (int r = warp; r < cols && n0 + r < NO; r += SKB_CONSUMERS / 32) {
+      const uint4* ba = reinterpret_cast<const uint4*>(st + (size_t)r * row_bytes);
+      const uint4* bg = reinterpret_cast<const uint4*>(st + (size_t)(cols + r) * row_bytes);
+      float acc[MT], accg[MT];
+#pragma unroll
+      for (int m = 0; m < MT; ++m) acc[m] = accg[m] = 0.f;
+#pragma unroll 4
+      for (int c = lane; c < kc; c += 32) {
+        const uint4 b0 = ba[c];
+        uint4 b1 = make_uint4(0u, 0u, 0u, 0u);
+        if (EPI == DB1_EPI_GEGLU) b1 = bg[c];
+#pragma unroll
+        for (int m = 0; m < MT; ++m) {
+          const uint4 a0 = sA[m * kc + c];
+          acc[m] = dot8(a0, b0, acc[m]);
+          if (EPI == DB1_EPI_GEGLU) accg[m] = dot8(a0, b1, accg[m]);
+        }
+      }
+#pragma unroll
+      for (int m = 0; m < MT; ++m) {
+#pragma unroll
+        for (int o = 16; o; o >>= 1) {
+          acc[m] += __shfl_xor_sync(0xffffffffu, acc[m], o);
+          if (EPI == DB1_EPI_GEGLU) accg[m] += __shfl_xor_sync(0xffffffffu, accg[m], o);
+        }
+      }
+      float mine = 0.f, mine_g = 0.f;
+#pragma unroll
+      for (int m = 0; m < MT; ++m)
+        if (lane == m) {
+          mine = acc[m] * p.alpha;
+          mine_g = accg[m] * p.alpha;
+        }
+      const int m = lane, n = n0 + r;
+      if (m < p.M) {
+        if (EPI == DB1_EPI_PLAIN) {
+          float f = mine;
+          if (p.bias) f += __half2float(p.bias[n]);
+          if (p.resid) f = __half2float(p.resid[(long long)m * p.ldr + n]) + f;
+          p.C[(long long)m * p.ldc + n] = __float2half_rn(f);
+        } else if (EPI == DB1_EPI_QKV) {
+          __half* crow = p.C + (long long)m * p.ldc;
+          if (n < p.d_model) {
+            crow[n] = __float2half_rn(mine + __half2float(p.u[n]));
+            crow[p.d_model + n] = __float2half_rn(mine + __half2float(p.v[n]));
+          } else {
+            crow[p.d_model + n] = __float2half_rn(mine);
+          }
+        } else {
+          float a = mine, gg = mine_g;
+          if (p.bias) {
+            a += __half2float(p.bias[n]);
+            gg += __half2float(p.bias[p.F + n]);
+          }
+          const __half ha = __float2half_rn(a), hg = __float2half_rn(gg);
+          if (p.H) {
+            p.H[(long long)m * p.ldh + n] = ha;
+            p.H[(long long)m * p.ldh + p.F + n] = hg;
+          }
+          p.C[(long long)m * p.ldc + n] = __float2half_rn(__half2float(ha) * gelu_erf(__half2float(hg)));
+        }
+      }
+    }
+    __syncwarp();
+    if (lane == 0) mbar_arrive(&empty[s]);
+    if (++s == cfg.stages) {
+      s = 0;
+      ph ^= 1;
+    }
+  }
+}
+
+// false: the shape does not fit (the caller falls back to the register-streaming kernel)
+template <int MT, int EPI>
+static bool launch_skinny_bulk(const SkinnyParams& p, cudaStream_t stream, int* rc) {
+  static int on = -1;
+  if (on < 0) on = getenv("DB1_SKINNY_BULK") ? 1 : 0;
+  if (!on) return false;
+  const long long row_bytes = (long long)p.K * 2;
+  if (row_bytes % 16 != 0 || (p.ldb * 2) % 16 != 0 || row_bytes > 32768) return false;
+  SkinnyBulkCfg cfg;
+  cfg.a_bytes = (int)(((long long)MT * row_bytes + 127) / 128 * 128);
+  int rb = (int)(32768 / row_bytes);  // rows per 32 KB stage
+  if (EPI == DB1_EPI_GEGLU) rb &= ~1;
+  if (rb > 32) rb = 32;
+  if (rb < (EPI == DB1_EPI_GEGLU ? 2 : 1)) return false;
+  cfg.rb = rb;
+  cfg.stage_bytes = (int)(rb * row_bytes);
+  // at most ~half of an SM's shared memory: the next launch's CTAs (programmatic dependent launch) must fit beside this
+  // one's for its weight stream to start under this kernel's tail
+  static int half = -1;
+  if (half < 0) half = getenv("DB1_SKINNY_FULL_SMEM") ? 0 : 1;
+  const int budget = (half ? 110 : 227) * 1024 - cfg.a_bytes - 2 * SKB_MAX_STAGES * 8 - 128;
+  int stages = budget / cfg.stage_bytes;
+  if (stages > SKB_MAX_STAGES) stages = SKB_MAX_STAGES;
+  if (stages < 2) return false;
+  cfg.stages = stages;
+  const size_t smem = (size_t)cfg.a_bytes + (size_t)stages * cfg.stage_bytes + 2 * SKB_MAX_STAGES * 8;
+  static size_t configured = 0;
+  if (smem > configured) {
+    if (cudaFuncSetAttribute(skinny_bulk_kernel<MT, EPI>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) {
+      cudaGetLastError();
+      return false;
+    }
+    configured = smem;
+  }
+  const int NO = (EPI == DB1_EPI_GEGLU) ? p.F : p.N;
+  const int cols = (EPI == DB1_EPI_GEGLU) ? rb / 2 : rb;
+  const int nblocks = cdiv(NO, cols);
+  int grid = nblocks < sm_count() ? nblocks : sm_count();
+  cudaError_t e = launch_pdl(skinny_bulk_kernel<MT, EPI>, dim3(grid), dim3(SKB_THREADS), smem, stream, 1, p, cfg);
+  *rc = (e == cudaSuccess) ? 0 : set_err((int)e, "skinny_bulk_kernel launch failed: %s", cudaGetErrorString(e));
+  return true;
+}
+
 template <int MT, int EPI, int R>
 static int launch_skinny_mer(const SkinnyParams& p, cudaStream_t stream) {
   const size_t smem = (size_t)MT * p.K * 2;
@@ -187,6 +415,8 @@ static int launch_skinny_mer(const SkinnyParams& p, cudaStream_t stream) {
 
 template <int MT, int EPI>
 static int launch_skinny_me(const SkinnyParams& p, cudaStream_t stream) {
+  int rc = 0;
+  if (launch_skinny_bulk<MT, EPI>(p, stream, &rc)) return rc;
   // chunks per lane and weight row: K / 256. With 16 loads in flight per lane, R * (GeGLU ? 2 : 1) * chunks <= 16 keeps a
   // column group to one memory round trip.
   const int per_lane = cdiv(p.K, 256);
@@ -224,7 +454,7 @@ int skinny_gemm(const db1_gemm_desc* d, cudaStream_t stream) {
   p.A = (const __half*)d->A; p.lda = d->lda; p.B = (const __half*)d->B; p.ldb = d->ldb;
   p.C = (__half*)d->C; p.ldc = d->ldc; p.bias = (const __half*)d->bias; p.resid = (const __half*)d->resid; p.ldr = d->ldr;
   p.u = (const __half*)d->u; p.v = (const __half*)d->v; p.H = (__half*)d->H; p.ldh = d->ldh;
-  p.M = d->M; p.N = d->N; p.K = d->K; p.F = d->F; p.d_model = d->d_model; p.alpha = d->alpha;
+  p.M = d->M; p.N = d->N; p.K = d->K; p.F = d->F; p.d_model = d->d_model; p.alpha = d->alpha; p.b_static = d->b_static;
   switch (d->epilogue) {
     case DB1_EPI_PLAIN: return launch_skinny_e<DB1_EPI_PLAIN>(p, stream);
     case DB1_EPI_QKV: return launch_skinny_e<DB1_EPI_QKV>(p, stream);

@@ -35,6 +35,7 @@ class GemmDesc(C.Structure):
         ("window", C.c_int32), ("bn_hint", C.c_int32),
         ("dot_with", C.c_void_p), ("ld_dot", C.c_int64), ("dot_out", C.c_void_p),
         ("dot_L", C.c_int32), ("dot_H", C.c_int32),
+        ("b_static", C.c_int32),
     ]
 
 

@@ -467,7 +467,7 @@ def attn_block_cached(w, li, mem, r, Wqkv, Wr, Wo, u, v, gamma, beta, H, eps, wi
         x2 = x2.contiguous()
     qkv4 = torch.empty(B * Q, 4 * d, dtype=f16, device=dev)
     ops.gemm(x2, Wqkv, qkv4, B * Q, 3 * d, d, lda=d, ldb=d, ldc=4 * d, epilogue=ops.EPI_QKV, u=u.reshape(d), v=v.reshape(d),
-             d_model=d)
+             d_model=d, b_static=True)
     rk = mem.rk.get((li, K))
     if rk is None:  # depends on the layer's r_net and on klen only
         rk = torch.empty(K, d, dtype=f16, device=dev)
@@ -482,7 +482,7 @@ def attn_block_cached(w, li, mem, r, Wqkv, Wr, Wo, u, v, gamma, beta, H, eps, wi
     ops.ring_append([(x2, mem.hid[li]), (qkv4[:, 2 * d:3 * d], mem.k[li]), (qkv4[:, 3 * d:], mem.v[li])], mem.head, B, Q,
                     head_dev=mem.head_dev)
     y = torch.empty(B * Q, d, dtype=f16, device=dev)
-    ops.gemm(o, Wo, y, B * Q, d, d, lda=d, ldb=d, ldc=d, resid=x2, ldr=d)
+    ops.gemm(o, Wo, y, B * Q, d, d, lda=d, ldb=d, ldc=d, resid=x2, ldr=d, b_static=True)
     out = torch.empty(B * Q, d, dtype=f16, device=dev)
     stats = torch.empty(B * Q, 2, dtype=torch.float32, device=dev)
     ops.layernorm_fwd(y, gamma, beta, out, stats, eps)
@@ -505,10 +505,13 @@ class FFBlockFn(torch.autograd.Function):
             x2 = x2.contiguous()
         Hb = torch.empty(rows, F2, dtype=torch.float16, device=dev)
         g = torch.empty(rows, F, dtype=torch.float16, device=dev)
-        ops.gemm(x2, W1, g, rows, F2, d, lda=d, ldb=d, ldc=F, epilogue=ops.EPI_GEGLU, bias=b1, H=Hb, ldh=F2, F=F)
+        static = not any(ctx.needs_input_grad)  # inference (no_grad): the weights are not being written by anyone
+        ops.gemm(x2, W1, g, rows, F2, d, lda=d, ldb=d, ldc=F, epilogue=ops.EPI_GEGLU, bias=b1, H=Hb, ldh=F2, F=F,
+                 b_static=static)
         seed = seeds.next() if drop_p > 0 else 0
         y = torch.empty(rows, d, dtype=torch.float16, device=dev)
-        ops.gemm(g, W2, y, rows, d, F, lda=F, ldb=F, ldc=d, bias=b2, resid=x2, ldr=d, drop_p=drop_p, seed=seed)
+        ops.gemm(g, W2, y, rows, d, F, lda=F, ldb=F, ldc=d, bias=b2, resid=x2, ldr=d, drop_p=drop_p, seed=seed,
+                 b_static=static)
         out = torch.empty(rows, d, dtype=torch.float16, device=dev)
         stats = torch.empty(rows, 2, dtype=torch.float32, device=dev)
         ops.layernorm_fwd(y, gamma, beta, out, stats, eps)
@@ -607,7 +610,7 @@ def head_logits(hidden, W):
     Vp = (V + 127) // 128 * 128
     h2 = hidden.reshape(rows, d).contiguous()
     buf = torch.empty(rows, Vp, dtype=torch.float16, device=hidden.device)
-    ops.gemm(h2, W, buf, rows, V, d, lda=d, ldb=d, ldc=Vp)
+    ops.gemm(h2, W, buf, rows, V, d, lda=d, ldb=d, ldc=Vp, b_static=True)
     return buf.view(B, L, Vp)[:, :, :V]
 
 

@@ -103,7 +103,7 @@ def _ensure_gemm_workspace(device):
 def gemm(A, B, C_out, M, N, K, *, lda, ldb, ldc, a_mn=False, b_mn=False, epilogue=EPI_PLAIN, alpha=1.0,
          accumulate=False, bias=None, resid=None, ldr=0, drop_p=0.0, seed=0, u=None, v=None, d_model=0, H=None,
          ldh=0, F=0, Z1=1, Z2=1, a_z=(0, 0), b_z=(0, 0), c_z=(0, 0), reduce_z2=False, k_mode=K_FULL,
-         skip_upper=False, P=None, C2=None, Drow=None, window=0, bn_hint=0, dot=None):
+         skip_upper=False, P=None, C2=None, Drow=None, window=0, bn_hint=0, dot=None, b_static=False):
     """C[M,N] (+)= epilogue(alpha * A[M,K] @ B[N,K]^T) per batch index; see include/db1_sm100.h:db1_gemm_f16."""
     _need_cuda_half(A, B, C_out, bias, resid, u, v, H, P, C2)
     _ensure_gemm_workspace(A.device)
@@ -138,6 +138,7 @@ def gemm(A, B, C_out, M, N, K, *, lda, ldb, ldc, a_mn=False, b_mn=False, epilogu
     d.Drow = Drow.data_ptr() if Drow is not None else None
     d.window = window
     d.bn_hint = bn_hint
+    d.b_static = int(b_static)  # B = weights nobody is writing (inference): the few-row path may prefetch them early
     if dot is not None:  # (X fp16 [M, ld], out fp32 [M / L, H, L], L, H): out = per-head rowsum(C * X), head dim 128
         X, dout_t, dL, dH = dot
         _need_cuda_half(X)

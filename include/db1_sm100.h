@@ -23,7 +23,7 @@ extern "C" {
 #endif
 
 const char* db1_last_error(void);
-/* ABI version of this header; bumped whenever a struct layout changes. */
+/* ABI version of this header; bumped whenever a struct layout changes (3: db1_gemm_desc.b_static appended). */
 int db1_abi_version(void);
 /* Number of SMs the persistent kernels may cover (0 = all). Lower it while a long-running communication kernel occupies
  * SMs (DB1Engine does during backward at world size > 1: physical SMs minus NCCL's CTAs), so that a grid never needs a
@@ -96,6 +96,10 @@ typedef struct db1_gemm_desc {
   int64_t ld_dot;
   float* dot_out;       /* fp32 [M / dot_L, dot_H, dot_L] */
   int32_t dot_L, dot_H;
+  /* ABI version 3. 1: B holds parameters that no kernel enqueued just before this call writes (model weights during
+   * inference): the few-row path (M <= 8) may then request them before the stream's previous kernel has completed
+   * (programmatic dependent launch) - its weight stream overlaps that kernel's tail. 0 (default): B is read only after it. */
+  int32_t b_static;
 } db1_gemm_desc;
 
 int db1_gemm_f16(const db1_gemm_desc* d, void* stream);
