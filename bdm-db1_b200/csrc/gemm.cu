@@ -1366,6 +1366,7 @@ extern "C" int db1_gemm_f16(const db1_gemm_desc* d, void* stream_) {
   const bool batched = Z1 * Z2 > 1;
   // one to eight activation rows (the decode step): a stream over B on the CUDA cores, HBM-bound (csrc/skinny.cu)
   if (skinny_gemm_applies(d)) return skinny_gemm(d, stream);
+  DB1_CHECK_ARG(d->ln_gamma == nullptr, "gemm: LayerNorm-on-load (ln_gamma) exists on the few-row path only (M <= 8)");
   DB1_CHECK_ARG((d->a_z1 % 8 == 0) && (d->a_z2 % 8 == 0) && (d->b_z1 % 8 == 0) && (d->b_z2 % 8 == 0) &&
                     (d->c_z1 % 8 == 0) && (d->c_z2 % 8 == 0),
                 "gemm: batch strides must be multiples of 8 elements");

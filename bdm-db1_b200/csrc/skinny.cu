@@ -43,6 +43,10 @@ struct SkinnyParams {
   int M, N, K, F, d_model;
   float alpha;
   int b_static;  // weights: may be requested before griddepcontrol.wait
+  const __half* ln_gamma;  // LayerNorm of the activation rows on load (NULL: off)
+  const __half* ln_beta;
+  float ln_eps;
+  __half* ln_out;  // [M, K] normalised rows (optional)
 };
 
 DEVI uint4 ldg_stream(const __half* p) {
@@ -61,6 +65,68 @@ DEVI float dot8(const uint4& a, const uint4& b, float acc) {
   acc = fmaf(a2.x, b2.x, acc); acc = fmaf(a2.y, b2.y, acc);
   acc = fmaf(a3.x, b3.x, acc); acc = fmaf(a3.y, b3.y, acc);
   return acc;
+}
+
+// LayerNorm of the staged activation rows, in place (db1_gemm_desc.ln_*): all threads of the CTA on one row at a time,
+// two-pass statistics and the fp16 rounding of db1_layernorm_fwd (csrc/elementwise.cu: ln_fwd_warp_kernel), every CTA for
+// itself (M * K <= 8 * 8192 elements); the CTA with `write` also stores the rows to ln_out. The first two gamma / beta
+// chunks of every thread (all of them for K <= 2048) arrive as arguments: they were requested before
+// griddepcontrol.wait, LayerNorm weights being as static as the GEMM's own.
+template <int NT>
+DEVI float block_sum_nt(float v, float* red, int lane, int warp) {
+#pragma unroll
+  for (int o = 16; o; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  if (lane == 0) red[warp] = v;
+  __syncthreads();
+  float t = 0.f;
+#pragma unroll
+  for (int w = 0; w < NT / 32; ++w) t += red[w];
+  return t;
+}
+
+template <int NT>
+DEVI void layernorm_rows_in_smem(uint4* sA, const SkinnyParams& p, int kc, int tid, bool write, const uint4 (&pg)[2],
+                                 const uint4 (&pb)[2], float (*red)[NT / 32]) {
+  const int lane = tid & 31, warp = tid >> 5;
+  for (int m = 0; m < p.M; ++m) {
+    uint4* row = sA + (size_t)m * kc;
+    float sum = 0.f;
+    for (int c = tid; c < kc; c += NT) {
+      const uint4 a = row[c];
+      const float2 x0 = unpack_half2(a.x), x1 = unpack_half2(a.y), x2 = unpack_half2(a.z), x3 = unpack_half2(a.w);
+      sum += ((x0.x + x0.y) + (x1.x + x1.y)) + ((x2.x + x2.y) + (x3.x + x3.y));
+    }
+    const float mean = block_sum_nt<NT>(sum, red[0], lane, warp) / (float)p.K;
+    float var = 0.f;
+    for (int c = tid; c < kc; c += NT) {
+      const uint4 a = row[c];
+      const uint32_t w[4] = {a.x, a.y, a.z, a.w};
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        const float2 x = unpack_half2(w[i]);
+        var = fmaf(x.x - mean, x.x - mean, var);
+        var = fmaf(x.y - mean, x.y - mean, var);
+      }
+    }
+    const float rstd = rsqrtf(block_sum_nt<NT>(var, red[1], lane, warp) / (float)p.K + p.ln_eps);
+    int it = 0;
+    for (int c = tid; c < kc; c += NT, ++it) {
+      const uint4 a = row[c];
+      const uint4 g = it < 2 ? pg[it < 2 ? it : 0] : *reinterpret_cast<const uint4*>(p.ln_gamma + c * 8);
+      const uint4 b = it < 2 ? pb[it < 2 ? it : 0] : *reinterpret_cast<const uint4*>(p.ln_beta + c * 8);
+      const uint32_t wa[4] = {a.x, a.y, a.z, a.w}, wg[4] = {g.x, g.y, g.z, g.w}, wb[4] = {b.x, b.y, b.z, b.w};
+      uint32_t wo[4];
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        const float2 x = unpack_half2(wa[i]), gg = unpack_half2(wg[i]), bb = unpack_half2(wb[i]);
+        wo[i] = pack_half2((x.x - mean) * rstd * gg.x + bb.x, (x.y - mean) * rstd * gg.y + bb.y);
+      }
+      const uint4 o4 = make_uint4(wo[0], wo[1], wo[2], wo[3]);
+      row[c] = o4;
+      if (write && p.ln_out != nullptr) *reinterpret_cast<uint4*>(p.ln_out + (size_t)m * p.K + c * 8) = o4;
+    }
+    __syncthreads();  // red[] is reused by the next row; the normalised row is visible to every warp
+  }
 }
 
 // MT: compile-time bound on the activation rows (1, 2, 4, 8). NR weight rows per pass: SK_ROWS, twice that for GeGLU
@@ -92,12 +158,26 @@ __global__ void __launch_bounds__(SK_THREADS) skinny_gemm_kernel(const SkinnyPar
       for (int x = 0; x < U; ++x) pre[x][r] = ldg_stream(row + (lane + 32 * x) * 8);
     }
   }
+  __shared__ float ln_red[2][SK_THREADS / 32];
+  uint4 pg[2], pb[2];  // LayerNorm weights of this thread's first two chunks (static like B: requested before the wait)
+  if (p.ln_gamma != nullptr) {
+#pragma unroll
+    for (int it = 0; it < 2; ++it) {
+      const int c = tid + it * SK_THREADS;
+      pg[it] = pb[it] = make_uint4(0u, 0u, 0u, 0u);
+      if (c < kc) {
+        pg[it] = *reinterpret_cast<const uint4*>(p.ln_gamma + c * 8);
+        pb[it] = *reinterpret_cast<const uint4*>(p.ln_beta + c * 8);
+      }
+    }
+  }
   pdl_wait();
   for (int idx = tid; idx < MT * kc; idx += SK_THREADS) {
     const int m = idx / kc, c = idx - m * kc;
     sA[idx] = (m < p.M) ? *reinterpret_cast<const uint4*>(p.A + (long long)m * p.lda + c * 8) : make_uint4(0u, 0u, 0u, 0u);
   }
   __syncthreads();
+  if (p.ln_gamma != nullptr) layernorm_rows_in_smem<SK_THREADS>(sA, p, kc, tid, blockIdx.x == 0, pg, pb, ln_red);
   for (int g = g_first; g < ngroups; g += nwarps) {
     const int n0 = g * SK_ROWS;
     const __half* brow[NR];
@@ -358,7 +438,7 @@ template <int MT, int EPI>
 static bool launch_skinny_bulk(const SkinnyParams& p, cudaStream_t stream, int* rc) {
   static int on = -1;
   if (on < 0) on = getenv("DB1_SKINNY_BULK") ? 1 : 0;
-  if (!on) return false;
+  if (!on || p.ln_gamma != nullptr) return false;
   const long long row_bytes = (long long)p.K * 2;
   if (row_bytes % 16 != 0 || (p.ldb * 2) % 16 != 0 || row_bytes > 32768) return false;
   SkinnyBulkCfg cfg;
@@ -455,6 +535,11 @@ int skinny_gemm(const db1_gemm_desc* d, cudaStream_t stream) {
   p.C = (__half*)d->C; p.ldc = d->ldc; p.bias = (const __half*)d->bias; p.resid = (const __half*)d->resid; p.ldr = d->ldr;
   p.u = (const __half*)d->u; p.v = (const __half*)d->v; p.H = (__half*)d->H; p.ldh = d->ldh;
   p.M = d->M; p.N = d->N; p.K = d->K; p.F = d->F; p.d_model = d->d_model; p.alpha = d->alpha; p.b_static = d->b_static;
+  p.ln_gamma = (const __half*)d->ln_gamma; p.ln_beta = (const __half*)d->ln_beta; p.ln_eps = d->ln_eps; p.ln_out = (__half*)d->ln_out;
+  if (p.ln_gamma != nullptr) {
+    DB1_CHECK_ARG(p.ln_beta != nullptr && ((((uintptr_t)p.ln_gamma) | ((uintptr_t)p.ln_beta) | ((uintptr_t)p.ln_out)) & 15) == 0,
+                  "gemm(ln): ln_beta missing or ln_gamma / ln_beta / ln_out not 16-byte aligned");
+  }
   switch (d->epilogue) {
     case DB1_EPI_PLAIN: return launch_skinny_e<DB1_EPI_PLAIN>(p, stream);
     case DB1_EPI_QKV: return launch_skinny_e<DB1_EPI_QKV>(p, stream);

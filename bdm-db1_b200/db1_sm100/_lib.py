@@ -36,6 +36,7 @@ class GemmDesc(C.Structure):
         ("dot_with", C.c_void_p), ("ld_dot", C.c_int64), ("dot_out", C.c_void_p),
         ("dot_L", C.c_int32), ("dot_H", C.c_int32),
         ("b_static", C.c_int32),
+        ("ln_gamma", C.c_void_p), ("ln_beta", C.c_void_p), ("ln_eps", C.c_float), ("ln_out", C.c_void_p),
     ]
 
 

@@ -489,6 +489,79 @@ def attn_block_cached(w, li, mem, r, Wqkv, Wr, Wo, u, v, gamma, beta, H, eps, wi
     return out.view(B, Q, d)
 
 
+def decode_step_fused(model, hidden, mem, pos_rows, window):
+    """One cached decode step with rows = B * Q <= 8, all layers and the tied head: every LayerNorm is applied by the
+    few-row GEMM that consumes it (db1_gemm_desc.ln_*: normalise-on-load; the normalised rows are written once, by that
+    GEMM, for the residual add and the memory append that need them) - 49 launches less than block-by-block execution.
+    Same arithmetic and the same fp16 rounding points as attn_block_cached + FFBlockFn + head_logits. Returns the logits."""
+    B, Q, d = hidden.shape
+    rows = B * Q
+    dev = hidden.device
+    f16 = torch.float16
+    K = mem.cap + Q
+    x2 = hidden.reshape(rows, d)
+    if not x2.is_contiguous():
+        x2 = x2.contiguous()
+    pend = None  # (pre-norm rows, gamma, beta, eps) of the previous block
+    for li, layer in enumerate(model.h):
+        at, ff = layer.dec_attn, layer.pos_ff
+        H = at.n_head
+        dh = d // H
+        # ---- attention block: qkv (LayerNorm of the previous block on load), attention over the cache, o_net + residual
+        qkv4 = torch.empty(rows, 4 * d, dtype=f16, device=dev)
+        if pend is not None:
+            xin = torch.empty(rows, d, dtype=f16, device=dev)
+            ops.gemm(pend[0], at.qkv_net.weight, qkv4, rows, 3 * d, d, lda=d, ldb=d, ldc=4 * d, epilogue=ops.EPI_QKV,
+                     u=at.r_w_bias.reshape(d), v=at.r_r_bias.reshape(d), d_model=d, b_static=True,
+                     ln=(pend[1], pend[2], pend[3], xin))
+            x2 = xin
+        else:
+            ops.gemm(x2, at.qkv_net.weight, qkv4, rows, 3 * d, d, lda=d, ldb=d, ldc=4 * d, epilogue=ops.EPI_QKV,
+                     u=at.r_w_bias.reshape(d), v=at.r_r_bias.reshape(d), d_model=d, b_static=True)
+        rk = mem.rk.get((li, K))
+        if rk is None:
+            rk = torch.empty(K, d, dtype=f16, device=dev)
+            ops.gemm(pos_rows, at.r_net.weight, rk, K, d, d, lda=d, ldb=d, ldc=d)
+            mem.rk[(li, K)] = rk
+        need = rows * H * ops.decode_splits(B, Q, H) * (dh + 2)
+        if mem.ws is None or mem.ws.numel() < need:
+            mem.ws = torch.empty(need, dtype=torch.float32, device=dev)
+        o = torch.empty(rows, d, dtype=f16, device=dev)
+        ops.relattn_decode(qkv4, mem.k[li], mem.v[li], mem.head, rk, o, mem.ws, B, Q, H, dh, window, 1.0 / math.sqrt(dh),
+                           head_dev=mem.head_dev)
+        ops.ring_append([(x2, mem.hid[li]), (qkv4[:, 2 * d:3 * d], mem.k[li]), (qkv4[:, 3 * d:], mem.v[li])], mem.head, B, Q,
+                        head_dev=mem.head_dev)
+        ya = torch.empty(rows, d, dtype=f16, device=dev)
+        ops.gemm(o, at.o_net.weight, ya, rows, d, d, lda=d, ldb=d, ldc=d, resid=x2, ldr=d, b_static=True)
+        # ---- feed-forward block: ff1 + GeGLU (the attention block's LayerNorm on load), ff2 + bias + residual
+        W1, b1, W2, b2 = ff.CoreNet[0].weight, ff.CoreNet[0].bias, ff.CoreNet[2].weight, ff.CoreNet[2].bias
+        F = W1.shape[0] // 2
+        x3 = torch.empty(rows, d, dtype=f16, device=dev)
+        g = torch.empty(rows, F, dtype=f16, device=dev)
+        ops.gemm(ya, W1, g, rows, 2 * F, d, lda=d, ldb=d, ldc=F, epilogue=ops.EPI_GEGLU, bias=b1, F=F, b_static=True,
+                 ln=(at.layer_norm.weight, at.layer_norm.bias, at.layer_norm.eps, x3))
+        yf = torch.empty(rows, d, dtype=f16, device=dev)
+        ops.gemm(g, W2, yf, rows, d, F, lda=F, ldb=F, ldc=d, bias=b2, resid=x3, ldr=d, b_static=True)
+        pend = (yf, ff.layer_norm.weight, ff.layer_norm.bias, ff.layer_norm.eps)
+    W = model.word_embedding.weight if model.share_input_output_embedding else model.lm_head.weight
+    V = W.shape[0]
+    Vp = (V + 127) // 128 * 128
+    buf = torch.empty(rows, Vp, dtype=f16, device=dev)
+    ops.gemm(pend[0], W, buf, rows, V, d, lda=d, ldb=d, ldc=Vp, b_static=True, ln=(pend[1], pend[2], pend[3], None))
+    return buf.view(B, Q, Vp)[:, :, :V]
+
+
+def decode_step_fused_applies(model, rows, d):
+    """rows <= 8 on the few-row GEMM path, the released layer type (post-LN, GeGLU)."""
+    import os
+    if os.environ.get("DB1_DECODE_UNFUSED"):
+        return False
+    if not ops.few_row_gemm_applies(rows, d, d):
+        return False
+    l0 = model.h[0]
+    return (not l0.dec_attn.pre_lnorm) and getattr(l0.pos_ff, "activation", "geglu") == "geglu" and len(model.h) > 0
+
+
 class FFBlockFn(torch.autograd.Function):
     """PositionwiseFF.forward, post-LN branch with GeGLU (transformer_xl.py:276-292, activations.py:19-32):
     out = LayerNorm(x + dropout(W2 (a * gelu(g)) + b2)), [a|g] = W1 x + b1."""

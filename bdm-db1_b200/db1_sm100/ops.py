@@ -9,7 +9,7 @@ import torch
 
 from . import _lib
 from ._lib import (EPI_DGEGLU, EPI_DS, EPI_GEGLU, EPI_PLAIN, EPI_QKV, K_BEGIN_BY_ROW, K_BEGIN_REV, K_END_BY_ROW,
-                   K_FULL, GemmDesc, check, cur_stream, ptr)
+                   K_FULL, Db1Error, GemmDesc, check, cur_stream, ptr)
 
 
 class Profile:
@@ -103,7 +103,7 @@ def _ensure_gemm_workspace(device):
 def gemm(A, B, C_out, M, N, K, *, lda, ldb, ldc, a_mn=False, b_mn=False, epilogue=EPI_PLAIN, alpha=1.0,
          accumulate=False, bias=None, resid=None, ldr=0, drop_p=0.0, seed=0, u=None, v=None, d_model=0, H=None,
          ldh=0, F=0, Z1=1, Z2=1, a_z=(0, 0), b_z=(0, 0), c_z=(0, 0), reduce_z2=False, k_mode=K_FULL,
-         skip_upper=False, P=None, C2=None, Drow=None, window=0, bn_hint=0, dot=None, b_static=False):
+         skip_upper=False, P=None, C2=None, Drow=None, window=0, bn_hint=0, dot=None, b_static=False, ln=None):
     """C[M,N] (+)= epilogue(alpha * A[M,K] @ B[N,K]^T) per batch index; see include/db1_sm100.h:db1_gemm_f16."""
     _need_cuda_half(A, B, C_out, bias, resid, u, v, H, P, C2)
     _ensure_gemm_workspace(A.device)
@@ -139,6 +139,13 @@ def gemm(A, B, C_out, M, N, K, *, lda, ldb, ldc, a_mn=False, b_mn=False, epilogu
     d.window = window
     d.bn_hint = bn_hint
     d.b_static = int(b_static)  # B = weights nobody is writing (inference): the few-row path may prefetch them early
+    if ln is not None:  # (gamma, beta, eps, out or None): LayerNorm of A's rows on load (few-row path, M <= 8)
+        g_, b_, eps_, o_ = ln
+        _need_cuda_half(g_, b_, o_)
+        if not few_row_gemm_applies(M, K, lda, a_mn, b_mn, Z1 * Z2, accumulate, drop_p, epilogue):
+            raise Db1Error("gemm(ln=...): LayerNorm-on-load exists on the few-row path only (M <= 8)")
+        d.ln_gamma, d.ln_beta, d.ln_eps = g_.data_ptr(), b_.data_ptr(), float(eps_)
+        d.ln_out = o_.data_ptr() if o_ is not None else None
     if dot is not None:  # (X fp16 [M, ld], out fp32 [M / L, H, L], L, H): out = per-head rowsum(C * X), head dim 128
         X, dout_t, dL, dH = dot
         _need_cuda_half(X)
@@ -152,6 +159,14 @@ def gemm(A, B, C_out, M, N, K, *, lda, ldb, ldc, a_mn=False, b_mn=False, epilogu
     with _Launch(name, 1, flops):
         check(_lib.lib().db1_gemm_f16(C.byref(d), cur_stream()), "db1_gemm_f16")
     return C_out
+
+
+def few_row_gemm_applies(M, K, lda, a_mn=False, b_mn=False, batch=1, accumulate=False, drop_p=0.0, epilogue=EPI_PLAIN):
+    """Host-side mirror of skinny_gemm_applies (csrc/skinny.cu): whether db1_gemm_f16 will take the weight-streaming path."""
+    import os
+    return (1 <= M <= 8 and batch == 1 and not a_mn and not b_mn and not accumulate and drop_p == 0.0 and K % 8 == 0
+            and lda % 8 == 0 and 16 * K <= 200 * 1024 and epilogue in (EPI_PLAIN, EPI_QKV, EPI_GEGLU)
+            and not os.environ.get("DB1_NO_SKINNY"))
 
 
 def gemm_dot_supported(M, N, H, dh):

@@ -309,6 +309,13 @@ class TransformerXL(nn.Module):
             window = 1 << 30
         pos_rows = self.pos_emb.rows(klen, self.clamp_len, self.drop.p if self.training else 0.0)
 
+        if cached and F_.decode_step_fused_applies(self, hidden.size(0) * qlen, hidden.size(2)):
+            # few new rows: all layers + the head with every LayerNorm applied inside the consuming few-row GEMM
+            with torch.no_grad():
+                lm_logits = F_.decode_step_fused(self, hidden, mems, pos_rows, window)
+            mems.advance(qlen)
+            return (lm_logits, None, mems)
+
         hids = []
         for li, block in enumerate(self.h):
             if mems is not None and not cached:

@@ -23,7 +23,7 @@ extern "C" {
 #endif
 
 const char* db1_last_error(void);
-/* ABI version of this header; bumped whenever a struct layout changes (3: db1_gemm_desc.b_static appended). */
+/* ABI version of this header; bumped whenever a struct layout changes (3: db1_gemm_desc.b_static and ln_* appended). */
 int db1_abi_version(void);
 /* Number of SMs the persistent kernels may cover (0 = all). Lower it while a long-running communication kernel occupies
  * SMs (DB1Engine does during backward at world size > 1: physical SMs minus NCCL's CTAs), so that a grid never needs a
@@ -100,6 +100,15 @@ typedef struct db1_gemm_desc {
    * inference): the few-row path (M <= 8) may then request them before the stream's previous kernel has completed
    * (programmatic dependent launch) - its weight stream overlaps that kernel's tail. 0 (default): B is read only after it. */
   int32_t b_static;
+  /* ABI version 3, few-row path only (M <= 8, K-major A; the tensor-core path rejects it): the rows of A are LayerNorm-ed
+   * over K before the product - A' = (A - mean) * rstd * ln_gamma + ln_beta, rounded to fp16 exactly as db1_layernorm_fwd
+   * stores it (transformer_xl.py:238, :290 feeding :138 / :265 / :595) - so that the decode step needs no LayerNorm
+   * launch between a block's last GEMM and the next block's first. ln_out (optional, [M, K] fp16, row stride K) receives
+   * the normalised rows (the next residual / memory row). */
+  const void* ln_gamma; /* [K] fp16 or NULL */
+  const void* ln_beta;  /* [K] fp16 */
+  float ln_eps;
+  void* ln_out;
 } db1_gemm_desc;
 
 int db1_gemm_f16(const db1_gemm_desc* d, void* stream);

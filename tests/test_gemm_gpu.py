@@ -373,3 +373,40 @@ def test_few_row_gemm_matches_fp32_and_the_tensor_core_path(cuda, M):
     assert _rel(Hb, h) < 2e-3
     hh = Hb.float()
     assert _rel(G, hh[:, :F] * Fn.gelu(hh[:, F:])) < 2e-3
+
+
+@pytest.mark.parametrize("M", [1, 5])
+def test_few_row_gemm_layernorm_on_load(cuda, M):
+    """db1_gemm_desc.ln_*: the few-row path LayerNorms A's rows while staging them (what lets the decode step drop its
+    LayerNorm launches); product and the written-out normalised rows against torch on the same fp16 inputs, for the
+    plain, QKV and GeGLU epilogues; the tensor-core path (M > 8) refuses the option."""
+    import torch.nn.functional as Fn
+    from db1_sm100 import ops
+    from db1_sm100._lib import Db1Error
+    K, N, d, F = 512, 1000, 256, 384
+    A = _mk((M, K), cuda, 2.0, 31) + 0.5
+    gamma, beta = _mk((K,), cuda, 0.3, 32) + 1.0, _mk((K,), cuda, 0.3, 33)
+    ref_ln = Fn.layer_norm(A.float(), (K,), gamma.float(), beta.float(), 1e-5)
+    ln16 = ref_ln.half()
+    B = _mk((N, K), cuda, 0.1, 34)
+    C1 = torch.empty(M, N, dtype=torch.half, device=cuda)
+    lnout = torch.zeros(M, K, dtype=torch.half, device=cuda)
+    ops.gemm(A, B, C1, M, N, K, lda=K, ldb=K, ldc=N, ln=(gamma, beta, 1e-5, lnout), b_static=True)
+    assert _rel(lnout, ref_ln) < 2e-3
+    assert _rel(C1, ln16.float() @ B.float().t()) < 3e-3
+    Wqkv = _mk((3 * d, K), cuda, 0.1, 35)
+    u, v = _mk((d,), cuda, 1.0, 36), _mk((d,), cuda, 1.0, 37)
+    Q4 = torch.empty(M, 4 * d, dtype=torch.half, device=cuda)
+    ops.gemm(A, Wqkv, Q4, M, 3 * d, K, lda=K, ldb=K, ldc=4 * d, epilogue=ops.EPI_QKV, u=u, v=v, d_model=d,
+             ln=(gamma, beta, 1e-5, None))
+    qkv = ln16.float() @ Wqkv.float().t()
+    assert _rel(Q4, torch.cat([qkv[:, :d] + u.float(), qkv[:, :d] + v.float(), qkv[:, d:]], 1)) < 3e-3
+    W1, b1 = _mk((2 * F, K), cuda, 0.1, 38), _mk((2 * F,), cuda, 0.5, 39)
+    G = torch.empty(M, F, dtype=torch.half, device=cuda)
+    ops.gemm(A, W1, G, M, 2 * F, K, lda=K, ldb=K, ldc=F, epilogue=ops.EPI_GEGLU, bias=b1, F=F, ln=(gamma, beta, 1e-5, None))
+    h = (ln16.float() @ W1.float().t() + b1.float()).half().float()
+    assert _rel(G, h[:, :F] * Fn.gelu(h[:, F:])) < 3e-3
+    A9 = _mk((9, K), cuda, 1.0, 40)
+    with pytest.raises(Db1Error):
+        ops.gemm(A9, B, torch.empty(9, N, dtype=torch.half, device=cuda), 9, N, K, lda=K, ldb=K, ldc=N,
+                 ln=(gamma, beta, 1e-5, None))
