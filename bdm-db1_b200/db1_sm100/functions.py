@@ -1,7 +1,9 @@
 """autograd.Function wrappers: each forward/backward is a fixed sequence of C-ABI kernel launches (db1_sm100.ops).
 
-Nothing here computes with torch ops on the data path; torch supplies device buffers, the current stream and the
-autograd graph. Shapes: activations are [rows = B*L, d] fp16 row-major.
+No arithmetic of the path runs as torch ops; torch supplies device buffers, the current stream and the autograd graph,
+plus buffer plumbing (zero-fills of gradient accumulators, the loss mask's cast to fp32, concatenation of task segments,
+contiguous copies of strided views: ~70 small ATen launches per step, < 1 % of its time, profiles/kernels_r2.md).
+Shapes: activations are [rows = B*L, d] fp16 row-major.
 """
 import math
 import threading

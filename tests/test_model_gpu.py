@@ -321,3 +321,33 @@ def test_deepspeed_layout_checkpoint_into_db1_module(cuda, tmp_path):
     assert torch.equal(after, want)
     for b in eng.buckets:
         assert torch.equal(b.master, b.pflat.float()) and b.m.abs().max().item() == 0
+
+
+def test_vqa_input_takes_the_image_caption_path(cuda):
+    """VQATaskInput (reference _forward_vqa, transformer_xl.py:705-748) embeds prompt | image patches | text exactly like
+    ICTaskInput (:675-703): the same tensors wrapped in either dataclass give bit-identical logits and loss and the same gradients."""
+    from src.data.input_specs import ICTaskInput, VQATaskInput
+    g = util.load_golden("tiny_mixed_images")
+    cfg = util.golden_cfg(g)
+    tasks = util.tasks_from_golden(g)
+    inputs = util.to_model_inputs(tasks, cuda)
+    ics = [t for t in inputs if isinstance(t, ICTaskInput)]
+    assert ics, "the mixed golden holds an image-caption segment"
+    ic = ics[0]
+    vqa = VQATaskInput(position_id=ic.position_id, attention_mask=ic.attention_mask, loss_mask=ic.loss_mask, label=ic.label,
+                       prompt_seq=ic.prompt_seq, img_seq=ic.img_seq, text_seq=ic.text_seq, img_id_seq=ic.img_id_seq,
+                       ques_id_seq=None, ques_len=torch.full((ic.text_seq.shape[0],), 3, device=cuda))
+    outs = []
+    for task in (ic, vqa):
+        model, _sd = _build(cfg, int(g["seed"][0]), cuda)
+        model.eval()
+        logits, loss = model([task])
+        (loss * 4096.0).backward()
+        torch.cuda.synchronize()
+        outs.append((logits.clone(), loss.clone(), {k: p.grad.clone() for k, p in model.named_parameters() if p.grad is not None}))
+    assert torch.equal(outs[0][0], outs[1][0]) and torch.equal(outs[0][1], outs[1][1])
+    assert outs[0][2].keys() == outs[1][2].keys() and len(outs[0][2]) > 20
+    for k in outs[0][2]:
+        # forward is deterministic; several gradients are accumulated with atomics (embedding scatter, fp32 column sums),
+        # whose order varies between two runs of the SAME input - hence a tolerance instead of equality
+        assert util.rel_l2(outs[0][2][k].float(), outs[1][2][k].float()) < 2e-3, k
