@@ -19,15 +19,19 @@
 //           dR_prev += band_prev^T . Qv_I over all tiles of the diagonal; one fp32 reduction per item. (Reducing dR
 //           per key step costs a 64 KB fp32 reduction per step: measured 6.3k cycles with red.v4, 3.0k with
 //           cp.reduce.async.bulk when all SMs do it - as long as the whole step. tools/ubench_red.cu.)
-// Roles (320 threads): warp 0 TMA producer, warp 1 MMA issuer, warps 2-5 un-shift (thread = tile row), warps 6-9 TMEM
-// drain (epilogue / dR reduction; accumulators are double-buffered so it overlaps the next item).
+// Roles (448 threads): warp 0 TMA producer, warp 1 MMA issuer, warps 2-9 un-shift (two threads per tile row: warps 2-5
+// produce the row's shifted chunks 0-8, warps 6-9 chunks 9-16 - each reads only the half of the row it needs, and the
+// compiler prunes the other half of the shifter), warps 10-13 TMEM drain (epilogue / dR reduction; accumulators are
+// double-buffered so it overlaps the next item).
+#include <type_traits>
+
 #include "../../include/db1_sm100.h"
 #include "common.cuh"
 #include "ptx.cuh"
 
 namespace db1 {
 
-constexpr int BW_THREADS = 320;
+constexpr int BW_THREADS = 448;  // TMA warp, MMA warp, 8 un-shift warps (two threads per tile row), 4 drain warps
 
 struct BandParams {
   int L, H, B, dh, window;
@@ -91,19 +95,21 @@ DEVI void red_add_v4(float* p, float a, float b, float c, float d) {
   asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(p), "f"(a), "f"(b), "f"(c), "f"(d) : "memory");
 }
 
-// band chunk positions [16*part, 16*part + 16) of row r: data chunks out[c] at position a + c, zeros elsewhere
+// band chunk positions [16*part, 16*part + 16) of row r: data chunks out[c] at position a + c, zeros elsewhere. The row's
+// two threads split the work: thread HS writes the data chunks c in [9*HS, 9 + 8*HS) and the zero chunks q in [8*HS, 8*HS + 8).
+template <int HS>
 DEVI void store_band_half(uint32_t band_base, int r, int a, int part, const uint32_t (&out)[17][4]) {
   const uint32_t rowb = band_base + (uint32_t)r * 128u;
   const int rx = r & 7;
 #pragma unroll
-  for (int c = 0; c < 17; ++c) {
+  for (int c = 9 * HS; c < 9 + 8 * HS; ++c) {
     const int pos = a + c;
     if ((pos >> 4) == part)
       sts128(rowb + (uint32_t)(pos >> 3) * 16384u + (uint32_t)(((pos & 7) ^ rx) * 16), out[c][0], out[c][1], out[c][2],
              out[c][3]);
   }
 #pragma unroll
-  for (int q = 0; q < 16; ++q) {
+  for (int q = 8 * HS; q < 8 * HS + 8; ++q) {
     const int pos = part * 16 + q;
     if (pos < a || pos > a + 16) sts128(rowb + (uint32_t)(pos >> 3) * 16384u + (uint32_t)(((pos & 7) ^ rx) * 16), 0u, 0u, 0u, 0u);
   }
@@ -215,14 +221,14 @@ relattn_bwd_band_kernel(const __grid_constant__ CUtensorMap tmK, const __grid_co
     if (lane == 0) {
       mbar_init(bar_ds + 0, 1);
       mbar_init(bar_ds + 1, 1);
-      mbar_init(ds_free + 0, KIND == 0 ? 5 : 4);
-      mbar_init(ds_free + 1, KIND == 0 ? 5 : 4);
+      mbar_init(ds_free + 0, KIND == 0 ? 9 : 8);  // the 8 un-shift warps (+ KIND 0: the dQu MMAs' commit)
+      mbar_init(ds_free + 1, KIND == 0 ? 9 : 8);
       mbar_init(bar_b + 0, 1);
       mbar_init(bar_b + 1, 1);
       mbar_init(b_free + 0, 1);
       mbar_init(b_free + 1, 1);
-      mbar_init(full_prev, 4);
-      mbar_init(full_new, 4);
+      mbar_init(full_prev, 8);
+      mbar_init(full_new, 8);
       mbar_init(free_prev, 1);
       mbar_init(free_new, 1);
       mbar_init(acc_full + 0, 1);
@@ -361,61 +367,69 @@ relattn_bwd_band_kernel(const __grid_constant__ CUtensorMap tmK, const __grid_co
         ++ti;
       }
     }
-  } else if (warp < 6) {
-    // ------------------------------------------------------------------ un-shift warps: thread = tile row
-    const int r = (warp - 2) * 32 + lane;
+  } else if (warp < 10) {
+    // ------------------------------------------------------------------ un-shift warps: two threads per tile row
+    const int r = ((warp - 2) & 3) * 32 + lane;
     const int sft = 127 - r;
     const int a = sft >> 3, rem = sft & 7;
     const int rx = r & 7;
     const uint32_t band = smem_u32(smem + SM::BAND);
-    int gs = 0;
-    for (int pass = 0; pass < n_pass; ++pass) {
-      const int k = item_of(pass);
-      if (k < 0) continue;
-      const Item it = decode(k);
-      for (int st = 0; st < it.nsteps; ++st, ++gs) {
-        const int buf = gs & 1;
-        const bool with_prev = (KIND == 0) ? (st > 0) : (it.t > 0);
-        // the row from the TMA-written tile: 16 conflict-free 128-bit shared loads (128-byte swizzle)
-        uint32_t W[64];
-        mbar_wait(bar_ds + buf, (gs >> 1) & 1);
-        {
-          const uint32_t dsrow = smem_u32(smem + SM::DS + buf * 32768) + (uint32_t)r * 128u;
+    auto body = [&](auto hs_tag) {
+      constexpr int HS = decltype(hs_tag)::value;
+      int gs = 0;
+      for (int pass = 0; pass < n_pass; ++pass) {
+        const int k = item_of(pass);
+        if (k < 0) continue;
+        const Item it = decode(k);
+        for (int st = 0; st < it.nsteps; ++st, ++gs) {
+          const int buf = gs & 1;
+          const bool with_prev = (KIND == 0) ? (st > 0) : (it.t > 0);
+          // this thread's half of the row from the TMA-written tile: conflict-free 128-bit shared loads (128-byte
+          // swizzle); words outside [32*HS, 36 + 28*HS) are never used by the chunks this thread produces
+          uint32_t W[64];
 #pragma unroll
-          for (int c = 0; c < 16; ++c) {
-            const Half8 h8 = lds_half8(dsrow + (uint32_t)(c >> 3) * 16384u + (uint32_t)(((c & 7) ^ rx) * 16));
-            W[4 * c] = h8.u.x; W[4 * c + 1] = h8.u.y; W[4 * c + 2] = h8.u.z; W[4 * c + 3] = h8.u.w;
+          for (int m = 0; m < 64; ++m) W[m] = 0u;
+          mbar_wait(bar_ds + buf, (gs >> 1) & 1);
+          {
+            const uint32_t dsrow = smem_u32(smem + SM::DS + buf * 32768) + (uint32_t)r * 128u;
+#pragma unroll
+            for (int c = 8 * HS; c < 9 + 7 * HS; ++c) {
+              const Half8 h8 = lds_half8(dsrow + (uint32_t)(c >> 3) * 16384u + (uint32_t)(((c & 7) ^ rx) * 16));
+              W[4 * c] = h8.u.x; W[4 * c + 1] = h8.u.y; W[4 * c + 2] = h8.u.z; W[4 * c + 3] = h8.u.w;
+            }
+          }
+          uint32_t out[17][4];
+          unshift_row(W, rem, out);
+          __syncwarp();
+          if (lane == 0) mbar_arrive(ds_free + buf);  // the row is in registers
+          if (KIND == 0) {
+            if (gs > 0) mbar_wait(free_prev, (gs - 1) & 1);
+            if (with_prev) store_band_half<HS>(band, r, a, 1, out);
+            fence_proxy_async_smem();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(full_prev);
+            if (gs > 0) mbar_wait(free_new, (gs - 1) & 1);
+            store_band_half<HS>(band, r, a, 0, out);
+            fence_proxy_async_smem();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(full_new);
+          } else {
+            if (gs > 0) mbar_wait(free_new, (gs - 1) & 1);
+            store_band_half<HS>(band, r, a, 0, out);
+            fence_proxy_async_smem();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(full_new);
+            if (gs > 0) mbar_wait(free_prev, (gs - 1) & 1);
+            if (with_prev) store_band_half<HS>(band, r, a, 1, out);
+            fence_proxy_async_smem();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(full_prev);
           }
         }
-        uint32_t out[17][4];
-        unshift_row(W, rem, out);
-        __syncwarp();
-        if (lane == 0) mbar_arrive(ds_free + buf);  // the row is in registers
-        if (KIND == 0) {
-          if (gs > 0) mbar_wait(free_prev, (gs - 1) & 1);
-          if (with_prev) store_band_half(band, r, a, 1, out);
-          fence_proxy_async_smem();
-          __syncwarp();
-          if (lane == 0) mbar_arrive(full_prev);
-          if (gs > 0) mbar_wait(free_new, (gs - 1) & 1);
-          store_band_half(band, r, a, 0, out);
-          fence_proxy_async_smem();
-          __syncwarp();
-          if (lane == 0) mbar_arrive(full_new);
-        } else {
-          if (gs > 0) mbar_wait(free_new, (gs - 1) & 1);
-          store_band_half(band, r, a, 0, out);
-          fence_proxy_async_smem();
-          __syncwarp();
-          if (lane == 0) mbar_arrive(full_new);
-          if (gs > 0) mbar_wait(free_prev, (gs - 1) & 1);
-          if (with_prev) store_band_half(band, r, a, 1, out);
-          fence_proxy_async_smem();
-          __syncwarp();
-          if (lane == 0) mbar_arrive(full_prev);
-        }
       }
-    }
+    };
+    if (warp < 6) body(std::integral_constant<int, 0>{});
+    else body(std::integral_constant<int, 1>{});
   } else {
     // ------------------------------------------------------------------ TMEM drain warps (one per lane quadrant)
     const int q = warp & 3;
